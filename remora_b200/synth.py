@@ -1,0 +1,80 @@
+"""Seeded synthetic chunk batches and reads (SURVEY.md §8d "Synthetic inputs").
+
+Used by tests/, tests/golden/make_golden.py and bench.py.  Everything is generated with
+``numpy.random.default_rng(seed)`` so the same seed gives the same arrays here and on the GPU box.
+
+Array layout follows the reference's compact chunk format
+(``CoreRemoraDataset._core_dtypes``, reference src/remora/data_chunks.py:942-948):
+  signal                      float32 [N, 1, T]
+  sequence                    int8    [N, Lmax + kmer_len - 1]   values -1..3 (-1 = N / beyond read end)
+  sequence_to_signal_mapping  int16   [N, Lmax + 1]              monotone, [0] == 0, [seq_len] == T
+  sequence_lengths            int16   [N]
+Padding past ``seq_len`` is filled with garbage on purpose (the reference leaves it
+uninitialised, data_chunks.py:1379-1388): kernels must never read it.
+"""
+import numpy as np
+
+
+def synth_chunks(n, chunk_len=100, kmer_context_bases=(4, 4), seed=0, stride=5,
+                 frac_n=0.01, frac_edge=0.05, max_seq_len=None, garbage_padding=True):
+    rng = np.random.default_rng(seed)
+    kmer_len = sum(kmer_context_bases) + 1
+    T = int(chunk_len)
+    lmax = T // stride if max_seq_len is None else int(max_seq_len)
+    n_slots = (T - 1) // stride  # interior multiples of `stride` strictly inside (0, T)
+    signal = rng.standard_normal((n, 1, T), dtype=np.float32)
+    seq_w = lmax + kmer_len - 1
+    if garbage_padding:
+        sequence = rng.integers(-128, 127, size=(n, seq_w), dtype=np.int8)
+        mapping = rng.integers(-32768, 32767, size=(n, lmax + 1), dtype=np.int16)
+    else:
+        sequence = np.full((n, seq_w), -1, dtype=np.int8)
+        mapping = np.zeros((n, lmax + 1), dtype=np.int16)
+    # number of bases per chunk: mean dwell ~ 8-12 samples, at least 1, at most lmax
+    lo = max(1, T // 12)
+    hi = max(lo, min(lmax, T // 8))
+    seq_lens = rng.integers(lo, hi + 1, size=n).astype(np.int16)
+    for i in range(n):
+        L = int(seq_lens[i])
+        n_inner = min(L - 1, n_slots)
+        inner = np.sort(rng.choice(n_slots, size=n_inner, replace=False) + 1) * stride
+        bounds = np.concatenate([[0], inner, [T]])
+        if bounds.size < L + 1:  # more bases than stride slots: repeat boundaries (zero-dwell bases)
+            extra = rng.choice(bounds, size=L + 1 - bounds.size)
+            bounds = np.sort(np.concatenate([bounds, extra]))
+            bounds[0], bounds[-1] = 0, T
+        mapping[i, : L + 1] = bounds
+        bases = rng.integers(0, 4, size=L + kmer_len - 1).astype(np.int8)
+        bases[rng.random(bases.size) < frac_n] = -1
+        if rng.random() < frac_edge:  # read-edge padding (reference data_chunks.py:394-409)
+            run = int(rng.integers(1, max(2, kmer_len)))
+            if rng.random() < 0.5:
+                bases[:run] = -1
+            else:
+                bases[-run:] = -1
+        sequence[i, : L + kmer_len - 1] = bases
+    return {
+        "signal": signal,
+        "sequence": sequence,
+        "sequence_to_signal_mapping": mapping,
+        "sequence_lengths": seq_lens,
+        "kmer_context_bases": tuple(int(x) for x in kmer_context_bases),
+        "chunk_len": T,
+    }
+
+
+def synth_read(n_bases=400, seed=0, mean_dwell=10, frac_n=0.0):
+    """Raw pieces of a synthetic read: (dacs int16-valued float array, shift, scale,
+    seq_to_sig_map int64, int_seq int64).  Mirrors the argument list of the reference's
+    ``RemoraRead`` dataclass (data_chunks.py:151-160)."""
+    rng = np.random.default_rng(seed)
+    dwells = rng.integers(max(1, mean_dwell // 3), mean_dwell * 2, size=n_bases)
+    seq_to_sig_map = np.concatenate([[0], np.cumsum(dwells)]).astype(np.int64)
+    int_seq = rng.integers(0, 4, size=n_bases).astype(np.int64)
+    if frac_n > 0:
+        int_seq[rng.random(n_bases) < frac_n] = -1
+    levels = rng.normal(0.0, 1.0, size=n_bases)
+    sig = np.repeat(levels, dwells) + rng.normal(0.0, 0.3, size=int(dwells.sum()))
+    shift, scale = 431.5, 87.25
+    dacs = np.round(sig * scale + shift).astype(np.int16)
+    return dacs, shift, scale, seq_to_sig_map, int_seq

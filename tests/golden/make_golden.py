@@ -1,0 +1,198 @@
+"""Generate the committed golden vectors by RUNNING THE REFERENCE (nanoporetech/remora at
+/root/reference) in the build container.  Not run on the GPU box (no reference there).
+
+    python tests/golden/make_golden.py
+
+Outputs (all under tests/golden/):
+  convlstm_s64_k9.pt        TorchScript export (reference model_util.export_model_torchscript) of
+                            models/ConvLSTM_w_ref.py, size 64, kmer_context (4,4), 2 outputs,
+                            chunk_context (50,50), motif CG:0, seeded weights + randomised BN stats
+  convlstm_s64_k9_hot.pt    same architecture, conv x3, LSTM x8, fc x16 weights ("trained-scale": logits span +-3)
+  convlstm_s16_k6_o3.pt     size 16, kmer_context (2,3), 3 outputs (mod_bases "hm"), chunk_context (25,30), motif C:0
+  conv_s64_k9.pt            models/Conv_w_ref.py, size 64, kmer_context (4,4), chunk_context (50,50)
+  encode_cases.npz          inputs + bit-packed outputs of the reference's Cython encoder
+  forward_cases.npz         compact inputs + logits of the reference TorchScript modules (CPU fp32)
+  read_cases.npz / .json    synthetic reads + outputs of reference inference.call_read_mods
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_harness  # noqa: E402
+from remora_b200.synth import synth_chunks, synth_read  # noqa: E402
+
+ref_harness.import_reference()
+from remora import encoded_kmers, inference, model_util  # noqa: E402
+from remora.data_chunks import RemoraRead  # noqa: E402
+
+torch.set_grad_enabled(False)
+torch.set_num_threads(4)
+
+
+def make_model(arch, size, kmer_context, num_out, chunk_context, motifs, mod_bases, mod_long_names,
+               seed, path, hot=(1.0, 1.0, 1.0)):
+    kmer_len = sum(kmer_context) + 1
+    torch.manual_seed(seed)
+    model = model_util._load_python_model(
+        ref_harness.reference_model_path(arch), size=size, kmer_len=kmer_len, num_out=num_out)
+    gen = torch.Generator().manual_seed(seed + 1000)
+    for name, mod in model.named_modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):  # exercise BN folding
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=gen) * 0.5)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=gen) * 1.5 + 0.5)
+            mod.weight.copy_(torch.rand(mod.weight.shape, generator=gen) + 0.5)
+            mod.bias.copy_(torch.randn(mod.bias.shape, generator=gen) * 0.2)
+    # default-init logits barely depend on the input (std over chunks ~4e-5, below the 1e-4
+    # parity tolerance), so the "hot" fixtures scale conv / LSTM / fc weights until logits span a
+    # trained-model range (std ~0.5, +-3) and a wrong kernel cannot hide behind the tolerance.
+    conv_s, lstm_s, fc_s = hot
+    for name, p in model.named_parameters():
+        if "conv" in name and name.endswith("weight"):
+            p.mul_(conv_s)
+        elif name.startswith("lstm"):
+            p.mul_(lstm_s)
+        elif name.startswith("fc"):
+            p.mul_(fc_s)
+    ckpt = {
+        "kmer_context_bases": tuple(kmer_context), "chunk_context": tuple(chunk_context),
+        "modified_base_labels": True, "mod_bases": mod_bases, "reverse_signal": False,
+        "refine_kmer_center_idx": 0, "refine_do_rough_rescale": False, "refine_scale_iters": -1,
+        "refine_algo": "dwell_penalty", "refine_half_bandwidth": 5, "base_start_justify": False,
+        "offset": 0, "pa_scaling": None,
+        "model_params": {"size": size, "kmer_len": kmer_len, "num_out": num_out},
+        "mod_long_names": mod_long_names, "motifs": motifs, "refine_kmer_levels": None,
+        "refine_sd_arr": None, "model_version": 3,
+    }
+    model_util.export_model_torchscript(ckpt, model, path)
+
+
+MODELS = {
+    "convlstm_s64_k9": dict(arch="ConvLSTM_w_ref", size=64, kmer_context=(4, 4), num_out=2,
+                            chunk_context=(50, 50), motifs=[("CG", 0)], mod_bases="m",
+                            mod_long_names=["5mC"], seed=0),
+    "convlstm_s64_k9_hot": dict(arch="ConvLSTM_w_ref", size=64, kmer_context=(4, 4), num_out=2,
+                                chunk_context=(50, 50), motifs=[("CG", 0)], mod_bases="m",
+                                mod_long_names=["5mC"], seed=3, hot=(3.0, 8.0, 16.0)),
+    "convlstm_s16_k6_o3": dict(arch="ConvLSTM_w_ref", size=16, kmer_context=(2, 3), num_out=3,
+                               chunk_context=(25, 30), motifs=[("C", 0)], mod_bases="hm",
+                               mod_long_names=["5hmC", "5mC"], seed=1, hot=(3.0, 8.0, 16.0)),
+    "conv_s64_k9": dict(arch="Conv_w_ref", size=64, kmer_context=(4, 4), num_out=2,
+                        chunk_context=(50, 50), motifs=[("CG", 0)], mod_bases="m",
+                        mod_long_names=["5mC"], seed=2, hot=(2.5, 1.0, 8.0)),
+}
+
+
+def encode_cases():
+    out = {}
+    # SURVEY.md §8c known-answer case
+    seqs = np.array([[0, 1, 2, 3, -1, 0, 1, 2, 3, 0]], dtype=np.int8)
+    maps = np.array([[0, 3, 5]], dtype=np.int16)
+    lens = np.array([2], dtype=np.int16)
+    enc = encoded_kmers.compute_encoded_kmer_batch(4, 4, seqs, maps, lens)
+    assert enc.shape == (1, 36, 5) and enc.sum() == 40
+    out.update(kat_seqs=seqs, kat_maps=maps, kat_lens=lens, kat_out=enc)
+    cases = []
+    cid = 0
+    for ctx in [(4, 4), (2, 3), (1, 10), (0, 0)]:
+        for T in [55, 100, 200, 400]:
+            d = synth_chunks(12, T, ctx, seed=100 + cid, frac_n=0.05, frac_edge=0.3)
+            # edge cases: a chunk with a single base, and one with zero-dwell bases
+            d["sequence_lengths"][1] = 1
+            d["sequence_to_signal_mapping"][1, :2] = [0, T]
+            L2 = int(d["sequence_lengths"][2])
+            if L2 >= 3:
+                d["sequence_to_signal_mapping"][2, 1] = d["sequence_to_signal_mapping"][2, 2]
+            enc = encoded_kmers.compute_encoded_kmer_batch(
+                ctx[0], ctx[1], d["sequence"], d["sequence_to_signal_mapping"],
+                d["sequence_lengths"])
+            assert set(np.unique(enc)) <= {0.0, 1.0}
+            out[f"c{cid}_seqs"] = d["sequence"]
+            out[f"c{cid}_maps"] = d["sequence_to_signal_mapping"]
+            out[f"c{cid}_lens"] = d["sequence_lengths"]
+            out[f"c{cid}_bits"] = np.packbits(enc.astype(bool).reshape(-1))
+            out[f"c{cid}_shape"] = np.array(enc.shape)
+            cases.append([cid, ctx[0], ctx[1], T])
+            cid += 1
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "encode_cases.npz"), **out)
+    print("encode cases:", len(cases))
+
+
+def forward_cases():
+    out = {}
+    index = []
+    plans = [
+        ("convlstm_s64_k9", [(64, 100, 10), (7, 100, 11), (33, 200, 12), (5, 400, 13), (9, 64, 14)]),
+        ("convlstm_s64_k9_hot", [(64, 100, 20), (7, 100, 21), (33, 200, 22), (5, 400, 23), (9, 64, 24)]),
+        ("convlstm_s16_k6_o3", [(40, 55, 30), (3, 100, 31)]),
+        ("conv_s64_k9", [(48, 100, 40), (1, 100, 41)]),
+    ]
+    for name, cfgs in plans:
+        model, md = model_util.load_model(os.path.join(HERE, name + ".pt"), eval_only=True)
+        ctx = tuple(md["kmer_context_bases"])
+        for (n, T, seed) in cfgs:
+            d = synth_chunks(n, T, ctx, seed=seed)
+            enc = encoded_kmers.compute_encoded_kmer_batch(
+                ctx[0], ctx[1], d["sequence"], d["sequence_to_signal_mapping"],
+                d["sequence_lengths"])
+            logits = model(torch.from_numpy(d["signal"]), torch.from_numpy(enc)).numpy()
+            key = f"{name}__n{n}_T{T}"
+            out[key + "__signal"] = d["signal"]
+            out[key + "__seqs"] = d["sequence"]
+            out[key + "__maps"] = d["sequence_to_signal_mapping"]
+            out[key + "__lens"] = d["sequence_lengths"]
+            out[key + "__logits"] = logits.astype(np.float32)
+            index.append(key)
+            print(key, "logit range", float(logits.min()), float(logits.max()))
+    out["index"] = np.array(index)
+    np.savez_compressed(os.path.join(HERE, "forward_cases.npz"), **out)
+
+
+def read_cases():
+    arrays = {}
+    meta = []
+    plans = [("convlstm_s64_k9_hot", 600, 50), ("convlstm_s64_k9", 90, 51),
+             ("convlstm_s16_k6_o3", 300, 52), ("conv_s64_k9", 400, 53)]
+    for idx, (name, n_bases, seed) in enumerate(plans):
+        model, md = model_util.load_model(os.path.join(HERE, name + ".pt"), eval_only=True)
+        dacs, shift, scale, ssm, int_seq = synth_read(n_bases, seed=seed,
+                                                      frac_n=0.01 if idx == 2 else 0.0)
+        read = RemoraRead(dacs=dacs, shift=shift, scale=scale, seq_to_sig_map=ssm, int_seq=int_seq,
+                          read_id=f"read{idx}")
+        nn_out, labels, pos = inference.call_read_mods(read.copy(), model, md)
+        probs, _, pos2 = inference.call_read_mods(read.copy(), model, md, return_mod_probs=True)
+        mm, ml = inference.call_read_mods(read.copy(), model, md, return_mm_ml_tags=True)
+        assert np.array_equal(pos, pos2)
+        k = f"r{idx}_"
+        arrays.update({k + "dacs": dacs, k + "ssm": ssm, k + "int_seq": int_seq,
+                       k + "nn_out": nn_out.astype(np.float32), k + "labels": labels,
+                       k + "pos": pos, k + "probs": probs, k + "ml": np.frombuffer(ml, dtype=np.uint8)})
+        meta.append({"model": name, "shift": shift, "scale": scale, "mm": mm,
+                     "n_calls": int(pos.size), "str_seq": read.str_seq})
+        print(name, n_bases, "calls", pos.size, "mm", mm[:40])
+    # the reference's own spoofed test read (data_chunks.py:178-189), used by scripts/api_example.py
+    model, md = model_util.load_model(os.path.join(HERE, "convlstm_s64_k9.pt"), eval_only=True)
+    tr = RemoraRead.test_read()
+    nn_out, labels, pos = inference.call_read_mods(tr, model, md)
+    arrays.update({"test_read_nn_out": nn_out.astype(np.float32), "test_read_pos": pos,
+                   "test_read_labels": labels})
+    np.savez_compressed(os.path.join(HERE, "read_cases.npz"), **arrays)
+    with open(os.path.join(HERE, "read_cases.json"), "w") as fh:
+        json.dump(meta, fh, indent=1)
+
+
+if __name__ == "__main__":
+    for name, kw in MODELS.items():
+        make_model(path=os.path.join(HERE, name + ".pt"), **kw)
+    encode_cases()
+    forward_cases()
+    read_cases()
+    print("golden vectors written to", HERE)
