@@ -1,0 +1,149 @@
+/*
+ * remora_b200 — C ABI of the B200 (sm_100a) implementation of Remora's per-chunk
+ * modified-base inference hot path.
+ *
+ * This is the drop-in boundary.  The reference (nanoporetech/remora v3.2.0)
+ * has no FFI layer of its own; the native/operator surface this library replaces is
+ *
+ *   - the Cython op      compute_encoded_kmer_batch          src/remora/encoded_kmers.pyx:13-45
+ *   - the model call     network.forward(sigs, seqs)         models/ConvLSTM_w_ref.py:39-58
+ *                                                            models/Conv_w_ref.py:44-62
+ *     as reached from    RemoraRead.run_model                src/remora/data_chunks.py:516-540
+ *                        inference.run_model_batched         src/remora/inference.py:277-316
+ *
+ * Conventions: every entry point is extern "C", takes plain pointers and sizes (no torch
+ * types), returns 0 (RB200_OK) or an error code; rb200_last_error() returns a thread-local
+ * message.  Pointers suffixed _dev are device pointers on the handle's device, _host are host
+ * pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
+ * launches are asynchronous on `stream` unless stated otherwise.  The caller owns all buffers.
+ * A handle may be used from several host threads concurrently (duplex inference does this,
+ * src/remora/inference.py:973-982): calls are serialised per handle while they enqueue work.
+ *
+ * There is NO CPU fallback anywhere behind this interface.
+ */
+#ifndef REMORA_B200_H
+#define REMORA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB200_ABI_VERSION 1
+
+enum rb200_status {
+    RB200_OK = 0,
+    RB200_ERR_INVALID = 1,     /* bad argument / shape */
+    RB200_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+    RB200_ERR_UNSUPPORTED = 3, /* valid request this build has no kernel for */
+    RB200_ERR_NOMEM = 4
+};
+
+enum rb200_arch {
+    RB200_ARCH_CONVLSTM_W_REF = 1, /* models/ConvLSTM_w_ref.py */
+    RB200_ARCH_CONV_W_REF = 2      /* models/Conv_w_ref.py */
+};
+
+enum rb200_impl {
+    RB200_IMPL_AUTO = 0,    /* fused kernels when the model/shape qualifies, else layer kernels */
+    RB200_IMPL_LAYERS = 1,  /* one CUDA kernel per layer, any size / kmer_len / chunk_len */
+    RB200_IMPL_FUSED = 2    /* fused sm_100a kernels (ConvLSTM_w_ref, size 64); error if n/a */
+};
+
+#define RB200_MAX_CONVS 4
+
+/* One Conv1d(+eval BatchNorm folded)+swish layer.  Weights are float32 [c_out][c_in][kw] with
+ * the BatchNorm already folded in (W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta;
+ * same fold as torch fuse_conv_bn_eval used by the reference at src/remora/model_util.py:216).
+ * Offsets count floats from the start of the weight blob. */
+typedef struct rb200_conv_desc {
+    int32_t c_in, c_out, kw, stride;
+    int64_t w_off, b_off;
+} rb200_conv_desc;
+
+typedef struct rb200_model_desc {
+    int32_t struct_size; /* = sizeof(rb200_model_desc), ABI guard */
+    int32_t arch;        /* enum rb200_arch */
+    int32_t size;        /* channel width ("size" model parameter) */
+    int32_t kmer_len;    /* sequence track has 4*kmer_len rows */
+    int32_t num_out;     /* classifier outputs */
+    int32_t n_sig_conv, n_seq_conv, n_merge_conv;
+    rb200_conv_desc sig_conv[RB200_MAX_CONVS];
+    rb200_conv_desc seq_conv[RB200_MAX_CONVS];
+    rb200_conv_desc merge_conv[RB200_MAX_CONVS];
+    int32_t n_lstm; /* 2 for ConvLSTM_w_ref, 0 for Conv_w_ref */
+    /* torch.nn.LSTM layout: w_ih [4H][H], w_hh [4H][H], gate order i,f,g,o;
+     * b = bias_ih + bias_hh [4H] (scripts/convert_ts_to_ont_json.py:134-135) */
+    int64_t lstm_w_ih_off[2], lstm_w_hh_off[2], lstm_b_off[2];
+    int32_t fc_in; /* Linear in_features (size, or size*T_final for Conv_w_ref) */
+    int32_t reserved;
+    int64_t fc_w_off, fc_b_off; /* [num_out][fc_in], [num_out] */
+} rb200_model_desc;
+
+typedef struct rb200_model *rb200_handle;
+
+int rb200_version(void);
+const char *rb200_last_error(void);
+
+/* Uploads the (host) weight blob to `device`, builds the kernel-specific weight layouts.
+ * Replaces: torch.jit.load + module.to(device) at src/remora/model_util.py:468-481. */
+int rb200_create(const rb200_model_desc *desc, const float *weights_host, int64_t n_floats,
+                 int device, rb200_handle *out);
+int rb200_destroy(rb200_handle h);
+
+/* Test / benchmarking controls. */
+int rb200_set_impl(rb200_handle h, int impl); /* enum rb200_impl */
+int rb200_last_impl(rb200_handle h);          /* impl used by the last forward on this handle */
+uint64_t rb200_launch_count(rb200_handle h);  /* kernels launched through this handle so far */
+int rb200_set_debug(rb200_handle h, int keep); /* keep layer outputs of the next LAYERS forward */
+/* Copies a kept layer output (float32, [B][C][T] channel-first) to dst_dev.  Names: sig1 sig2
+ * sig3 seq1 seq2 seq3 merge1..merge4 lstm1 lstm2.  *n_floats receives the element count. */
+int rb200_debug_tensor(rb200_handle h, const char *name, float *dst_dev, int64_t capacity,
+                       int64_t *n_floats, int32_t *channels, int32_t *steps, void *stream);
+
+/* Dense k-mer one-hot encoding, bit-exact with the reference's Cython op
+ *   compute_encoded_kmer_batch(before, after, seqs, seq_mappings, seq_lens)
+ *   (src/remora/encoded_kmers.pyx:13-45): out[c, 4*p+base, map[c,s]:map[c,s+1]] = 1.0f for
+ * every k-mer offset p < before+after+1 and s < seq_lens[c] with base = seqs[c, s+p] != -1;
+ * everything else 0.0f.  out_dev: float32 [n_chunks][4*(before+after+1)][sig_len].
+ * sig_len is passed explicitly (the reference reads it from chunk 0, pyx:23); mapping entries are
+ * clipped to [0, sig_len].  Never reads seqs past s+p < seq_len+kmer_len-1 nor maps past seq_len. */
+int rb200_encode_dense(const int8_t *seqs_dev, int32_t seq_width, const int16_t *maps_dev,
+                       int32_t map_width, const int16_t *lens_dev, int32_t n_chunks,
+                       int32_t before, int32_t after, int32_t sig_len, float *out_dev,
+                       void *stream);
+
+/* model(sigs, enc_kmers): the reference model call with its dense arguments
+ * (sigs float32 [B][1][T], enc float32 [B][4*kmer_len][T]) -> logits float32 [B][num_out].
+ * Replaces network.forward at models/ConvLSTM_w_ref.py:39-58 / models/Conv_w_ref.py:44-62. */
+int rb200_forward_dense(rb200_handle h, const float *sigs_dev, const float *enc_dev, int32_t B,
+                        int32_t T, float *logits_dev, void *stream);
+
+/* Fused encode + forward on the reference's compact chunk arrays
+ * (CoreRemoraDataset._core_dtypes, src/remora/data_chunks.py:942-948): the one-hot tensor is never
+ * materialised.  Precondition (true for every chunk the reference produces): each mapping row
+ * is non-decreasing on [0, seq_len] with map[0] == 0 and map[seq_len] == T. */
+int rb200_forward_compact(rb200_handle h, const float *sigs_dev, const int8_t *seqs_dev,
+                          int32_t seq_width, const int16_t *maps_dev, int32_t map_width,
+                          const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
+                          void *stream);
+
+/* End-to-end convenience for host callers (the bench's e2e leg and non-torch hosts): copies the
+ * compact arrays host->device through pinned staging, runs rb200_forward_compact, copies the
+ * logits back and synchronises.  Host buffers may be pageable. */
+int rb200_infer_host(rb200_handle h, const float *sigs_host, const int8_t *seqs_host,
+                     int32_t seq_width, const int16_t *maps_host, int32_t map_width,
+                     const int16_t *lens_host, int32_t B, int32_t T, float *logits_host);
+
+/* Post-processing on device ("next" row 2): softmax over num_out, drop class 0,
+ * probs float32 [B][num_out-1] (may be NULL) and ML bytes uint8 [B][num_out-1]
+ * = min(floor(p*256), 255)  (src/remora/util.py:182-186, 532-535). */
+int rb200_softmax_ml(const float *logits_dev, int32_t B, int32_t num_out, float *probs_dev,
+                     uint8_t *ml_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REMORA_B200_H */

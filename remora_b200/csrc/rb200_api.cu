@@ -1,0 +1,360 @@
+// C-ABI entry points (include/remora_b200.h): handle lifetime, argument checks, dispatch between
+// the fused sm_100a kernels and the layer-per-kernel path, host-buffer convenience call.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "rb200_internal.cuh"
+
+namespace rb200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int Workspace::ensure(size_t need) {
+    if (need <= bytes) return RB200_OK;
+    if (base) {
+        cudaDeviceSynchronize();  // earlier launches may still read the old buffer
+        cudaFree(base);
+        base = nullptr;
+        bytes = 0;
+    }
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&base, want);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        base = nullptr;
+        return RB200_ERR_NOMEM;
+    }
+    bytes = want;
+    return RB200_OK;
+}
+
+void Workspace::release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    bytes = 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static bool conv_in_blob(const rb200_conv_desc &c, int64_t n) {
+    if (c.c_in <= 0 || c.c_out <= 0 || c.kw <= 0 || c.stride <= 0) return false;
+    if (c.w_off < 0 || c.b_off < 0) return false;
+    return c.w_off + (int64_t)c.c_in * c.c_out * c.kw <= n && c.b_off + c.c_out <= n;
+}
+
+static int check_desc(const rb200_model_desc *d, int64_t n) {
+    RB200_REQUIRE(d->struct_size == (int32_t)sizeof(rb200_model_desc),
+                  "rb200_model_desc size mismatch (%d vs %zu): header/library ABI skew",
+                  d->struct_size, sizeof(rb200_model_desc));
+    RB200_REQUIRE(d->arch == RB200_ARCH_CONVLSTM_W_REF || d->arch == RB200_ARCH_CONV_W_REF,
+                  "unknown architecture %d", d->arch);
+    RB200_REQUIRE(d->size > 0 && d->kmer_len > 0 && d->num_out > 0, "bad model dimensions");
+    RB200_REQUIRE(d->n_sig_conv >= 1 && d->n_sig_conv <= RB200_MAX_CONVS && d->n_seq_conv >= 1 &&
+                      d->n_seq_conv <= RB200_MAX_CONVS && d->n_merge_conv >= 1 &&
+                      d->n_merge_conv <= RB200_MAX_CONVS,
+                  "bad conv layer counts");
+    for (int i = 0; i < d->n_sig_conv; ++i)
+        RB200_REQUIRE(conv_in_blob(d->sig_conv[i], n), "sig_conv%d outside weight blob", i + 1);
+    for (int i = 0; i < d->n_seq_conv; ++i)
+        RB200_REQUIRE(conv_in_blob(d->seq_conv[i], n), "seq_conv%d outside weight blob", i + 1);
+    for (int i = 0; i < d->n_merge_conv; ++i)
+        RB200_REQUIRE(conv_in_blob(d->merge_conv[i], n), "merge_conv%d outside weight blob", i + 1);
+    RB200_REQUIRE(d->sig_conv[0].c_in == 1, "signal track must have 1 input channel");
+    RB200_REQUIRE(d->seq_conv[0].c_in == 4 * d->kmer_len, "seq_conv1 c_in != 4*kmer_len");
+    RB200_REQUIRE(d->sig_conv[d->n_sig_conv - 1].c_out == d->size &&
+                      d->seq_conv[d->n_seq_conv - 1].c_out == d->size &&
+                      d->merge_conv[0].c_in == 2 * d->size,
+                  "track widths do not match the merge convolution");
+    for (int i = 1; i < d->n_sig_conv; ++i)
+        RB200_REQUIRE(d->sig_conv[i].c_in == d->sig_conv[i - 1].c_out, "sig conv chain mismatch");
+    for (int i = 1; i < d->n_seq_conv; ++i)
+        RB200_REQUIRE(d->seq_conv[i].c_in == d->seq_conv[i - 1].c_out, "seq conv chain mismatch");
+    for (int i = 1; i < d->n_merge_conv; ++i)
+        RB200_REQUIRE(d->merge_conv[i].c_in == d->merge_conv[i - 1].c_out, "merge chain mismatch");
+    if (d->arch == RB200_ARCH_CONVLSTM_W_REF) {
+        RB200_REQUIRE(d->n_lstm == 2, "ConvLSTM_w_ref needs 2 LSTM layers");
+        RB200_REQUIRE(d->merge_conv[d->n_merge_conv - 1].c_out == d->size && d->fc_in == d->size,
+                      "LSTM width mismatch");
+        const int64_t H = d->size;
+        for (int l = 0; l < 2; ++l)
+            RB200_REQUIRE(d->lstm_w_ih_off[l] >= 0 && d->lstm_w_ih_off[l] + 4 * H * H <= n &&
+                              d->lstm_w_hh_off[l] >= 0 && d->lstm_w_hh_off[l] + 4 * H * H <= n &&
+                              d->lstm_b_off[l] >= 0 && d->lstm_b_off[l] + 4 * H <= n,
+                          "lstm%d outside weight blob", l + 1);
+    } else {
+        RB200_REQUIRE(d->n_lstm == 0, "Conv_w_ref has no LSTM");
+    }
+    RB200_REQUIRE(d->fc_in > 0 && d->fc_w_off >= 0 &&
+                      d->fc_w_off + (int64_t)d->fc_in * d->num_out <= n && d->fc_b_off >= 0 &&
+                      d->fc_b_off + d->num_out <= n,
+                  "fc outside weight blob");
+    return RB200_OK;
+}
+
+static int forward_common(rb200_model *m, const float *sigs, const float *enc, const int8_t *seqs,
+                          int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
+                          int B, int T, float *logits, void *stream_v) {
+    RB200_REQUIRE(m != nullptr, "null handle");
+    RB200_REQUIRE(B >= 0 && T > 0, "bad batch (%d) / chunk_len (%d)", B, T);
+    if (B == 0) return RB200_OK;
+    RB200_REQUIRE(sigs && logits, "null buffer");
+    const bool compact = enc == nullptr;
+    if (compact) {
+        RB200_REQUIRE(seqs && maps && lens, "null compact input");
+        RB200_REQUIRE(map_width >= 2 && seq_width >= m->desc.kmer_len,
+                      "compact arrays too narrow (seq_width %d, map_width %d)", seq_width, map_width);
+        RB200_REQUIRE(T < 32768, "chunk_len %d does not fit the int16 mapping", T);
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    DeviceGuard guard(m->device);
+    RB200_REQUIRE(guard.ok, "cannot select device %d", m->device);
+    std::lock_guard<std::mutex> lock(m->mu);
+    Workspace &ws = m->workspaces[stream_v];
+    int impl = m->impl;
+    const bool fused_ok =
+        compact && m->fused != nullptr && fused_shape_ok(m, T, seq_width, map_width);
+    if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED : RB200_IMPL_LAYERS;
+    if (impl == RB200_IMPL_FUSED) {
+        if (!fused_ok) {
+            set_error("fused kernels not available for this model/shape/input form");
+            return RB200_ERR_UNSUPPORTED;
+        }
+        m->last_impl = RB200_IMPL_FUSED;
+        return fused_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T,
+                                     logits, stream);
+    }
+    m->last_impl = RB200_IMPL_LAYERS;
+    return layers_forward(m, ws, sigs, enc, seqs, seq_width, maps, map_width, lens, B, T, logits,
+                          stream);
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" {
+
+int rb200_version(void) { return RB200_ABI_VERSION; }
+
+const char *rb200_last_error(void) { return g_err; }
+
+int rb200_create(const rb200_model_desc *desc, const float *weights_host, int64_t n_floats,
+                 int device, rb200_handle *out) {
+    RB200_REQUIRE(desc && weights_host && out && n_floats > 0, "null argument");
+    int rc = check_desc(desc, n_floats);
+    if (rc) return rc;
+    int n_dev = 0;
+    RB200_CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    RB200_REQUIRE(device >= 0 && device < n_dev, "device %d out of range (%d visible)", device,
+                  n_dev);
+    DeviceGuard guard(device);
+    RB200_REQUIRE(guard.ok, "cannot select device %d", device);
+    cudaDeviceProp prop;
+    RB200_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return RB200_ERR_UNSUPPORTED;
+    }
+    rb200_model *m = new rb200_model();
+    m->desc = *desc;
+    m->device = device;
+    m->sm_count = prop.multiProcessorCount;
+    m->blob_floats = n_floats;
+    cudaError_t e = cudaMalloc(&m->blob_dev, n_floats * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(m->blob_dev, weights_host, n_floats * sizeof(float),
+                       cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("weight upload failed: %s", cudaGetErrorString(e));
+        if (m->blob_dev) cudaFree(m->blob_dev);
+        delete m;
+        return RB200_ERR_CUDA;
+    }
+    if (fused_supported(m->desc)) {
+        rc = fused_create(m, weights_host);
+        if (rc) {
+            cudaFree(m->blob_dev);
+            delete m;
+            return rc;
+        }
+    }
+    *out = m;
+    return RB200_OK;
+}
+
+int rb200_destroy(rb200_handle h) {
+    if (!h) return RB200_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    fused_destroy(h);
+    for (auto &kv : h->workspaces) kv.second.release();
+    if (h->blob_dev) cudaFree(h->blob_dev);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->staging_dev) cudaFree(h->staging_dev);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+    return RB200_OK;
+}
+
+int rb200_set_impl(rb200_handle h, int impl) {
+    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_FUSED, "bad argument");
+    if (impl == RB200_IMPL_FUSED && h->fused == nullptr) {
+        set_error("fused kernels not available for this model");
+        return RB200_ERR_UNSUPPORTED;
+    }
+    h->impl = impl;
+    return RB200_OK;
+}
+
+int rb200_last_impl(rb200_handle h) { return h ? h->last_impl : 0; }
+
+uint64_t rb200_launch_count(rb200_handle h) { return h ? h->launches.load() : 0; }
+
+int rb200_set_debug(rb200_handle h, int keep) {
+    RB200_REQUIRE(h, "null handle");
+    h->keep_debug = keep != 0;
+    if (!keep) h->debug.clear();
+    return RB200_OK;
+}
+
+int rb200_debug_tensor(rb200_handle h, const char *name, float *dst_dev, int64_t capacity,
+                       int64_t *n_floats, int32_t *channels, int32_t *steps, void *stream) {
+    RB200_REQUIRE(h && name && n_floats, "null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    for (const auto &t : h->debug) {
+        if (t.name == name) {
+            const int64_t n = (int64_t)t.B * t.C * t.T;
+            *n_floats = n;
+            if (channels) *channels = t.C;
+            if (steps) *steps = t.T;
+            if (dst_dev) {
+                RB200_REQUIRE(capacity >= n, "debug tensor %s needs %lld floats", name,
+                              (long long)n);
+                DeviceGuard guard(h->device);
+                RB200_CUDA_TRY(cudaMemcpyAsync(dst_dev, t.ptr, n * sizeof(float),
+                                               cudaMemcpyDeviceToDevice,
+                                               static_cast<cudaStream_t>(stream)));
+            }
+            return RB200_OK;
+        }
+    }
+    set_error("no kept tensor named %s (enable rb200_set_debug and run a LAYERS forward)", name);
+    return RB200_ERR_INVALID;
+}
+
+int rb200_encode_dense(const int8_t *seqs_dev, int32_t seq_width, const int16_t *maps_dev,
+                       int32_t map_width, const int16_t *lens_dev, int32_t n_chunks,
+                       int32_t before, int32_t after, int32_t sig_len, float *out_dev,
+                       void *stream) {
+    RB200_REQUIRE(n_chunks >= 0 && before >= 0 && after >= 0 && sig_len > 0, "bad argument");
+    if (n_chunks == 0) return RB200_OK;
+    RB200_REQUIRE(seqs_dev && maps_dev && lens_dev && out_dev, "null buffer");
+    const int kmer_len = before + after + 1;
+    RB200_REQUIRE(map_width >= 2 && seq_width >= kmer_len, "compact arrays too narrow");
+    int dev = 0, sms = 148;
+    RB200_CUDA_TRY(cudaGetDevice(&dev));
+    RB200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_encode_dense(seqs_dev, seq_width, maps_dev, map_width, lens_dev, n_chunks,
+                               kmer_len, sig_len, out_dev, sms, static_cast<cudaStream_t>(stream),
+                               nullptr);
+}
+
+int rb200_forward_dense(rb200_handle h, const float *sigs_dev, const float *enc_dev, int32_t B,
+                        int32_t T, float *logits_dev, void *stream) {
+    RB200_REQUIRE(enc_dev || B == 0, "null enc_kmers");
+    return forward_common(h, sigs_dev, enc_dev, nullptr, 0, nullptr, 0, nullptr, B, T, logits_dev,
+                          stream);
+}
+
+int rb200_forward_compact(rb200_handle h, const float *sigs_dev, const int8_t *seqs_dev,
+                          int32_t seq_width, const int16_t *maps_dev, int32_t map_width,
+                          const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
+                          void *stream) {
+    return forward_common(h, sigs_dev, nullptr, seqs_dev, seq_width, maps_dev, map_width, lens_dev,
+                          B, T, logits_dev, stream);
+}
+
+int rb200_infer_host(rb200_handle h, const float *sigs_host, const int8_t *seqs_host,
+                     int32_t seq_width, const int16_t *maps_host, int32_t map_width,
+                     const int16_t *lens_host, int32_t B, int32_t T, float *logits_host) {
+    RB200_REQUIRE(h, "null handle");
+    RB200_REQUIRE(B >= 0 && T > 0, "bad batch / chunk_len");
+    if (B == 0) return RB200_OK;
+    RB200_REQUIRE(sigs_host && seqs_host && maps_host && lens_host && logits_host, "null buffer");
+    DeviceGuard guard(h->device);
+    RB200_REQUIRE(guard.ok, "cannot select device %d", h->device);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t b_sig = up((size_t)B * T * 4), b_seq = up((size_t)B * seq_width),
+                 b_map = up((size_t)B * map_width * 2), b_len = up((size_t)B * 2),
+                 b_out = up((size_t)B * h->desc.num_out * 4);
+    const size_t total = b_sig + b_seq + b_map + b_len + b_out;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        if (!h->host_stream)
+            RB200_CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+        if (total > h->pinned_bytes) {
+            RB200_CUDA_TRY(cudaStreamSynchronize(h->host_stream));
+            if (h->pinned) cudaFreeHost(h->pinned);
+            if (h->staging_dev) cudaFree(h->staging_dev);
+            h->pinned = nullptr;
+            h->staging_dev = nullptr;
+            h->pinned_bytes = 0;
+            RB200_CUDA_TRY(cudaMallocHost(&h->pinned, total));
+            RB200_CUDA_TRY(cudaMalloc(&h->staging_dev, total));
+            h->pinned_bytes = total;
+            h->staging_bytes = total;
+        }
+    }
+    // NB: the staging buffers make this call non-reentrant per handle; callers that need
+    // concurrency use rb200_forward_compact with their own device buffers.
+    char *p = h->pinned;
+    char *d = h->staging_dev;
+    cudaStream_t s = h->host_stream;
+    memcpy(p, sigs_host, (size_t)B * T * 4);
+    memcpy(p + b_sig, seqs_host, (size_t)B * seq_width);
+    memcpy(p + b_sig + b_seq, maps_host, (size_t)B * map_width * 2);
+    memcpy(p + b_sig + b_seq + b_map, lens_host, (size_t)B * 2);
+    const size_t in_bytes = b_sig + b_seq + b_map + b_len;
+    RB200_CUDA_TRY(cudaMemcpyAsync(d, p, in_bytes, cudaMemcpyHostToDevice, s));
+    int rc = rb200_forward_compact(
+        h, reinterpret_cast<const float *>(d), reinterpret_cast<const int8_t *>(d + b_sig),
+        seq_width, reinterpret_cast<const int16_t *>(d + b_sig + b_seq), map_width,
+        reinterpret_cast<const int16_t *>(d + b_sig + b_seq + b_map), B, T,
+        reinterpret_cast<float *>(d + in_bytes), s);
+    if (rc) return rc;
+    RB200_CUDA_TRY(cudaMemcpyAsync(p + in_bytes, d + in_bytes, (size_t)B * h->desc.num_out * 4,
+                                   cudaMemcpyDeviceToHost, s));
+    RB200_CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(logits_host, p + in_bytes, (size_t)B * h->desc.num_out * 4);
+    return RB200_OK;
+}
+
+int rb200_softmax_ml(const float *logits_dev, int32_t B, int32_t num_out, float *probs_dev,
+                     uint8_t *ml_dev, void *stream) {
+    RB200_REQUIRE(B >= 0 && num_out >= 2, "bad argument");
+    if (B == 0) return RB200_OK;
+    RB200_REQUIRE(logits_dev && (probs_dev || ml_dev), "null buffer");
+    return launch_softmax_ml(logits_dev, B, num_out, probs_dev, ml_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

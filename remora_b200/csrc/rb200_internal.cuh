@@ -1,0 +1,116 @@
+// Internal declarations shared by the CUDA translation units of librb200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "remora_b200.h"
+
+namespace rb200 {
+
+void set_error(const char *fmt, ...);
+
+#define RB200_CUDA_TRY(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            rb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                             __FILE__, __LINE__);                                         \
+            return RB200_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+#define RB200_REQUIRE(cond, ...)                                                          \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            rb200::set_error(__VA_ARGS__);                                                \
+            return RB200_ERR_INVALID;                                                     \
+        }                                                                                 \
+    } while (0)
+
+// ---- device math shared by all kernels ------------------------------------------------------
+// swish(x) = x * sigmoid(x)   (reference src/remora/activations.py:18)
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+// fast variants: ex2.approx based; abs error of sigmoid < 2e-7 (measured in tests)
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+    return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float swishf_fast(float x) { return x * sigmoidf_fast(x); }
+__device__ __forceinline__ float tanhf_fast(float x) {
+    // tanh(x) = 2*sigmoid(2x) - 1
+    return 2.0f * sigmoidf_fast(2.0f * x) - 1.0f;
+}
+
+// ---- growable device scratch, one per (handle, stream) ---------------------------------------
+struct Workspace {
+    char *base = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need);  // grows (synchronising free + malloc) when too small
+    void release();
+};
+
+struct DebugTensor {
+    std::string name;
+    const float *ptr;  // into the workspace of the forward that produced it
+    int B, C, T;
+};
+
+struct FusedWeights;  // rb200_fused.cu
+
+}  // namespace rb200
+
+struct rb200_model {
+    rb200_model_desc desc;
+    int device = 0;
+    int sm_count = 148;
+    float *blob_dev = nullptr;  // canonical (PyTorch-layout, BN-folded) weights
+    int64_t blob_floats = 0;
+    int impl = RB200_IMPL_AUTO;
+    int last_impl = 0;
+    std::atomic<uint64_t> launches{0};
+    bool keep_debug = false;
+    std::vector<rb200::DebugTensor> debug;
+    std::mutex mu;
+    std::map<void *, rb200::Workspace> workspaces;  // keyed by stream
+    rb200::FusedWeights *fused = nullptr;           // non-null when the fused path applies
+    // pinned + device staging for rb200_infer_host
+    char *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    char *staging_dev = nullptr;
+    size_t staging_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+
+namespace rb200 {
+
+// rb200_encode.cu
+int launch_encode_dense(const int8_t *seqs, int seq_width, const int16_t *maps, int map_width,
+                        const int16_t *lens, int n_chunks, int kmer_len, int T, float *out,
+                        int sm_count, cudaStream_t stream, uint64_t *launches);
+
+// rb200_layers.cu : layer-per-kernel path, any architecture / size
+size_t layers_workspace_bytes(const rb200_model_desc &d, int B, int T, bool compact);
+int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float *enc,
+                   const int8_t *seqs, int seq_width, const int16_t *maps, int map_width,
+                   const int16_t *lens, int B, int T, float *logits, cudaStream_t stream);
+int launch_softmax_ml(const float *logits, int B, int num_out, float *probs, uint8_t *ml,
+                      cudaStream_t stream);
+
+// rb200_fused.cu : fused sm_100a kernels for ConvLSTM_w_ref size 64
+bool fused_supported(const rb200_model_desc &d);
+int fused_create(rb200_model *m, const float *blob_host);
+void fused_destroy(rb200_model *m);
+bool fused_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
+size_t fused_workspace_bytes(const rb200_model *m, int B, int T);
+int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
+                          int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
+                          int B, int T, float *logits, cudaStream_t stream);
+
+}  // namespace rb200

@@ -1,0 +1,355 @@
+"""Parity tests proper (run on the B200 box): every call goes through the C-ABI library.
+
+Tolerances: k-mer one-hot encode bit-exact; float32 logits <= 1e-4 max-abs against the reference's
+own CPU logits (BASELINE.json north_star), in practice ~1e-6; per-layer activations <= 2e-5."""
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import remora_oracle as ro
+from conftest import GOLDEN, load_golden_model, unpack_encode_case
+from remora_b200 import RemoraError, data_chunks, encoded_kmers, inference, model_util
+from remora_b200.synth import synth_chunks, synth_read
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-4  # north_star tolerance
+
+_MODELS = {}
+
+
+def gpu_model(name):
+    if name not in _MODELS:
+        _MODELS[name] = model_util.load_model(os.path.join(GOLDEN, name + ".pt"),
+                                              device=torch.device("cuda:0"), eval_only=True)
+    return _MODELS[name]
+
+
+def impls_for(model):
+    return ["layers", "fused"] if model.info["arch"] == "ConvLSTM_w_ref" and \
+        model.info["size"] == 64 and fused_available(model) else ["layers"]
+
+
+def fused_available(model):
+    try:
+        model.set_impl("fused")
+        model.set_impl("auto")
+        return True
+    except RemoraError:
+        return False
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder: bit-exact
+# ---------------------------------------------------------------------------------------------
+def test_encode_known_answer(encode_cases):
+    got = encoded_kmers.compute_encoded_kmer_batch(4, 4, encode_cases["kat_seqs"],
+                                                   encode_cases["kat_maps"],
+                                                   encode_cases["kat_lens"])
+    assert got.dtype == np.float32 and np.array_equal(got, encode_cases["kat_out"])
+
+
+def test_encode_bit_exact_vs_golden(encode_cases):
+    for cid, kb, ka, T in encode_cases["cases"]:
+        seqs, maps, lens, want = unpack_encode_case(encode_cases, cid)
+        got = encoded_kmers.compute_encoded_kmer_batch(int(kb), int(ka), seqs, maps, lens)
+        assert got.shape == want.shape and np.array_equal(got, want), f"case {cid} k=({kb},{ka}) T={T}"
+
+
+@pytest.mark.parametrize("n,T,ctx", [(1, 100, (4, 4)), (1000, 100, (4, 4)), (333, 200, (4, 4)),
+                                     (77, 400, (2, 3)), (50, 1000, (4, 4)), (40, 3000, (1, 1))])
+def test_encode_bit_exact_vs_oracle(n, T, ctx):
+    d = synth_chunks(n, T, ctx, seed=n + T, frac_n=0.03, frac_edge=0.2)
+    want = ro.encode_kmers_c(ctx[0], ctx[1], d["sequence"], d["sequence_to_signal_mapping"],
+                             d["sequence_lengths"])
+    got = encoded_kmers.compute_encoded_kmer_batch(ctx[0], ctx[1], d["sequence"],
+                                                   d["sequence_to_signal_mapping"],
+                                                   d["sequence_lengths"])
+    assert np.array_equal(got, want)
+
+
+def test_encode_full_size_properties():
+    """BASELINE-size batch (8192 x 36 x 100): size-independent properties of the one-hot tensor."""
+    n, T = 8192, 100
+    d = synth_chunks(n, T, (4, 4), seed=4242)
+    out = encoded_kmers.compute_encoded_kmer_batch_torch(
+        4, 4, torch.from_numpy(d["sequence"]), torch.from_numpy(d["sequence_to_signal_mapping"]),
+        torch.from_numpy(d["sequence_lengths"]), sig_len=T, device=torch.device("cuda:0"))
+    assert out.shape == (n, 36, T)
+    assert bool(((out == 0) | (out == 1)).all())
+    per_group = out.view(n, 9, 4, T).sum(dim=2)  # at most one base per (k-mer offset, time)
+    assert float(per_group.max()) == 1.0
+    # column sums: number of non-N bases in the k-mer covering each sample = checksum of oracle
+    want = ro.encode_kmers_c(4, 4, d["sequence"][:64], d["sequence_to_signal_mapping"][:64],
+                             d["sequence_lengths"][:64])
+    assert np.array_equal(out[:64].cpu().numpy(), want)
+    total = int(out.sum().item())
+    # checksum of checksums: total ones = sum over bases of dwell * valid k-mer entries
+    exp = 0
+    for c in range(n):
+        L = int(d["sequence_lengths"][c])
+        dw = np.diff(d["sequence_to_signal_mapping"][c, :L + 1].astype(np.int64))
+        sq = d["sequence"][c]
+        for p in range(9):
+            exp += int(dw[sq[p:p + L] != -1].sum())
+    assert total == exp
+
+
+# ---------------------------------------------------------------------------------------------
+# forward: logits within 1e-4 of the reference's CPU logits
+# ---------------------------------------------------------------------------------------------
+def _case_inputs(forward_cases, key):
+    return (forward_cases[key + "__signal"], forward_cases[key + "__seqs"],
+            forward_cases[key + "__maps"], forward_cases[key + "__lens"],
+            forward_cases[key + "__logits"])
+
+
+def test_forward_compact_vs_reference_logits(forward_cases):
+    for key in forward_cases["index"]:
+        key = str(key)
+        model, md = gpu_model(key.split("__")[0])
+        sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+        for impl in impls_for(model):
+            model.set_impl(impl)
+            got = model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
+                                        torch.from_numpy(maps), torch.from_numpy(lens))
+            assert model.last_impl == impl
+            err = np.abs(got.cpu().numpy() - want).max()
+            assert err < LOGIT_TOL, f"{key} [{impl}] max-abs err {err}"
+        model.set_impl("auto")
+
+
+def test_forward_dense_vs_reference_logits(forward_cases):
+    """model(sigs, enc_kmers): the reference's own call form, dense one-hot input."""
+    for key in forward_cases["index"]:
+        key = str(key)
+        model, md = gpu_model(key.split("__")[0])
+        sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+        ctx = md["kmer_context_bases"]
+        enc = ro.encode_kmers_c(ctx[0], ctx[1], seqs, maps, lens)
+        got = model(torch.from_numpy(sig).cuda(), torch.from_numpy(enc).cuda())
+        assert got.shape == want.shape and got.dtype == torch.float32 and got.is_cuda
+        assert np.abs(got.detach().cpu().numpy() - want).max() < LOGIT_TOL, key
+
+
+def test_per_layer_activations_vs_oracle(forward_cases):
+    """Layer kernels against the oracle's torch restatement, layer by layer."""
+    key = "convlstm_s64_k9_hot__n64_T100"
+    model, md = gpu_model("convlstm_s64_k9_hot")
+    sd, _ = load_golden_model("convlstm_s64_k9_hot")
+    sd = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
+    sig, seqs, maps, lens, _ = _case_inputs(forward_cases, key)
+    enc = torch.from_numpy(ro.encode_kmers_c(4, 4, seqs, maps, lens))
+    with torch.no_grad():
+        s1 = ro._conv_bn_swish(torch.from_numpy(sig), sd, "sig_conv1", "sig_bn1")
+        s2 = ro._conv_bn_swish(s1, sd, "sig_conv2", "sig_bn2")
+        s3 = ro._conv_bn_swish(s2, sd, "sig_conv3", "sig_bn3", stride=3)
+        q1 = ro._conv_bn_swish(enc, sd, "seq_conv1", "seq_bn1")
+        q2 = ro._conv_bn_swish(q1, sd, "seq_conv2", "seq_bn2", stride=3)
+        cat = torch.cat((s3, q2), 1)
+        m1 = ro._conv_bn_swish(cat, sd, "merge_conv1", "merge_bn")
+        l1 = ro._swish(ro._lstm_forward(m1.permute(2, 0, 1), sd, "lstm1")).permute(1, 2, 0)
+    model.set_impl("layers")
+    model.set_debug(True)
+    model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs), torch.from_numpy(maps),
+                          torch.from_numpy(lens))
+    for name, want in (("sig1", s1), ("sig2", s2), ("seq1", q1), ("cat", cat), ("merge1", m1),
+                       ("lstm1", l1)):
+        got = model.debug_tensor(name).cpu()
+        assert got.shape == want.shape, name
+        assert (got - want).abs().max() < 2e-5, name
+    model.set_debug(False)
+    model.set_impl("auto")
+
+
+@pytest.mark.parametrize("B", [1, 2, 63, 64, 65, 1024, 4096])
+def test_batch_sizes_and_ragged_batches(B):
+    """Any B in [1, batch_size] (ragged last batch, inference.py:308-310); per-chunk independence:
+    the logits of chunk i do not depend on the batch it is in."""
+    model, md = gpu_model("convlstm_s64_k9_hot")
+    sd, _ = load_golden_model("convlstm_s64_k9_hot")
+    d = synth_chunks(B, 100, (4, 4), seed=B)
+    args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                             "sequence_lengths")]
+    outs = {}
+    for impl in impls_for(model):
+        model.set_impl(impl)
+        outs[impl] = model.forward_compact(*args).cpu().numpy()
+    model.set_impl("auto")
+    n_chk = min(B, 48)
+    want = ro.oracle_infer_compact(sd, (4, 4), d["signal"][:n_chk], d["sequence"][:n_chk],
+                                   d["sequence_to_signal_mapping"][:n_chk],
+                                   d["sequence_lengths"][:n_chk])
+    for impl, got in outs.items():
+        assert got.shape == (B, 2) and np.isfinite(got).all()
+        assert np.abs(got[:n_chk] - want).max() < LOGIT_TOL, impl
+    # independence / determinism: tail chunks re-run as their own small batch
+    k = min(B, 5)
+    tail = [a[B - k:] for a in args]
+    again = model.forward_compact(*tail).cpu().numpy()
+    ref = outs[impls_for(model)[-1]][B - k:]
+    assert np.abs(again - ref).max() < 2e-6
+
+
+def test_empty_batch():
+    model, _ = gpu_model("convlstm_s64_k9")
+    out = model.forward_compact(torch.zeros((0, 1, 100)), torch.zeros((0, 28), dtype=torch.int8),
+                                torch.zeros((0, 21), dtype=torch.int16),
+                                torch.zeros((0,), dtype=torch.int16))
+    assert out.shape == (0, 2)
+
+
+def test_conv_w_ref_rejects_other_chunk_len():
+    """Stock Conv_w_ref only accepts chunk_len 100 (models/Conv_w_ref.py:42): loud error."""
+    model, _ = gpu_model("conv_s64_k9")
+    d = synth_chunks(4, 200, (4, 4), seed=1)
+    with pytest.raises(RemoraError):
+        model.forward_compact(torch.from_numpy(d["signal"]), torch.from_numpy(d["sequence"]),
+                              torch.from_numpy(d["sequence_to_signal_mapping"]),
+                              torch.from_numpy(d["sequence_lengths"]))
+
+
+def test_bad_arguments_raise():
+    model, _ = gpu_model("convlstm_s64_k9")
+    with pytest.raises(RemoraError):
+        model(torch.zeros((2, 1, 100)).cuda(), torch.zeros((2, 35, 100)).cuda())
+    with pytest.raises(RemoraError):
+        model(torch.zeros((2, 1, 100), dtype=torch.float64).cuda(),
+              torch.zeros((2, 36, 100)).cuda())
+    with pytest.raises(RemoraError):  # shorter than the receptive field
+        model(torch.zeros((2, 1, 12)).cuda(), torch.zeros((2, 36, 12)).cuda())
+
+
+def test_model_quacks_like_the_reference_module():
+    model, md = gpu_model("convlstm_s64_k9")
+    assert next(model.parameters()).device == torch.device("cuda:0")
+    assert all(not p.requires_grad for p in model.parameters())
+    assert model.eval() is model
+    assert md["chunk_len"] == 100 and md["kmer_len"] == 9
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary: call_read_mods / run_model_batched / infer_host / softmax+ML
+# ---------------------------------------------------------------------------------------------
+def test_call_read_mods_matches_reference(read_cases):
+    meta, g = read_cases
+    for i, m in enumerate(meta):
+        model, md = gpu_model(m["model"])
+        def fresh():
+            return data_chunks.RemoraRead(dacs=g[f"r{i}_dacs"], shift=m["shift"],
+                                          scale=m["scale"], seq_to_sig_map=g[f"r{i}_ssm"],
+                                          int_seq=g[f"r{i}_int_seq"])
+        order = np.argsort(g[f"r{i}_pos"])
+        nn_out, labels, pos = inference.call_read_mods(fresh(), model, md)
+        assert np.array_equal(pos, g[f"r{i}_pos"][order])
+        assert np.array_equal(labels, g[f"r{i}_labels"][order])
+        assert np.abs(nn_out - g[f"r{i}_nn_out"][order]).max() < LOGIT_TOL
+        probs, _, _ = inference.call_read_mods(fresh(), model, md, return_mod_probs=True)
+        assert probs.dtype == np.float64
+        assert np.abs(probs - g[f"r{i}_probs"][order]).max() < LOGIT_TOL
+        mm, ml = inference.call_read_mods(fresh(), model, md, return_mm_ml_tags=True)
+        assert mm == m["mm"]
+        ml = np.frombuffer(ml, dtype=np.uint8).astype(int)
+        # a 1e-6 logit difference can move a probability across a 1/256 bin edge
+        diff = np.abs(ml - g[f"r{i}_ml"].astype(int))
+        assert diff.max() <= 1 and (diff != 0).mean() <= 0.02
+
+
+def test_reference_test_read(read_cases):
+    """scripts/api_example.py flow: load_model -> RemoraRead.test_read() -> call_read_mods."""
+    _, g = read_cases
+    model, md = gpu_model("convlstm_s64_k9")
+    nn_out, labels, pos = inference.call_read_mods(data_chunks.RemoraRead.test_read(), model, md)
+    order = np.argsort(g["test_read_pos"])
+    assert np.array_equal(pos, g["test_read_pos"][order])
+    assert np.abs(nn_out - g["test_read_nn_out"][order]).max() < LOGIT_TOL
+
+
+def test_run_model_batched_generator(forward_cases):
+    key = "convlstm_s64_k9_hot__n64_T100"
+    model, md = gpu_model("convlstm_s64_k9_hot")
+    sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+    enc = ro.encode_kmers_c(4, 4, seqs, maps, lens)
+    items = [("C", sig[:32], enc[:32], np.arange(32), ["r"] * 32),   # full batch -> pinned path
+             ("C", sig[32:50], enc[32:50], np.arange(18), ["r"] * 18)]  # ragged
+    outs = list(inference.run_model_batched(items, {"C": model}, [md], batch_size=32))
+    got = np.concatenate([o[1].cpu().numpy() for o in outs])
+    assert np.abs(got - want[:50]).max() < LOGIT_TOL
+
+
+def test_infer_host_roundtrip(forward_cases):
+    key = "convlstm_s64_k9_hot__n64_T100"
+    model, _ = gpu_model("convlstm_s64_k9_hot")
+    sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+    got = model.infer_host(sig, seqs, maps, lens)
+    assert np.abs(got - want).max() < LOGIT_TOL
+    got2 = model.infer_host(sig[:3], seqs[:3], maps[:3], lens[:3])  # smaller batch reuses staging
+    assert np.abs(got2 - want[:3]).max() < LOGIT_TOL
+
+
+def test_softmax_ml_kernel():
+    import ctypes
+    from remora_b200 import _native, util
+    lib = _native.load_library()
+    rng = np.random.default_rng(0)
+    logits = (rng.standard_normal((1000, 3)) * 4).astype(np.float32)
+    logits[0] = [0, 50, -50]  # p -> 1.0 must clip to 255
+    lg = torch.from_numpy(logits).cuda()
+    probs = torch.empty((1000, 2), dtype=torch.float32, device="cuda")
+    ml = torch.empty((1000, 2), dtype=torch.uint8, device="cuda")
+    rc = lib.rb200_softmax_ml(ctypes.c_void_p(lg.data_ptr()), 1000, 3,
+                              ctypes.c_void_p(probs.data_ptr()), ctypes.c_void_p(ml.data_ptr()),
+                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _native.check(rc, "rb200_softmax_ml")
+    want_p = util.softmax_axis1(logits)[:, 1:]
+    assert np.abs(probs.cpu().numpy() - want_p).max() < 1e-6
+    want_ml = ro.ml_bytes(want_p)
+    diff = np.abs(ml.cpu().numpy().astype(int) - want_ml.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01 and ml[0, 0] == 255
+
+
+def test_concurrent_threads_share_one_model(forward_cases):
+    """Duplex inference calls one model from several threads (inference.py:973-982)."""
+    key = "convlstm_s64_k9_hot__n64_T100"
+    model, _ = gpu_model("convlstm_s64_k9_hot")
+    sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+    errs = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(20):
+                idx = rng.permutation(64)[: rng.integers(1, 64)]
+                got = model.forward_compact(torch.from_numpy(sig[idx]), torch.from_numpy(seqs[idx]),
+                                            torch.from_numpy(maps[idx]),
+                                            torch.from_numpy(lens[idx])).cpu().numpy()
+                if np.abs(got - want[idx]).max() >= LOGIT_TOL:
+                    errs.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+
+
+def test_full_size_batch_properties():
+    """BASELINE-size step (1024 chunks, T=100) and a large one (8192): permutation equivariance
+    (chunks are independent) and agreement between the two CUDA paths."""
+    model, _ = gpu_model("convlstm_s64_k9_hot")
+    for B in (1024, 8192):
+        d = synth_chunks(B, 100, (4, 4), seed=B + 1)
+        args = [torch.from_numpy(d[k]).cuda() for k in
+                ("signal", "sequence", "sequence_to_signal_mapping", "sequence_lengths")]
+        out = model.forward_compact(*args)
+        perm = torch.randperm(B, device="cuda")
+        out_p = model.forward_compact(*[a[perm] for a in args])
+        assert (out[perm] - out_p).abs().max() < 2e-6
+        if "fused" in impls_for(model):
+            model.set_impl("layers")
+            ref = model.forward_compact(*args)
+            model.set_impl("auto")
+            assert (out - ref).abs().max() < 2e-5
