@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the Remora per-chunk modified-base inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): chunks/sec at chunk_len=100, kmer_context=(4,4), ConvLSTM_w_ref (size 64),
+batch=1024 per GPU.  One "step" = one batch of 1024 synthetic chunks through the hot path
+(k-mer encode fused into the forward).  `value` times K steps with the compact chunk arrays
+already resident in HBM; `e2e` times the same steps through the host-buffer C-ABI call
+(rb200_infer_host: pinned staging, H2D, kernels, D2H) every step.  Weights are seeded random
+(tests/golden/convlstm_s64_k9_hot.pt, exported by the reference's own exporter) and data is
+synthetic: no datasets or checkpoints are reachable.
+
+Timing hygiene: W>=3 warm-up steps; every step reads a different batch of a resident pool that is
+larger than the 126 MB L2 (inputs come from HBM); device timing with CUDA events bracketed by
+barrier + synchronize; max over ranks; SM clocks sampled with nvidia-smi during the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK_LEN = 100
+KMER_CONTEXT = (4, 4)
+BATCH = 1024
+MODEL_PT = os.path.join(ROOT, "tests", "golden", "convlstm_s64_k9_hot.pt")
+# algorithmic bytes / flops per chunk
+BYTES_IFACE_A = 4 * CHUNK_LEN + 4 * 36 * CHUNK_LEN + 4 * 2   # 14 808 B: what the reference model call consumes
+DENSE_MFLOP = 6.989312                                       # 3 494 656 MAC, ConvLSTM_w_ref T=100
+METRIC = "chunks/sec (chunk_len=100, batch=1024)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pool(n_batches, seed):
+    from remora_b200.synth import synth_chunks
+    d = synth_chunks(n_batches * BATCH, CHUNK_LEN, KMER_CONTEXT, seed=seed)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the reference's own CPU implementation of the path
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_runner():
+    """Returns (step_fn(batch_dict) -> logits, kind, description).  encode = the reference's own
+    Cython encoder compiled into oracle/_ref (else the C restatement); forward = the TorchScript
+    module exported by the reference's export_model_torchscript, run on CPU by torch.jit."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import remora_oracle as ro
+    ref_enc = ro.load_ref_encoder()
+    kind = "reference" if ref_enc is not None else "port"
+    torch.set_grad_enabled(False)
+    n_threads = os.cpu_count() or 1
+    torch.set_num_threads(n_threads)
+    module = torch.jit.load(MODEL_PT, map_location="cpu").eval()
+
+    def step(d):
+        if ref_enc is not None:
+            enc = ref_enc.compute_encoded_kmer_batch(KMER_CONTEXT[0], KMER_CONTEXT[1], d["sequence"],
+                                                     d["sequence_to_signal_mapping"],
+                                                     d["sequence_lengths"])
+        else:
+            enc = ro.encode_kmers_c(KMER_CONTEXT[0], KMER_CONTEXT[1], d["sequence"],
+                                    d["sequence_to_signal_mapping"], d["sequence_lengths"])
+        return module(torch.from_numpy(d["signal"]), torch.from_numpy(np.asarray(enc)))
+
+    desc = ("encode: reference Cython compute_encoded_kmer_batch (oracle/_ref, 1 thread as in the "
+            "reference) + forward: reference TorchScript module on CPU, torch intra-op threads = all "
+            "host cores") if kind == "reference" else \
+        "encode: C restatement (oracle/oracle_encode.c) + forward: reference TorchScript module on CPU"
+    return step, kind, n_threads, desc
+
+
+def slice_batch(pool, i):
+    sl = slice(i * BATCH, (i + 1) * BATCH)
+    return {k: (v[sl] if isinstance(v, np.ndarray) else v) for k, v in pool.items()}
+
+
+def run_cpu_sample(max_seconds=12.0, max_batches=400, warm=2):
+    step, kind, threads, desc = cpu_reference_runner()
+    pool = make_pool(8, seed=99)
+    for i in range(warm):
+        step(slice_batch(pool, i % 8))
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_batches and time.perf_counter() - t0 < max_seconds:
+        step(slice_batch(pool, n % 8))
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * BATCH / dt, "unit": "chunks/s", "cores": threads, "kind": kind,
+            "sample": f"{n} batches of {BATCH} chunks (chunk_len {CHUNK_LEN}) in {dt:.1f} s; {desc}"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, kind, threads, desc = cpu_reference_runner()
+    pool = make_pool(8, seed=99)
+    for i in range(args.warmup):
+        step(slice_batch(pool, i % 8))
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(slice_batch(pool, i % 8))
+    dt = time.perf_counter() - t0
+    value = args.steps * BATCH / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "chunks/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic chunks, chunk_len=100, kmer_context=(4,4), "
+                               "ConvLSTM_w_ref size 64, batch=1024 (BASELINE configs[1])",
+                   "batch": BATCH, "chunk_len": CHUNK_LEN, "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} batches of {BATCH} chunks; {desc}"},
+        "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from remora_b200 import model_util
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    model, md = model_util.load_model(MODEL_PT, device=device, eval_only=True)
+    assert md["chunk_len"] == CHUNK_LEN and md["kmer_len"] == 9
+    # resident pool: > L2 (126 MB) of compact inputs so every step streams its batch from HBM.
+    n_pool = args.pool_batches
+    pool = make_pool(n_pool, seed=1 + rank)
+    dev_pool = {k: torch.from_numpy(pool[k]).to(device) for k in
+                ("signal", "sequence", "sequence_to_signal_mapping", "sequence_lengths")}
+    pool_bytes = sum(v.numel() * v.element_size() for v in dev_pool.values())
+
+    def dev_batch(i):
+        sl = slice((i % n_pool) * BATCH, (i % n_pool + 1) * BATCH)
+        return (dev_pool["signal"][sl], dev_pool["sequence"][sl],
+                dev_pool["sequence_to_signal_mapping"][sl], dev_pool["sequence_lengths"][sl])
+
+    def barrier():
+        if distributed:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(device)
+
+    gathered = None
+    if distributed:
+        gathered = torch.empty((world * BATCH, model.num_out), dtype=torch.float32, device=device)
+
+    def step(i):
+        out = model.forward_compact(*dev_batch(i))
+        if distributed:
+            # the only exchange step the path has: 8 B/chunk of logits to the consumer ranks
+            return dist.all_gather_into_tensor(gathered, out, async_op=True)
+        return None
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    impl_used = model.last_impl
+    launches0 = model.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    work = None
+    for i in range(args.steps):
+        work = step(args.warmup + i)
+    if work is not None:
+        work.wait()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = model.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * BATCH * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI host call, H2D + D2H inside the timed region ----------
+    host_batches = [slice_batch(pool, i) for i in range(min(n_pool, 16))]
+
+    def e2e_step(i):
+        d = host_batches[i % len(host_batches)]
+        return model.infer_host(d["signal"], d["sequence"], d["sequence_to_signal_mapping"],
+                                d["sequence_lengths"])
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = args.steps
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize(device)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * e2e_steps / float(t.item())
+    h2d = BATCH * (CHUNK_LEN * 4 + pool["sequence"].shape[1] + pool["sequence_to_signal_mapping"].shape[1] * 2 + 2)
+    d2h = BATCH * model.num_out * 4
+
+    # ---- per-kernel device times (separate pass: event records would perturb the headline) --------
+    prof = None
+    if impl_used == "fused":
+        model.set_profile(True)
+        for i in range(args.steps):
+            model.forward_compact(*dev_batch(i))
+        torch.cuda.synchronize(device)
+        ms3, n_fw = model.get_profile()
+        model.set_profile(False)
+        prof = {"k1_front_ms": ms3[0] / n_fw, "k2_merge_xproj_ms": ms3[1] / n_fw,
+                "k3_lstm_ms": ms3[2] / n_fw, "forwards": n_fw}
+
+    # ---- dense encode kernel alone (the HBM-bound kernel of the path) ------------------------------
+    from remora_b200 import encoded_kmers
+    enc_n = 8192
+    sl = slice(0, enc_n)
+    enc_args = (dev_pool["sequence"][sl], dev_pool["sequence_to_signal_mapping"][sl],
+                dev_pool["sequence_lengths"][sl])
+    for _ in range(3):
+        encoded_kmers.compute_encoded_kmer_batch_torch(4, 4, *enc_args, sig_len=CHUNK_LEN, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+    enc_ms = []
+    for _ in range(5):
+        flush.fill_(1.0)  # write > L2 between timed launches
+        e0.record()
+        encoded_kmers.compute_encoded_kmer_batch_torch(4, 4, *enc_args, sig_len=CHUNK_LEN, device=device)
+        e1.record()
+        torch.cuda.synchronize(device)
+        enc_ms.append(e0.elapsed_time(e1))
+    del flush
+    enc_ms = float(np.median(enc_ms))
+
+    if rank == 0:
+        peak_gbs, peak_src, peaks = measured_peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "synthetic chunks, chunk_len=100, kmer_context=(4,4), "
+                                   "ConvLSTM_w_ref size 64 (134082 params), batch=1024 per GPU "
+                                   "(BASELINE configs[1]); fp32 FMA arithmetic, logits within 1e-4 of "
+                                   "the reference CPU forward",
+                       "batch_per_gpu": BATCH, "global_batch": world * BATCH,
+                       "chunk_len": CHUNK_LEN, "kmer_context": list(KMER_CONTEXT),
+                       "parallelism": f"batch-shard x{world}" if world > 1 else "single GPU",
+                       "impl": impl_used,
+                       "l2_policy": f"inputs larger than L2: each step reads a different batch of a "
+                                    f"{pool_bytes / 1e6:.0f} MB resident pool ({n_pool} batches)"},
+            "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "path": "B200Model.infer_host -> rb200_infer_host"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if prof is not None:
+            k2_s = prof["k2_merge_xproj_ms"] * 1e-3
+            # dominant kernel: K2 (merge conv + LSTM input projection).  Its algorithmic bytes:
+            # reads cat [28][128] f32, writes xp [24][256] f32 per chunk (DESIGN.md "K2").
+            k2_bytes = BATCH * (28 * 128 * 4 + 24 * 256 * 4)
+            k2_flop = BATCH * 2.0 * (983040 + 393216)
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # FFMA2 issue peak at the sampled clock
+            line["roofline"] = {
+                "kernel": "k2_merge_kernel", "bound": "hbm",
+                "achieved": k2_bytes / k2_s / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": k2_bytes / k2_s / 1e9 / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "note": "the kernel is fp32-FMA bound, not HBM bound (472 FLOP/B at the reference "
+                        "interface): see roofline_fp32 for the binding roof",
+            }
+            line["roofline_fp32"] = {
+                "kernel": "k2_merge_kernel", "bound": "fp32 FFMA2 issue",
+                "achieved": k2_flop / k2_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": k2_flop / k2_s / 1e12 / fp32_peak,
+                "peak_source": f"148 SM x 128 lanes x 2 flop x {sm_mhz:.0f} MHz (sampled clock)",
+            }
+            step_s = ms_max / args.steps * 1e-3
+            line["roofline_step"] = {
+                "iface_a_bytes_per_chunk": BYTES_IFACE_A,
+                "hbm_frac_iface_a": world * BATCH * BYTES_IFACE_A / step_s / 1e9 / (peak_gbs * world),
+                "dense_mflop_per_chunk": DENSE_MFLOP,
+                "fp32_frac_dense": BATCH * DENSE_MFLOP * 1e6 / step_s / 1e12 / fp32_peak,
+            }
+            line["kernels_ms"] = prof
+        enc_bytes = enc_n * 36 * CHUNK_LEN * 4
+        line["roofline_encode"] = {
+            "kernel": "encode_dense_tma_kernel", "bound": "hbm", "achieved": enc_bytes / (enc_ms * 1e-3) / 1e9,
+            "peak": peak_gbs, "unit": "GB/s", "frac": enc_bytes / (enc_ms * 1e-3) / 1e9 / peak_gbs,
+            "chunks": enc_n, "ms": enc_ms, "l2": "flushed between launches",
+        }
+        if world == 1:
+            line["cpu_baseline"] = run_cpu_sample()
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool-batches", type=int, default=400,
+                    help="resident batches of compact inputs (400 x 1024 x 480 B = 197 MB > L2)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

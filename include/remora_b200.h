@@ -103,6 +103,13 @@ int rb200_set_debug(rb200_handle h, int keep); /* keep layer outputs of the next
 int rb200_debug_tensor(rb200_handle h, const char *name, float *dst_dev, int64_t capacity,
                        int64_t *n_floats, int32_t *channels, int32_t *steps, void *stream);
 
+/* Per-kernel device timing of the fused path (CUDA events recorded on the caller's stream between
+ * K1/K2/K3).  rb200_set_profile(h, 1) enables it and zeroes the accumulators;
+ * rb200_get_profile synchronises the recorded events and returns the accumulated milliseconds of
+ * {K1 front, K2 merge+projection, K3 lstm} and the number of forwards measured. */
+int rb200_set_profile(rb200_handle h, int on);
+int rb200_get_profile(rb200_handle h, float ms_out[3], int32_t *n_forwards);
+
 /* Dense k-mer one-hot encoding, bit-exact with the reference's Cython op
  *   compute_encoded_kmer_batch(before, after, seqs, seq_mappings, seq_lens)
  *   (src/remora/encoded_kmers.pyx:13-45): out[c, 4*p+base, map[c,s]:map[c,s+1]] = 1.0f for

@@ -205,6 +205,7 @@ int rb200_destroy(rb200_handle h) {
     if (!h) return RB200_OK;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     fused_destroy(h);
     for (auto &kv : h->workspaces) kv.second.release();
     if (h->blob_dev) cudaFree(h->blob_dev);
@@ -259,6 +260,44 @@ int rb200_debug_tensor(rb200_handle h, const char *name, float *dst_dev, int64_t
     }
     set_error("no kept tensor named %s (enable rb200_set_debug and run a LAYERS forward)", name);
     return RB200_ERR_INVALID;
+}
+
+static int drain_profile(rb200_model *h) {
+    for (size_t i = 0; i + 3 < h->prof_events.size(); i += 4) {
+        RB200_CUDA_TRY(cudaEventSynchronize(h->prof_events[i + 3]));
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            RB200_CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[i + k], h->prof_events[i + k + 1]));
+            h->prof_ms[k] += ms;
+        }
+        h->prof_forwards++;
+    }
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
+    return RB200_OK;
+}
+
+int rb200_set_profile(rb200_handle h, int on) {
+    RB200_REQUIRE(h, "null handle");
+    DeviceGuard guard(h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    int rc = drain_profile(h);
+    if (rc) return rc;
+    h->profile = on != 0;
+    h->prof_ms[0] = h->prof_ms[1] = h->prof_ms[2] = 0.f;
+    h->prof_forwards = 0;
+    return RB200_OK;
+}
+
+int rb200_get_profile(rb200_handle h, float ms_out[3], int32_t *n_forwards) {
+    RB200_REQUIRE(h && ms_out, "null argument");
+    DeviceGuard guard(h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    int rc = drain_profile(h);
+    if (rc) return rc;
+    for (int k = 0; k < 3; ++k) ms_out[k] = h->prof_ms[k];
+    if (n_forwards) *n_forwards = h->prof_forwards;
+    return RB200_OK;
 }
 
 int rb200_encode_dense(const int8_t *seqs_dev, int32_t seq_width, const int16_t *maps_dev,

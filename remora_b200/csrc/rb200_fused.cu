@@ -1,14 +1,1011 @@
-// placeholder, replaced below
+// Fused sm_100a kernels for ConvLSTM_w_ref (size 64) on the reference's COMPACT chunk arrays:
+// the k-mer one-hot tensor is never materialised.
+//
+//   K1  front   : move-table expansion + seq_conv1 in gather-add form (one-hot conv == sum of
+//                 weight columns), sig_conv1..3, seq_conv2  -> cat [B][T3][128] channel-last
+//   K2  merge   : merge_conv1 (implicit GEMM M=64,K=640) + LSTM1 input projection (M=256,K=64)
+//                 -> xp [B][TM][256]
+//   K3  lstm    : LSTM1 recurrence with W_hh resident in registers, the single needed step of the
+//                 time-reversed LSTM2, fc with warp-shuffle reduction -> logits
+//
+// Reference semantics: models/ConvLSTM_w_ref.py:39-58 with eval BatchNorm folded into the convs.
+// All arithmetic is fp32 FMA (packed FFMA2, `fma.rn.f32x2`, two output channels per instruction),
+// fp32 accumulate.  Activations are channel-last so that 4 input channels arrive per LDS.128 and the
+// two halves of an FFMA2 are two adjacent output channels; weights are staged in shared memory
+// k-major by bulk asynchronous copies (TMA, cp.async.bulk + mbarrier), shared by every chunk of the
+// CTA and read as warp-wide broadcasts.
+#include <cstring>
+
 #include "rb200_internal.cuh"
+
 namespace rb200 {
-struct FusedWeights {};
-bool fused_supported(const rb200_model_desc &) { return false; }
-int fused_create(rb200_model *, const float *) { return RB200_OK; }
-void fused_destroy(rb200_model *) {}
-bool fused_shape_ok(const rb200_model *, int, int, int) { return false; }
-size_t fused_workspace_bytes(const rb200_model *, int, int) { return 0; }
-int fused_forward_compact(rb200_model *, Workspace &, const float *, const int8_t *, int,
-                          const int16_t *, int, const int16_t *, int, int, float *, cudaStream_t) {
-    return RB200_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int SIZE = 64;          // channel width this file is specialised for
+constexpr int XP = 2 * SIZE + 4;  // cat row pitch in floats (128 channels + 4 pad)
+constexpr int MP = SIZE + 4;      // merge-out row pitch in shared memory
+constexpr int QP = 20;            // 16-channel row pitch (s2 / q1) in shared memory
+constexpr int NR1 = 7;            // K1: output positions per thread
+constexpr int NR2 = 6;            // K2: output positions per thread
+constexpr int MAX_CL = 8;         // chunks per CTA (lane = tb * CL + chunk)
+constexpr int THREADS = 256;
+constexpr int SLAB_C = 32;                              // merge conv: input channels per slab
+constexpr int SLAB_FLOATS = 5 * SLAB_C * SIZE;          // 10240 floats = 40 KB
+constexpr int N_SLABS = 2 * SIZE / SLAB_C;              // 4
+constexpr int KW_SIG1 = 5, KW_SIG2 = 5, KW_SIG3 = 9, KW_SEQ1 = 5, KW_SEQ2 = 13, KW_MRG = 5;
+
+// ---- PTX helpers: mbarrier + bulk async copy (TMA) --------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy, completion counted on `bar`; bytes % 16 == 0, 16 B aligned both ends
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_addr(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) {
+    // SASS: FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO  (scalar operand broadcast to both halves)
+    return __ffma2_rn(a, make_float2(b, b), c);
+}
+
+struct FrontOffsets {  // float offsets inside the K1 weight blob (all multiples of 4)
+    int w_sig1, b_sig1, w_sig2, b_sig2, w_sig3, b_sig3, w_seq1, b_seq1, w_seq2, b_seq2, total;
+};
+
+__host__ __device__ inline FrontOffsets front_offsets(int kmer_len) {
+    FrontOffsets o;
+    int cur = 0;
+    auto take = [&](int n) {
+        int at = cur;
+        cur += (n + 3) & ~3;
+        return at;
+    };
+    o.w_sig1 = take(KW_SIG1 * 4);            // [j][co]
+    o.b_sig1 = take(4);
+    o.w_sig2 = take(KW_SIG2 * 4 * 16);       // [j][ci][co]
+    o.b_sig2 = take(16);
+    o.w_sig3 = take(KW_SIG3 * 16 * SIZE);    // [j*16+ci][co]
+    o.b_sig3 = take(SIZE);
+    o.w_seq1 = take(KW_SEQ1 * kmer_len * 4 * 16);  // [j][p][base][co]
+    o.b_seq1 = take(16);
+    o.w_seq2 = take(KW_SEQ2 * 16 * SIZE);    // [j*16+ci][co]
+    o.b_seq2 = take(SIZE);
+    o.total = cur;
+    return o;
+}
+
+struct Geometry {
+    int T, T1, T2, T3, TM;  // chunk_len, after sig_conv1, sig_conv2, sig_conv3 (= after seq_conv2), merge
+    int Q1;                 // after seq_conv1
+    int NB1, NB2, CL;       // position blocks per chunk in K1 / K2, max chunks per CTA
+    int s2_stride, q1_stride, act_stride;  // per-chunk strides (floats) of the 16-channel tiles
+    int cat_stride;                        // per-chunk stride (floats) of cat rows in HBM and smem
+    bool ok;
+};
+
+__host__ __device__ inline int odd_quads(int floats) {
+    // pad so that stride/4 is odd: 8 lanes reading 16 B at this stride hit 8 different bank groups
+    int s = (floats + 3) & ~3;
+    if (((s >> 2) & 1) == 0) s += 4;
+    return s;
+}
+
+__host__ __device__ inline Geometry make_geometry(int T) {
+    Geometry g;
+    g.T = T;
+    g.T1 = T - (KW_SIG1 - 1);
+    g.T2 = g.T1 - (KW_SIG2 - 1);
+    g.T3 = g.T2 >= KW_SIG3 ? (g.T2 - KW_SIG3) / 3 + 1 : 0;
+    g.Q1 = T - (KW_SEQ1 - 1);
+    const int q2 = g.Q1 >= KW_SEQ2 ? (g.Q1 - KW_SEQ2) / 3 + 1 : 0;
+    g.TM = g.T3 - (KW_MRG - 1);
+    g.ok = g.T3 > 0 && q2 == g.T3 && g.TM > 0;
+    g.NB1 = (g.T3 + NR1 - 1) / NR1;
+    g.NB2 = (g.TM + NR2 - 1) / NR2;
+    const int nb = g.NB1 > g.NB2 ? g.NB1 : g.NB2;
+    g.CL = nb > 0 ? 32 / nb : 0;
+    if (g.CL > MAX_CL) g.CL = MAX_CL;
+    if (g.CL < 1) g.ok = false;
+    g.s2_stride = odd_quads(g.T2 * QP);
+    g.q1_stride = odd_quads(g.Q1 * QP);
+    g.act_stride = g.s2_stride > g.q1_stride ? g.s2_stride : g.q1_stride;
+    g.cat_stride = odd_quads(g.T3 * XP);
+    return g;
+}
+
+// =================================================================================================
+// K1: front
+// =================================================================================================
+struct K1Smem {  // float offsets in dynamic shared memory
+    int weights, sig, s1, act, sidx, seq, map, len, total_bytes;
+};
+
+__host__ __device__ inline K1Smem k1_smem(const Geometry &g, int kmer_len, int seq_width,
+                                          int map_width) {
+    K1Smem s;
+    const FrontOffsets fo = front_offsets(kmer_len);
+    int cur = 4;  // floats 0..1 hold the mbarrier
+    auto take = [&](int n) {
+        int at = cur;
+        cur += (n + 3) & ~3;
+        return at;
+    };
+    s.weights = take(fo.total);
+    s.sig = take(g.CL * g.T);
+    s.s1 = take(g.CL * g.T1 * 4);
+    s.act = take(g.CL * g.act_stride);
+    s.sidx = take((g.CL * g.T + 1) / 2);        // int16 per sample
+    s.seq = take((g.CL * seq_width + 3) / 4);   // int8
+    s.map = take((g.CL * map_width + 1) / 2);   // int16
+    s.len = take(g.CL);
+    s.total_bytes = cur * 4;
+    return s;
+}
+
+// Implicit-GEMM conv, stride 3, 16 input channels (channel-last, pitch QP) -> 64 output channels.
+// Warp w owns output channels [8w, 8w+8); lane = tb * CL + chunk owns NR1 consecutive output steps.
+template <int KW>
+__device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, int x_stride,
+                                                 const float *__restrict__ ws,
+                                                 const float *__restrict__ bias,
+                                                 float *__restrict__ cat, int cat_stride,
+                                                 int ch_off, int C, int CL, int NB, int T3) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = warp * 8;
+    int tb = lane / CL, chunk = lane - tb * CL;
+    const bool lane_ok = tb < NB && chunk < C;
+    if (tb >= NB) tb = NB - 1;
+    if (chunk >= C) chunk = C - 1;
+    const int t0 = tb * NR1;
+    const float *xrow[NR1];
+#pragma unroll
+    for (int n = 0; n < NR1; ++n) {
+        int t = t0 + n;
+        if (t > T3 - 1) t = T3 - 1;
+        xrow[n] = xs + chunk * x_stride + 3 * t * QP;
+    }
+    float2 acc[NR1][4];
+#pragma unroll
+    for (int n = 0; n < NR1; ++n)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[n][p] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+    for (int j = 0; j < KW; ++j) {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; c4 += 4) {
+            float4 x[NR1];
+#pragma unroll
+            for (int n = 0; n < NR1; ++n)
+                x[n] = *reinterpret_cast<const float4 *>(xrow[n] + j * QP + c4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 *wp =
+                    reinterpret_cast<const float4 *>(ws + (j * 16 + c4 + kk) * SIZE + m0);
+                const float4 wa = wp[0], wb = wp[1];
+                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
+                const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+#pragma unroll
+                for (int n = 0; n < NR1; ++n) {
+                    const float xv = kk == 0 ? x[n].x : kk == 1 ? x[n].y : kk == 2 ? x[n].z : x[n].w;
+                    acc[n][0] = ffma2(w0, xv, acc[n][0]);
+                    acc[n][1] = ffma2(w1, xv, acc[n][1]);
+                    acc[n][2] = ffma2(w2, xv, acc[n][2]);
+                    acc[n][3] = ffma2(w3, xv, acc[n][3]);
+                }
+            }
+        }
+    }
+    if (!lane_ok) return;
+    float b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = bias[m0 + i];
+#pragma unroll
+    for (int n = 0; n < NR1; ++n) {
+        const int t = t0 + n;
+        if (t < T3) {
+            float4 o0, o1;
+            o0.x = swishf(acc[n][0].x + b[0]);
+            o0.y = swishf(acc[n][0].y + b[1]);
+            o0.z = swishf(acc[n][1].x + b[2]);
+            o0.w = swishf(acc[n][1].y + b[3]);
+            o1.x = swishf(acc[n][2].x + b[4]);
+            o1.y = swishf(acc[n][2].y + b[5]);
+            o1.z = swishf(acc[n][3].x + b[6]);
+            o1.w = swishf(acc[n][3].y + b[7]);
+            float4 *dst = reinterpret_cast<float4 *>(cat + (size_t)chunk * cat_stride + t * XP +
+                                                     ch_off + m0);
+            dst[0] = o0;
+            dst[1] = o1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
+                const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
+                const float *__restrict__ wfront, float *__restrict__ cat, int B, int CPB, int T,
+                int kmer_len) {
+    extern __shared__ __align__(128) float sm[];
+    const Geometry g = make_geometry(T);
+    const K1Smem lay = k1_smem(g, kmer_len, seq_width, map_width);
+    const FrontOffsets fo = front_offsets(kmer_len);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+    float *wsm = sm + lay.weights;
+    float *sig_s = sm + lay.sig;
+    float *s1_s = sm + lay.s1;
+    float *act_s = sm + lay.act;
+    int16_t *sidx_s = reinterpret_cast<int16_t *>(sm + lay.sidx);
+    int8_t *seq_s = reinterpret_cast<int8_t *>(sm + lay.seq);
+    int16_t *map_s = reinterpret_cast<int16_t *>(sm + lay.map);
+    int *len_s = reinterpret_cast<int *>(sm + lay.len);
+
+    const int tid = threadIdx.x;
+    const int chunk0 = blockIdx.x * CPB;
+    const int C = min(CPB, B - chunk0);
+    const int CL = g.CL;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)fo.total * 4u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(wsm, wfront, bytes, bar);
+    }
+    // ---- stage the compact inputs of this CTA's chunks ------------------------------------------
+    for (int i = tid; i < C * T; i += THREADS) {
+        sig_s[i] = sigs[(size_t)chunk0 * T + i];
+        sidx_s[i] = -1;
+    }
+    for (int i = tid; i < C; i += THREADS) {
+        int L = lens[chunk0 + i];
+        L = max(0, min(L, min(map_width - 1, seq_width - kmer_len + 1)));
+        len_s[i] = L;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * seq_width; i += THREADS) {
+        const int c = i / seq_width, s = i - c * seq_width;
+        // padding past seq_len + kmer_len - 1 is uninitialised in the reference's arrays: never read
+        seq_s[i] = s < len_s[c] + kmer_len - 1 ? seqs[(size_t)(chunk0 + c) * seq_width + s] : (int8_t)-1;
+    }
+    for (int i = tid; i < C * map_width; i += THREADS) {
+        const int c = i / map_width, s = i - c * map_width;
+        map_s[i] = s <= len_s[c] ? maps[(size_t)(chunk0 + c) * map_width + s] : (int16_t)0;
+    }
+    __syncthreads();
+    // ---- move-table expansion: sidx[t] = index of the base whose dwell covers sample t ----------
+    for (int i = tid; i < C * (map_width - 1); i += THREADS) {
+        const int c = i / (map_width - 1), s = i - c * (map_width - 1);
+        if (s < len_s[c]) {
+            const int st = max((int)map_s[c * map_width + s], 0);
+            const int en = min((int)map_s[c * map_width + s + 1], T);
+            for (int t = st; t < en; ++t) sidx_s[c * T + t] = (int16_t)s;
+        }
+    }
+    mbar_wait(bar, 0);  // weights have landed
+    __syncthreads();
+
+    // ---- sig_conv1 (1 -> 4, k5) -------------------------------------------------------------------
+    {
+        const float *w = wsm + fo.w_sig1;  // [j][co]
+        const float *b = wsm + fo.b_sig1;
+        for (int i = tid; i < C * g.T1; i += THREADS) {
+            const int c = i / g.T1, t = i - c * g.T1;
+            const float *x = sig_s + c * T + t;
+            float4 a = *reinterpret_cast<const float4 *>(b);
+#pragma unroll
+            for (int j = 0; j < KW_SIG1; ++j) {
+                const float xv = x[j];
+                const float4 wv = *reinterpret_cast<const float4 *>(w + 4 * j);
+                a.x = fmaf(wv.x, xv, a.x);
+                a.y = fmaf(wv.y, xv, a.y);
+                a.z = fmaf(wv.z, xv, a.z);
+                a.w = fmaf(wv.w, xv, a.w);
+            }
+            a.x = swishf(a.x);
+            a.y = swishf(a.y);
+            a.z = swishf(a.z);
+            a.w = swishf(a.w);
+            *reinterpret_cast<float4 *>(s1_s + (size_t)i * 4) = a;
+        }
+    }
+    __syncthreads();
+    // ---- sig_conv2 (4 -> 16, k5): one thread per (chunk, t, 8-channel half) ----------------------
+    {
+        const float *w = wsm + fo.w_sig2;  // [j][ci][co]
+        const float *b = wsm + fo.b_sig2;
+        for (int i = tid; i < C * g.T2 * 2; i += THREADS) {
+            const int half = i & 1;
+            const int ct = i >> 1;
+            const int c = ct / g.T2, t = ct - c * g.T2;
+            float acc[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] = b[half * 8 + o];
+#pragma unroll
+            for (int j = 0; j < KW_SIG2; ++j) {
+                const float4 xv = *reinterpret_cast<const float4 *>(s1_s + (size_t)(c * g.T1 + t + j) * 4);
+                const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const float4 *wp = reinterpret_cast<const float4 *>(w + (j * 4 + ci) * 16 + half * 8);
+                    const float4 wa = wp[0], wb = wp[1];
+                    acc[0] = fmaf(wa.x, xs4[ci], acc[0]);
+                    acc[1] = fmaf(wa.y, xs4[ci], acc[1]);
+                    acc[2] = fmaf(wa.z, xs4[ci], acc[2]);
+                    acc[3] = fmaf(wa.w, xs4[ci], acc[3]);
+                    acc[4] = fmaf(wb.x, xs4[ci], acc[4]);
+                    acc[5] = fmaf(wb.y, xs4[ci], acc[5]);
+                    acc[6] = fmaf(wb.z, xs4[ci], acc[6]);
+                    acc[7] = fmaf(wb.w, xs4[ci], acc[7]);
+                }
+            }
+            float4 *dst = reinterpret_cast<float4 *>(act_s + c * g.s2_stride + t * QP + half * 8);
+            dst[0] = make_float4(swishf(acc[0]), swishf(acc[1]), swishf(acc[2]), swishf(acc[3]));
+            dst[1] = make_float4(swishf(acc[4]), swishf(acc[5]), swishf(acc[6]), swishf(acc[7]));
+        }
+    }
+    __syncthreads();
+    float *cat_cta = cat + (size_t)chunk0 * g.cat_stride;
+    // ---- sig_conv3 (16 -> 64, k9, stride 3) -> cat[:, :, 0:64] -----------------------------------
+    conv16_s3_to_cat<KW_SIG3>(act_s, g.s2_stride, wsm + fo.w_sig3, wsm + fo.b_sig3, cat_cta,
+                              g.cat_stride, 0, C, CL, g.NB1, g.T3);
+    __syncthreads();
+    // ---- seq_conv1 on the (virtual) one-hot input = gather-add of weight columns -----------------
+    // q1[t][o] = swish(b[o] + sum_{j<5} sum_{p<k} W[o][4p + base(t+j, p)][j]),
+    // base(t, p) = seq[sidx[t] + p]; -1 bases and uncovered samples contribute nothing
+    // (encoded_kmers.pyx:39-40).  One thread per (chunk, t, 4-channel quarter).
+    {
+        const float *w = wsm + fo.w_seq1;  // [j][p][base][co]
+        const float *b = wsm + fo.b_seq1;
+        for (int i = tid; i < C * g.Q1 * 4; i += THREADS) {
+            const int quarter = i & 3;
+            const int ct = i >> 2;
+            const int c = ct / g.Q1, t = ct - c * g.Q1;
+            float4 a = *reinterpret_cast<const float4 *>(b + quarter * 4);
+            const int8_t *sq = seq_s + c * seq_width;
+#pragma unroll
+            for (int j = 0; j < KW_SEQ1; ++j) {
+                const int s = sidx_s[c * T + t + j];
+                if (s < 0) continue;
+                const float *wj = w + (size_t)j * kmer_len * 64 + quarter * 4;
+                for (int p = 0; p < kmer_len; ++p) {
+                    const int base = sq[s + p];
+                    if (base < 0 || base > 3) continue;
+                    const float4 wv = *reinterpret_cast<const float4 *>(wj + (p * 4 + base) * 16);
+                    a.x += wv.x;
+                    a.y += wv.y;
+                    a.z += wv.z;
+                    a.w += wv.w;
+                }
+            }
+            a.x = swishf(a.x);
+            a.y = swishf(a.y);
+            a.z = swishf(a.z);
+            a.w = swishf(a.w);
+            *reinterpret_cast<float4 *>(act_s + c * g.q1_stride + t * QP + quarter * 4) = a;
+        }
+    }
+    __syncthreads();
+    // ---- seq_conv2 (16 -> 64, k13, stride 3) -> cat[:, :, 64:128] --------------------------------
+    conv16_s3_to_cat<KW_SEQ2>(act_s, g.q1_stride, wsm + fo.w_seq2, wsm + fo.b_seq2, cat_cta,
+                              g.cat_stride, SIZE, C, CL, g.NB1, g.T3);
+}
+
+// =================================================================================================
+// K2: merge_conv1 + LSTM1 input projection
+// =================================================================================================
+struct K2Smem {
+    int xs, ws, total_bytes;
+};
+__host__ __device__ inline K2Smem k2_smem(const Geometry &g) {
+    K2Smem s;
+    int cur = 8;  // 4 mbarriers
+    s.xs = cur;
+    int x_floats = g.CL * g.cat_stride;
+    const int ms_floats = 192 * MP;  // x-projection input rows (<= 32 lanes * NR2 positions)
+    if (x_floats < ms_floats) x_floats = ms_floats;
+    cur += (x_floats + 31) & ~31;
+    s.ws = cur;
+    cur += 2 * SLAB_FLOATS;
+    s.total_bytes = cur * 4;
+    return s;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
+                const float *__restrict__ bmerge, const float *__restrict__ wih1T,
+                const float *__restrict__ b1, float *__restrict__ xp, int B, int CPB, int T) {
+    extern __shared__ __align__(128) float sm[];
+    const Geometry g = make_geometry(T);
+    const K2Smem lay = k2_smem(g);
+    uint64_t *bar_x = reinterpret_cast<uint64_t *>(sm);
+    uint64_t *bar_w = bar_x + 1;  // [2]
+    float *xs = sm + lay.xs;
+    float *ws = sm + lay.ws;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk0 = blockIdx.x * CPB;
+    const int C = min(CPB, B - chunk0);
+    const int CL = g.CL;
+
+    if (tid == 0) {
+        mbar_init(bar_x, 1);
+        mbar_init(&bar_w[0], 1);
+        mbar_init(&bar_w[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t xbytes = (uint32_t)C * g.cat_stride * 4u;
+        mbar_expect_tx(bar_x, xbytes);
+        bulk_g2s(xs, cat + (size_t)chunk0 * g.cat_stride, xbytes, bar_x);
+        for (int s = 0; s < 2; ++s) {
+            mbar_expect_tx(&bar_w[s], SLAB_FLOATS * 4u);
+            bulk_g2s(ws + s * SLAB_FLOATS, wslabs + (size_t)s * SLAB_FLOATS, SLAB_FLOATS * 4u,
+                     &bar_w[s]);
+        }
+    }
+    // ---- merge conv: warp w -> output channels [8w, 8w+8); lane = tb*CL + chunk -> NR2 steps -------
+    const int m0 = warp * 8;
+    int tb = lane / CL, chunk = lane - tb * CL;
+    const bool lane_ok = tb < g.NB2 && chunk < C;
+    if (tb >= g.NB2) tb = g.NB2 - 1;
+    if (chunk >= C) chunk = C - 1;
+    const int t0 = tb * NR2;
+    // window rows t0 .. t0+NR2+3 (clamped into the chunk)
+    const float *xrow[NR2 + KW_MRG - 1];
+#pragma unroll
+    for (int r = 0; r < NR2 + KW_MRG - 1; ++r) {
+        int t = t0 + r;
+        if (t > g.T3 - 1) t = g.T3 - 1;
+        xrow[r] = xs + chunk * g.cat_stride + t * XP;
+    }
+    float2 acc[NR2][4];
+#pragma unroll
+    for (int n = 0; n < NR2; ++n)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[n][p] = make_float2(0.f, 0.f);
+
+    mbar_wait(bar_x, 0);
+#pragma unroll 1
+    for (int s = 0; s < N_SLABS; ++s) {
+        const float *wbuf = ws + (s & 1) * SLAB_FLOATS;
+        mbar_wait(&bar_w[s & 1], (s >> 1) & 1);
+#pragma unroll 1
+        for (int c4 = 0; c4 < SLAB_C; c4 += 4) {
+            float4 x[NR2 + KW_MRG - 1];
+#pragma unroll
+            for (int r = 0; r < NR2 + KW_MRG - 1; ++r)
+                x[r] = *reinterpret_cast<const float4 *>(xrow[r] + s * SLAB_C + c4);
+#pragma unroll
+            for (int j = 0; j < KW_MRG; ++j) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 *wp = reinterpret_cast<const float4 *>(
+                        wbuf + (j * SLAB_C + c4 + kk) * SIZE + m0);
+                    const float4 wa = wp[0], wb = wp[1];
+                    const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
+                    const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+#pragma unroll
+                    for (int n = 0; n < NR2; ++n) {
+                        const float4 xq = x[n + j];
+                        const float xv = kk == 0 ? xq.x : kk == 1 ? xq.y : kk == 2 ? xq.z : xq.w;
+                        acc[n][0] = ffma2(w0, xv, acc[n][0]);
+                        acc[n][1] = ffma2(w1, xv, acc[n][1]);
+                        acc[n][2] = ffma2(w2, xv, acc[n][2]);
+                        acc[n][3] = ffma2(w3, xv, acc[n][3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with this slab buffer
+        if (tid == 0) {
+            if (s + 2 < N_SLABS) {
+                mbar_expect_tx(&bar_w[s & 1], SLAB_FLOATS * 4u);
+                bulk_g2s(ws + (s & 1) * SLAB_FLOATS, wslabs + (size_t)(s + 2) * SLAB_FLOATS,
+                         SLAB_FLOATS * 4u, &bar_w[s & 1]);
+            } else {
+                // W_ih1^T half (32 k-rows x 256) into the buffer that just became free
+                const int h = s - (N_SLABS - 2);
+                mbar_expect_tx(&bar_w[s & 1], 32 * 256 * 4u);
+                bulk_g2s(ws + (s & 1) * SLAB_FLOATS, wih1T + (size_t)h * 32 * 256, 32 * 256 * 4u,
+                         &bar_w[s & 1]);
+            }
+        }
+    }
+    // ---- merge epilogue: bias + swish -> ms[(chunk*TM + t)][MP] (aliases xs; all warps synced) -----
+    float *ms = xs;
+    if (lane_ok) {
+        float b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = bmerge[m0 + i];
+#pragma unroll
+        for (int n = 0; n < NR2; ++n) {
+            const int t = t0 + n;
+            if (t < g.TM) {
+                float4 o0, o1;
+                o0.x = swishf(acc[n][0].x + b[0]);
+                o0.y = swishf(acc[n][0].y + b[1]);
+                o0.z = swishf(acc[n][1].x + b[2]);
+                o0.w = swishf(acc[n][1].y + b[3]);
+                o1.x = swishf(acc[n][2].x + b[4]);
+                o1.y = swishf(acc[n][2].y + b[5]);
+                o1.z = swishf(acc[n][3].x + b[6]);
+                o1.w = swishf(acc[n][3].y + b[7]);
+                float4 *dst = reinterpret_cast<float4 *>(ms + (chunk * g.TM + t) * MP + m0);
+                dst[0] = o0;
+                dst[1] = o1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- LSTM1 input projection: xp[pos][r] = b1[r] + sum_k W_ih1[r][k] * m[pos][k] ---------------
+    // warp w -> gate rows [16w, 16w+16) and [128+16w, ...); lane -> positions lane + 32 n
+    const int npos = C * g.TM;
+    const float *mrow[NR2];
+#pragma unroll
+    for (int n = 0; n < NR2; ++n) {
+        int pos = lane + 32 * n;
+        if (pos > npos - 1) pos = npos - 1;
+        mrow[n] = ms + pos * MP;
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int r0 = pass * 128 + warp * 16;
+        float2 pa[NR2][8];
+#pragma unroll
+        for (int n = 0; n < NR2; ++n)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) pa[n][p] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            // half h of W_ih1^T lives in buffer ((N_SLABS-2+h) & 1); its load was the
+            // (N_SLABS-2+h)/2 + 1 -th use of that barrier -> parity below
+            const int sidx_buf = (N_SLABS - 2 + h) & 1;
+            const int use = ((N_SLABS - 2 + h) >> 1) + 1;
+            if (pass == 0) mbar_wait(&bar_w[sidx_buf], use & 1);
+            const float *wbuf = ws + sidx_buf * SLAB_FLOATS;
+#pragma unroll 1
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+                float4 x[NR2];
+#pragma unroll
+                for (int n = 0; n < NR2; ++n)
+                    x[n] = *reinterpret_cast<const float4 *>(mrow[n] + h * 32 + c4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 *wp = reinterpret_cast<const float4 *>(wbuf + (c4 + kk) * 256 + r0);
+                    const float4 wa = wp[0], wb = wp[1], wc = wp[2], wd = wp[3];
+                    const float2 w[8] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w),
+                                         make_float2(wb.x, wb.y), make_float2(wb.z, wb.w),
+                                         make_float2(wc.x, wc.y), make_float2(wc.z, wc.w),
+                                         make_float2(wd.x, wd.y), make_float2(wd.z, wd.w)};
+#pragma unroll
+                    for (int n = 0; n < NR2; ++n) {
+                        const float xv = kk == 0 ? x[n].x : kk == 1 ? x[n].y : kk == 2 ? x[n].z : x[n].w;
+#pragma unroll
+                        for (int p = 0; p < 8; ++p) pa[n][p] = ffma2(w[p], xv, pa[n][p]);
+                    }
+                }
+            }
+        }
+        float bb[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bb[i] = b1[r0 + i];
+#pragma unroll
+        for (int n = 0; n < NR2; ++n) {
+            const int pos = lane + 32 * n;
+            if (pos < npos) {
+                float4 *dst = reinterpret_cast<float4 *>(xp + ((size_t)chunk0 * g.TM + pos) * 256 + r0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    dst[q] = make_float4(pa[n][2 * q].x + bb[4 * q], pa[n][2 * q].y + bb[4 * q + 1],
+                                         pa[n][2 * q + 1].x + bb[4 * q + 2],
+                                         pa[n][2 * q + 1].y + bb[4 * q + 3]);
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// K3: LSTM1 recurrence (W_hh in registers) + single-step LSTM2 + fc
+// =================================================================================================
+constexpr int C3MAX = 8;
+
+__global__ void __launch_bounds__(THREADS, 1)
+k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
+               const float *__restrict__ wih2T, const float *__restrict__ b2,
+               const float *__restrict__ fcw, const float *__restrict__ fcb,
+               float *__restrict__ logits, int B, int CPB, int TM, int num_out) {
+    __shared__ __align__(16) float h_s[SIZE][C3MAX];      // h[k][chunk]
+    __shared__ __align__(16) float g_s[C3MAX][4 * SIZE];  // gate pre-activations
+    __shared__ __align__(16) float y_s[C3MAX][SIZE];
+    const int tid = threadIdx.x;
+    const int r = tid;  // gate row: i 0..63, f 64..127, g 128..191, o 192..255
+    const int chunk0 = blockIdx.x * CPB;
+    const int C = min(CPB, B - chunk0);
+
+    float w[SIZE];
+#pragma unroll
+    for (int q = 0; q < SIZE / 4; ++q) {
+        const float4 v = whh4[q * 256 + r];
+        w[4 * q] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+    }
+    for (int i = tid; i < SIZE * C3MAX; i += THREADS) (&h_s[0][0])[i] = 0.f;
+    const int u = tid & 63, q = tid >> 6;  // cell-update role: unit u, chunks q and q+4
+    float cst0 = 0.f, cst1 = 0.f, hlast0 = 0.f, hlast1 = 0.f;
+
+    float xnext[C3MAX];
+#pragma unroll
+    for (int c = 0; c < C3MAX; ++c)
+        xnext[c] = c < C ? xp[((size_t)(chunk0 + c) * TM) * 256 + r] : 0.f;
+    __syncthreads();
+
+#pragma unroll 1
+    for (int t = 0; t < TM; ++t) {
+        float2 a[C3MAX / 2];
+#pragma unroll
+        for (int p = 0; p < C3MAX / 2; ++p) a[p] = make_float2(xnext[2 * p], xnext[2 * p + 1]);
+        if (t + 1 < TM) {
+#pragma unroll
+            for (int c = 0; c < C3MAX; ++c)
+                if (c < C) xnext[c] = xp[((size_t)(chunk0 + c) * TM + t + 1) * 256 + r];
+        }
+#pragma unroll
+        for (int k = 0; k < SIZE; ++k) {
+            const float4 ha = *reinterpret_cast<const float4 *>(&h_s[k][0]);
+            const float4 hb = *reinterpret_cast<const float4 *>(&h_s[k][4]);
+            a[0] = ffma2(make_float2(ha.x, ha.y), w[k], a[0]);
+            a[1] = ffma2(make_float2(ha.z, ha.w), w[k], a[1]);
+            a[2] = ffma2(make_float2(hb.x, hb.y), w[k], a[2]);
+            a[3] = ffma2(make_float2(hb.z, hb.w), w[k], a[3]);
+        }
+#pragma unroll
+        for (int p = 0; p < C3MAX / 2; ++p) {
+            g_s[2 * p][r] = a[p].x;
+            g_s[2 * p + 1][r] = a[p].y;
+        }
+        __syncthreads();
+        {
+            const int c0 = q, c1 = q + 4;
+            float ig = sigmoidf_acc(g_s[c0][u]), fg = sigmoidf_acc(g_s[c0][64 + u]);
+            float gg = tanhf(g_s[c0][128 + u]), og = sigmoidf_acc(g_s[c0][192 + u]);
+            cst0 = fg * cst0 + ig * gg;
+            hlast0 = og * tanhf(cst0);
+            ig = sigmoidf_acc(g_s[c1][u]);
+            fg = sigmoidf_acc(g_s[c1][64 + u]);
+            gg = tanhf(g_s[c1][128 + u]);
+            og = sigmoidf_acc(g_s[c1][192 + u]);
+            cst1 = fg * cst1 + ig * gg;
+            hlast1 = og * tanhf(cst1);
+            h_s[u][c0] = hlast0;
+            h_s[u][c1] = hlast1;
+        }
+        __syncthreads();
+    }
+    // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54):
+    // x = swish(h1[T-1]), h0 = c0 = 0  =>  c = sig(i) * tanh(g), h = sig(o) * tanh(c)
+    h_s[u][q] = swishf(hlast0);
+    h_s[u][q + 4] = swishf(hlast1);
+    __syncthreads();
+    {
+        float a2[C3MAX];
+        const float bias = b2[r];
+#pragma unroll
+        for (int c = 0; c < C3MAX; ++c) a2[c] = bias;
+#pragma unroll 4
+        for (int k = 0; k < SIZE; ++k) {
+            const float wv = wih2T[k * 256 + r];
+            const float4 ha = *reinterpret_cast<const float4 *>(&h_s[k][0]);
+            const float4 hb = *reinterpret_cast<const float4 *>(&h_s[k][4]);
+            a2[0] = fmaf(wv, ha.x, a2[0]);
+            a2[1] = fmaf(wv, ha.y, a2[1]);
+            a2[2] = fmaf(wv, ha.z, a2[2]);
+            a2[3] = fmaf(wv, ha.w, a2[3]);
+            a2[4] = fmaf(wv, hb.x, a2[4]);
+            a2[5] = fmaf(wv, hb.y, a2[5]);
+            a2[6] = fmaf(wv, hb.z, a2[6]);
+            a2[7] = fmaf(wv, hb.w, a2[7]);
+        }
+#pragma unroll
+        for (int c = 0; c < C3MAX; ++c) g_s[c][r] = a2[c];
+    }
+    __syncthreads();
+    {
+        const int cc[2] = {q, q + 4};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = cc[i];
+            const float c2 = sigmoidf_acc(g_s[c][u]) * tanhf(g_s[c][128 + u]);
+            const float h2 = sigmoidf_acc(g_s[c][192 + u]) * tanhf(c2);
+            y_s[c][u] = swishf(h2);
+        }
+    }
+    __syncthreads();
+    // ---- fc: one warp per chunk, warp-shuffle reduction over the 64 features ---------------------
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < C) {
+            for (int o = 0; o < num_out; ++o) {
+                float part = fcw[o * SIZE + lane] * y_s[warp][lane] +
+                             fcw[o * SIZE + lane + 32] * y_s[warp][lane + 32];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                if (lane == 0) logits[(size_t)(chunk0 + warp) * num_out + o] = part + fcb[o];
+            }
+        }
+    }
+}
+
+// repack a channel-last strided activation into canonical [B][C][T] for rb200_debug_tensor
+__global__ void repack_kernel(const float *__restrict__ src, int64_t chunk_stride, int row_pitch,
+                              int ch_off, float *__restrict__ dst, int B, int C, int T) {
+    const int64_t total = (int64_t)B * C * T;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const int c = (int)((i / T) % C);
+        const int b = (int)(i / ((int64_t)T * C));
+        dst[i] = src[b * chunk_stride + (int64_t)t * row_pitch + ch_off + c];
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct FusedWeights {
+    float *dev = nullptr;  // one allocation holding every re-laid-out tensor
+    size_t off_front = 0, off_slabs = 0, off_bmerge = 0, off_wih1T = 0, off_b1 = 0, off_whh4 = 0,
+           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0;
+    int kmer_len = 0, num_out = 0;
+};
+
+bool fused_supported(const rb200_model_desc &d) {
+    if (d.arch != RB200_ARCH_CONVLSTM_W_REF || d.size != SIZE) return false;
+    if (d.n_sig_conv != 3 || d.n_seq_conv != 2 || d.n_merge_conv != 1 || d.n_lstm != 2) return false;
+    auto is = [](const rb200_conv_desc &c, int ci, int co, int kw, int st) {
+        return c.c_in == ci && c.c_out == co && c.kw == kw && c.stride == st;
+    };
+    if (d.kmer_len > 16) return false;
+    return is(d.sig_conv[0], 1, 4, KW_SIG1, 1) && is(d.sig_conv[1], 4, 16, KW_SIG2, 1) &&
+           is(d.sig_conv[2], 16, SIZE, KW_SIG3, 3) &&
+           is(d.seq_conv[0], 4 * d.kmer_len, 16, KW_SEQ1, 1) &&
+           is(d.seq_conv[1], 16, SIZE, KW_SEQ2, 3) && is(d.merge_conv[0], 2 * SIZE, SIZE, KW_MRG, 1);
+}
+
+int fused_create(rb200_model *m, const float *blob) {
+    const rb200_model_desc &d = m->desc;
+    const int K = d.kmer_len;
+    const FrontOffsets fo = front_offsets(K);
+    std::vector<float> host;
+    auto reserve = [&](size_t n) {
+        size_t at = host.size();
+        host.resize(at + ((n + 31) & ~(size_t)31), 0.f);  // 128-byte aligned pieces
+        return at;
+    };
+    FusedWeights *fw = new FusedWeights();
+    fw->kmer_len = K;
+    fw->num_out = d.num_out;
+    // --- K1 blob ---
+    fw->off_front = reserve(fo.total);
+    {
+        float *f = host.data() + fw->off_front;
+        const float *w = blob + d.sig_conv[0].w_off;  // [co=4][ci=1][j=5]
+        for (int j = 0; j < KW_SIG1; ++j)
+            for (int co = 0; co < 4; ++co) f[fo.w_sig1 + j * 4 + co] = w[co * KW_SIG1 + j];
+        memcpy(f + fo.b_sig1, blob + d.sig_conv[0].b_off, 4 * sizeof(float));
+        w = blob + d.sig_conv[1].w_off;  // [16][4][5]
+        for (int j = 0; j < KW_SIG2; ++j)
+            for (int ci = 0; ci < 4; ++ci)
+                for (int co = 0; co < 16; ++co)
+                    f[fo.w_sig2 + (j * 4 + ci) * 16 + co] = w[(co * 4 + ci) * KW_SIG2 + j];
+        memcpy(f + fo.b_sig2, blob + d.sig_conv[1].b_off, 16 * sizeof(float));
+        w = blob + d.sig_conv[2].w_off;  // [64][16][9]
+        for (int j = 0; j < KW_SIG3; ++j)
+            for (int ci = 0; ci < 16; ++ci)
+                for (int co = 0; co < SIZE; ++co)
+                    f[fo.w_sig3 + (j * 16 + ci) * SIZE + co] = w[(co * 16 + ci) * KW_SIG3 + j];
+        memcpy(f + fo.b_sig3, blob + d.sig_conv[2].b_off, SIZE * sizeof(float));
+        w = blob + d.seq_conv[0].w_off;  // [16][4K][5], input row = 4p + base
+        for (int j = 0; j < KW_SEQ1; ++j)
+            for (int row = 0; row < 4 * K; ++row)
+                for (int co = 0; co < 16; ++co)
+                    f[fo.w_seq1 + (j * 4 * K + row) * 16 + co] = w[(co * 4 * K + row) * KW_SEQ1 + j];
+        memcpy(f + fo.b_seq1, blob + d.seq_conv[0].b_off, 16 * sizeof(float));
+        w = blob + d.seq_conv[1].w_off;  // [64][16][13]
+        for (int j = 0; j < KW_SEQ2; ++j)
+            for (int ci = 0; ci < 16; ++ci)
+                for (int co = 0; co < SIZE; ++co)
+                    f[fo.w_seq2 + (j * 16 + ci) * SIZE + co] = w[(co * 16 + ci) * KW_SEQ2 + j];
+        memcpy(f + fo.b_seq2, blob + d.seq_conv[1].b_off, SIZE * sizeof(float));
+    }
+    // --- K2: merge conv slabs [s][j][c_local][m], bias, W_ih1^T [k][r], b1 ---
+    fw->off_slabs = reserve((size_t)N_SLABS * SLAB_FLOATS);
+    {
+        const float *w = blob + d.merge_conv[0].w_off;  // [64][128][5]
+        for (int s = 0; s < N_SLABS; ++s)
+            for (int j = 0; j < KW_MRG; ++j)
+                for (int cl = 0; cl < SLAB_C; ++cl)
+                    for (int mo = 0; mo < SIZE; ++mo)
+                        host[fw->off_slabs + (size_t)s * SLAB_FLOATS + (j * SLAB_C + cl) * SIZE + mo] =
+                            w[(mo * 2 * SIZE + s * SLAB_C + cl) * KW_MRG + j];
+    }
+    fw->off_bmerge = reserve(SIZE);
+    memcpy(host.data() + fw->off_bmerge, blob + d.merge_conv[0].b_off, SIZE * sizeof(float));
+    fw->off_wih1T = reserve(SIZE * 256);
+    for (int k = 0; k < SIZE; ++k)
+        for (int r = 0; r < 256; ++r)
+            host[fw->off_wih1T + k * 256 + r] = blob[d.lstm_w_ih_off[0] + r * SIZE + k];
+    fw->off_b1 = reserve(256);
+    memcpy(host.data() + fw->off_b1, blob + d.lstm_b_off[0], 256 * sizeof(float));
+    // --- K3: W_hh1 as float4 [k/4][r], W_ih2^T, b2, fc ---
+    fw->off_whh4 = reserve(SIZE * 256);
+    for (int q = 0; q < SIZE / 4; ++q)
+        for (int r = 0; r < 256; ++r)
+            for (int i = 0; i < 4; ++i)
+                host[fw->off_whh4 + (q * 256 + r) * 4 + i] = blob[d.lstm_w_hh_off[0] + r * SIZE + 4 * q + i];
+    fw->off_wih2T = reserve(SIZE * 256);
+    for (int k = 0; k < SIZE; ++k)
+        for (int r = 0; r < 256; ++r)
+            host[fw->off_wih2T + k * 256 + r] = blob[d.lstm_w_ih_off[1] + r * SIZE + k];
+    fw->off_b2 = reserve(256);
+    memcpy(host.data() + fw->off_b2, blob + d.lstm_b_off[1], 256 * sizeof(float));
+    fw->off_fcw = reserve((size_t)d.num_out * SIZE);
+    memcpy(host.data() + fw->off_fcw, blob + d.fc_w_off, (size_t)d.num_out * SIZE * sizeof(float));
+    fw->off_fcb = reserve(d.num_out);
+    memcpy(host.data() + fw->off_fcb, blob + d.fc_b_off, d.num_out * sizeof(float));
+
+    cudaError_t e = cudaMalloc(&fw->dev, host.size() * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(fw->dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("fused weight upload failed: %s", cudaGetErrorString(e));
+        if (fw->dev) cudaFree(fw->dev);
+        delete fw;
+        return RB200_ERR_CUDA;
+    }
+    const int max_smem = 227 * 1024;
+    cudaFuncSetAttribute(k1_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k2_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    m->fused = fw;
+    return RB200_OK;
+}
+
+void fused_destroy(rb200_model *m) {
+    if (!m->fused) return;
+    if (m->fused->dev) cudaFree(m->fused->dev);
+    delete m->fused;
+    m->fused = nullptr;
+}
+
+bool fused_shape_ok(const rb200_model *m, int T, int seq_width, int map_width) {
+    const Geometry g = make_geometry(T);
+    if (!g.ok) return false;
+    if (k1_smem(g, m->desc.kmer_len, seq_width, map_width).total_bytes > 227 * 1024) return false;
+    if (k2_smem(g).total_bytes > 227 * 1024) return false;
+    return true;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t fused_workspace_bytes(const rb200_model *m, int B, int T) {
+    const Geometry g = make_geometry(T);
+    return align256((size_t)B * g.cat_stride * 4) + align256((size_t)B * g.TM * 256 * 4) + 1024;
+}
+
+// chunks per CTA: minimise (waves * chunks-per-CTA), prefer the larger CTA on ties
+static int pick_cpb(int B, int cmax, int sm_count) {
+    int best = 1;
+    long best_cost = -1;
+    for (int c = 1; c <= cmax; ++c) {
+        const long ctas = (B + c - 1) / c;
+        const long waves = (ctas + sm_count - 1) / sm_count;
+        const long cost = waves * c;
+        if (best_cost < 0 || cost <= best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
+                          int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
+                          int B, int T, float *logits, cudaStream_t stream) {
+    const FusedWeights *fw = m->fused;
+    const Geometry g = make_geometry(T);
+    RB200_REQUIRE(g.ok, "chunk_len %d not supported by the fused kernels", T);
+    const size_t live_bytes =
+        align256((size_t)B * g.cat_stride * 4) + align256((size_t)B * g.TM * 256 * 4);
+    const size_t n_cat = (size_t)B * 128 * g.T3, n_xp = (size_t)B * 256 * g.TM;
+    size_t need = live_bytes + 1024;
+    if (m->keep_debug) need += align256(n_cat * 4) + align256(n_xp * 4);
+    int rc = ws.ensure(need);
+    if (rc) return rc;
+    float *cat = reinterpret_cast<float *>(ws.base);
+    float *xp = reinterpret_cast<float *>(ws.base + align256((size_t)B * g.cat_stride * 4));
+    const int cpb = pick_cpb(B, g.CL, m->sm_count);
+    const int grid = (B + cpb - 1) / cpb;
+    const K1Smem l1 = k1_smem(g, fw->kmer_len, seq_width, map_width);
+    const K2Smem l2 = k2_smem(g);
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (m->profile) {
+        for (int i = 0; i < 4; ++i) {
+            RB200_CUDA_TRY(cudaEventCreate(&ev[i]));
+            m->prof_events.push_back(ev[i]);
+        }
+        RB200_CUDA_TRY(cudaEventRecord(ev[0], stream));
+    }
+    k1_front_kernel<<<grid, THREADS, l1.total_bytes, stream>>>(
+        sigs, seqs, seq_width, maps, map_width, lens, fw->dev + fw->off_front, cat, B, cpb, T,
+        fw->kmer_len);
+    RB200_CUDA_TRY(cudaGetLastError());
+    if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[1], stream));
+    k2_merge_kernel<<<grid, THREADS, l2.total_bytes, stream>>>(
+        cat, fw->dev + fw->off_slabs, fw->dev + fw->off_bmerge, fw->dev + fw->off_wih1T,
+        fw->dev + fw->off_b1, xp, B, cpb, T);
+    RB200_CUDA_TRY(cudaGetLastError());
+    if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[2], stream));
+    const int cpb3 = pick_cpb(B, C3MAX, m->sm_count);
+    const int grid3 = (B + cpb3 - 1) / cpb3;
+    k3_lstm_kernel<<<grid3, THREADS, 0, stream>>>(
+        xp, reinterpret_cast<const float4 *>(fw->dev + fw->off_whh4), fw->dev + fw->off_wih2T,
+        fw->dev + fw->off_b2, fw->dev + fw->off_fcw, fw->dev + fw->off_fcb, logits, B, cpb3, g.TM,
+        fw->num_out);
+    RB200_CUDA_TRY(cudaGetLastError());
+    if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[3], stream));
+    m->launches += 3;
+    if (m->keep_debug) {
+        // canonical [B][C][T] copies appended behind the live buffers
+        m->debug.clear();
+        float *dcat = reinterpret_cast<float *>(ws.base + live_bytes);
+        float *dxp = reinterpret_cast<float *>(ws.base + live_bytes + align256(n_cat * 4));
+        repack_kernel<<<256, 256, 0, stream>>>(cat, g.cat_stride, XP, 0, dcat, B, 128, g.T3);
+        repack_kernel<<<256, 256, 0, stream>>>(xp, (int64_t)g.TM * 256, 256, 0, dxp, B, 256, g.TM);
+        RB200_CUDA_TRY(cudaGetLastError());
+        m->debug.push_back({"cat", dcat, B, 128, g.T3});
+        m->debug.push_back({"xproj", dxp, B, 256, g.TM});
+    }
+    return RB200_OK;
+}
+
 }  // namespace rb200

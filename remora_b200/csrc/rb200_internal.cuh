@@ -86,6 +86,11 @@ struct rb200_model {
     char *staging_dev = nullptr;
     size_t staging_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // per-kernel profiling of the fused path
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;  // 4 per profiled forward
+    float prof_ms[3] = {0.f, 0.f, 0.f};
+    int prof_forwards = 0;
 };
 
 namespace rb200 {

@@ -211,6 +211,17 @@ class B200Model(nn.Module):
     def launch_count(self):
         return int(self._lib.rb200_launch_count(self._handle))
 
+    def set_profile(self, on=True):
+        _native.check(self._lib.rb200_set_profile(self._handle, int(on)), "rb200_set_profile")
+
+    def get_profile(self):
+        """(ms of K1, K2, K3 accumulated over the profiled forwards, number of forwards)."""
+        ms = (ctypes.c_float * 3)()
+        n = ctypes.c_int32()
+        _native.check(self._lib.rb200_get_profile(self._handle, ctypes.byref(ms), ctypes.byref(n)),
+                      "rb200_get_profile")
+        return [float(v) for v in ms], int(n.value)
+
     def set_debug(self, keep=True):
         _native.check(self._lib.rb200_set_debug(self._handle, int(keep)), "rb200_set_debug")
 

@@ -160,6 +160,23 @@ def test_per_layer_activations_vs_oracle(forward_cases):
         got = model.debug_tensor(name).cpu()
         assert got.shape == want.shape, name
         assert (got - want).abs().max() < 2e-5, name
+    cat_layers = model.debug_tensor("cat").cpu()
+    if "fused" in impls_for(model):
+        # intermediates of the fused kernels: cat (K1 output) and the LSTM1 input projection (K2)
+        model.set_impl("fused")
+        model.set_debug(True)
+        model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
+                              torch.from_numpy(maps), torch.from_numpy(lens))
+        got_cat = model.debug_tensor("cat").cpu()
+        assert (got_cat[:, :64] - cat[:, :64]).abs().max() < 2e-5, "fused sig track"
+        assert (got_cat[:, 64:] - cat[:, 64:]).abs().max() < 2e-5, "fused seq track"
+        assert (got_cat - cat_layers).abs().max() < 2e-5
+        with torch.no_grad():
+            want_xp = torch.einsum("rk,bkt->brt", sd["lstm1.weight_ih_l0"], m1) + \
+                (sd["lstm1.bias_ih_l0"] + sd["lstm1.bias_hh_l0"])[None, :, None]
+        got_xp = model.debug_tensor("xproj").cpu()
+        assert got_xp.shape == want_xp.shape
+        assert (got_xp - want_xp).abs().max() < 1e-4, "fused merge conv + input projection"
     model.set_debug(False)
     model.set_impl("auto")
 
