@@ -120,9 +120,11 @@ int launch_encode_dense(const int8_t *seqs, int seq_width, const int16_t *maps, 
         RB200_CUDA_TRY(cudaFuncSetAttribute(encode_dense_tma_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem_cap));
-        const int ctas_per_sm = smem <= 100 * 1024 ? 2 : 1;
+        // latency-bound per chunk (zero fill, scatter, two barriers): keep many small CTAs resident
+        int ctas_per_sm = (int)(smem_cap / (smem + 1024));
+        ctas_per_sm = max(1, min(ctas_per_sm, 8));
         const int grid = min(n_chunks, sm_count * ctas_per_sm);
-        encode_dense_tma_kernel<<<grid, 256, smem, stream>>>(seqs, seq_width, maps, map_width, lens,
+        encode_dense_tma_kernel<<<grid, 128, smem, stream>>>(seqs, seq_width, maps, map_width, lens,
                                                              n_chunks, kmer_len, T, out, n_buf);
     } else {
         int tile_t = (int)(smem_cap / 2 / (rows * sizeof(float)));

@@ -177,6 +177,51 @@ __host__ __device__ inline K1Smem k1_smem(const Geometry &g, int kmer_len, int s
 
 // Implicit-GEMM conv, stride 3, 16 input channels (channel-last, pitch QP) -> 64 output channels.
 // Warp w owns output channels [8w, 8w+8); lane = tb * CL + chunk owns NR1 consecutive output steps.
+// Taps are processed by residue class rho = j mod 3: taps rho, rho+3, rho+6, ... of output step t
+// read input rows 3(t+i)+rho, i.e. a stride-1 window over the decimated rows u = t+i.  One window of
+// NR1 + ntaps - 1 rows (LDS.128 each) then serves ntaps * NR1 row uses.
+template <int KW, int RHO>
+__device__ __forceinline__ void conv16_s3_residue(float2 (&acc)[NR1][4], const float *__restrict__ xbase,
+                                                  int t0, int T3, const float *__restrict__ ws,
+                                                  int m0) {
+    constexpr int NT = (KW - RHO + 2) / 3;  // taps in this residue class
+    constexpr int NW = NR1 + NT - 1;        // window rows
+    const float *xrow[NW];
+#pragma unroll
+    for (int r = 0; r < NW; ++r) {
+        int u = t0 + r;
+        if (u > T3 + NT - 2) u = T3 + NT - 2;  // last row any valid output step touches
+        xrow[r] = xbase + (3 * u + RHO) * QP;
+    }
+#pragma unroll 1
+    for (int c4 = 0; c4 < 16; c4 += 4) {
+        float4 x[NW];
+#pragma unroll
+        for (int r = 0; r < NW; ++r) x[r] = *reinterpret_cast<const float4 *>(xrow[r] + c4);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int j = RHO + 3 * i;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 *wp =
+                    reinterpret_cast<const float4 *>(ws + (j * 16 + c4 + kk) * SIZE + m0);
+                const float4 wa = wp[0], wb = wp[1];
+                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
+                const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+#pragma unroll
+                for (int n = 0; n < NR1; ++n) {
+                    const float4 xq = x[n + i];
+                    const float xv = kk == 0 ? xq.x : kk == 1 ? xq.y : kk == 2 ? xq.z : xq.w;
+                    acc[n][0] = ffma2(w0, xv, acc[n][0]);
+                    acc[n][1] = ffma2(w1, xv, acc[n][1]);
+                    acc[n][2] = ffma2(w2, xv, acc[n][2]);
+                    acc[n][3] = ffma2(w3, xv, acc[n][3]);
+                }
+            }
+        }
+    }
+}
+
 template <int KW>
 __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, int x_stride,
                                                  const float *__restrict__ ws,
@@ -190,45 +235,15 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
     if (tb >= NB) tb = NB - 1;
     if (chunk >= C) chunk = C - 1;
     const int t0 = tb * NR1;
-    const float *xrow[NR1];
-#pragma unroll
-    for (int n = 0; n < NR1; ++n) {
-        int t = t0 + n;
-        if (t > T3 - 1) t = T3 - 1;
-        xrow[n] = xs + chunk * x_stride + 3 * t * QP;
-    }
+    const float *xbase = xs + chunk * x_stride;
     float2 acc[NR1][4];
 #pragma unroll
     for (int n = 0; n < NR1; ++n)
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[n][p] = make_float2(0.f, 0.f);
-
-#pragma unroll 1
-    for (int j = 0; j < KW; ++j) {
-#pragma unroll
-        for (int c4 = 0; c4 < 16; c4 += 4) {
-            float4 x[NR1];
-#pragma unroll
-            for (int n = 0; n < NR1; ++n)
-                x[n] = *reinterpret_cast<const float4 *>(xrow[n] + j * QP + c4);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const float4 *wp =
-                    reinterpret_cast<const float4 *>(ws + (j * 16 + c4 + kk) * SIZE + m0);
-                const float4 wa = wp[0], wb = wp[1];
-                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
-                const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
-#pragma unroll
-                for (int n = 0; n < NR1; ++n) {
-                    const float xv = kk == 0 ? x[n].x : kk == 1 ? x[n].y : kk == 2 ? x[n].z : x[n].w;
-                    acc[n][0] = ffma2(w0, xv, acc[n][0]);
-                    acc[n][1] = ffma2(w1, xv, acc[n][1]);
-                    acc[n][2] = ffma2(w2, xv, acc[n][2]);
-                    acc[n][3] = ffma2(w3, xv, acc[n][3]);
-                }
-            }
-        }
-    }
+    conv16_s3_residue<KW, 0>(acc, xbase, t0, T3, ws, m0);
+    conv16_s3_residue<KW, 1>(acc, xbase, t0, T3, ws, m0);
+    conv16_s3_residue<KW, 2>(acc, xbase, t0, T3, ws, m0);
     if (!lane_ok) return;
     float b[8];
 #pragma unroll
@@ -238,14 +253,14 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
         const int t = t0 + n;
         if (t < T3) {
             float4 o0, o1;
-            o0.x = swishf(acc[n][0].x + b[0]);
-            o0.y = swishf(acc[n][0].y + b[1]);
-            o0.z = swishf(acc[n][1].x + b[2]);
-            o0.w = swishf(acc[n][1].y + b[3]);
-            o1.x = swishf(acc[n][2].x + b[4]);
-            o1.y = swishf(acc[n][2].y + b[5]);
-            o1.z = swishf(acc[n][3].x + b[6]);
-            o1.w = swishf(acc[n][3].y + b[7]);
+            o0.x = swishf_fast(acc[n][0].x + b[0]);
+            o0.y = swishf_fast(acc[n][0].y + b[1]);
+            o0.z = swishf_fast(acc[n][1].x + b[2]);
+            o0.w = swishf_fast(acc[n][1].y + b[3]);
+            o1.x = swishf_fast(acc[n][2].x + b[4]);
+            o1.y = swishf_fast(acc[n][2].y + b[5]);
+            o1.z = swishf_fast(acc[n][3].x + b[6]);
+            o1.w = swishf_fast(acc[n][3].y + b[7]);
             float4 *dst = reinterpret_cast<float4 *>(cat + (size_t)chunk * cat_stride + t * XP +
                                                      ch_off + m0);
             dst[0] = o0;
@@ -338,10 +353,10 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
                 a.z = fmaf(wv.z, xv, a.z);
                 a.w = fmaf(wv.w, xv, a.w);
             }
-            a.x = swishf(a.x);
-            a.y = swishf(a.y);
-            a.z = swishf(a.z);
-            a.w = swishf(a.w);
+            a.x = swishf_fast(a.x);
+            a.y = swishf_fast(a.y);
+            a.z = swishf_fast(a.z);
+            a.w = swishf_fast(a.w);
             *reinterpret_cast<float4 *>(s1_s + (size_t)i * 4) = a;
         }
     }
@@ -376,8 +391,8 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
                 }
             }
             float4 *dst = reinterpret_cast<float4 *>(act_s + c * g.s2_stride + t * QP + half * 8);
-            dst[0] = make_float4(swishf(acc[0]), swishf(acc[1]), swishf(acc[2]), swishf(acc[3]));
-            dst[1] = make_float4(swishf(acc[4]), swishf(acc[5]), swishf(acc[6]), swishf(acc[7]));
+            dst[0] = make_float4(swishf_fast(acc[0]), swishf_fast(acc[1]), swishf_fast(acc[2]), swishf_fast(acc[3]));
+            dst[1] = make_float4(swishf_fast(acc[4]), swishf_fast(acc[5]), swishf_fast(acc[6]), swishf_fast(acc[7]));
         }
     }
     __syncthreads();
@@ -389,36 +404,41 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
     // ---- seq_conv1 on the (virtual) one-hot input = gather-add of weight columns -----------------
     // q1[t][o] = swish(b[o] + sum_{j<5} sum_{p<k} W[o][4p + base(t+j, p)][j]),
     // base(t, p) = seq[sidx[t] + p]; -1 bases and uncovered samples contribute nothing
-    // (encoded_kmers.pyx:39-40).  One thread per (chunk, t, 4-channel quarter).
+    // (encoded_kmers.pyx:39-40).  One thread per (chunk, t): 16 channels as 8 packed float2 sums.
     {
         const float *w = wsm + fo.w_seq1;  // [j][p][base][co]
         const float *b = wsm + fo.b_seq1;
-        for (int i = tid; i < C * g.Q1 * 4; i += THREADS) {
-            const int quarter = i & 3;
-            const int ct = i >> 2;
-            const int c = ct / g.Q1, t = ct - c * g.Q1;
-            float4 a = *reinterpret_cast<const float4 *>(b + quarter * 4);
+        for (int i = tid; i < C * g.Q1; i += THREADS) {
+            const int c = i / g.Q1, t = i - c * g.Q1;
+            float2 a[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
             const int8_t *sq = seq_s + c * seq_width;
 #pragma unroll
             for (int j = 0; j < KW_SEQ1; ++j) {
                 const int s = sidx_s[c * T + t + j];
                 if (s < 0) continue;
-                const float *wj = w + (size_t)j * kmer_len * 64 + quarter * 4;
+                const float *wj = w + (size_t)j * kmer_len * 64;
                 for (int p = 0; p < kmer_len; ++p) {
                     const int base = sq[s + p];
                     if (base < 0 || base > 3) continue;
-                    const float4 wv = *reinterpret_cast<const float4 *>(wj + (p * 4 + base) * 16);
-                    a.x += wv.x;
-                    a.y += wv.y;
-                    a.z += wv.z;
-                    a.w += wv.w;
+                    const float4 *wv = reinterpret_cast<const float4 *>(wj + (p * 4 + base) * 16);
+                    const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
+                    a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+                    a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+                    a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+                    a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+                    a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+                    a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+                    a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+                    a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
                 }
             }
-            a.x = swishf(a.x);
-            a.y = swishf(a.y);
-            a.z = swishf(a.z);
-            a.w = swishf(a.w);
-            *reinterpret_cast<float4 *>(act_s + c * g.q1_stride + t * QP + quarter * 4) = a;
+            float4 *dst = reinterpret_cast<float4 *>(act_s + c * g.q1_stride + t * QP);
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                dst[o] = make_float4(swishf_fast(a[2 * o].x), swishf_fast(a[2 * o].y),
+                                     swishf_fast(a[2 * o + 1].x), swishf_fast(a[2 * o + 1].y));
         }
     }
     __syncthreads();
@@ -559,14 +579,14 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
             const int t = t0 + n;
             if (t < g.TM) {
                 float4 o0, o1;
-                o0.x = swishf(acc[n][0].x + b[0]);
-                o0.y = swishf(acc[n][0].y + b[1]);
-                o0.z = swishf(acc[n][1].x + b[2]);
-                o0.w = swishf(acc[n][1].y + b[3]);
-                o1.x = swishf(acc[n][2].x + b[4]);
-                o1.y = swishf(acc[n][2].y + b[5]);
-                o1.z = swishf(acc[n][3].x + b[6]);
-                o1.w = swishf(acc[n][3].y + b[7]);
+                o0.x = swishf_fast(acc[n][0].x + b[0]);
+                o0.y = swishf_fast(acc[n][0].y + b[1]);
+                o0.z = swishf_fast(acc[n][1].x + b[2]);
+                o0.w = swishf_fast(acc[n][1].y + b[3]);
+                o1.x = swishf_fast(acc[n][2].x + b[4]);
+                o1.y = swishf_fast(acc[n][2].y + b[5]);
+                o1.z = swishf_fast(acc[n][3].x + b[6]);
+                o1.w = swishf_fast(acc[n][3].y + b[7]);
                 float4 *dst = reinterpret_cast<float4 *>(ms + (chunk * g.TM + t) * MP + m0);
                 dst[0] = o0;
                 dst[1] = o1;
@@ -644,32 +664,50 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
 // =================================================================================================
 // K3: LSTM1 recurrence (W_hh in registers) + single-step LSTM2 + fc
 // =================================================================================================
+// Per step and chunk the recurrence is a 256x64 mat-vec.  Thread (rb, kg) keeps the 4x16 block
+// W_hh[4*rb .. 4*rb+3][16*kg .. 16*kg+15] in 64 registers for the whole kernel; h lives in shared
+// memory as h[k][chunk] so one LDS.128 feeds 4 chunks and the FFMA2 halves are two chunks.  The four
+// k-groups of a row block sit in adjacent lanes: their partial sums are combined with a two-round
+// transposing butterfly (xor 2, xor 1) that leaves lane kg with the finished row 4*rb + kg for all
+// 8 chunks.  Shared-memory traffic per step is 32 LDS.128 per thread instead of 128.
 constexpr int C3MAX = 8;
+constexpr int HG = 16 * C3MAX + 4;  // floats per k-group of h (16 k x 8 chunks + 4 pad)
+
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int mask) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+}
+__device__ __forceinline__ float2 sel2(bool take_a, float2 a, float2 b) {
+    return make_float2(take_a ? a.x : b.x, take_a ? a.y : b.y);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
                const float *__restrict__ wih2T, const float *__restrict__ b2,
                const float *__restrict__ fcw, const float *__restrict__ fcb,
                float *__restrict__ logits, int B, int CPB, int TM, int num_out) {
-    __shared__ __align__(16) float h_s[SIZE][C3MAX];      // h[k][chunk]
+    __shared__ __align__(16) float h_s[4 * HG];           // h[k][chunk], k-group stride HG
     __shared__ __align__(16) float g_s[C3MAX][4 * SIZE];  // gate pre-activations
     __shared__ __align__(16) float y_s[C3MAX][SIZE];
-    const int tid = threadIdx.x;
-    const int r = tid;  // gate row: i 0..63, f 64..127, g 128..191, o 192..255
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int kg = lane & 3;  // k-group: k in [16 kg, 16 kg + 16)
+    const int r = tid;        // finished gate row owned after the butterfly: i 0..63, f, g, o
     const int chunk0 = blockIdx.x * CPB;
     const int C = min(CPB, B - chunk0);
 
-    float w[SIZE];
+    // w[i][kl] = W_hh[4*(tid>>2) + i][16*kg + kl], host layout [q][tid] float4 with q = 4*i + kl/4
+    float w[4][16];
 #pragma unroll
-    for (int q = 0; q < SIZE / 4; ++q) {
-        const float4 v = whh4[q * 256 + r];
-        w[4 * q] = v.x;
-        w[4 * q + 1] = v.y;
-        w[4 * q + 2] = v.z;
-        w[4 * q + 3] = v.w;
+    for (int q = 0; q < 16; ++q) {
+        const float4 v = whh4[q * 256 + tid];
+        w[q >> 2][(q & 3) * 4 + 0] = v.x;
+        w[q >> 2][(q & 3) * 4 + 1] = v.y;
+        w[q >> 2][(q & 3) * 4 + 2] = v.z;
+        w[q >> 2][(q & 3) * 4 + 3] = v.w;
     }
-    for (int i = tid; i < SIZE * C3MAX; i += THREADS) (&h_s[0][0])[i] = 0.f;
+    for (int i = tid; i < 4 * HG; i += THREADS) h_s[i] = 0.f;
     const int u = tid & 63, q = tid >> 6;  // cell-update role: unit u, chunks q and q+4
+    const int hu = (u >> 4) * HG + (u & 15) * C3MAX;
     float cst0 = 0.f, cst1 = 0.f, hlast0 = 0.f, hlast1 = 0.f;
 
     float xnext[C3MAX];
@@ -677,53 +715,82 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
     for (int c = 0; c < C3MAX; ++c)
         xnext[c] = c < C ? xp[((size_t)(chunk0 + c) * TM) * 256 + r] : 0.f;
     __syncthreads();
+    const float *hk = h_s + kg * HG;
+    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
 
 #pragma unroll 1
     for (int t = 0; t < TM; ++t) {
-        float2 a[C3MAX / 2];
+        float xcur[C3MAX];
 #pragma unroll
-        for (int p = 0; p < C3MAX / 2; ++p) a[p] = make_float2(xnext[2 * p], xnext[2 * p + 1]);
+        for (int c = 0; c < C3MAX; ++c) xcur[c] = xnext[c];
         if (t + 1 < TM) {
 #pragma unroll
             for (int c = 0; c < C3MAX; ++c)
                 if (c < C) xnext[c] = xp[((size_t)(chunk0 + c) * TM + t + 1) * 256 + r];
         }
+        float2 a[4][4];  // [row][chunk pair]
 #pragma unroll
-        for (int k = 0; k < SIZE; ++k) {
-            const float4 ha = *reinterpret_cast<const float4 *>(&h_s[k][0]);
-            const float4 hb = *reinterpret_cast<const float4 *>(&h_s[k][4]);
-            a[0] = ffma2(make_float2(ha.x, ha.y), w[k], a[0]);
-            a[1] = ffma2(make_float2(ha.z, ha.w), w[k], a[1]);
-            a[2] = ffma2(make_float2(hb.x, hb.y), w[k], a[2]);
-            a[3] = ffma2(make_float2(hb.z, hb.w), w[k], a[3]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a[i][p] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int kl = 0; kl < 16; ++kl) {
+            const float4 ha = *reinterpret_cast<const float4 *>(hk + kl * C3MAX);
+            const float4 hb = *reinterpret_cast<const float4 *>(hk + kl * C3MAX + 4);
+            const float2 h01 = make_float2(ha.x, ha.y), h23 = make_float2(ha.z, ha.w);
+            const float2 h45 = make_float2(hb.x, hb.y), h67 = make_float2(hb.z, hb.w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i][0] = ffma2(h01, w[i][kl], a[i][0]);
+                a[i][1] = ffma2(h23, w[i][kl], a[i][1]);
+                a[i][2] = ffma2(h45, w[i][kl], a[i][2]);
+                a[i][3] = ffma2(h67, w[i][kl], a[i][3]);
+            }
+        }
+        // butterfly over the 4 k-groups: round 1 keeps rows {2*b1, 2*b1+1}, round 2 keeps row kg
+        float2 rA[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float2 send = sel2(hi2, a[j][p], a[2 + j][p]);
+                const float2 keep = sel2(hi2, a[2 + j][p], a[j][p]);
+                rA[j][p] = add2(keep, shfl_xor2(send, 2));
+            }
+        float2 g4[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float2 send = sel2(hi1, rA[0][p], rA[1][p]);
+            const float2 keep = sel2(hi1, rA[1][p], rA[0][p]);
+            g4[p] = add2(keep, shfl_xor2(send, 1));
         }
 #pragma unroll
-        for (int p = 0; p < C3MAX / 2; ++p) {
-            g_s[2 * p][r] = a[p].x;
-            g_s[2 * p + 1][r] = a[p].y;
+        for (int p = 0; p < 4; ++p) {
+            g_s[2 * p][r] = g4[p].x + xcur[2 * p];
+            g_s[2 * p + 1][r] = g4[p].y + xcur[2 * p + 1];
         }
         __syncthreads();
         {
             const int c0 = q, c1 = q + 4;
-            float ig = sigmoidf_acc(g_s[c0][u]), fg = sigmoidf_acc(g_s[c0][64 + u]);
-            float gg = tanhf(g_s[c0][128 + u]), og = sigmoidf_acc(g_s[c0][192 + u]);
+            float ig = sigmoidf_fast(g_s[c0][u]), fg = sigmoidf_fast(g_s[c0][64 + u]);
+            float gg = tanhf_fast(g_s[c0][128 + u]), og = sigmoidf_fast(g_s[c0][192 + u]);
             cst0 = fg * cst0 + ig * gg;
-            hlast0 = og * tanhf(cst0);
-            ig = sigmoidf_acc(g_s[c1][u]);
-            fg = sigmoidf_acc(g_s[c1][64 + u]);
-            gg = tanhf(g_s[c1][128 + u]);
-            og = sigmoidf_acc(g_s[c1][192 + u]);
+            hlast0 = og * tanhf_fast(cst0);
+            ig = sigmoidf_fast(g_s[c1][u]);
+            fg = sigmoidf_fast(g_s[c1][64 + u]);
+            gg = tanhf_fast(g_s[c1][128 + u]);
+            og = sigmoidf_fast(g_s[c1][192 + u]);
             cst1 = fg * cst1 + ig * gg;
-            hlast1 = og * tanhf(cst1);
-            h_s[u][c0] = hlast0;
-            h_s[u][c1] = hlast1;
+            hlast1 = og * tanhf_fast(cst1);
+            h_s[hu + c0] = hlast0;
+            h_s[hu + c1] = hlast1;
         }
         __syncthreads();
     }
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54):
     // x = swish(h1[T-1]), h0 = c0 = 0  =>  c = sig(i) * tanh(g), h = sig(o) * tanh(c)
-    h_s[u][q] = swishf(hlast0);
-    h_s[u][q + 4] = swishf(hlast1);
+    h_s[hu + q] = swishf(hlast0);
+    h_s[hu + q + 4] = swishf(hlast1);
     __syncthreads();
     {
         float a2[C3MAX];
@@ -733,8 +800,9 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
 #pragma unroll 4
         for (int k = 0; k < SIZE; ++k) {
             const float wv = wih2T[k * 256 + r];
-            const float4 ha = *reinterpret_cast<const float4 *>(&h_s[k][0]);
-            const float4 hb = *reinterpret_cast<const float4 *>(&h_s[k][4]);
+            const float *hp = h_s + (k >> 4) * HG + (k & 15) * C3MAX;
+            const float4 ha = *reinterpret_cast<const float4 *>(hp);
+            const float4 hb = *reinterpret_cast<const float4 *>(hp + 4);
             a2[0] = fmaf(wv, ha.x, a2[0]);
             a2[1] = fmaf(wv, ha.y, a2[1]);
             a2[2] = fmaf(wv, ha.z, a2[2]);
@@ -761,7 +829,7 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
     __syncthreads();
     // ---- fc: one warp per chunk, warp-shuffle reduction over the 64 features ---------------------
     {
-        const int warp = tid >> 5, lane = tid & 31;
+        const int warp = tid >> 5;
         if (warp < C) {
             for (int o = 0; o < num_out; ++o) {
                 float part = fcw[o * SIZE + lane] * y_s[warp][lane] +
@@ -879,10 +947,13 @@ int fused_create(rb200_model *m, const float *blob) {
     memcpy(host.data() + fw->off_b1, blob + d.lstm_b_off[0], 256 * sizeof(float));
     // --- K3: W_hh1 as float4 [k/4][r], W_ih2^T, b2, fc ---
     fw->off_whh4 = reserve(SIZE * 256);
-    for (int q = 0; q < SIZE / 4; ++q)
-        for (int r = 0; r < 256; ++r)
-            for (int i = 0; i < 4; ++i)
-                host[fw->off_whh4 + (q * 256 + r) * 4 + i] = blob[d.lstm_w_hh_off[0] + r * SIZE + 4 * q + i];
+    for (int q = 0; q < 16; ++q)
+        for (int tid = 0; tid < 256; ++tid)
+            for (int e = 0; e < 4; ++e) {
+                const int i = q >> 2, kl = (q & 3) * 4 + e;
+                const int row = 4 * (tid >> 2) + i, k = 16 * (tid & 3) + kl;
+                host[fw->off_whh4 + (q * 256 + tid) * 4 + e] = blob[d.lstm_w_hh_off[0] + row * SIZE + k];
+            }
     fw->off_wih2T = reserve(SIZE * 256);
     for (int k = 0; k < SIZE; ++k)
         for (int r = 0; r < 256; ++r)

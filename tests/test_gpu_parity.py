@@ -369,4 +369,4 @@ def test_full_size_batch_properties():
             model.set_impl("layers")
             ref = model.forward_compact(*args)
             model.set_impl("auto")
-            assert (out - ref).abs().max() < 2e-5
+            assert (out - ref).abs().max() < LOGIT_TOL  # two fp32 paths, both within tolerance of the oracle
