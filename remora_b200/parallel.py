@@ -1,0 +1,67 @@
+"""Multi-GPU batch sharding: one process per GPU, chunks are independent, so a batch
+is split into contiguous shards, every rank runs the whole network on its shard with replicated
+weights, and the only exchange the path has is the gather of float32 logits (8 B/chunk for two
+classes) back to the consumer rank(s).  ``torch.distributed`` over NCCL (NVLink/NVSwitch) on the
+GPU box; the same code runs over gloo on CPU for the host-logic tests.
+
+The reference has no multi-device mode at all (one ``--device`` int, src/remora/parsers.py:1373-1377);
+``ShardedCaller.call`` produces, on every rank, exactly the [B, num_out] tensor a single-device
+``model(sigs, enc_kmers)`` would have produced, in the original chunk order, so that the reference's
+order-sensitive ``unbatch`` stage (src/remora/inference.py:331-367) can consume it unchanged.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous, balanced split: the first ``n_items % world_size`` ranks get one extra item."""
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items, world_size):
+    return [shard_bounds(n_items, world_size, r)[1] - shard_bounds(n_items, world_size, r)[0]
+            for r in range(world_size)]
+
+
+class ShardedCaller:
+    """Runs ``compute(*shard_arrays) -> [n_shard, num_out]`` on this rank's shard of a global batch
+    and returns the all-gathered [B, num_out] logits in chunk order on every rank."""
+
+    def __init__(self, compute, num_out, group=None):
+        self.compute = compute
+        self.num_out = num_out
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def my_slice(self, n_items):
+        return slice(*shard_bounds(n_items, self.world, self.rank))
+
+    def call(self, *global_arrays, async_op=False):
+        """``global_arrays``: per-chunk tensors with the full batch on dim 0 (each rank holds, or can
+        slice, its own part; nothing but its shard is touched)."""
+        n = global_arrays[0].shape[0]
+        sl = self.my_slice(n)
+        local = self.compute(*[a[sl] for a in global_arrays])
+        return self.gather(local, n, async_op=async_op)
+
+    def gather(self, local_logits, n_items, async_op=False):
+        if self.world == 1:
+            return local_logits
+        sizes = shard_sizes(n_items, self.world)
+        if len(set(sizes)) == 1:  # even split: one all_gather into a contiguous tensor
+            out = torch.empty((n_items, self.num_out), dtype=local_logits.dtype,
+                              device=local_logits.device)
+            work = dist.all_gather_into_tensor(out, local_logits.contiguous(), group=self.group,
+                                               async_op=async_op)
+            return (out, work) if async_op else out
+        # ragged last shards: pad to the largest shard, gather, trim
+        pad = max(sizes)
+        buf = torch.zeros((pad, self.num_out), dtype=local_logits.dtype, device=local_logits.device)
+        buf[: local_logits.shape[0]] = local_logits
+        parts = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(parts, buf, group=self.group)
+        out = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+        return (out, None) if async_op else out
