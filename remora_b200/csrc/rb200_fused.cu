@@ -82,7 +82,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) {
 }
 
 struct FrontOffsets {  // float offsets inside the K1 weight blob (all multiples of 4)
-    int w_sig1, b_sig1, w_sig2, b_sig2, w_sig3, b_sig3, w_seq1, b_seq1, w_seq2, b_seq2, total;
+    int w_sig1, b_sig1, w_sig2, b_sig2, w_sig3, b_sig3, w_seq1, z_seq1, b_seq1, w_seq2, b_seq2, total;
 };
 
 __host__ __device__ inline FrontOffsets front_offsets(int kmer_len) {
@@ -100,6 +100,7 @@ __host__ __device__ inline FrontOffsets front_offsets(int kmer_len) {
     o.w_sig3 = take(KW_SIG3 * 16 * SIZE);    // [j*16+ci][co]
     o.b_sig3 = take(SIZE);
     o.w_seq1 = take(KW_SEQ1 * kmer_len * 4 * 16);  // [j][p][base][co]
+    o.z_seq1 = take(16);                           // all-zero row: target of N bases / uncovered samples
     o.b_seq1 = take(16);
     o.w_seq2 = take(KW_SEQ2 * 16 * SIZE);    // [j*16+ci][co]
     o.b_seq2 = take(SIZE);
@@ -269,6 +270,55 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
     }
 }
 
+// seq_conv1 on the (virtual) one-hot input = gather-add of weight columns:
+// q1[t][o] = swish(b[o] + sum_{j<5} sum_{p<k} W[o][4p + base(t+j, p)][j]),  base(t, p) = seq[sidx[t] + p].
+// -1 bases and uncovered samples contribute nothing (encoded_kmers.pyx:39-40): they are redirected to
+// an all-zero table row so that the 5*k gathers of one output step are branch-free and independent.
+// One thread per (chunk, t): 16 channels as 8 packed float2 sums.  KT = compile-time kmer_len (0 = runtime).
+template <int KT>
+__device__ __forceinline__ void seq1_gather(const float *__restrict__ w, const float *__restrict__ b,
+                                            int zero_off, const int8_t *__restrict__ seq_s,
+                                            const int16_t *__restrict__ sidx_s,
+                                            float *__restrict__ act_s, int seq_width, int C, int T,
+                                            int Q1, int q1_stride, int kmer_rt) {
+    const int K = KT > 0 ? KT : kmer_rt;
+    for (int i = threadIdx.x; i < C * Q1; i += THREADS) {
+        const int c = i / Q1, t = i - c * Q1;
+        float2 a[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
+        const int8_t *sq = seq_s + c * seq_width;
+#pragma unroll
+        for (int j = 0; j < KW_SEQ1; ++j) {
+            const int s = sidx_s[c * T + t + j];
+            const int8_t *sp = sq + (s < 0 ? 0 : s);
+            const int joff = j * K * 64;
+#pragma unroll
+            for (int p = 0; p < (KT > 0 ? KT : 16); ++p) {
+                if (KT == 0 && p >= K) break;
+                const int base = sp[p];
+                const bool ok = s >= 0 && base >= 0 && base <= 3;
+                const int off = ok ? joff + (p * 4 + base) * 16 : zero_off;
+                const float4 *wv = reinterpret_cast<const float4 *>(w + off);
+                const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
+                a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+                a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+                a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+                a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+                a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+                a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+                a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+                a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(act_s + c * q1_stride + t * QP);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            dst[o] = make_float4(swishf_fast(a[2 * o].x), swishf_fast(a[2 * o].y),
+                                 swishf_fast(a[2 * o + 1].x), swishf_fast(a[2 * o + 1].y));
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
                 const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
@@ -402,45 +452,12 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
                               g.cat_stride, 0, C, CL, g.NB1, g.T3);
     __syncthreads();
     // ---- seq_conv1 on the (virtual) one-hot input = gather-add of weight columns -----------------
-    // q1[t][o] = swish(b[o] + sum_{j<5} sum_{p<k} W[o][4p + base(t+j, p)][j]),
-    // base(t, p) = seq[sidx[t] + p]; -1 bases and uncovered samples contribute nothing
-    // (encoded_kmers.pyx:39-40).  One thread per (chunk, t): 16 channels as 8 packed float2 sums.
-    {
-        const float *w = wsm + fo.w_seq1;  // [j][p][base][co]
-        const float *b = wsm + fo.b_seq1;
-        for (int i = tid; i < C * g.Q1; i += THREADS) {
-            const int c = i / g.Q1, t = i - c * g.Q1;
-            float2 a[8];
-#pragma unroll
-            for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
-            const int8_t *sq = seq_s + c * seq_width;
-#pragma unroll
-            for (int j = 0; j < KW_SEQ1; ++j) {
-                const int s = sidx_s[c * T + t + j];
-                if (s < 0) continue;
-                const float *wj = w + (size_t)j * kmer_len * 64;
-                for (int p = 0; p < kmer_len; ++p) {
-                    const int base = sq[s + p];
-                    if (base < 0 || base > 3) continue;
-                    const float4 *wv = reinterpret_cast<const float4 *>(wj + (p * 4 + base) * 16);
-                    const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
-                    a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
-                    a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
-                    a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
-                    a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
-                    a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
-                    a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
-                    a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
-                    a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
-                }
-            }
-            float4 *dst = reinterpret_cast<float4 *>(act_s + c * g.q1_stride + t * QP);
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
-                dst[o] = make_float4(swishf_fast(a[2 * o].x), swishf_fast(a[2 * o].y),
-                                     swishf_fast(a[2 * o + 1].x), swishf_fast(a[2 * o + 1].y));
-        }
-    }
+    if (kmer_len == 9)
+        seq1_gather<9>(wsm + fo.w_seq1, wsm + fo.b_seq1, fo.z_seq1 - fo.w_seq1, seq_s, sidx_s, act_s,
+                       seq_width, C, T, g.Q1, g.q1_stride, kmer_len);
+    else
+        seq1_gather<0>(wsm + fo.w_seq1, wsm + fo.b_seq1, fo.z_seq1 - fo.w_seq1, seq_s, sidx_s, act_s,
+                       seq_width, C, T, g.Q1, g.q1_stride, kmer_len);
     __syncthreads();
     // ---- seq_conv2 (16 -> 64, k13, stride 3) -> cat[:, :, 64:128] --------------------------------
     conv16_s3_to_cat<KW_SEQ2>(act_s, g.q1_stride, wsm + fo.w_seq2, wsm + fo.b_seq2, cat_cta,
@@ -668,10 +685,16 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
 // W_hh[4*rb .. 4*rb+3][16*kg .. 16*kg+15] in 64 registers for the whole kernel; h lives in shared
 // memory as h[k][chunk] so one LDS.128 feeds 4 chunks and the FFMA2 halves are two chunks.  The four
 // k-groups of a row block sit in adjacent lanes: their partial sums are combined with a two-round
-// transposing butterfly (xor 2, xor 1) that leaves lane kg with the finished row 4*rb + kg for all
-// 8 chunks.  Shared-memory traffic per step is 32 LDS.128 per thread instead of 128.
+// transposing butterfly (xor 2, xor 1) that leaves lane kg with the finished row 4*rb + kg.
+//
+// The CTA's (up to) 8 chunks are processed as two half-batches A (chunks 0..3) and B (4..7) that
+// are software-pipelined against each other: between two barriers every thread runs the mat-vec of
+// one half AND the gate non-linearities of the other half, so the MUFU/latency chain of the cell
+// update hides behind the other half's FFMA2 stream instead of idling the SM:
+//     mv(A,0) | bar | mv(B,0)+cell(A,0) | bar | mv(A,1)+cell(B,0) | bar | mv(B,1)+cell(A,1) | ...
 constexpr int C3MAX = 8;
-constexpr int HG = 16 * C3MAX + 4;  // floats per k-group of h (16 k x 8 chunks + 4 pad)
+constexpr int HC = 4;              // chunks per half-batch
+constexpr int HG = 16 * HC + 4;    // floats per k-group of h (16 k x 4 chunks + 4 pad)
 
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int mask) {
     return make_float2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
@@ -681,128 +704,155 @@ __device__ __forceinline__ float2 sel2(bool take_a, float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
+// gate pre-activations of one half-batch: g[c][r] = xp[c][r] + sum_k W_hh[r][k] h[k][c]
+__device__ __forceinline__ void lstm_matvec_half(const float (&w)[4][16], const float *__restrict__ hk,
+                                                 const float (&xin)[HC], float *__restrict__ g_half,
+                                                 int r, bool hi2, bool hi1) {
+    float2 a[4][2];  // [row][chunk pair]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i][0] = a[i][1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int kl = 0; kl < 16; ++kl) {
+        const float4 hv = *reinterpret_cast<const float4 *>(hk + kl * HC);
+        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i][0] = ffma2(h01, w[i][kl], a[i][0]);
+            a[i][1] = ffma2(h23, w[i][kl], a[i][1]);
+        }
+    }
+    float2 rA[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const float2 send = sel2(hi2, a[j][p], a[2 + j][p]);
+            const float2 keep = sel2(hi2, a[2 + j][p], a[j][p]);
+            rA[j][p] = add2(keep, shfl_xor2(send, 2));
+        }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const float2 send = sel2(hi1, rA[0][p], rA[1][p]);
+        const float2 keep = sel2(hi1, rA[1][p], rA[0][p]);
+        const float2 g2 = add2(keep, shfl_xor2(send, 1));
+        g_half[(2 * p) * 256 + r] = g2.x + xin[2 * p];
+        g_half[(2 * p + 1) * 256 + r] = g2.y + xin[2 * p + 1];
+    }
+}
+
+// cell update of (unit u, chunk q) of one half-batch; writes h into the half's h[k][chunk] tile
+__device__ __forceinline__ float lstm_cell_half(const float *__restrict__ g_half, float *__restrict__ h_half,
+                                                int u, int q, int hu, float &cst) {
+    const float *g = g_half + q * 256;
+    const float ig = sigmoidf_fast(g[u]), fg = sigmoidf_fast(g[64 + u]);
+    const float gg = tanhf_fast(g[128 + u]), og = sigmoidf_fast(g[192 + u]);
+    cst = fg * cst + ig * gg;
+    const float h = og * tanhf_fast(cst);
+    h_half[hu + q] = h;
+    return h;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
                const float *__restrict__ wih2T, const float *__restrict__ b2,
                const float *__restrict__ fcw, const float *__restrict__ fcb,
                float *__restrict__ logits, int B, int CPB, int TM, int num_out) {
-    __shared__ __align__(16) float h_s[4 * HG];           // h[k][chunk], k-group stride HG
-    __shared__ __align__(16) float g_s[C3MAX][4 * SIZE];  // gate pre-activations
-    __shared__ __align__(16) float y_s[C3MAX][SIZE];
+    extern __shared__ __align__(128) float sm3[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm3);
+    float *w2_s = sm3 + 4;                    // W_ih2^T [64][256], TMA bulk copy
+    float *h_s = w2_s + SIZE * 256;           // 2 halves x 4 k-groups x HG
+    float *g_s = h_s + 2 * 4 * HG;            // 2 halves x [HC][256] gate pre-activations
+    float *y_s = g_s + 2 * HC * 256;          // [C3MAX][SIZE]
     const int tid = threadIdx.x, lane = tid & 31;
     const int kg = lane & 3;  // k-group: k in [16 kg, 16 kg + 16)
     const int r = tid;        // finished gate row owned after the butterfly: i 0..63, f, g, o
     const int chunk0 = blockIdx.x * CPB;
     const int C = min(CPB, B - chunk0);
 
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, SIZE * 256 * 4u);
+        bulk_g2s(w2_s, wih2T, SIZE * 256 * 4u, bar);
+    }
     // w[i][kl] = W_hh[4*(tid>>2) + i][16*kg + kl], host layout [q][tid] float4 with q = 4*i + kl/4
     float w[4][16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const float4 v = whh4[q * 256 + tid];
-        w[q >> 2][(q & 3) * 4 + 0] = v.x;
-        w[q >> 2][(q & 3) * 4 + 1] = v.y;
-        w[q >> 2][(q & 3) * 4 + 2] = v.z;
-        w[q >> 2][(q & 3) * 4 + 3] = v.w;
+    for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 v = whh4[q4 * 256 + tid];
+        w[q4 >> 2][(q4 & 3) * 4 + 0] = v.x;
+        w[q4 >> 2][(q4 & 3) * 4 + 1] = v.y;
+        w[q4 >> 2][(q4 & 3) * 4 + 2] = v.z;
+        w[q4 >> 2][(q4 & 3) * 4 + 3] = v.w;
     }
-    for (int i = tid; i < 4 * HG; i += THREADS) h_s[i] = 0.f;
-    const int u = tid & 63, q = tid >> 6;  // cell-update role: unit u, chunks q and q+4
-    const int hu = (u >> 4) * HG + (u & 15) * C3MAX;
-    float cst0 = 0.f, cst1 = 0.f, hlast0 = 0.f, hlast1 = 0.f;
+    for (int i = tid; i < 2 * 4 * HG; i += THREADS) h_s[i] = 0.f;
+    const int u = tid & 63, q = tid >> 6;  // cell-update role: unit u, chunk q of each half
+    const int hu = (u >> 4) * HG + (u & 15) * HC;
+    float *hA = h_s, *hB = h_s + 4 * HG;
+    float *gA = g_s, *gB = g_s + HC * 256;
+    const float *hkA = hA + kg * HG, *hkB = hB + kg * HG;
+    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+    float cstA = 0.f, cstB = 0.f, hlastA = 0.f, hlastB = 0.f;
 
-    float xnext[C3MAX];
+    // xp rows of this thread for the current and the next step, per half
+    const float *xrow[C3MAX];
 #pragma unroll
     for (int c = 0; c < C3MAX; ++c)
-        xnext[c] = c < C ? xp[((size_t)(chunk0 + c) * TM) * 256 + r] : 0.f;
+        xrow[c] = xp + ((size_t)(chunk0 + (c < C ? c : 0)) * TM) * 256 + r;
+    float xa[HC], xb[HC];
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+        xa[c] = c < C ? xrow[c][0] : 0.f;
+        xb[c] = HC + c < C ? xrow[HC + c][0] : 0.f;
+    }
     __syncthreads();
-    const float *hk = h_s + kg * HG;
-    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
 
+    lstm_matvec_half(w, hkA, xa, gA, r, hi2, hi1);  // mv(A, 0)
+    __syncthreads();
 #pragma unroll 1
     for (int t = 0; t < TM; ++t) {
-        float xcur[C3MAX];
+        // prefetch next step's input projections (L2 hits) while this step computes
+        float xa_n[HC], xb_n[HC];
+        const int tn = t + 1 < TM ? t + 1 : t;
 #pragma unroll
-        for (int c = 0; c < C3MAX; ++c) xcur[c] = xnext[c];
-        if (t + 1 < TM) {
-#pragma unroll
-            for (int c = 0; c < C3MAX; ++c)
-                if (c < C) xnext[c] = xp[((size_t)(chunk0 + c) * TM + t + 1) * 256 + r];
+        for (int c = 0; c < HC; ++c) {
+            xa_n[c] = c < C ? xrow[c][(size_t)tn * 256] : 0.f;
+            xb_n[c] = HC + c < C ? xrow[HC + c][(size_t)tn * 256] : 0.f;
         }
-        float2 a[4][4];  // [row][chunk pair]
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) a[i][p] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int kl = 0; kl < 16; ++kl) {
-            const float4 ha = *reinterpret_cast<const float4 *>(hk + kl * C3MAX);
-            const float4 hb = *reinterpret_cast<const float4 *>(hk + kl * C3MAX + 4);
-            const float2 h01 = make_float2(ha.x, ha.y), h23 = make_float2(ha.z, ha.w);
-            const float2 h45 = make_float2(hb.x, hb.y), h67 = make_float2(hb.z, hb.w);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                a[i][0] = ffma2(h01, w[i][kl], a[i][0]);
-                a[i][1] = ffma2(h23, w[i][kl], a[i][1]);
-                a[i][2] = ffma2(h45, w[i][kl], a[i][2]);
-                a[i][3] = ffma2(h67, w[i][kl], a[i][3]);
-            }
-        }
-        // butterfly over the 4 k-groups: round 1 keeps rows {2*b1, 2*b1+1}, round 2 keeps row kg
-        float2 rA[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const float2 send = sel2(hi2, a[j][p], a[2 + j][p]);
-                const float2 keep = sel2(hi2, a[2 + j][p], a[j][p]);
-                rA[j][p] = add2(keep, shfl_xor2(send, 2));
-            }
-        float2 g4[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const float2 send = sel2(hi1, rA[0][p], rA[1][p]);
-            const float2 keep = sel2(hi1, rA[1][p], rA[0][p]);
-            g4[p] = add2(keep, shfl_xor2(send, 1));
-        }
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            g_s[2 * p][r] = g4[p].x + xcur[2 * p];
-            g_s[2 * p + 1][r] = g4[p].y + xcur[2 * p + 1];
-        }
+        // region 1: mat-vec of half B for step t  +  cell update of half A for step t
+        lstm_matvec_half(w, hkB, xb, gB, r, hi2, hi1);
+        hlastA = lstm_cell_half(gA, hA, u, q, hu, cstA);
         __syncthreads();
-        {
-            const int c0 = q, c1 = q + 4;
-            float ig = sigmoidf_fast(g_s[c0][u]), fg = sigmoidf_fast(g_s[c0][64 + u]);
-            float gg = tanhf_fast(g_s[c0][128 + u]), og = sigmoidf_fast(g_s[c0][192 + u]);
-            cst0 = fg * cst0 + ig * gg;
-            hlast0 = og * tanhf_fast(cst0);
-            ig = sigmoidf_fast(g_s[c1][u]);
-            fg = sigmoidf_fast(g_s[c1][64 + u]);
-            gg = tanhf_fast(g_s[c1][128 + u]);
-            og = sigmoidf_fast(g_s[c1][192 + u]);
-            cst1 = fg * cst1 + ig * gg;
-            hlast1 = og * tanhf_fast(cst1);
-            h_s[hu + c0] = hlast0;
-            h_s[hu + c1] = hlast1;
-        }
+        // region 2: mat-vec of half A for step t+1  +  cell update of half B for step t
+        if (t + 1 < TM) lstm_matvec_half(w, hkA, xa_n, gA, r, hi2, hi1);
+        hlastB = lstm_cell_half(gB, hB, u, q, hu, cstB);
         __syncthreads();
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+            xa[c] = xa_n[c];
+            xb[c] = xb_n[c];
+        }
     }
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54):
     // x = swish(h1[T-1]), h0 = c0 = 0  =>  c = sig(i) * tanh(g), h = sig(o) * tanh(c)
-    h_s[hu + q] = swishf(hlast0);
-    h_s[hu + q + 4] = swishf(hlast1);
+    hA[hu + q] = swishf(hlastA);
+    hB[hu + q] = swishf(hlastB);
+    mbar_wait(bar, 0);  // W_ih2^T landed long ago
     __syncthreads();
     {
         float a2[C3MAX];
         const float bias = b2[r];
 #pragma unroll
         for (int c = 0; c < C3MAX; ++c) a2[c] = bias;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 0; k < SIZE; ++k) {
-            const float wv = wih2T[k * 256 + r];
-            const float *hp = h_s + (k >> 4) * HG + (k & 15) * C3MAX;
-            const float4 ha = *reinterpret_cast<const float4 *>(hp);
-            const float4 hb = *reinterpret_cast<const float4 *>(hp + 4);
+            const float wv = w2_s[k * 256 + r];
+            const int ho = (k >> 4) * HG + (k & 15) * HC;
+            const float4 ha = *reinterpret_cast<const float4 *>(hA + ho);
+            const float4 hb = *reinterpret_cast<const float4 *>(hB + ho);
             a2[0] = fmaf(wv, ha.x, a2[0]);
             a2[1] = fmaf(wv, ha.y, a2[1]);
             a2[2] = fmaf(wv, ha.z, a2[2]);
@@ -813,17 +863,17 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
             a2[7] = fmaf(wv, hb.w, a2[7]);
         }
 #pragma unroll
-        for (int c = 0; c < C3MAX; ++c) g_s[c][r] = a2[c];
+        for (int c = 0; c < C3MAX; ++c) g_s[c * 256 + r] = a2[c];  // gA rows 0..3, gB rows 4..7
     }
     __syncthreads();
     {
-        const int cc[2] = {q, q + 4};
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int c = cc[i];
-            const float c2 = sigmoidf_acc(g_s[c][u]) * tanhf(g_s[c][128 + u]);
-            const float h2 = sigmoidf_acc(g_s[c][192 + u]) * tanhf(c2);
-            y_s[c][u] = swishf(h2);
+            const int c = q + HC * i;
+            const float *g = g_s + c * 256;
+            const float c2 = sigmoidf_acc(g[u]) * tanhf(g[128 + u]);
+            const float h2 = sigmoidf_acc(g[192 + u]) * tanhf(c2);
+            y_s[c * SIZE + u] = swishf(h2);
         }
     }
     __syncthreads();
@@ -832,8 +882,8 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
         const int warp = tid >> 5;
         if (warp < C) {
             for (int o = 0; o < num_out; ++o) {
-                float part = fcw[o * SIZE + lane] * y_s[warp][lane] +
-                             fcw[o * SIZE + lane + 32] * y_s[warp][lane + 32];
+                float part = fcw[o * SIZE + lane] * y_s[warp * SIZE + lane] +
+                             fcw[o * SIZE + lane + 32] * y_s[warp * SIZE + lane + 32];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
                 if (lane == 0) logits[(size_t)(chunk0 + warp) * num_out + o] = part + fcb[o];
@@ -841,6 +891,7 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
         }
     }
 }
+constexpr int K3_SMEM_BYTES = (4 + SIZE * 256 + 2 * 4 * HG + 2 * HC * 256 + C3MAX * SIZE) * 4;
 
 // repack a channel-last strided activation into canonical [B][C][T] for rb200_debug_tensor
 __global__ void repack_kernel(const float *__restrict__ src, int64_t chunk_stride, int row_pitch,
@@ -977,6 +1028,7 @@ int fused_create(rb200_model *m, const float *blob) {
     const int max_smem = 227 * 1024;
     cudaFuncSetAttribute(k1_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k2_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k3_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES);
     m->fused = fw;
     return RB200_OK;
 }
@@ -1058,7 +1110,7 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[2], stream));
     const int cpb3 = pick_cpb(B, C3MAX, m->sm_count);
     const int grid3 = (B + cpb3 - 1) / cpb3;
-    k3_lstm_kernel<<<grid3, THREADS, 0, stream>>>(
+    k3_lstm_kernel<<<grid3, THREADS, K3_SMEM_BYTES, stream>>>(
         xp, reinterpret_cast<const float4 *>(fw->dev + fw->off_whh4), fw->dev + fw->off_wih2T,
         fw->dev + fw->off_b2, fw->dev + fw->off_fcw, fw->dev + fw->off_fcb, logits, B, cpb3, g.TM,
         fw->num_out);
