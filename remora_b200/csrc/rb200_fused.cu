@@ -29,7 +29,10 @@ constexpr int QP = 20;            // 16-channel row pitch (s2 / q1) in shared me
 constexpr int NR1 = 7;            // K1: output positions per thread
 constexpr int NR2 = 6;            // K2: output positions per thread
 constexpr int MAX_CL = 8;         // chunks per CTA (lane = tb * CL + chunk)
-constexpr int THREADS = 256;
+constexpr int MRW = 8;                        // output channels per warp in the implicit GEMMs
+constexpr int NWARPS = SIZE / MRW;            // 8 warps (16 warps x 4 channels measured no faster)
+constexpr int THREADS = NWARPS * 32;          // 256
+constexpr int XR = 256 / NWARPS / 2;          // x-projection: gate rows per warp per pass (2 passes)
 constexpr int SLAB_C = 32;                              // merge conv: input channels per slab
 constexpr int SLAB_FLOATS = 5 * SLAB_C * SIZE;          // 10240 floats = 40 KB
 constexpr int N_SLABS = 2 * SIZE / SLAB_C;              // 4
@@ -74,6 +77,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
             "r"(smem_addr(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
         : "memory");
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still draining; everything before
+// pdl_wait() (barrier init, TMA weight loads, register-resident weights) overlaps that tail, and
+// nothing produced by the predecessor is touched before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) {
@@ -177,12 +189,12 @@ __host__ __device__ inline K1Smem k1_smem(const Geometry &g, int kmer_len, int s
 }
 
 // Implicit-GEMM conv, stride 3, 16 input channels (channel-last, pitch QP) -> 64 output channels.
-// Warp w owns output channels [8w, 8w+8); lane = tb * CL + chunk owns NR1 consecutive output steps.
+// Warp w owns output channels [MRW*w, MRW*w+MRW); lane = tb * CL + chunk owns NR1 consecutive steps.
 // Taps are processed by residue class rho = j mod 3: taps rho, rho+3, rho+6, ... of output step t
 // read input rows 3(t+i)+rho, i.e. a stride-1 window over the decimated rows u = t+i.  One window of
 // NR1 + ntaps - 1 rows (LDS.128 each) then serves ntaps * NR1 row uses.
 template <int KW, int RHO>
-__device__ __forceinline__ void conv16_s3_residue(float2 (&acc)[NR1][4], const float *__restrict__ xbase,
+__device__ __forceinline__ void conv16_s3_residue(float2 (&acc)[NR1][MRW / 2], const float *__restrict__ xbase,
                                                   int t0, int T3, const float *__restrict__ ws,
                                                   int m0) {
     constexpr int NT = (KW - RHO + 2) / 3;  // taps in this residue class
@@ -206,17 +218,19 @@ __device__ __forceinline__ void conv16_s3_residue(float2 (&acc)[NR1][4], const f
             for (int kk = 0; kk < 4; ++kk) {
                 const float4 *wp =
                     reinterpret_cast<const float4 *>(ws + (j * 16 + c4 + kk) * SIZE + m0);
-                const float4 wa = wp[0], wb = wp[1];
-                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
-                const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+                float2 w[MRW / 2];
+#pragma unroll
+                for (int q = 0; q < MRW / 4; ++q) {
+                    const float4 wv = wp[q];
+                    w[2 * q] = make_float2(wv.x, wv.y);
+                    w[2 * q + 1] = make_float2(wv.z, wv.w);
+                }
 #pragma unroll
                 for (int n = 0; n < NR1; ++n) {
                     const float4 xq = x[n + i];
                     const float xv = kk == 0 ? xq.x : kk == 1 ? xq.y : kk == 2 ? xq.z : xq.w;
-                    acc[n][0] = ffma2(w0, xv, acc[n][0]);
-                    acc[n][1] = ffma2(w1, xv, acc[n][1]);
-                    acc[n][2] = ffma2(w2, xv, acc[n][2]);
-                    acc[n][3] = ffma2(w3, xv, acc[n][3]);
+#pragma unroll
+                    for (int p2 = 0; p2 < MRW / 2; ++p2) acc[n][p2] = ffma2(w[p2], xv, acc[n][p2]);
                 }
             }
         }
@@ -230,42 +244,37 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
                                                  float *__restrict__ cat, int cat_stride,
                                                  int ch_off, int C, int CL, int NB, int T3) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = warp * 8;
+    const int m0 = warp * MRW;
     int tb = lane / CL, chunk = lane - tb * CL;
     const bool lane_ok = tb < NB && chunk < C;
     if (tb >= NB) tb = NB - 1;
     if (chunk >= C) chunk = C - 1;
     const int t0 = tb * NR1;
     const float *xbase = xs + chunk * x_stride;
-    float2 acc[NR1][4];
+    float2 acc[NR1][MRW / 2];
 #pragma unroll
     for (int n = 0; n < NR1; ++n)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) acc[n][p] = make_float2(0.f, 0.f);
+        for (int p = 0; p < MRW / 2; ++p) acc[n][p] = make_float2(0.f, 0.f);
     conv16_s3_residue<KW, 0>(acc, xbase, t0, T3, ws, m0);
     conv16_s3_residue<KW, 1>(acc, xbase, t0, T3, ws, m0);
     conv16_s3_residue<KW, 2>(acc, xbase, t0, T3, ws, m0);
     if (!lane_ok) return;
-    float b[8];
+    float b[MRW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) b[i] = bias[m0 + i];
+    for (int i = 0; i < MRW; ++i) b[i] = bias[m0 + i];
 #pragma unroll
     for (int n = 0; n < NR1; ++n) {
         const int t = t0 + n;
         if (t < T3) {
-            float4 o0, o1;
-            o0.x = swishf_fast(acc[n][0].x + b[0]);
-            o0.y = swishf_fast(acc[n][0].y + b[1]);
-            o0.z = swishf_fast(acc[n][1].x + b[2]);
-            o0.w = swishf_fast(acc[n][1].y + b[3]);
-            o1.x = swishf_fast(acc[n][2].x + b[4]);
-            o1.y = swishf_fast(acc[n][2].y + b[5]);
-            o1.z = swishf_fast(acc[n][3].x + b[6]);
-            o1.w = swishf_fast(acc[n][3].y + b[7]);
             float4 *dst = reinterpret_cast<float4 *>(cat + (size_t)chunk * cat_stride + t * XP +
                                                      ch_off + m0);
-            dst[0] = o0;
-            dst[1] = o1;
+#pragma unroll
+            for (int q = 0; q < MRW / 4; ++q)
+                dst[q] = make_float4(swishf_fast(acc[n][2 * q].x + b[4 * q]),
+                                     swishf_fast(acc[n][2 * q].y + b[4 * q + 1]),
+                                     swishf_fast(acc[n][2 * q + 1].x + b[4 * q + 2]),
+                                     swishf_fast(acc[n][2 * q + 1].y + b[4 * q + 3]));
         }
     }
 }
@@ -343,6 +352,7 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
     const int C = min(CPB, B - chunk0);
     const int CL = g.CL;
 
+    pdl_launch_dependents();  // K2 may begin its weight prefetch as soon as SMs free up
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -353,6 +363,7 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
         mbar_expect_tx(bar, bytes);
         bulk_g2s(wsm, wfront, bytes, bar);
     }
+    pdl_wait();  // inputs (and the cat buffer we overwrite) belong to earlier work in the stream
     // ---- stage the compact inputs of this CTA's chunks ------------------------------------------
     for (int i = tid; i < C * T; i += THREADS) {
         sig_s[i] = sigs[(size_t)chunk0 * T + i];
@@ -500,6 +511,7 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
     const int C = min(CPB, B - chunk0);
     const int CL = g.CL;
 
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(bar_x, 1);
         mbar_init(&bar_w[0], 1);
@@ -508,17 +520,20 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t xbytes = (uint32_t)C * g.cat_stride * 4u;
-        mbar_expect_tx(bar_x, xbytes);
-        bulk_g2s(xs, cat + (size_t)chunk0 * g.cat_stride, xbytes, bar_x);
         for (int s = 0; s < 2; ++s) {
             mbar_expect_tx(&bar_w[s], SLAB_FLOATS * 4u);
             bulk_g2s(ws + s * SLAB_FLOATS, wslabs + (size_t)s * SLAB_FLOATS, SLAB_FLOATS * 4u,
                      &bar_w[s]);
         }
     }
-    // ---- merge conv: warp w -> output channels [8w, 8w+8); lane = tb*CL + chunk -> NR2 steps -------
-    const int m0 = warp * 8;
+    pdl_wait();  // cat is produced by K1
+    if (tid == 0) {
+        const uint32_t xbytes = (uint32_t)C * g.cat_stride * 4u;
+        mbar_expect_tx(bar_x, xbytes);
+        bulk_g2s(xs, cat + (size_t)chunk0 * g.cat_stride, xbytes, bar_x);
+    }
+    // ---- merge conv: warp w -> output channels [MRW*w, MRW*w+MRW); lane = tb*CL + chunk -> NR2 steps
+    const int m0 = warp * MRW;
     int tb = lane / CL, chunk = lane - tb * CL;
     const bool lane_ok = tb < g.NB2 && chunk < C;
     if (tb >= g.NB2) tb = g.NB2 - 1;
@@ -532,11 +547,11 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
         if (t > g.T3 - 1) t = g.T3 - 1;
         xrow[r] = xs + chunk * g.cat_stride + t * XP;
     }
-    float2 acc[NR2][4];
+    float2 acc[NR2][MRW / 2];
 #pragma unroll
     for (int n = 0; n < NR2; ++n)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) acc[n][p] = make_float2(0.f, 0.f);
+        for (int p = 0; p < MRW / 2; ++p) acc[n][p] = make_float2(0.f, 0.f);
 
     mbar_wait(bar_x, 0);
 #pragma unroll 1
@@ -555,17 +570,19 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
                 for (int kk = 0; kk < 4; ++kk) {
                     const float4 *wp = reinterpret_cast<const float4 *>(
                         wbuf + (j * SLAB_C + c4 + kk) * SIZE + m0);
-                    const float4 wa = wp[0], wb = wp[1];
-                    const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
-                    const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+                    float2 w[MRW / 2];
+#pragma unroll
+                    for (int q = 0; q < MRW / 4; ++q) {
+                        const float4 wv = wp[q];
+                        w[2 * q] = make_float2(wv.x, wv.y);
+                        w[2 * q + 1] = make_float2(wv.z, wv.w);
+                    }
 #pragma unroll
                     for (int n = 0; n < NR2; ++n) {
                         const float4 xq = x[n + j];
                         const float xv = kk == 0 ? xq.x : kk == 1 ? xq.y : kk == 2 ? xq.z : xq.w;
-                        acc[n][0] = ffma2(w0, xv, acc[n][0]);
-                        acc[n][1] = ffma2(w1, xv, acc[n][1]);
-                        acc[n][2] = ffma2(w2, xv, acc[n][2]);
-                        acc[n][3] = ffma2(w3, xv, acc[n][3]);
+#pragma unroll
+                        for (int p2 = 0; p2 < MRW / 2; ++p2) acc[n][p2] = ffma2(w[p2], xv, acc[n][p2]);
                     }
                 }
             }
@@ -588,31 +605,26 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
     // ---- merge epilogue: bias + swish -> ms[(chunk*TM + t)][MP] (aliases xs; all warps synced) -----
     float *ms = xs;
     if (lane_ok) {
-        float b[8];
+        float b[MRW];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = bmerge[m0 + i];
+        for (int i = 0; i < MRW; ++i) b[i] = bmerge[m0 + i];
 #pragma unroll
         for (int n = 0; n < NR2; ++n) {
             const int t = t0 + n;
             if (t < g.TM) {
-                float4 o0, o1;
-                o0.x = swishf_fast(acc[n][0].x + b[0]);
-                o0.y = swishf_fast(acc[n][0].y + b[1]);
-                o0.z = swishf_fast(acc[n][1].x + b[2]);
-                o0.w = swishf_fast(acc[n][1].y + b[3]);
-                o1.x = swishf_fast(acc[n][2].x + b[4]);
-                o1.y = swishf_fast(acc[n][2].y + b[5]);
-                o1.z = swishf_fast(acc[n][3].x + b[6]);
-                o1.w = swishf_fast(acc[n][3].y + b[7]);
                 float4 *dst = reinterpret_cast<float4 *>(ms + (chunk * g.TM + t) * MP + m0);
-                dst[0] = o0;
-                dst[1] = o1;
+#pragma unroll
+                for (int q = 0; q < MRW / 4; ++q)
+                    dst[q] = make_float4(swishf_fast(acc[n][2 * q].x + b[4 * q]),
+                                         swishf_fast(acc[n][2 * q].y + b[4 * q + 1]),
+                                         swishf_fast(acc[n][2 * q + 1].x + b[4 * q + 2]),
+                                         swishf_fast(acc[n][2 * q + 1].y + b[4 * q + 3]));
             }
         }
     }
     __syncthreads();
     // ---- LSTM1 input projection: xp[pos][r] = b1[r] + sum_k W_ih1[r][k] * m[pos][k] ---------------
-    // warp w -> gate rows [16w, 16w+16) and [128+16w, ...); lane -> positions lane + 32 n
+    // warp w, pass p -> gate rows [128 p + XR w, +XR); lane -> positions lane + 32 n
     const int npos = C * g.TM;
     const float *mrow[NR2];
 #pragma unroll
@@ -623,12 +635,12 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
     }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        const int r0 = pass * 128 + warp * 16;
-        float2 pa[NR2][8];
+        const int r0 = pass * 128 + warp * XR;
+        float2 pa[NR2][XR / 2];
 #pragma unroll
         for (int n = 0; n < NR2; ++n)
 #pragma unroll
-            for (int p = 0; p < 8; ++p) pa[n][p] = make_float2(0.f, 0.f);
+            for (int p = 0; p < XR / 2; ++p) pa[n][p] = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             // half h of W_ih1^T lives in buffer ((N_SLABS-2+h) & 1); its load was the
@@ -646,30 +658,32 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const float4 *wp = reinterpret_cast<const float4 *>(wbuf + (c4 + kk) * 256 + r0);
-                    const float4 wa = wp[0], wb = wp[1], wc = wp[2], wd = wp[3];
-                    const float2 w[8] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w),
-                                         make_float2(wb.x, wb.y), make_float2(wb.z, wb.w),
-                                         make_float2(wc.x, wc.y), make_float2(wc.z, wc.w),
-                                         make_float2(wd.x, wd.y), make_float2(wd.z, wd.w)};
+                    float2 w[XR / 2];
+#pragma unroll
+                    for (int q = 0; q < XR / 4; ++q) {
+                        const float4 wv = wp[q];
+                        w[2 * q] = make_float2(wv.x, wv.y);
+                        w[2 * q + 1] = make_float2(wv.z, wv.w);
+                    }
 #pragma unroll
                     for (int n = 0; n < NR2; ++n) {
                         const float xv = kk == 0 ? x[n].x : kk == 1 ? x[n].y : kk == 2 ? x[n].z : x[n].w;
 #pragma unroll
-                        for (int p = 0; p < 8; ++p) pa[n][p] = ffma2(w[p], xv, pa[n][p]);
+                        for (int p = 0; p < XR / 2; ++p) pa[n][p] = ffma2(w[p], xv, pa[n][p]);
                     }
                 }
             }
         }
-        float bb[16];
+        float bb[XR];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bb[i] = b1[r0 + i];
+        for (int i = 0; i < XR; ++i) bb[i] = b1[r0 + i];
 #pragma unroll
         for (int n = 0; n < NR2; ++n) {
             const int pos = lane + 32 * n;
             if (pos < npos) {
                 float4 *dst = reinterpret_cast<float4 *>(xp + ((size_t)chunk0 * g.TM + pos) * 256 + r0);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < XR / 4; ++q)
                     dst[q] = make_float4(pa[n][2 * q].x + bb[4 * q], pa[n][2 * q].y + bb[4 * q + 1],
                                          pa[n][2 * q + 1].x + bb[4 * q + 2],
                                          pa[n][2 * q + 1].y + bb[4 * q + 3]);
@@ -752,7 +766,23 @@ __device__ __forceinline__ float lstm_cell_half(const float *__restrict__ g_half
     return h;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// named-barrier helpers (producer: arrive, consumer: sync; `count` threads take part in total)
+__device__ __forceinline__ void nbar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nbar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+constexpr int K3_MV_THREADS = 256;   // warps 0..7 : mat-vec (W_hh in registers)
+constexpr int K3_CELL_THREADS = 128; // warps 8..11: gate non-linearities / cell update
+constexpr int K3_THREADS = K3_MV_THREADS + K3_CELL_THREADS;
+enum { BAR_GA = 1, BAR_HA = 2, BAR_GB = 3, BAR_HB = 4 };
+
+// Warp-specialised schedule (A = chunks 0..3, B = chunks 4..7 of the CTA):
+//   mat-vec warps : mv(A,0) | mv(B,t) , wait h_A(t) , mv(A,t+1) , wait h_B(t) ...
+//   cell warps    :           wait g_A(t) , cell(A,t) -> h_A , wait g_B(t) , cell(B,t) -> h_B ...
+// so the MUFU-latency chain of one half's cell update runs under the other half's FFMA2 stream.
+__global__ void __launch_bounds__(K3_THREADS, 1)
 k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
                const float *__restrict__ wih2T, const float *__restrict__ b2,
                const float *__restrict__ fcw, const float *__restrict__ fcb,
@@ -764,85 +794,105 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
     float *g_s = h_s + 2 * 4 * HG;            // 2 halves x [HC][256] gate pre-activations
     float *y_s = g_s + 2 * HC * 256;          // [C3MAX][SIZE]
     const int tid = threadIdx.x, lane = tid & 31;
-    const int kg = lane & 3;  // k-group: k in [16 kg, 16 kg + 16)
-    const int r = tid;        // finished gate row owned after the butterfly: i 0..63, f, g, o
     const int chunk0 = blockIdx.x * CPB;
     const int C = min(CPB, B - chunk0);
+    float *hA = h_s, *hB = h_s + 4 * HG;
+    float *gA = g_s, *gB = g_s + HC * 256;
 
+    pdl_launch_dependents();  // the next forward's K1 may stage its weights under our tail
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
+    for (int i = tid; i < 2 * 4 * HG; i += K3_THREADS) h_s[i] = 0.f;
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, SIZE * 256 * 4u);
         bulk_g2s(w2_s, wih2T, SIZE * 256 * 4u, bar);
     }
-    // w[i][kl] = W_hh[4*(tid>>2) + i][16*kg + kl], host layout [q][tid] float4 with q = 4*i + kl/4
-    float w[4][16];
-#pragma unroll
-    for (int q4 = 0; q4 < 16; ++q4) {
-        const float4 v = whh4[q4 * 256 + tid];
-        w[q4 >> 2][(q4 & 3) * 4 + 0] = v.x;
-        w[q4 >> 2][(q4 & 3) * 4 + 1] = v.y;
-        w[q4 >> 2][(q4 & 3) * 4 + 2] = v.z;
-        w[q4 >> 2][(q4 & 3) * 4 + 3] = v.w;
-    }
-    for (int i = tid; i < 2 * 4 * HG; i += THREADS) h_s[i] = 0.f;
-    const int u = tid & 63, q = tid >> 6;  // cell-update role: unit u, chunk q of each half
-    const int hu = (u >> 4) * HG + (u & 15) * HC;
-    float *hA = h_s, *hB = h_s + 4 * HG;
-    float *gA = g_s, *gB = g_s + HC * 256;
-    const float *hkA = hA + kg * HG, *hkB = hB + kg * HG;
-    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
-    float cstA = 0.f, cstB = 0.f, hlastA = 0.f, hlastB = 0.f;
 
-    // xp rows of this thread for the current and the next step, per half
-    const float *xrow[C3MAX];
+    if (tid < K3_MV_THREADS) {
+        // ================================ mat-vec warps ==========================================
+        const int kg = lane & 3;  // k-group: k in [16 kg, 16 kg + 16)
+        const int r = tid;        // finished gate row owned after the butterfly: i 0..63, f, g, o
+        // w[i][kl] = W_hh[4*(tid>>2) + i][16*kg + kl], host layout [q][tid] float4, q = 4*i + kl/4
+        float w[4][16];
 #pragma unroll
-    for (int c = 0; c < C3MAX; ++c)
-        xrow[c] = xp + ((size_t)(chunk0 + (c < C ? c : 0)) * TM) * 256 + r;
-    float xa[HC], xb[HC];
+        for (int q4 = 0; q4 < 16; ++q4) {
+            const float4 v = whh4[q4 * 256 + tid];
+            w[q4 >> 2][(q4 & 3) * 4 + 0] = v.x;
+            w[q4 >> 2][(q4 & 3) * 4 + 1] = v.y;
+            w[q4 >> 2][(q4 & 3) * 4 + 2] = v.z;
+            w[q4 >> 2][(q4 & 3) * 4 + 3] = v.w;
+        }
+        const float *hkA = hA + kg * HG, *hkB = hB + kg * HG;
+        const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+        pdl_wait();  // xp is produced by K2
+        const float *xrow[C3MAX];
 #pragma unroll
-    for (int c = 0; c < HC; ++c) {
-        xa[c] = c < C ? xrow[c][0] : 0.f;
-        xb[c] = HC + c < C ? xrow[HC + c][0] : 0.f;
-    }
-    __syncthreads();
-
-    lstm_matvec_half(w, hkA, xa, gA, r, hi2, hi1);  // mv(A, 0)
-    __syncthreads();
+        for (int c = 0; c < C3MAX; ++c)
+            xrow[c] = xp + ((size_t)(chunk0 + (c < C ? c : 0)) * TM) * 256 + r;
+        float xa[HC], xb[HC];
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+            xa[c] = c < C ? xrow[c][0] : 0.f;
+            xb[c] = HC + c < C ? xrow[HC + c][0] : 0.f;
+        }
+        lstm_matvec_half(w, hkA, xa, gA, r, hi2, hi1);  // mv(A, 0)
+        nbar_arrive(BAR_GA, K3_THREADS);
 #pragma unroll 1
-    for (int t = 0; t < TM; ++t) {
-        // prefetch next step's input projections (L2 hits) while this step computes
-        float xa_n[HC], xb_n[HC];
-        const int tn = t + 1 < TM ? t + 1 : t;
+        for (int t = 0; t < TM; ++t) {
+            float xa_n[HC], xb_n[HC];
+            const int tn = t + 1 < TM ? t + 1 : t;
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-            xa_n[c] = c < C ? xrow[c][(size_t)tn * 256] : 0.f;
-            xb_n[c] = HC + c < C ? xrow[HC + c][(size_t)tn * 256] : 0.f;
-        }
-        // region 1: mat-vec of half B for step t  +  cell update of half A for step t
-        lstm_matvec_half(w, hkB, xb, gB, r, hi2, hi1);
-        hlastA = lstm_cell_half(gA, hA, u, q, hu, cstA);
-        __syncthreads();
-        // region 2: mat-vec of half A for step t+1  +  cell update of half B for step t
-        if (t + 1 < TM) lstm_matvec_half(w, hkA, xa_n, gA, r, hi2, hi1);
-        hlastB = lstm_cell_half(gB, hB, u, q, hu, cstB);
-        __syncthreads();
+            for (int c = 0; c < HC; ++c) {
+                xa_n[c] = c < C ? xrow[c][(size_t)tn * 256] : 0.f;
+                xb_n[c] = HC + c < C ? xrow[HC + c][(size_t)tn * 256] : 0.f;
+            }
+            if (t > 0) nbar_sync(BAR_HB, K3_THREADS);  // h_B(t-1) written
+            lstm_matvec_half(w, hkB, xb, gB, r, hi2, hi1);  // mv(B, t)
+            nbar_arrive(BAR_GB, K3_THREADS);
+            nbar_sync(BAR_HA, K3_THREADS);  // h_A(t) written
+            if (t + 1 < TM) {
+                lstm_matvec_half(w, hkA, xa_n, gA, r, hi2, hi1);  // mv(A, t+1)
+                nbar_arrive(BAR_GA, K3_THREADS);
+            }
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-            xa[c] = xa_n[c];
-            xb[c] = xb_n[c];
+            for (int c = 0; c < HC; ++c) xb[c] = xb_n[c];
         }
+        nbar_sync(BAR_HB, K3_THREADS);  // h_B(TM-1)
+    } else {
+        // ================================ cell-update warps ======================================
+        const int ct = tid - K3_MV_THREADS;  // 0..127: cells ct and ct+128 of each half
+        const int u0 = ct & 63, q0 = ct >> 6, q1 = q0 + 2;
+        const int hu = (u0 >> 4) * HG + (u0 & 15) * HC;
+        float cA0 = 0.f, cA1 = 0.f, cB0 = 0.f, cB1 = 0.f;
+        float hA0 = 0.f, hA1 = 0.f, hB0 = 0.f, hB1 = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < TM; ++t) {
+            nbar_sync(BAR_GA, K3_THREADS);
+            hA0 = lstm_cell_half(gA, hA, u0, q0, hu, cA0);
+            hA1 = lstm_cell_half(gA, hA, u0, q1, hu, cA1);
+            nbar_arrive(BAR_HA, K3_THREADS);
+            nbar_sync(BAR_GB, K3_THREADS);
+            hB0 = lstm_cell_half(gB, hB, u0, q0, hu, cB0);
+            hB1 = lstm_cell_half(gB, hB, u0, q1, hu, cB1);
+            nbar_arrive(BAR_HB, K3_THREADS);
+        }
+        // ---- LSTM2 input: x = swish(h1[T-1]) (ConvLSTM_w_ref.py:53) -------------------------------
+        // (the mat-vec warps have passed their last BAR_HB sync only after these cells' arrive, and
+        //  read h again only after the __syncthreads below)
+        hA[hu + q0] = swishf(hA0);
+        hA[hu + q1] = swishf(hA1);
+        hB[hu + q0] = swishf(hB0);
+        hB[hu + q1] = swishf(hB1);
     }
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54):
-    // x = swish(h1[T-1]), h0 = c0 = 0  =>  c = sig(i) * tanh(g), h = sig(o) * tanh(c)
-    hA[hu + q] = swishf(hlastA);
-    hB[hu + q] = swishf(hlastB);
+    // h0 = c0 = 0  =>  c = sig(i) * tanh(g), h = sig(o) * tanh(c)
     mbar_wait(bar, 0);  // W_ih2^T landed long ago
     __syncthreads();
-    {
+    if (tid < K3_MV_THREADS) {
+        const int r = tid;
         float a2[C3MAX];
         const float bias = b2[r];
 #pragma unroll
@@ -866,7 +916,8 @@ k3_lstm_kernel(const float *__restrict__ xp, const float4 *__restrict__ whh4,
         for (int c = 0; c < C3MAX; ++c) g_s[c * 256 + r] = a2[c];  // gA rows 0..3, gB rows 4..7
     }
     __syncthreads();
-    {
+    if (tid < K3_MV_THREADS) {
+        const int u = tid & 63, q = tid >> 6;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int c = q + HC * i;
@@ -1055,6 +1106,24 @@ size_t fused_workspace_bytes(const rb200_model *m, int B, int T) {
     return align256((size_t)B * g.cat_stride * 4) + align256((size_t)B * g.TM * 256 * 4) + 1024;
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel's prologue may overlap
+// the tail of the previous kernel in the stream; the kernel itself orders its reads with pdl_wait().
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // chunks per CTA: minimise (waves * chunks-per-CTA), prefer the larger CTA on ties
 static int pick_cpb(int B, int cmax, int sm_count) {
     int best = 1;
@@ -1098,22 +1167,50 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
         }
         RB200_CUDA_TRY(cudaEventRecord(ev[0], stream));
     }
-    k1_front_kernel<<<grid, THREADS, l1.total_bytes, stream>>>(
-        sigs, seqs, seq_width, maps, map_width, lens, fw->dev + fw->off_front, cat, B, cpb, T,
-        fw->kmer_len);
+    // with profiling events between the kernels PDL cannot overlap them; launch plainly then
+    const bool pdl = !m->profile;
+    if (pdl) {
+        RB200_CUDA_TRY(launch_pdl(k1_front_kernel, grid, THREADS, l1.total_bytes, stream, sigs, seqs,
+                                  seq_width, maps, map_width, lens,
+                                  (const float *)(fw->dev + fw->off_front), cat, B, cpb, T,
+                                  fw->kmer_len));
+    } else {
+        k1_front_kernel<<<grid, THREADS, l1.total_bytes, stream>>>(
+            sigs, seqs, seq_width, maps, map_width, lens, fw->dev + fw->off_front, cat, B, cpb, T,
+            fw->kmer_len);
+    }
     RB200_CUDA_TRY(cudaGetLastError());
     if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[1], stream));
-    k2_merge_kernel<<<grid, THREADS, l2.total_bytes, stream>>>(
-        cat, fw->dev + fw->off_slabs, fw->dev + fw->off_bmerge, fw->dev + fw->off_wih1T,
-        fw->dev + fw->off_b1, xp, B, cpb, T);
+    if (pdl) {
+        RB200_CUDA_TRY(launch_pdl(k2_merge_kernel, grid, THREADS, l2.total_bytes, stream,
+                                  (const float *)cat, (const float *)(fw->dev + fw->off_slabs),
+                                  (const float *)(fw->dev + fw->off_bmerge),
+                                  (const float *)(fw->dev + fw->off_wih1T),
+                                  (const float *)(fw->dev + fw->off_b1), xp, B, cpb, T));
+    } else {
+        k2_merge_kernel<<<grid, THREADS, l2.total_bytes, stream>>>(
+            cat, fw->dev + fw->off_slabs, fw->dev + fw->off_bmerge, fw->dev + fw->off_wih1T,
+            fw->dev + fw->off_b1, xp, B, cpb, T);
+    }
     RB200_CUDA_TRY(cudaGetLastError());
     if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[2], stream));
     const int cpb3 = pick_cpb(B, C3MAX, m->sm_count);
     const int grid3 = (B + cpb3 - 1) / cpb3;
-    k3_lstm_kernel<<<grid3, THREADS, K3_SMEM_BYTES, stream>>>(
-        xp, reinterpret_cast<const float4 *>(fw->dev + fw->off_whh4), fw->dev + fw->off_wih2T,
-        fw->dev + fw->off_b2, fw->dev + fw->off_fcw, fw->dev + fw->off_fcb, logits, B, cpb3, g.TM,
-        fw->num_out);
+    if (pdl) {
+        RB200_CUDA_TRY(launch_pdl(k3_lstm_kernel, grid3, K3_THREADS, (size_t)K3_SMEM_BYTES, stream,
+                                  (const float *)xp,
+                                  reinterpret_cast<const float4 *>(fw->dev + fw->off_whh4),
+                                  (const float *)(fw->dev + fw->off_wih2T),
+                                  (const float *)(fw->dev + fw->off_b2),
+                                  (const float *)(fw->dev + fw->off_fcw),
+                                  (const float *)(fw->dev + fw->off_fcb), logits, B, cpb3, g.TM,
+                                  fw->num_out));
+    } else {
+        k3_lstm_kernel<<<grid3, K3_THREADS, K3_SMEM_BYTES, stream>>>(
+            xp, reinterpret_cast<const float4 *>(fw->dev + fw->off_whh4), fw->dev + fw->off_wih2T,
+            fw->dev + fw->off_b2, fw->dev + fw->off_fcw, fw->dev + fw->off_fcb, logits, B, cpb3,
+            g.TM, fw->num_out);
+    }
     RB200_CUDA_TRY(cudaGetLastError());
     if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[3], stream));
     m->launches += 3;
