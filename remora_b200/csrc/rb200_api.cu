@@ -131,15 +131,16 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
     int impl = m->impl;
     const bool fused_ok =
         compact && m->fused != nullptr && fused_shape_ok(m, T, seq_width, map_width);
-    if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED : RB200_IMPL_LAYERS;
-    if (impl == RB200_IMPL_FUSED) {
+    // AUTO prefers the tensor-core variant of the fused path (falls back to FFMA2 inside when the
+    // CTA's rows do not fit two M tiles)
+    if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_LAYERS;
+    if (impl == RB200_IMPL_FUSED || impl == RB200_IMPL_FUSED_TC) {
         if (!fused_ok) {
             set_error("fused kernels not available for this model/shape/input form");
             return RB200_ERR_UNSUPPORTED;
         }
-        m->last_impl = RB200_IMPL_FUSED;
         return fused_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T,
-                                     logits, stream);
+                                     logits, stream, impl == RB200_IMPL_FUSED_TC);
     }
     m->last_impl = RB200_IMPL_LAYERS;
     return layers_forward(m, ws, sigs, enc, seqs, seq_width, maps, map_width, lens, B, T, logits,
@@ -217,8 +218,8 @@ int rb200_destroy(rb200_handle h) {
 }
 
 int rb200_set_impl(rb200_handle h, int impl) {
-    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_FUSED, "bad argument");
-    if (impl == RB200_IMPL_FUSED && h->fused == nullptr) {
+    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_FUSED_TC, "bad argument");
+    if (impl >= RB200_IMPL_FUSED && h->fused == nullptr) {
         set_error("fused kernels not available for this model");
         return RB200_ERR_UNSUPPORTED;
     }

@@ -14,6 +14,8 @@
 // two halves of an FFMA2 are two adjacent output channels; weights are staged in shared memory
 // k-major by bulk asynchronous copies (TMA, cp.async.bulk + mbarrier), shared by every chunk of the
 // CTA and read as warp-wide broadcasts.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rb200_internal.cuh"
@@ -188,6 +190,18 @@ __host__ __device__ inline K1Smem k1_smem(const Geometry &g, int kmer_len, int s
     return s;
 }
 
+// a = hi + lo with hi exactly representable in TF32 (round to nearest) and lo = a - hi (exact in fp32);
+// hi*b_hi + lo*b_hi + hi*b_lo on the tensor cores then carries ~2^-21 relative error ("3xTF32").
+__device__ __forceinline__ float tf32_hi(float a) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(const float4 &a, float4 &hi, float4 &lo) {
+    hi = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+    lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+}
+
 // Implicit-GEMM conv, stride 3, 16 input channels (channel-last, pitch QP) -> 64 output channels.
 // Warp w owns output channels [MRW*w, MRW*w+MRW); lane = tb * CL + chunk owns NR1 consecutive steps.
 // Taps are processed by residue class rho = j mod 3: taps rho, rho+3, rho+6, ... of output step t
@@ -242,7 +256,8 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
                                                  const float *__restrict__ ws,
                                                  const float *__restrict__ bias,
                                                  float *__restrict__ cat, int cat_stride,
-                                                 int ch_off, int C, int CL, int NB, int T3) {
+                                                 int ch_off, int C, int CL, int NB, int T3,
+                                                 int tc_rpad) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = warp * MRW;
     int tb = lane / CL, chunk = lane - tb * CL;
@@ -267,14 +282,31 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
     for (int n = 0; n < NR1; ++n) {
         const int t = t0 + n;
         if (t < T3) {
-            float4 *dst = reinterpret_cast<float4 *>(cat + (size_t)chunk * cat_stride + t * XP +
-                                                     ch_off + m0);
+            float4 o[MRW / 4];
 #pragma unroll
             for (int q = 0; q < MRW / 4; ++q)
-                dst[q] = make_float4(swishf_fast(acc[n][2 * q].x + b[4 * q]),
-                                     swishf_fast(acc[n][2 * q].y + b[4 * q + 1]),
-                                     swishf_fast(acc[n][2 * q + 1].x + b[4 * q + 2]),
-                                     swishf_fast(acc[n][2 * q + 1].y + b[4 * q + 3]));
+                o[q] = make_float4(swishf_fast(acc[n][2 * q].x + b[4 * q]),
+                                   swishf_fast(acc[n][2 * q].y + b[4 * q + 1]),
+                                   swishf_fast(acc[n][2 * q + 1].x + b[4 * q + 2]),
+                                   swishf_fast(acc[n][2 * q + 1].y + b[4 * q + 3]));
+            if (tc_rpad == 0) {
+                float4 *dst = reinterpret_cast<float4 *>(cat + (size_t)chunk * cat_stride + t * XP +
+                                                         ch_off + m0);
+#pragma unroll
+                for (int q = 0; q < MRW / 4; ++q) dst[q] = o[q];
+            } else {
+                // tensor-core image of this CTA: [hi|lo][channel block][row][32 ch, 128B-swizzled]
+                const int row = chunk * T3 + t;
+#pragma unroll
+                for (int q = 0; q < MRW / 4; ++q) {
+                    const int ch = ch_off + m0 + 4 * q;
+                    const int off = ((ch >> 5) * tc_rpad + row) * 32 + ((((ch & 31) >> 2) ^ (row & 7)) << 2);
+                    float4 hi, lo;
+                    split_tf32(o[q], hi, lo);
+                    *reinterpret_cast<float4 *>(cat + off) = hi;
+                    *reinterpret_cast<float4 *>(cat + 4 * tc_rpad * 32 + off) = lo;
+                }
+            }
         }
     }
 }
@@ -332,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
                 const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
                 const float *__restrict__ wfront, float *__restrict__ cat, int B, int CPB, int T,
-                int kmer_len) {
+                int kmer_len, int tc_rpad) {
     extern __shared__ __align__(128) float sm[];
     const Geometry g = make_geometry(T);
     const K1Smem lay = k1_smem(g, kmer_len, seq_width, map_width);
@@ -457,10 +489,12 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
         }
     }
     __syncthreads();
-    float *cat_cta = cat + (size_t)chunk0 * g.cat_stride;
+    // classic layout: chunk-major rows; tensor-core layout: one pre-swizzled hi/lo image per CTA
+    float *cat_cta = tc_rpad ? cat + (size_t)blockIdx.x * (2 * 4 * tc_rpad * 32)
+                             : cat + (size_t)chunk0 * g.cat_stride;
     // ---- sig_conv3 (16 -> 64, k9, stride 3) -> cat[:, :, 0:64] -----------------------------------
     conv16_s3_to_cat<KW_SIG3>(act_s, g.s2_stride, wsm + fo.w_sig3, wsm + fo.b_sig3, cat_cta,
-                              g.cat_stride, 0, C, CL, g.NB1, g.T3);
+                              g.cat_stride, 0, C, CL, g.NB1, g.T3, tc_rpad);
     __syncthreads();
     // ---- seq_conv1 on the (virtual) one-hot input = gather-add of weight columns -----------------
     if (kmer_len == 9)
@@ -472,7 +506,7 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
     __syncthreads();
     // ---- seq_conv2 (16 -> 64, k13, stride 3) -> cat[:, :, 64:128] --------------------------------
     conv16_s3_to_cat<KW_SEQ2>(act_s, g.q1_stride, wsm + fo.w_seq2, wsm + fo.b_seq2, cat_cta,
-                              g.cat_stride, SIZE, C, CL, g.NB1, g.T3);
+                              g.cat_stride, SIZE, C, CL, g.NB1, g.T3, tc_rpad);
 }
 
 // =================================================================================================
@@ -691,6 +725,347 @@ k2_merge_kernel(const float *__restrict__ cat, const float *__restrict__ wslabs,
         }
     }
 }
+
+// =================================================================================================
+// K2-TC: merge_conv1 + LSTM1 input projection on the 5th-generation tensor cores (tcgen05)
+// =================================================================================================
+// Both are GEMMs, so they run as tcgen05.mma kind::tf32 with the accumulators in TMEM.  A single TF32
+// pass (10-bit mantissa) cannot meet the 1e-4 fp32 parity gate, so every product is issued as the
+// 3xTF32 split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (fp32 accumulate in TMEM, ~2^-21 relative).
+//   * positions are the MMA's M dimension (128 rows = (chunk, t) pairs), output channels its N;
+//   * the convolution's taps need no im2col: tap j is the same 128B-swizzled K-major activation tile
+//     with the descriptor start address advanced by j rows (j*128 B) - the swizzle is a function of
+//     the absolute shared-memory address, so shifted descriptors stay consistent (verified on B200,
+//     scripts/microbench/umma_test.cu);
+//   * K1 writes the activations already split into hi/lo and pre-swizzled, one image per CTA, so a
+//     plain bulk TMA copy lands them MMA-ready; weights are pre-split/pre-swizzled on the host;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+//     warps 2..5 = epilogue (TMEM -> registers -> bias/swish/split -> shared memory or HBM).
+namespace tc {
+constexpr int WST_BYTES = 2 * 64 * 128;      // merge weights of one (channel block, tap): hi + lo
+constexpr int N_WST = 4;                     // weight ring depth (16 KB stages)
+constexpr int XST_BYTES = 2 * 128 * 128;     // W_ih tile (128 gate rows x 32 k): hi + lo
+constexpr int N_XST = 2;
+constexpr int MT_BYTES = 128 * 128;          // one [128 rows][32 k] tile
+constexpr int THREADS_TC = 192;
+constexpr int TMEM_COLS = 512;
+
+struct Geo {
+    int R;        // activation rows of the CTA = chunks * T3
+    int rpad;     // rows per K-block tile in the image (multiple of 8, >= R + 8)
+    int n_mt;     // 1 or 2 M-tiles of 128 rows
+    int base1;    // first row of the second M-tile (= R - 128, overlaps the first)
+};
+__host__ __device__ inline int rpad_for(int cl, int T3) { return ((cl * T3 + 7) & ~7) + 8; }
+
+struct Smem {
+    int bars, a_ring, w_ring, total;
+    int a_stage_bytes;
+};
+__host__ __device__ inline Smem smem_layout(int rpad) {
+    Smem l;
+    l.bars = 0;
+    l.a_ring = 1024;
+    l.a_stage_bytes = 2 * rpad * 128;  // hi + lo tile of one channel block
+    const int merge_bytes = 2 * l.a_stage_bytes + N_WST * WST_BYTES;
+    l.w_ring = l.a_ring + 2 * l.a_stage_bytes;
+    const int xproj_bytes = 2 * 2 * 2 * MT_BYTES + N_XST * XST_BYTES;  // m tiles [mt][kb][hi|lo] + W_ih ring
+    l.total = 1024 + (merge_bytes > xproj_bytes ? merge_bytes : xproj_bytes);
+    return l;
+}
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    // K-major, SWIZZLE_128B, 8-row x 128 B atoms stacked every 1024 B, descriptor version 1 (sm_100)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    // D = f32 (bits 4-5 = 1), A = B = tf32 (format 2 at bits 7-9 / 10-12), K-major both, N>>3, M>>4
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 3xTF32: hi*hi + lo*hi + hi*lo over one 32-wide K block (4 MMAs of K = 8 each).  The tensor core adds
+// into the TMEM accumulator with truncation, so a long chain picks up a systematic bias
+// (scripts/microbench/umma_acc_test.cu: 5.7e-6 relative after 240 accumulate steps); the two small
+// correction products therefore go to their own accumulator and the main chain is kept short.
+__device__ __forceinline__ void mma3_kblock(uint32_t d_main, uint32_t d_small, uint32_t a_hi, uint32_t a_lo,
+                                            uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool first_main,
+                                            bool first_small) {
+#pragma unroll
+    for (int k8 = 0; k8 < 4; ++k8) {
+        const uint32_t o = k8 * 32;
+        mma_tf32(d_main, desc_sw128(a_hi + o), desc_sw128(b_hi + o), idesc, (first_main && k8 == 0) ? 0u : 1u);
+        mma_tf32(d_small, desc_sw128(a_lo + o), desc_sw128(b_hi + o), idesc, (first_small && k8 == 0) ? 0u : 1u);
+        mma_tf32(d_small, desc_sw128(a_hi + o), desc_sw128(b_lo + o), idesc, 1u);
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Bars {
+    uint64_t a_full[2], a_empty[2], w_full[N_WST], w_empty[N_WST], x_full[N_XST], x_empty[N_XST];
+    uint64_t d_full, m_ready, d2_full[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS_TC, 1)
+k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
+            const float *__restrict__ bmerge, const float *__restrict__ wih_tc,
+            const float *__restrict__ b1, float *__restrict__ xp, int B, int CPB, int T3, int TM,
+            int rpad, long long *__restrict__ stamps) {
+    extern __shared__ __align__(1024) uint8_t smt[];
+    // optional phase timestamps of CTA 0 (profiling aid; null in production)
+#define TC_STAMP(i) do { if (stamps && blockIdx.x == 0) stamps[i] = clock64(); } while (0)
+    const Smem lay = smem_layout(rpad);
+    Bars *bars = reinterpret_cast<Bars *>(smt);
+    uint8_t *a_ring = smt + lay.a_ring;
+    uint8_t *w_ring = smt + lay.w_ring;
+    uint8_t *m_tiles = smt + lay.a_ring;                       // xproj phase: aliases the A ring
+    uint8_t *x_ring = m_tiles + 2 * 2 * 2 * MT_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk0 = blockIdx.x * CPB;
+    const int C = min(CPB, B - chunk0);
+    const int R = C * T3;
+    const int n_mt = R > 128 ? 2 : 1;
+    const int mt_base[2] = {0, R > 128 ? R - 128 : 0};
+    const int tile_bytes = rpad * 128;
+
+    pdl_launch_dependents();
+    if (tid == 0) TC_STAMP(0);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->a_full[i], 1);
+            mbar_init(&bars->a_empty[i], 1);
+            mbar_init(&bars->d2_full[i], 1);
+        }
+        for (int i = 0; i < N_WST; ++i) {
+            mbar_init(&bars->w_full[i], 1);
+            mbar_init(&bars->w_empty[i], 1);
+        }
+        for (int i = 0; i < N_XST; ++i) {
+            mbar_init(&bars->x_full[i], 1);
+            mbar_init(&bars->x_empty[i], 1);
+        }
+        mbar_init(&bars->d_full, 1);
+        mbar_init(&bars->m_ready, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_addr(&bars->tmem_base)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================================== TMA producer ========================================
+        if (lane == 0) {
+            const float *img = cat_img + (size_t)blockIdx.x * (2 * 4 * rpad * 32);
+            const uint32_t a_bytes = (uint32_t)(((R + 7) & ~7) * 128);  // rows that exist in HBM
+            int wcount = 0;
+            // merge weights do not depend on K1: the first ring fill may run ahead of pdl_wait()
+            for (int cb = 0; cb < 4; ++cb) {
+                if (cb == 0) {
+                    // prefetch the first weight stages, then wait for K1's activations
+                    for (int tap = 0; tap < N_WST; ++tap) {
+                        mbar_expect_tx(&bars->w_full[tap], WST_BYTES);
+                        bulk_g2s(w_ring + tap * WST_BYTES, wm_tc + (size_t)(cb * 5 + tap) * (WST_BYTES / 4),
+                                 WST_BYTES, &bars->w_full[tap]);
+                    }
+                    pdl_wait();
+                    TC_STAMP(1);
+                }
+                const int as = cb & 1;
+                if (cb >= 2) mbar_wait(&bars->a_empty[as], ((cb >> 1) - 1) & 1);
+                mbar_expect_tx(&bars->a_full[as], 2 * a_bytes);
+                bulk_g2s(a_ring + as * lay.a_stage_bytes, img + (size_t)cb * rpad * 32, a_bytes,
+                         &bars->a_full[as]);
+                bulk_g2s(a_ring + as * lay.a_stage_bytes + tile_bytes,
+                         img + (size_t)(4 + cb) * rpad * 32, a_bytes, &bars->a_full[as]);
+                for (int tap = 0; tap < 5; ++tap, ++wcount) {
+                    if (wcount < N_WST) continue;  // already issued above
+                    const int ws = wcount % N_WST;
+                    mbar_wait(&bars->w_empty[ws], ((wcount / N_WST) - 1) & 1);
+                    mbar_expect_tx(&bars->w_full[ws], WST_BYTES);
+                    bulk_g2s(w_ring + ws * WST_BYTES, wm_tc + (size_t)wcount * (WST_BYTES / 4), WST_BYTES,
+                             &bars->w_full[ws]);
+                }
+            }
+            // x-projection weights: the ring aliases the merge rings, so wait until the merge MMAs
+            // have drained them (d_full) before the first fill
+            mbar_wait(&bars->d_full, 0);
+            for (int i = 0; i < 4; ++i) {  // i = nh * 2 + kb
+                const int xs = i % N_XST;
+                if (i >= N_XST) mbar_wait(&bars->x_empty[xs], ((i / N_XST) - 1) & 1);
+                mbar_expect_tx(&bars->x_full[xs], XST_BYTES);
+                bulk_g2s(x_ring + xs * XST_BYTES, wih_tc + (size_t)i * (XST_BYTES / 4), XST_BYTES,
+                         &bars->x_full[xs]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ==========================================
+        if (lane == 0) {
+            constexpr uint32_t idesc_m = idesc_tf32(128, 64);
+            constexpr uint32_t idesc_x = idesc_tf32(128, 128);
+            int wcount = 0;
+            for (int cb = 0; cb < 4; ++cb) {
+                const int as = cb & 1;
+                mbar_wait(&bars->a_full[as], (cb >> 1) & 1);
+                if (cb == 0) TC_STAMP(2);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_addr(a_ring + as * lay.a_stage_bytes);
+                const uint32_t a_lo = a_hi + tile_bytes;
+                for (int tap = 0; tap < 5; ++tap, ++wcount) {
+                    const int ws = wcount % N_WST;
+                    mbar_wait(&bars->w_full[ws], (wcount / N_WST) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_hi = smem_addr(w_ring + ws * WST_BYTES);
+                    const uint32_t b_lo = b_hi + 64 * 128;
+                    for (int mt = 0; mt < n_mt; ++mt) {
+                        // per M tile: two main chains (channel blocks {0,1} and {2,3}) + one for the
+                        // correction products: TMEM columns mt*192 + {0, 64, 128}
+                        const uint32_t row_off = (uint32_t)(mt_base[mt] + tap) * 128u;
+                        const uint32_t d0 = tmem + mt * 192;
+                        mma3_kblock(d0 + (cb >> 1) * 64, d0 + 128, a_hi + row_off, a_lo + row_off, b_hi,
+                                    b_lo, idesc_m, (cb & 1) == 0 && tap == 0, cb == 0 && tap == 0);
+                    }
+                    umma_commit(&bars->w_empty[ws]);
+                }
+                umma_commit(&bars->a_empty[as]);
+            }
+            umma_commit(&bars->d_full);
+            TC_STAMP(3);
+            // ---- x-projection: D2[nh][mt] (128 x 128) = m[mt] (128 x 64) . W_ih[nh]^T ----------------
+            mbar_wait(&bars->m_ready, 0);  // epilogue warps wrote the hi/lo m tiles
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TC_STAMP(5);
+            for (int i = 0; i < 4; ++i) {
+                const int nh = i >> 1, kb = i & 1, xs = i % N_XST;
+                mbar_wait(&bars->x_full[xs], (i / N_XST) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_hi = smem_addr(x_ring + xs * XST_BYTES);
+                const uint32_t b_lo = b_hi + 128 * 128;
+                for (int mt = 0; mt < n_mt; ++mt) {
+                    const uint32_t a_hi = smem_addr(m_tiles + ((mt * 2 + kb) * 2 + 0) * MT_BYTES);
+                    const uint32_t a_lo = a_hi + MT_BYTES;
+                    const uint32_t d2 = tmem + (nh * 2 + mt) * 128;  // 24 accumulate steps: one chain
+                    mma3_kblock(d2, d2, a_hi, a_lo, b_hi, b_lo, idesc_x, kb == 0, false);
+                }
+                umma_commit(&bars->x_empty[xs]);
+                if (kb == 1) umma_commit(&bars->d2_full[nh]);
+            }
+            TC_STAMP(6);
+        }
+    } else {
+        // ===================================== epilogue warps ======================================
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int row_in_tile = q * 32 + lane;
+        // ---- epilogue 1: merge accumulators -> bias + swish -> hi/lo m tiles (MMA-ready) ----------
+        mbar_wait(&bars->d_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) TC_STAMP(4);
+        for (int mt = 0; mt < n_mt; ++mt) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {  // 32 channels = one K block of the projection
+                float v[32];
+                {
+                    float v1[32], v2[32];
+                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + mt * 192 + half * 32;
+                    tmem_ld32(t0, v);
+                    tmem_ld32(t0 + 64, v1);
+                    tmem_ld32(t0 + 128, v2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = (v[i] + v1[i]) + v2[i];
+                }
+                float *t_hi = reinterpret_cast<float *>(m_tiles + ((mt * 2 + half) * 2 + 0) * MT_BYTES);
+                float *t_lo = reinterpret_cast<float *>(m_tiles + ((mt * 2 + half) * 2 + 1) * MT_BYTES);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float4 o;
+                    o.x = swishf_fast(v[4 * c4 + 0] + bmerge[half * 32 + 4 * c4 + 0]);
+                    o.y = swishf_fast(v[4 * c4 + 1] + bmerge[half * 32 + 4 * c4 + 1]);
+                    o.z = swishf_fast(v[4 * c4 + 2] + bmerge[half * 32 + 4 * c4 + 2]);
+                    o.w = swishf_fast(v[4 * c4 + 3] + bmerge[half * 32 + 4 * c4 + 3]);
+                    float4 hi, lo;
+                    split_tf32(o, hi, lo);
+                    const int off = row_in_tile * 32 + ((c4 ^ (row_in_tile & 7)) << 2);
+                    *reinterpret_cast<float4 *>(t_hi + off) = hi;
+                    *reinterpret_cast<float4 *>(t_lo + off) = lo;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> tensor-core reads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&bars->m_ready);
+        // ---- epilogue 2: projection accumulators + b1 -> xp[pos][256] in HBM ----------------------
+        for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&bars->d2_full[nh], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 64) TC_STAMP(7 + nh);
+            for (int mt = 0; mt < n_mt; ++mt) {
+                const int row = mt_base[mt] + row_in_tile;
+                const int chunk = row / T3, t = row - chunk * T3;
+                // rows of the second tile that the first one already covered are skipped
+                const bool ok = row < R && t < TM && (mt == 0 || row >= 128);
+                float *dst = xp + ((size_t)(chunk0 + chunk) * TM + t) * 256 + nh * 128;
+#pragma unroll 1
+                for (int cq = 0; cq < 4; ++cq) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (nh * 2 + mt) * 128 + cq * 32, v);
+                    if (ok) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(b1 + nh * 128 + cq * 32 + 4 * c4);
+                            *reinterpret_cast<float4 *>(dst + cq * 32 + 4 * c4) =
+                                make_float4(v[4 * c4] + bb.x, v[4 * c4 + 1] + bb.y, v[4 * c4 + 2] + bb.z,
+                                            v[4 * c4 + 3] + bb.w);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) TC_STAMP(9);
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+#undef TC_STAMP
+}
+}  // namespace tc
 
 // =================================================================================================
 // K3: LSTM1 recurrence (W_hh in registers) + single-step LSTM2 + fc
@@ -965,7 +1340,7 @@ __global__ void repack_kernel(const float *__restrict__ src, int64_t chunk_strid
 struct FusedWeights {
     float *dev = nullptr;  // one allocation holding every re-laid-out tensor
     size_t off_front = 0, off_slabs = 0, off_bmerge = 0, off_wih1T = 0, off_b1 = 0, off_whh4 = 0,
-           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0;
+           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0, off_wm_tc = 0, off_wih_tc = 0;
     int kmer_len = 0, num_out = 0;
 };
 
@@ -1067,6 +1442,43 @@ int fused_create(rb200_model *m, const float *blob) {
     fw->off_fcb = reserve(d.num_out);
     memcpy(host.data() + fw->off_fcb, blob + d.fc_b_off, d.num_out * sizeof(float));
 
+    // --- K2-TC: merge / W_ih weights split into TF32 hi + lo, K-major, 128B-swizzled tiles ---
+    auto tf32_split = [](float a, float &hi, float &lo) {
+        uint32_t u;
+        memcpy(&u, &a, 4);
+        u = (u + 0x1000u) & 0xFFFFE000u;  // round to nearest (ties away), low 13 mantissa bits cleared
+        memcpy(&hi, &u, 4);
+        lo = a - hi;
+    };
+    auto sw = [](int row, int k) { return row * 32 + ((((k >> 2) ^ (row & 7))) << 2) + (k & 3); };
+    fw->off_wm_tc = reserve((size_t)4 * 5 * 2 * 64 * 32);
+    {
+        const float *w = blob + d.merge_conv[0].w_off;  // [64][128][5]
+        for (int cb = 0; cb < 4; ++cb)
+            for (int tap = 0; tap < KW_MRG; ++tap) {
+                float *st = host.data() + fw->off_wm_tc + (size_t)(cb * 5 + tap) * (2 * 64 * 32);
+                for (int mo = 0; mo < SIZE; ++mo)
+                    for (int k = 0; k < 32; ++k) {
+                        float hi, lo;
+                        tf32_split(w[(mo * 2 * SIZE + cb * 32 + k) * KW_MRG + tap], hi, lo);
+                        st[sw(mo, k)] = hi;
+                        st[64 * 32 + sw(mo, k)] = lo;
+                    }
+            }
+    }
+    fw->off_wih_tc = reserve((size_t)4 * 2 * 128 * 32);
+    for (int nh = 0; nh < 2; ++nh)
+        for (int kb = 0; kb < 2; ++kb) {
+            float *st = host.data() + fw->off_wih_tc + (size_t)(nh * 2 + kb) * (2 * 128 * 32);
+            for (int row = 0; row < 128; ++row)
+                for (int k = 0; k < 32; ++k) {
+                    float hi, lo;
+                    tf32_split(blob[d.lstm_w_ih_off[0] + (nh * 128 + row) * SIZE + kb * 32 + k], hi, lo);
+                    st[sw(row, k)] = hi;
+                    st[128 * 32 + sw(row, k)] = lo;
+                }
+        }
+
     cudaError_t e = cudaMalloc(&fw->dev, host.size() * sizeof(float));
     if (e == cudaSuccess)
         e = cudaMemcpy(fw->dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -1080,6 +1492,7 @@ int fused_create(rb200_model *m, const float *blob) {
     cudaFuncSetAttribute(k1_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k2_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k3_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES);
+    cudaFuncSetAttribute(tc::k2tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     m->fused = fw;
     return RB200_OK;
 }
@@ -1142,21 +1555,26 @@ static int pick_cpb(int B, int cmax, int sm_count) {
 
 int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
                           int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
-                          int B, int T, float *logits, cudaStream_t stream) {
+                          int B, int T, float *logits, cudaStream_t stream, bool want_tc) {
     const FusedWeights *fw = m->fused;
     const Geometry g = make_geometry(T);
     RB200_REQUIRE(g.ok, "chunk_len %d not supported by the fused kernels", T);
-    const size_t live_bytes =
-        align256((size_t)B * g.cat_stride * 4) + align256((size_t)B * g.TM * 256 * 4);
+    const int cpb = pick_cpb(B, g.CL, m->sm_count);
+    const int grid = (B + cpb - 1) / cpb;
+    // tensor-core K2 (tcgen05 3xTF32) when requested / allowed and the CTA's rows fit two M tiles
+    const int tc_rpad = tc::rpad_for(cpb, g.T3);
+    const bool use_tc = want_tc && cpb * g.T3 <= 256 &&
+                        tc::smem_layout(tc_rpad).total <= 227 * 1024;
+    const size_t cat_bytes = use_tc ? align256((size_t)grid * 2 * 4 * tc_rpad * 32 * 4)
+                                    : align256((size_t)B * g.cat_stride * 4);
+    const size_t live_bytes = cat_bytes + align256((size_t)B * g.TM * 256 * 4);
     const size_t n_cat = (size_t)B * 128 * g.T3, n_xp = (size_t)B * 256 * g.TM;
     size_t need = live_bytes + 1024;
     if (m->keep_debug) need += align256(n_cat * 4) + align256(n_xp * 4);
     int rc = ws.ensure(need);
     if (rc) return rc;
     float *cat = reinterpret_cast<float *>(ws.base);
-    float *xp = reinterpret_cast<float *>(ws.base + align256((size_t)B * g.cat_stride * 4));
-    const int cpb = pick_cpb(B, g.CL, m->sm_count);
-    const int grid = (B + cpb - 1) / cpb;
+    float *xp = reinterpret_cast<float *>(ws.base + cat_bytes);
     const K1Smem l1 = k1_smem(g, fw->kmer_len, seq_width, map_width);
     const K2Smem l2 = k2_smem(g);
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1169,19 +1587,46 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     }
     // with profiling events between the kernels PDL cannot overlap them; launch plainly then
     const bool pdl = !m->profile;
+    const int k1_tc = use_tc ? tc_rpad : 0;
     if (pdl) {
         RB200_CUDA_TRY(launch_pdl(k1_front_kernel, grid, THREADS, l1.total_bytes, stream, sigs, seqs,
                                   seq_width, maps, map_width, lens,
                                   (const float *)(fw->dev + fw->off_front), cat, B, cpb, T,
-                                  fw->kmer_len));
+                                  fw->kmer_len, k1_tc));
     } else {
         k1_front_kernel<<<grid, THREADS, l1.total_bytes, stream>>>(
             sigs, seqs, seq_width, maps, map_width, lens, fw->dev + fw->off_front, cat, B, cpb, T,
-            fw->kmer_len);
+            fw->kmer_len, k1_tc);
     }
     RB200_CUDA_TRY(cudaGetLastError());
     if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[1], stream));
-    if (pdl) {
+    if (use_tc) {
+        const int smem_tc = tc::smem_layout(tc_rpad).total;
+        static long long *stamps_dev = nullptr;  // profiling aid: RB200_TC_STAMPS=1
+        static const bool want_stamps = getenv("RB200_TC_STAMPS") != nullptr;
+        if (want_stamps && !stamps_dev) cudaMalloc(&stamps_dev, 16 * sizeof(long long));
+        if (pdl) {
+            RB200_CUDA_TRY(launch_pdl(tc::k2tc_kernel, grid, tc::THREADS_TC, (size_t)smem_tc, stream,
+                                      (const float *)cat, (const float *)(fw->dev + fw->off_wm_tc),
+                                      (const float *)(fw->dev + fw->off_bmerge),
+                                      (const float *)(fw->dev + fw->off_wih_tc),
+                                      (const float *)(fw->dev + fw->off_b1), xp, B, cpb, g.T3, g.TM,
+                                      tc_rpad, stamps_dev));
+        } else {
+            tc::k2tc_kernel<<<grid, tc::THREADS_TC, smem_tc, stream>>>(
+                cat, fw->dev + fw->off_wm_tc, fw->dev + fw->off_bmerge, fw->dev + fw->off_wih_tc,
+                fw->dev + fw->off_b1, xp, B, cpb, g.T3, g.TM, tc_rpad, stamps_dev);
+        }
+        if (want_stamps) {
+            long long h[16];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, stamps_dev, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[k2tc stamps, cycles from start] pdl_wait_done %lld  A0_ready %lld  merge_issued %lld  "
+                    "d_full %lld  m_ready %lld  xproj_issued %lld  d2_full0 %lld  d2_full1 %lld  end %lld\n",
+                    h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0],
+                    h[7] - h[0], h[8] - h[0], h[9] - h[0]);
+        }
+    } else if (pdl) {
         RB200_CUDA_TRY(launch_pdl(k2_merge_kernel, grid, THREADS, l2.total_bytes, stream,
                                   (const float *)cat, (const float *)(fw->dev + fw->off_slabs),
                                   (const float *)(fw->dev + fw->off_bmerge),
@@ -1214,15 +1659,18 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     RB200_CUDA_TRY(cudaGetLastError());
     if (m->profile) RB200_CUDA_TRY(cudaEventRecord(ev[3], stream));
     m->launches += 3;
+    m->last_impl = use_tc ? RB200_IMPL_FUSED_TC : RB200_IMPL_FUSED;
     if (m->keep_debug) {
         // canonical [B][C][T] copies appended behind the live buffers
         m->debug.clear();
         float *dcat = reinterpret_cast<float *>(ws.base + live_bytes);
         float *dxp = reinterpret_cast<float *>(ws.base + live_bytes + align256(n_cat * 4));
-        repack_kernel<<<256, 256, 0, stream>>>(cat, g.cat_stride, XP, 0, dcat, B, 128, g.T3);
+        if (!use_tc) {
+            repack_kernel<<<256, 256, 0, stream>>>(cat, g.cat_stride, XP, 0, dcat, B, 128, g.T3);
+            m->debug.push_back({"cat", dcat, B, 128, g.T3});
+        }
         repack_kernel<<<256, 256, 0, stream>>>(xp, (int64_t)g.TM * 256, 256, 0, dxp, B, 256, g.TM);
         RB200_CUDA_TRY(cudaGetLastError());
-        m->debug.push_back({"cat", dcat, B, 128, g.T3});
         m->debug.push_back({"xproj", dxp, B, 256, g.TM});
     }
     return RB200_OK;

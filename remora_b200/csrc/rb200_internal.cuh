@@ -116,6 +116,6 @@ bool fused_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
 size_t fused_workspace_bytes(const rb200_model *m, int B, int T);
 int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
                           int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
-                          int B, int T, float *logits, cudaStream_t stream);
+                          int B, int T, float *logits, cudaStream_t stream, bool want_tc);
 
 }  // namespace rb200

@@ -28,7 +28,9 @@ def gpu_model(name):
 
 
 def impls_for(model):
-    return ["layers", "fused"] if model.info["arch"] == "ConvLSTM_w_ref" and \
+    """CUDA paths to check for this model: layer kernels always; for ConvLSTM_w_ref/64 also the fused
+    fp32 FFMA2 kernels and the tcgen05 (3xTF32) variant."""
+    return ["layers", "fused", "fused_tc"] if model.info["arch"] == "ConvLSTM_w_ref" and \
         model.info["size"] == 64 and fused_available(model) else ["layers"]
 
 
@@ -115,7 +117,7 @@ def test_forward_compact_vs_reference_logits(forward_cases):
             model.set_impl(impl)
             got = model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
                                         torch.from_numpy(maps), torch.from_numpy(lens))
-            assert model.last_impl == impl
+            assert model.last_impl in (impl, "fused") if impl == "fused_tc" else model.last_impl == impl
             err = np.abs(got.cpu().numpy() - want).max()
             assert err < LOGIT_TOL, f"{key} [{impl}] max-abs err {err}"
         model.set_impl("auto")
@@ -177,6 +179,11 @@ def test_per_layer_activations_vs_oracle(forward_cases):
         got_xp = model.debug_tensor("xproj").cpu()
         assert got_xp.shape == want_xp.shape
         assert (got_xp - want_xp).abs().max() < 1e-4, "fused merge conv + input projection"
+        model.set_impl("fused_tc")
+        model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
+                              torch.from_numpy(maps), torch.from_numpy(lens))
+        got_xp = model.debug_tensor("xproj").cpu()
+        assert (got_xp - want_xp).abs().max() < 1e-4, "tcgen05 merge conv + input projection"
     model.set_debug(False)
     model.set_impl("auto")
 
@@ -205,9 +212,11 @@ def test_batch_sizes_and_ragged_batches(B):
     # independence / determinism: tail chunks re-run as their own small batch
     k = min(B, 5)
     tail = [a[B - k:] for a in args]
-    again = model.forward_compact(*tail).cpu().numpy()
-    ref = outs[impls_for(model)[-1]][B - k:]
-    assert np.abs(again - ref).max() < 2e-6
+    for impl in impls_for(model):
+        model.set_impl(impl)
+        again = model.forward_compact(*tail).cpu().numpy()
+        assert np.abs(again - outs[impl][B - k:]).max() < 2e-6, impl
+    model.set_impl("auto")
 
 
 def test_empty_batch():
@@ -368,5 +377,8 @@ def test_full_size_batch_properties():
         if "fused" in impls_for(model):
             model.set_impl("layers")
             ref = model.forward_compact(*args)
-            model.set_impl("auto")
             assert (out - ref).abs().max() < LOGIT_TOL  # two fp32 paths, both within tolerance of the oracle
+            model.set_impl("fused_tc")
+            out_tc = model.forward_compact(*args)
+            model.set_impl("auto")
+            assert (out_tc - ref).abs().max() < LOGIT_TOL  # tensor-core (3xTF32) path
