@@ -197,6 +197,10 @@ __device__ __forceinline__ float tf32_hi(float a) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
     return __uint_as_float(u);
 }
+// remainder after the tensor core's own fp32 -> TF32 conversion (truncation of the low 13 bits)
+__device__ __forceinline__ float tf32_trunc_lo(float a) {
+    return a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(const float4 &a, float4 &hi, float4 &lo) {
     hi = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
     lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
@@ -295,16 +299,14 @@ __device__ __forceinline__ void conv16_s3_to_cat(const float *__restrict__ xs, i
 #pragma unroll
                 for (int q = 0; q < MRW / 4; ++q) dst[q] = o[q];
             } else {
-                // tensor-core image of this CTA: [hi|lo][channel block][row][32 ch, 128B-swizzled]
+                // tensor-core image of this CTA: [channel block][row][32 ch, 128B-swizzled], plain fp32
+                // (the tensor core truncates it to TF32 = "hi"; K2-TC derives the "lo" tile on chip)
                 const int row = chunk * T3 + t;
 #pragma unroll
                 for (int q = 0; q < MRW / 4; ++q) {
                     const int ch = ch_off + m0 + 4 * q;
                     const int off = ((ch >> 5) * tc_rpad + row) * 32 + ((((ch & 31) >> 2) ^ (row & 7)) << 2);
-                    float4 hi, lo;
-                    split_tf32(o[q], hi, lo);
-                    *reinterpret_cast<float4 *>(cat + off) = hi;
-                    *reinterpret_cast<float4 *>(cat + 4 * tc_rpad * 32 + off) = lo;
+                    *reinterpret_cast<float4 *>(cat + off) = o[q];
                 }
             }
         }
@@ -490,7 +492,7 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
     }
     __syncthreads();
     // classic layout: chunk-major rows; tensor-core layout: one pre-swizzled hi/lo image per CTA
-    float *cat_cta = tc_rpad ? cat + (size_t)blockIdx.x * (2 * 4 * tc_rpad * 32)
+    float *cat_cta = tc_rpad ? cat + (size_t)blockIdx.x * (4 * tc_rpad * 32)
                              : cat + (size_t)chunk0 * g.cat_stride;
     // ---- sig_conv3 (16 -> 64, k9, stride 3) -> cat[:, :, 0:64] -----------------------------------
     conv16_s3_to_cat<KW_SIG3>(act_s, g.s2_stride, wsm + fo.w_sig3, wsm + fo.b_sig3, cat_cta,
@@ -747,7 +749,8 @@ constexpr int N_WST = 4;                     // weight ring depth (16 KB stages)
 constexpr int XST_BYTES = 2 * 128 * 128;     // W_ih tile (128 gate rows x 32 k): hi + lo
 constexpr int N_XST = 2;
 constexpr int MT_BYTES = 128 * 128;          // one [128 rows][32 k] tile
-constexpr int THREADS_TC = 192;
+constexpr int THREADS_TC = 320;              // producer + MMA + 8 epilogue/converter warps
+constexpr int EPI_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 
 struct Geo {
@@ -832,7 +835,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 struct Bars {
-    uint64_t a_full[2], a_empty[2], w_full[N_WST], w_empty[N_WST], x_full[N_XST], x_empty[N_XST];
+    uint64_t a_full[2], a_conv[2], a_empty[2], w_full[N_WST], w_empty[N_WST], x_full[N_XST], x_empty[N_XST];
     uint64_t d_full, m_ready, d2_full[2];
     uint32_t tmem_base;
 };
@@ -864,6 +867,7 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->a_full[i], 1);
+            mbar_init(&bars->a_conv[i], EPI_THREADS);
             mbar_init(&bars->a_empty[i], 1);
             mbar_init(&bars->d2_full[i], 1);
         }
@@ -876,7 +880,7 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
             mbar_init(&bars->x_empty[i], 1);
         }
         mbar_init(&bars->d_full, 1);
-        mbar_init(&bars->m_ready, 128);
+        mbar_init(&bars->m_ready, EPI_THREADS);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -893,7 +897,7 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
     if (warp == 0) {
         // ===================================== TMA producer ========================================
         if (lane == 0) {
-            const float *img = cat_img + (size_t)blockIdx.x * (2 * 4 * rpad * 32);
+            const float *img = cat_img + (size_t)blockIdx.x * (4 * rpad * 32);
             const uint32_t a_bytes = (uint32_t)(((R + 7) & ~7) * 128);  // rows that exist in HBM
             int wcount = 0;
             // merge weights do not depend on K1: the first ring fill may run ahead of pdl_wait()
@@ -910,11 +914,9 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
                 }
                 const int as = cb & 1;
                 if (cb >= 2) mbar_wait(&bars->a_empty[as], ((cb >> 1) - 1) & 1);
-                mbar_expect_tx(&bars->a_full[as], 2 * a_bytes);
+                mbar_expect_tx(&bars->a_full[as], a_bytes);
                 bulk_g2s(a_ring + as * lay.a_stage_bytes, img + (size_t)cb * rpad * 32, a_bytes,
                          &bars->a_full[as]);
-                bulk_g2s(a_ring + as * lay.a_stage_bytes + tile_bytes,
-                         img + (size_t)(4 + cb) * rpad * 32, a_bytes, &bars->a_full[as]);
                 for (int tap = 0; tap < 5; ++tap, ++wcount) {
                     if (wcount < N_WST) continue;  // already issued above
                     const int ws = wcount % N_WST;
@@ -943,7 +945,7 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
             int wcount = 0;
             for (int cb = 0; cb < 4; ++cb) {
                 const int as = cb & 1;
-                mbar_wait(&bars->a_full[as], (cb >> 1) & 1);
+                mbar_wait(&bars->a_conv[as], (cb >> 1) & 1);  // fp32 tile landed and its lo tile is written
                 if (cb == 0) TC_STAMP(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_addr(a_ring + as * lay.a_stage_bytes);
@@ -992,14 +994,33 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
     } else {
         // ===================================== epilogue warps ======================================
         const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int colh = (warp - 2) >> 2;  // two warps share a quarter: each takes half of the columns
         const int row_in_tile = q * 32 + lane;
+        const int et = tid - 64;           // 0..255
+        // ---- converter: lo = a - trunc_tf32(a) for every activation tile the producer lands -------
+        {
+            const int n4 = ((R + 7) & ~7) * 8;  // float4s per tile
+            for (int cb = 0; cb < 4; ++cb) {
+                const int as = cb & 1;
+                mbar_wait(&bars->a_full[as], (cb >> 1) & 1);
+                const float4 *src = reinterpret_cast<const float4 *>(a_ring + as * lay.a_stage_bytes);
+                float4 *dst = reinterpret_cast<float4 *>(a_ring + as * lay.a_stage_bytes + tile_bytes);
+                for (int i = et; i < n4; i += EPI_THREADS) {
+                    const float4 a = src[i];
+                    dst[i] = make_float4(tf32_trunc_lo(a.x), tf32_trunc_lo(a.y), tf32_trunc_lo(a.z),
+                                         tf32_trunc_lo(a.w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&bars->a_conv[as]);
+            }
+        }
         // ---- epilogue 1: merge accumulators -> bias + swish -> hi/lo m tiles (MMA-ready) ----------
         mbar_wait(&bars->d_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 64) TC_STAMP(4);
         for (int mt = 0; mt < n_mt; ++mt) {
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {  // 32 channels = one K block of the projection
+            {
+                const int half = colh;  // 32 channels = one K block of the projection
                 float v[32];
                 {
                     float v1[32], v2[32];
@@ -1042,7 +1063,7 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
                 const bool ok = row < R && t < TM && (mt == 0 || row >= 128);
                 float *dst = xp + ((size_t)(chunk0 + chunk) * TM + t) * 256 + nh * 128;
 #pragma unroll 1
-                for (int cq = 0; cq < 4; ++cq) {
+                for (int cq = 2 * colh; cq < 2 * colh + 2; ++cq) {
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (nh * 2 + mt) * 128 + cq * 32, v);
                     if (ok) {
@@ -1565,7 +1586,7 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     const int tc_rpad = tc::rpad_for(cpb, g.T3);
     const bool use_tc = want_tc && cpb * g.T3 <= 256 &&
                         tc::smem_layout(tc_rpad).total <= 227 * 1024;
-    const size_t cat_bytes = use_tc ? align256((size_t)grid * 2 * 4 * tc_rpad * 32 * 4)
+    const size_t cat_bytes = use_tc ? align256((size_t)grid * 4 * tc_rpad * 32 * 4)
                                     : align256((size_t)B * g.cat_stride * 4);
     const size_t live_bytes = cat_bytes + align256((size_t)B * g.TM * 256 * 4);
     const size_t n_cat = (size_t)B * 128 * g.T3, n_xp = (size_t)B * 256 * g.TM;
