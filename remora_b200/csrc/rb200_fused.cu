@@ -39,6 +39,7 @@ constexpr int SLAB_C = 32;                              // merge conv: input cha
 constexpr int SLAB_FLOATS = 5 * SLAB_C * SIZE;          // 10240 floats = 40 KB
 constexpr int N_SLABS = 2 * SIZE / SLAB_C;              // 4
 constexpr int KW_SIG1 = 5, KW_SIG2 = 5, KW_SIG3 = 9, KW_SEQ1 = 5, KW_SEQ2 = 13, KW_MRG = 5;
+constexpr int GROW = 20;  // pitch (floats) of 16-float gather rows: 20 r mod 32 spreads rows over all banks
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA) --------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
@@ -99,7 +100,7 @@ struct FrontOffsets {  // float offsets inside the K1 weight blob (all multiples
     int w_sig1, b_sig1, w_sig2, b_sig2, w_sig3, b_sig3, w_seq1, z_seq1, b_seq1, w_seq2, b_seq2, total;
 };
 
-__host__ __device__ inline FrontOffsets front_offsets(int kmer_len) {
+__host__ __device__ inline FrontOffsets front_offsets(int kmer_len, bool tc = false) {
     FrontOffsets o;
     int cur = 0;
     auto take = [&](int n) {
@@ -111,12 +112,12 @@ __host__ __device__ inline FrontOffsets front_offsets(int kmer_len) {
     o.b_sig1 = take(4);
     o.w_sig2 = take(KW_SIG2 * 4 * 16);       // [j][ci][co]
     o.b_sig2 = take(16);
-    o.w_sig3 = take(KW_SIG3 * 16 * SIZE);    // [j*16+ci][co]
+    o.w_sig3 = take(tc ? 0 : KW_SIG3 * 16 * SIZE);    // [j*16+ci][co] (tensor-core K1 streams its own tiles)
     o.b_sig3 = take(SIZE);
-    o.w_seq1 = take(KW_SEQ1 * kmer_len * 4 * 16);  // [j][p][base][co]
-    o.z_seq1 = take(16);                           // all-zero row: target of N bases / uncovered samples
+    o.w_seq1 = take(KW_SEQ1 * kmer_len * 4 * GROW);  // [j][p][base][co], row pitch GROW
+    o.z_seq1 = take(GROW);                           // all-zero row: target of N bases / uncovered samples
     o.b_seq1 = take(16);
-    o.w_seq2 = take(KW_SEQ2 * 16 * SIZE);    // [j*16+ci][co]
+    o.w_seq2 = take(tc ? 0 : KW_SEQ2 * 16 * SIZE);    // [j*16+ci][co]
     o.b_seq2 = take(SIZE);
     o.total = cur;
     return o;
@@ -323,7 +324,7 @@ __device__ __forceinline__ void seq1_gather(const float *__restrict__ w, const f
                                             int zero_off, const int8_t *__restrict__ seq_s,
                                             const int16_t *__restrict__ sidx_s,
                                             float *__restrict__ act_s, int seq_width, int C, int T,
-                                            int Q1, int q1_stride, int kmer_rt) {
+                                            int Q1, int q1_stride, int kmer_rt, int qp = QP) {
     const int K = KT > 0 ? KT : kmer_rt;
     for (int i = threadIdx.x; i < C * Q1; i += THREADS) {
         const int c = i / Q1, t = i - c * Q1;
@@ -335,13 +336,13 @@ __device__ __forceinline__ void seq1_gather(const float *__restrict__ w, const f
         for (int j = 0; j < KW_SEQ1; ++j) {
             const int s = sidx_s[c * T + t + j];
             const int8_t *sp = sq + (s < 0 ? 0 : s);
-            const int joff = j * K * 64;
+            const int joff = j * K * 4 * GROW;
 #pragma unroll
             for (int p = 0; p < (KT > 0 ? KT : 16); ++p) {
                 if (KT == 0 && p >= K) break;
                 const int base = sp[p];
                 const bool ok = s >= 0 && base >= 0 && base <= 3;
-                const int off = ok ? joff + (p * 4 + base) * 16 : zero_off;
+                const int off = ok ? joff + (p * 4 + base) * GROW : zero_off;
                 const float4 *wv = reinterpret_cast<const float4 *>(w + off);
                 const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
                 a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
@@ -354,7 +355,7 @@ __device__ __forceinline__ void seq1_gather(const float *__restrict__ w, const f
                 a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
             }
         }
-        float4 *dst = reinterpret_cast<float4 *>(act_s + c * q1_stride + t * QP);
+        float4 *dst = reinterpret_cast<float4 *>(act_s + c * q1_stride + t * qp);
 #pragma unroll
         for (int o = 0; o < 4; ++o)
             dst[o] = make_float4(swishf_fast(a[2 * o].x), swishf_fast(a[2 * o].y),
@@ -362,42 +363,87 @@ __device__ __forceinline__ void seq1_gather(const float *__restrict__ w, const f
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
-                const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
-                const float *__restrict__ wfront, float *__restrict__ cat, int B, int CPB, int T,
-                int kmer_len, int tc_rpad) {
-    extern __shared__ __align__(128) float sm[];
-    const Geometry g = make_geometry(T);
-    const K1Smem lay = k1_smem(g, kmer_len, seq_width, map_width);
-    const FrontOffsets fo = front_offsets(kmer_len);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
-    float *wsm = sm + lay.weights;
-    float *sig_s = sm + lay.sig;
-    float *s1_s = sm + lay.s1;
-    float *act_s = sm + lay.act;
-    int16_t *sidx_s = reinterpret_cast<int16_t *>(sm + lay.sidx);
-    int8_t *seq_s = reinterpret_cast<int8_t *>(sm + lay.seq);
-    int16_t *map_s = reinterpret_cast<int16_t *>(sm + lay.map);
-    int *len_s = reinterpret_cast<int *>(sm + lay.len);
-
-    const int tid = threadIdx.x;
-    const int chunk0 = blockIdx.x * CPB;
-    const int C = min(CPB, B - chunk0);
-    const int CL = g.CL;
-
-    pdl_launch_dependents();  // K2 may begin its weight prefetch as soon as SMs free up
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
+// Two-stage form of the seq_conv1 gather: every sample covered by the same base shares its k-mer, so
+// first sum the k weight columns once per (base, tap) - Gs[c][s][j][16] - and then add five of those
+// rows per output step.  Cuts the shared-memory gather traffic ~9x versus gathering 5*k columns per
+// output step (the direct form is bandwidth-bound on shared memory: 45 x 64 B per step).
+template <int KT>
+__device__ __forceinline__ void seq1_gather_two_stage(
+    const float *__restrict__ w, const float *__restrict__ b, int zero_off,
+    const int8_t *__restrict__ seq_s, const int16_t *__restrict__ sidx_s, const int *__restrict__ len_s,
+    float *__restrict__ gs, float *__restrict__ act_s, int seq_width, int LM, int C, int T, int Q1,
+    int q1_stride, int kmer_rt, int qp) {
+    const int K = KT > 0 ? KT : kmer_rt;
+    for (int i = threadIdx.x; i < C * LM * KW_SEQ1; i += THREADS) {
+        const int j = i % KW_SEQ1;
+        const int cs = i / KW_SEQ1;
+        const int c = cs / LM, sb = cs - c * LM;
+        if (sb >= len_s[c]) continue;
+        float2 a[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a[o] = make_float2(0.f, 0.f);
+        const int8_t *sp = seq_s + c * seq_width + sb;
+        const int joff = j * K * 4 * GROW;
+#pragma unroll
+        for (int p = 0; p < (KT > 0 ? KT : 16); ++p) {
+            if (KT == 0 && p >= K) break;
+            const int base = sp[p];
+            const int off = (base >= 0 && base <= 3) ? joff + (p * 4 + base) * GROW : zero_off;
+            const float4 *wv = reinterpret_cast<const float4 *>(w + off);
+            const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
+            a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+            a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+            a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+            a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+            a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+            a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+            a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+            a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+        }
+        float4 *dst = reinterpret_cast<float4 *>(gs + (size_t)i * GROW);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            dst[o] = make_float4(a[2 * o].x, a[2 * o].y, a[2 * o + 1].x, a[2 * o + 1].y);
     }
     __syncthreads();
-    if (tid == 0) {
-        const uint32_t bytes = (uint32_t)fo.total * 4u;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(wsm, wfront, bytes, bar);
+    for (int i = threadIdx.x; i < C * Q1; i += THREADS) {
+        const int c = i / Q1, t = i - c * Q1;
+        float2 a[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
+#pragma unroll
+        for (int j = 0; j < KW_SEQ1; ++j) {
+            const int sb = sidx_s[c * T + t + j];
+            if (sb < 0) continue;  // sample not covered by any base: no one-hot entries
+            const float4 *gv = reinterpret_cast<const float4 *>(gs + ((size_t)(c * LM + sb) * KW_SEQ1 + j) * GROW);
+            const float4 v0 = gv[0], v1 = gv[1], v2 = gv[2], v3 = gv[3];
+            a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+            a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+            a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+            a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+            a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+            a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+            a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+            a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+        }
+        float4 *dst = reinterpret_cast<float4 *>(act_s + c * q1_stride + t * qp);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            dst[o] = make_float4(swishf_fast(a[2 * o].x), swishf_fast(a[2 * o].y),
+                                 swishf_fast(a[2 * o + 1].x), swishf_fast(a[2 * o + 1].y));
     }
-    pdl_wait();  // inputs (and the cat buffer we overwrite) belong to earlier work in the stream
+}
+
+// Phases shared by both K1 variants.  k1_stage_inputs: stage the compact inputs, move-table expansion,
+// wait for the front weight blob.  k1_sig12: sig_conv1, sig_conv2 (output s2 channel-last with row
+// pitch `qp`, chunk stride `s2_stride`).
+__device__ __forceinline__ void k1_stage_inputs(
+    const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
+    const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens, int chunk0, int C,
+    int T, int kmer_len, const Geometry &g, const FrontOffsets &fo, uint64_t *bar, const float *wsm,
+    float *sig_s, float *s1_s, float *act_s, int16_t *sidx_s, int8_t *seq_s, int16_t *map_s, int *len_s,
+    int s2_stride, int qp) {
+    const int tid = threadIdx.x;
     // ---- stage the compact inputs of this CTA's chunks ------------------------------------------
     for (int i = tid; i < C * T; i += THREADS) {
         sig_s[i] = sigs[(size_t)chunk0 * T + i];
@@ -430,7 +476,12 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
     }
     mbar_wait(bar, 0);  // weights have landed
     __syncthreads();
+}
 
+__device__ __forceinline__ void k1_sig12(int C, int T, const Geometry &g, const FrontOffsets &fo,
+                                         const float *wsm, const float *sig_s, float *s1_s, float *act_s,
+                                         int s2_stride, int qp) {
+    const int tid = threadIdx.x;
     // ---- sig_conv1 (1 -> 4, k5) -------------------------------------------------------------------
     {
         const float *w = wsm + fo.w_sig1;  // [j][co]
@@ -485,12 +536,63 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
                     acc[7] = fmaf(wb.w, xs4[ci], acc[7]);
                 }
             }
-            float4 *dst = reinterpret_cast<float4 *>(act_s + c * g.s2_stride + t * QP + half * 8);
+            float4 *dst = reinterpret_cast<float4 *>(act_s + c * s2_stride + t * qp + half * 8);
             dst[0] = make_float4(swishf_fast(acc[0]), swishf_fast(acc[1]), swishf_fast(acc[2]), swishf_fast(acc[3]));
             dst[1] = make_float4(swishf_fast(acc[4]), swishf_fast(acc[5]), swishf_fast(acc[6]), swishf_fast(acc[7]));
         }
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void k1_stage_and_sig12(
+    const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
+    const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens, int chunk0, int C,
+    int T, int kmer_len, const Geometry &g, const FrontOffsets &fo, uint64_t *bar, const float *wsm,
+    float *sig_s, float *s1_s, float *act_s, int16_t *sidx_s, int8_t *seq_s, int16_t *map_s, int *len_s,
+    int s2_stride, int qp) {
+    k1_stage_inputs(sigs, seqs, seq_width, maps, map_width, lens, chunk0, C, T, kmer_len, g, fo, bar, wsm,
+                    sig_s, s1_s, act_s, sidx_s, seq_s, map_s, len_s, s2_stride, qp);
+    k1_sig12(C, T, g, fo, wsm, sig_s, s1_s, act_s, s2_stride, qp);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
+                const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
+                const float *__restrict__ wfront, float *__restrict__ cat, int B, int CPB, int T,
+                int kmer_len, int tc_rpad) {
+    extern __shared__ __align__(128) float sm[];
+    const Geometry g = make_geometry(T);
+    const K1Smem lay = k1_smem(g, kmer_len, seq_width, map_width);
+    const FrontOffsets fo = front_offsets(kmer_len);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+    float *wsm = sm + lay.weights;
+    float *sig_s = sm + lay.sig;
+    float *s1_s = sm + lay.s1;
+    float *act_s = sm + lay.act;
+    int16_t *sidx_s = reinterpret_cast<int16_t *>(sm + lay.sidx);
+    int8_t *seq_s = reinterpret_cast<int8_t *>(sm + lay.seq);
+    int16_t *map_s = reinterpret_cast<int16_t *>(sm + lay.map);
+    int *len_s = reinterpret_cast<int *>(sm + lay.len);
+
+    const int tid = threadIdx.x;
+    const int chunk0 = blockIdx.x * CPB;
+    const int C = min(CPB, B - chunk0);
+    const int CL = g.CL;
+
+    pdl_launch_dependents();  // K2 may begin its weight prefetch as soon as SMs free up
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)fo.total * 4u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(wsm, wfront, bytes, bar);
+    }
+    pdl_wait();  // inputs (and the cat buffer we overwrite) belong to earlier work in the stream
+    k1_stage_and_sig12(sigs, seqs, seq_width, maps, map_width, lens, chunk0, C, T, kmer_len, g, fo, bar, wsm,
+                       sig_s, s1_s, act_s, sidx_s, seq_s, map_s, len_s, g.s2_stride, QP);
     // classic layout: chunk-major rows; tensor-core layout: one pre-swizzled hi/lo image per CTA
     float *cat_cta = tc_rpad ? cat + (size_t)blockIdx.x * (4 * tc_rpad * 32)
                              : cat + (size_t)chunk0 * g.cat_stride;
@@ -1086,6 +1188,262 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 #undef TC_STAMP
 }
+
+// =================================================================================================
+// K1-TC: front kernel with sig_conv3 / seq_conv2 on tcgen05 (3xTF32), feeding K2-TC's image format
+// =================================================================================================
+// The two stride-3 convolutions are GEMMs with M = output steps (same two 128-row tiles as K2-TC),
+// N = 64 and K = taps x 16 channels.  A stride-3 window cannot be expressed as a descriptor shift, so
+// the im2col tile of one 32-wide K block (two taps x 16 channels = two adjacent 64-byte activation
+// rows, contiguous because the activation pitch is exactly 16 floats here) is copied into a
+// 128B-swizzled tile by all threads, together with its TF32 remainder tile; one elected thread then
+// issues that K block's MMAs, which run asynchronously while the CTA builds the next tile (two tile
+// stages, freed by tcgen05.commit -> mbarrier).  Weight tiles (hi/lo, pre-swizzled on the host) stream
+// through a 2-stage TMA ring driven by the same thread.  The sig_conv3 MMAs overlap the seq_conv1
+// gather phase; both accumulators are drained at the end into the fp32 image K2-TC consumes.
+constexpr int K1TC_NKB_SIG = (KW_SIG3 * 16 + 31) / 32;  // 5
+constexpr int K1TC_NKB_SEQ = (KW_SEQ2 * 16 + 31) / 32;  // 7
+constexpr int K1TC_MAX_CPB = 7;
+
+struct K1Bars {
+    uint64_t wfront, a_full[2], a_empty[2], w_full[3], w_empty[3], d_done;
+    uint32_t tmem_base;
+};
+struct K1TcSmem {
+    int a_stages, w_ring, weights, sig, s1, act, sidx, seq, map, len, total;  // byte offsets
+    int stage_bytes, act_stride;                                             // act_stride in floats
+};
+__host__ __device__ inline K1TcSmem k1tc_smem(const Geometry &g, int cl, int kmer_len, int seq_width,
+                                              int map_width, int rpad, int nw = 2) {
+    K1TcSmem l;
+    const FrontOffsets fo = front_offsets(kmer_len, true);
+    int cur = 1024;  // barriers
+    l.a_stages = cur;
+    l.stage_bytes = 2 * rpad * 128;
+    cur += 2 * l.stage_bytes;
+    l.w_ring = cur;
+    cur += nw * WST_BYTES;  // weight ring: 3 stages when they fit (hides the TMA latency), else 2
+    auto take = [&](int bytes) {
+        int at = cur;
+        cur += (bytes + 15) & ~15;
+        return at;
+    };
+    l.weights = take(fo.total * 4);
+    l.sig = take(cl * g.T * 4);
+    l.s1 = take(cl * g.T1 * 16);
+    l.act_stride = (g.Q1 > g.T2 ? g.Q1 : g.T2) * 16;
+    l.act = take(cl * l.act_stride * 4);
+    l.sidx = take(cl * g.T * 2);
+    l.seq = take(cl * seq_width);
+    l.map = take(cl * map_width * 2);
+    l.len = take(cl * 4);
+    l.total = cur;
+    return l;
+}
+
+// one stride-3 convolution.  Warp 0: streams the weight tiles (2-stage TMA ring) and issues the MMAs;
+// warps 1..7: build the im2col tiles (2 stages).  Producer/consumer hand-off through mbarriers only:
+// a_full (builders -> MMA warp), a_empty / w_empty (tcgen05.commit -> builders / TMA).
+constexpr int BUILDERS = THREADS - 32;
+template <int KW>
+__device__ __forceinline__ void k1tc_conv(const float *__restrict__ act, int act_stride, int T3, int R, int rpad,
+                                          uint8_t *a_stages, int stage_bytes, uint8_t *w_ring,
+                                          const float *__restrict__ w_tc, K1Bars *bars, uint32_t tmem_d,
+                                          int n_mt, int base1, int &kcount, int total_kb, int nw) {
+    constexpr int NKB = (KW * 16 + 31) / 32;
+    constexpr uint32_t idesc = idesc_tf32(128, 64);
+    const int k0 = kcount;
+    kcount += NKB;
+    if (threadIdx.x >= 32) {
+        // ---------------------------------- tile builders -------------------------------------------
+        const int bt = threadIdx.x - 32;
+        for (int kbk = 0; kbk < NKB; ++kbk) {
+            const int kc = k0 + kbk, st = kc & 1;
+            if (kc >= 2) mbar_wait(&bars->a_empty[st], ((kc >> 1) - 1) & 1);
+            float *t_hi = reinterpret_cast<float *>(a_stages + st * stage_bytes);
+            float *t_lo = t_hi + rpad * 32;
+            const bool tap_hi_ok = 2 * kbk + 1 < KW;
+            for (int i = bt; i < R * 8; i += BUILDERS) {
+                const int r = i >> 3, q = i & 7;
+                const int chunk = r / T3, tp = r - chunk * T3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < 4 || tap_hi_ok)
+                    v = *reinterpret_cast<const float4 *>(act + chunk * act_stride +
+                                                          (3 * tp + 2 * kbk + (q >> 2)) * 16 + (q & 3) * 4);
+                const int off = r * 32 + ((q ^ (r & 7)) << 2);
+                *reinterpret_cast<float4 *>(t_hi + off) = v;
+                *reinterpret_cast<float4 *>(t_lo + off) =
+                    make_float4(tf32_trunc_lo(v.x), tf32_trunc_lo(v.y), tf32_trunc_lo(v.z), tf32_trunc_lo(v.w));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&bars->a_full[st]);
+        }
+    } else if (threadIdx.x == 0) {
+        // ---------------------------------- TMA + MMA issuer ----------------------------------------
+        for (int kbk = 0; kbk < NKB; ++kbk) {
+            const int kc = k0 + kbk, st = kc & 1, ws = kc % nw;
+            mbar_wait(&bars->w_full[ws], (kc / nw) & 1);
+            mbar_wait(&bars->a_full[st], (kc >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_addr(a_stages + st * stage_bytes), a_lo = a_hi + rpad * 128;
+            const uint32_t b_hi = smem_addr(w_ring + ws * WST_BYTES), b_lo = b_hi + 64 * 128;
+            for (int mt = 0; mt < n_mt; ++mt) {
+                const uint32_t ro = (uint32_t)(mt ? base1 : 0) * 128u;
+                mma3_kblock(tmem_d + mt * 128, tmem_d + mt * 128 + 64, a_hi + ro, a_lo + ro, b_hi, b_lo, idesc,
+                            kbk == 0, kbk == 0);
+            }
+            umma_commit(&bars->a_empty[st]);
+            umma_commit(&bars->w_empty[ws]);
+            // keep the weight ring nw-1 K blocks ahead: K block kc+nw-1 goes into the stage that K block
+            // kc-1 used (its MMAs were issued one iteration ago)
+            const int nxt = kc + nw - 1;
+            if (nxt < total_kb) {
+                const int ns = nxt % nw;
+                if (nxt >= nw) mbar_wait(&bars->w_empty[ns], ((nxt / nw) - 1) & 1);
+                mbar_expect_tx(&bars->w_full[ns], WST_BYTES);
+                bulk_g2s(w_ring + ns * WST_BYTES, w_tc + (size_t)nxt * (WST_BYTES / 4), WST_BYTES,
+                         &bars->w_full[ns]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k1tc_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs, int seq_width,
+                  const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
+                  const float *__restrict__ wfront, const float *__restrict__ w_tc,
+                  float *__restrict__ cat_img, int B, int CPB, int T, int kmer_len, int rpad, int CLs,
+                  int nw, long long *__restrict__ stamps) {
+    extern __shared__ __align__(1024) uint8_t smk[];
+#define K1_STAMP(i) do { if (stamps && blockIdx.x == 1 && threadIdx.x == 0) stamps[i] = clock64(); } while (0)
+    const Geometry g = make_geometry(T);
+    const K1TcSmem lay = k1tc_smem(g, CLs, kmer_len, seq_width, map_width, rpad, nw);
+    const FrontOffsets fo = front_offsets(kmer_len, true);
+    K1Bars *bars = reinterpret_cast<K1Bars *>(smk);
+    uint8_t *a_stages = smk + lay.a_stages;
+    uint8_t *w_ring = smk + lay.w_ring;
+    float *wsm = reinterpret_cast<float *>(smk + lay.weights);
+    float *sig_s = reinterpret_cast<float *>(smk + lay.sig);
+    float *s1_s = reinterpret_cast<float *>(smk + lay.s1);
+    float *act_s = reinterpret_cast<float *>(smk + lay.act);
+    int16_t *sidx_s = reinterpret_cast<int16_t *>(smk + lay.sidx);
+    int8_t *seq_s = reinterpret_cast<int8_t *>(smk + lay.seq);
+    int16_t *map_s = reinterpret_cast<int16_t *>(smk + lay.map);
+    int *len_s = reinterpret_cast<int *>(smk + lay.len);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk0 = blockIdx.x * CPB;
+    const int C = min(CPB, B - chunk0);
+    const int R = C * g.T3;
+    const int n_mt = R > 128 ? 2 : 1;
+    const int base1 = R > 128 ? R - 128 : 0;
+    constexpr int TOTAL_KB = K1TC_NKB_SIG + K1TC_NKB_SEQ;
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        mbar_init(&bars->wfront, 1);
+        mbar_init(&bars->d_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->a_full[i], BUILDERS);
+            mbar_init(&bars->a_empty[i], 1);
+        }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&bars->w_full[i], 1);
+            mbar_init(&bars->w_empty[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_addr(&bars->tmem_base)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)fo.total * 4u;
+        mbar_expect_tx(&bars->wfront, bytes);
+        bulk_g2s(wsm, wfront, bytes, &bars->wfront);
+        for (int i = 0; i < nw - 1; ++i) {  // weights of the first nw-1 K blocks
+            mbar_expect_tx(&bars->w_full[i], WST_BYTES);
+            bulk_g2s(w_ring + i * WST_BYTES, w_tc + (size_t)i * (WST_BYTES / 4), WST_BYTES, &bars->w_full[i]);
+        }
+    }
+    K1_STAMP(0);
+    pdl_wait();  // inputs (and the image we overwrite) belong to earlier work in the stream
+    K1_STAMP(1);
+    k1_stage_inputs(sigs, seqs, seq_width, maps, map_width, lens, chunk0, C, T, kmer_len, g, fo, &bars->wfront,
+                    wsm, sig_s, s1_s, act_s, sidx_s, seq_s, map_s, len_s, lay.act_stride, 16);
+    // ---- sequence track first: seq_conv1 (two-stage gather; the per-base sums live in the still unused
+    // tile stages) -> q1 in act_s -> seq_conv2 on the tensor core, TMEM columns [256, 512) -----------------
+    {
+        float *gs = reinterpret_cast<float *>(a_stages);
+        const int LM = map_width - 1;
+        if (kmer_len == 9)
+            seq1_gather_two_stage<9>(wsm + fo.w_seq1, wsm + fo.b_seq1, fo.z_seq1 - fo.w_seq1, seq_s, sidx_s,
+                                     len_s, gs, act_s, seq_width, LM, C, T, g.Q1, lay.act_stride, kmer_len, 16);
+        else
+            seq1_gather_two_stage<0>(wsm + fo.w_seq1, wsm + fo.b_seq1, fo.z_seq1 - fo.w_seq1, seq_s, sidx_s,
+                                     len_s, gs, act_s, seq_width, LM, C, T, g.Q1, lay.act_stride, kmer_len, 16);
+    }
+    __syncthreads();
+    K1_STAMP(2);
+    int kcount = 0;
+    k1tc_conv<KW_SEQ2>(act_s, lay.act_stride, g.T3, R, rpad, a_stages, lay.stage_bytes, w_ring, w_tc, bars,
+                       tmem + 256, n_mt, base1, kcount, TOTAL_KB, nw);
+    K1_STAMP(3);
+    __syncthreads();  // every q1 row has been copied into tiles: act_s may be overwritten
+    // ---- signal track: sig_conv1, sig_conv2 (run while the tensor core finishes seq_conv2), then
+    // sig_conv3 on the tensor core, TMEM columns [0, 256) ------------------------------------------------
+    k1_sig12(C, T, g, fo, wsm, sig_s, s1_s, act_s, lay.act_stride, 16);
+    K1_STAMP(4);
+    k1tc_conv<KW_SIG3>(act_s, lay.act_stride, g.T3, R, rpad, a_stages, lay.stage_bytes, w_ring, w_tc, bars,
+                       tmem, n_mt, base1, kcount, TOTAL_KB, nw);
+    if (tid == 0) umma_commit(&bars->d_done);
+    K1_STAMP(5);
+    // ---- epilogue: TMEM -> bias + swish -> fp32 128B-swizzled image [channel block][row][32] -------
+    mbar_wait(&bars->d_done, 0);
+    K1_STAMP(6);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int q = warp & 3, gsel = warp >> 2;  // TMEM lane quarter; 0 = sig_conv3, 1 = seq_conv2
+        const float *bias = wsm + (gsel ? fo.b_seq2 : fo.b_sig3);
+        float *img = cat_img + (size_t)blockIdx.x * (4 * rpad * 32);
+        for (int mt = 0; mt < n_mt; ++mt) {
+            const int row = (mt ? base1 : 0) + q * 32 + lane;
+            const bool ok = row < R && (mt == 0 || row >= 128);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float v[32], v2[32];
+                const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + gsel * 256 + mt * 128 + half * 32;
+                tmem_ld32(t0, v);
+                tmem_ld32(t0 + 64, v2);
+                if (ok) {
+                    float *dst = img + ((size_t)(gsel * 2 + half) * rpad + row) * 32;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias + half * 32 + 4 * c4);
+                        float4 o;
+                        o.x = swishf_fast(v[4 * c4 + 0] + v2[4 * c4 + 0] + bb.x);
+                        o.y = swishf_fast(v[4 * c4 + 1] + v2[4 * c4 + 1] + bb.y);
+                        o.z = swishf_fast(v[4 * c4 + 2] + v2[4 * c4 + 2] + bb.z);
+                        o.w = swishf_fast(v[4 * c4 + 3] + v2[4 * c4 + 3] + bb.w);
+                        *reinterpret_cast<float4 *>(dst + ((c4 ^ (row & 7)) << 2)) = o;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    K1_STAMP(7);
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+#undef K1_STAMP
+}
 }  // namespace tc
 
 // =================================================================================================
@@ -1361,7 +1719,7 @@ __global__ void repack_kernel(const float *__restrict__ src, int64_t chunk_strid
 struct FusedWeights {
     float *dev = nullptr;  // one allocation holding every re-laid-out tensor
     size_t off_front = 0, off_slabs = 0, off_bmerge = 0, off_wih1T = 0, off_b1 = 0, off_whh4 = 0,
-           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0, off_wm_tc = 0, off_wih_tc = 0;
+           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0, off_wm_tc = 0, off_wih_tc = 0, off_front_tc = 0, off_w1_tc = 0;
     int kmer_len = 0, num_out = 0;
 };
 
@@ -1391,39 +1749,46 @@ int fused_create(rb200_model *m, const float *blob) {
     FusedWeights *fw = new FusedWeights();
     fw->kmer_len = K;
     fw->num_out = d.num_out;
-    // --- K1 blob ---
-    fw->off_front = reserve(fo.total);
-    {
-        float *f = host.data() + fw->off_front;
+    // --- K1 blob (FFMA2 variant) and its tensor-core twin (no FFMA2 weights for the stride-3 convs) ---
+    auto fill_front = [&](float *f, const FrontOffsets &o, bool tc) {
         const float *w = blob + d.sig_conv[0].w_off;  // [co=4][ci=1][j=5]
         for (int j = 0; j < KW_SIG1; ++j)
-            for (int co = 0; co < 4; ++co) f[fo.w_sig1 + j * 4 + co] = w[co * KW_SIG1 + j];
-        memcpy(f + fo.b_sig1, blob + d.sig_conv[0].b_off, 4 * sizeof(float));
+            for (int co = 0; co < 4; ++co) f[o.w_sig1 + j * 4 + co] = w[co * KW_SIG1 + j];
+        memcpy(f + o.b_sig1, blob + d.sig_conv[0].b_off, 4 * sizeof(float));
         w = blob + d.sig_conv[1].w_off;  // [16][4][5]
         for (int j = 0; j < KW_SIG2; ++j)
             for (int ci = 0; ci < 4; ++ci)
                 for (int co = 0; co < 16; ++co)
-                    f[fo.w_sig2 + (j * 4 + ci) * 16 + co] = w[(co * 4 + ci) * KW_SIG2 + j];
-        memcpy(f + fo.b_sig2, blob + d.sig_conv[1].b_off, 16 * sizeof(float));
-        w = blob + d.sig_conv[2].w_off;  // [64][16][9]
-        for (int j = 0; j < KW_SIG3; ++j)
-            for (int ci = 0; ci < 16; ++ci)
-                for (int co = 0; co < SIZE; ++co)
-                    f[fo.w_sig3 + (j * 16 + ci) * SIZE + co] = w[(co * 16 + ci) * KW_SIG3 + j];
-        memcpy(f + fo.b_sig3, blob + d.sig_conv[2].b_off, SIZE * sizeof(float));
+                    f[o.w_sig2 + (j * 4 + ci) * 16 + co] = w[(co * 4 + ci) * KW_SIG2 + j];
+        memcpy(f + o.b_sig2, blob + d.sig_conv[1].b_off, 16 * sizeof(float));
+        if (!tc) {
+            w = blob + d.sig_conv[2].w_off;  // [64][16][9]
+            for (int j = 0; j < KW_SIG3; ++j)
+                for (int ci = 0; ci < 16; ++ci)
+                    for (int co = 0; co < SIZE; ++co)
+                        f[o.w_sig3 + (j * 16 + ci) * SIZE + co] = w[(co * 16 + ci) * KW_SIG3 + j];
+        }
+        memcpy(f + o.b_sig3, blob + d.sig_conv[2].b_off, SIZE * sizeof(float));
         w = blob + d.seq_conv[0].w_off;  // [16][4K][5], input row = 4p + base
         for (int j = 0; j < KW_SEQ1; ++j)
             for (int row = 0; row < 4 * K; ++row)
                 for (int co = 0; co < 16; ++co)
-                    f[fo.w_seq1 + (j * 4 * K + row) * 16 + co] = w[(co * 4 * K + row) * KW_SEQ1 + j];
-        memcpy(f + fo.b_seq1, blob + d.seq_conv[0].b_off, 16 * sizeof(float));
-        w = blob + d.seq_conv[1].w_off;  // [64][16][13]
-        for (int j = 0; j < KW_SEQ2; ++j)
-            for (int ci = 0; ci < 16; ++ci)
-                for (int co = 0; co < SIZE; ++co)
-                    f[fo.w_seq2 + (j * 16 + ci) * SIZE + co] = w[(co * 16 + ci) * KW_SEQ2 + j];
-        memcpy(f + fo.b_seq2, blob + d.seq_conv[1].b_off, SIZE * sizeof(float));
-    }
+                    f[o.w_seq1 + (j * 4 * K + row) * GROW + co] = w[(co * 4 * K + row) * KW_SEQ1 + j];
+        memcpy(f + o.b_seq1, blob + d.seq_conv[0].b_off, 16 * sizeof(float));
+        if (!tc) {
+            w = blob + d.seq_conv[1].w_off;  // [64][16][13]
+            for (int j = 0; j < KW_SEQ2; ++j)
+                for (int ci = 0; ci < 16; ++ci)
+                    for (int co = 0; co < SIZE; ++co)
+                        f[o.w_seq2 + (j * 16 + ci) * SIZE + co] = w[(co * 16 + ci) * KW_SEQ2 + j];
+        }
+        memcpy(f + o.b_seq2, blob + d.seq_conv[1].b_off, SIZE * sizeof(float));
+    };
+    fw->off_front = reserve(fo.total);
+    fill_front(host.data() + fw->off_front, fo, false);
+    const FrontOffsets fo_tc = front_offsets(K, true);
+    fw->off_front_tc = reserve(fo_tc.total);
+    fill_front(host.data() + fw->off_front_tc, fo_tc, true);
     // --- K2: merge conv slabs [s][j][c_local][m], bias, W_ih1^T [k][r], b1 ---
     fw->off_slabs = reserve((size_t)N_SLABS * SLAB_FLOATS);
     {
@@ -1500,6 +1865,27 @@ int fused_create(rb200_model *m, const float *blob) {
                 }
         }
 
+    // K1-TC: stride-3 conv weights as [K block][hi|lo][64][32] tiles, k = (tap - 2*kb)*16 + channel
+    fw->off_w1_tc = reserve((size_t)(tc::K1TC_NKB_SIG + tc::K1TC_NKB_SEQ) * 2 * 64 * 32);
+    for (int conv = 0; conv < 2; ++conv) {
+        const int KW = conv ? KW_SEQ2 : KW_SIG3;
+        const int nkb = conv ? tc::K1TC_NKB_SEQ : tc::K1TC_NKB_SIG;
+        const float *w = blob + (conv ? d.seq_conv[1].w_off : d.sig_conv[2].w_off);  // [64][16][KW]
+        for (int kb = 0; kb < nkb; ++kb) {
+            // stream order = execution order: seq_conv2's K blocks first, then sig_conv3's
+            float *st = host.data() + fw->off_w1_tc +
+                        (size_t)((conv ? 0 : tc::K1TC_NKB_SEQ) + kb) * (2 * 64 * 32);
+            for (int mo = 0; mo < SIZE; ++mo)
+                for (int k = 0; k < 32; ++k) {
+                    const int tap = 2 * kb + (k >> 4), c = k & 15;
+                    float hi = 0.f, lo = 0.f;
+                    if (tap < KW) tf32_split(w[(mo * 16 + c) * KW + tap], hi, lo);
+                    st[sw(mo, k)] = hi;
+                    st[64 * 32 + sw(mo, k)] = lo;
+                }
+        }
+    }
+
     cudaError_t e = cudaMalloc(&fw->dev, host.size() * sizeof(float));
     if (e == cudaSuccess)
         e = cudaMemcpy(fw->dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -1514,6 +1900,7 @@ int fused_create(rb200_model *m, const float *blob) {
     cudaFuncSetAttribute(k2_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k3_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES);
     cudaFuncSetAttribute(tc::k2tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(tc::k1tc_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     m->fused = fw;
     return RB200_OK;
 }
@@ -1580,12 +1967,22 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     const FusedWeights *fw = m->fused;
     const Geometry g = make_geometry(T);
     RB200_REQUIRE(g.ok, "chunk_len %d not supported by the fused kernels", T);
-    const int cpb = pick_cpb(B, g.CL, m->sm_count);
+    // tensor-core variants (tcgen05 3xTF32) when requested and the CTA's rows fit two M tiles
+    int cpb = pick_cpb(B, want_tc && g.CL > tc::K1TC_MAX_CPB ? tc::K1TC_MAX_CPB : g.CL, m->sm_count);
+    int tc_rpad = tc::rpad_for(cpb, g.T3);
+    bool use_tc = want_tc && cpb * g.T3 <= 256 && tc::smem_layout(tc_rpad).total <= 227 * 1024;
+    const int k1_nw =
+        tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, 3).total <= 227 * 1024 ? 3 : 2;
+    const bool use_tc_k1 =
+        use_tc && !getenv("RB200_NO_K1TC") &&
+        tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, k1_nw).total <= 227 * 1024 &&
+        // the per-base gather sums borrow the (not yet used) tile stages
+        (size_t)cpb * (map_width - 1) * KW_SEQ1 * GROW * 4 <= (size_t)4 * tc_rpad * 128;
+    if (want_tc && !use_tc) {  // fall back to the fp32 kernels with their own best CTA size
+        cpb = pick_cpb(B, g.CL, m->sm_count);
+        tc_rpad = 0;
+    }
     const int grid = (B + cpb - 1) / cpb;
-    // tensor-core K2 (tcgen05 3xTF32) when requested / allowed and the CTA's rows fit two M tiles
-    const int tc_rpad = tc::rpad_for(cpb, g.T3);
-    const bool use_tc = want_tc && cpb * g.T3 <= 256 &&
-                        tc::smem_layout(tc_rpad).total <= 227 * 1024;
     const size_t cat_bytes = use_tc ? align256((size_t)grid * 4 * tc_rpad * 32 * 4)
                                     : align256((size_t)B * g.cat_stride * 4);
     const size_t live_bytes = cat_bytes + align256((size_t)B * g.TM * 256 * 4);
@@ -1609,7 +2006,31 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     // with profiling events between the kernels PDL cannot overlap them; launch plainly then
     const bool pdl = !m->profile;
     const int k1_tc = use_tc ? tc_rpad : 0;
-    if (pdl) {
+    if (use_tc_k1) {
+        const int smem1 = tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, k1_nw).total;
+        static long long *k1_stamps = nullptr;  // profiling aid: RB200_TC_STAMPS=1
+        static const bool want_k1_stamps = getenv("RB200_TC_STAMPS") != nullptr;
+        if (want_k1_stamps && !k1_stamps) cudaMalloc(&k1_stamps, 16 * sizeof(long long));
+        if (pdl) {
+            RB200_CUDA_TRY(launch_pdl(tc::k1tc_front_kernel, grid, THREADS, (size_t)smem1, stream, sigs,
+                                      seqs, seq_width, maps, map_width, lens,
+                                      (const float *)(fw->dev + fw->off_front_tc),
+                                      (const float *)(fw->dev + fw->off_w1_tc), cat, B, cpb, T,
+                                      fw->kmer_len, tc_rpad, cpb, k1_nw, k1_stamps));
+        } else {
+            tc::k1tc_front_kernel<<<grid, THREADS, smem1, stream>>>(
+                sigs, seqs, seq_width, maps, map_width, lens, fw->dev + fw->off_front_tc,
+                fw->dev + fw->off_w1_tc, cat, B, cpb, T, fw->kmer_len, tc_rpad, cpb, k1_nw, k1_stamps);
+        }
+        if (want_k1_stamps) {
+            long long h[16];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, k1_stamps, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[k1tc stamps, cycles] pdl_wait %lld  stage+gather %lld  seq2_loop %lld  sig12 %lld  "
+                    "sig3_loop %lld  mma_drain %lld  epilogue %lld\n", h[1] - h[0], h[2] - h[1], h[3] - h[2],
+                    h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
+        }
+    } else if (pdl) {
         RB200_CUDA_TRY(launch_pdl(k1_front_kernel, grid, THREADS, l1.total_bytes, stream, sigs, seqs,
                                   seq_width, maps, map_width, lens,
                                   (const float *)(fw->dev + fw->off_front), cat, B, cpb, T,

@@ -178,12 +178,14 @@ def test_per_layer_activations_vs_oracle(forward_cases):
                 (sd["lstm1.bias_ih_l0"] + sd["lstm1.bias_hh_l0"])[None, :, None]
         got_xp = model.debug_tensor("xproj").cpu()
         assert got_xp.shape == want_xp.shape
-        assert (got_xp - want_xp).abs().max() < 1e-4, "fused merge conv + input projection"
+        scale = float(want_xp.abs().max())  # the hot fixture's projection spans +-40
+        assert float((got_xp - want_xp).abs().max()) < 1e-5 * scale + 1e-5, "fused merge conv + projection"
         model.set_impl("fused_tc")
         model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
                               torch.from_numpy(maps), torch.from_numpy(lens))
         got_xp = model.debug_tensor("xproj").cpu()
-        assert (got_xp - want_xp).abs().max() < 1e-4, "tcgen05 merge conv + input projection"
+        err = float((got_xp - want_xp).abs().max())
+        assert err < 1e-5 * scale + 1e-5, f"tcgen05 convs + projection: err {err:.3e} at scale {scale:.1f}"
     model.set_debug(False)
     model.set_impl("auto")
 
