@@ -145,6 +145,18 @@ int rb200_infer_host(rb200_handle h, const float *sigs_host, const int8_t *seqs_
                      int32_t seq_width, const int16_t *maps_host, int32_t map_width,
                      const int16_t *lens_host, int32_t B, int32_t T, float *logits_host);
 
+/* Asynchronous form for pipelined callers: every buffer is a PINNED host buffer owned by the caller
+ * (cudaHostAlloc / torch pin_memory); the call enqueues H2D copies of the compact arrays, the kernels
+ * and the D2H copy of the logits on `stream` and returns immediately.  The caller synchronises the
+ * stream (or an event) before reading logits_pinned, and must not touch the input buffers until then.
+ * Alternating two streams overlaps step i+1's copies with step i's kernels, which is how the
+ * reference's queue-based pipeline (src/remora/inference.py:488-572) keeps its device busy.  Device
+ * staging is per (handle, stream). */
+int rb200_infer_host_async(rb200_handle h, const float *sigs_pinned, const int8_t *seqs_pinned,
+                           int32_t seq_width, const int16_t *maps_pinned, int32_t map_width,
+                           const int16_t *lens_pinned, int32_t B, int32_t T, float *logits_pinned,
+                           void *stream);
+
 /* Post-processing on device ("next" row 2): softmax over num_out, drop class 0,
  * probs float32 [B][num_out-1] (may be NULL) and ML bytes uint8 [B][num_out-1]
  * = min(floor(p*256), 255)  (src/remora/util.py:182-186, 532-535). */

@@ -209,6 +209,7 @@ int rb200_destroy(rb200_handle h) {
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     fused_destroy(h);
     for (auto &kv : h->workspaces) kv.second.release();
+    for (auto &kv : h->host_staging) kv.second.release();
     if (h->blob_dev) cudaFree(h->blob_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->staging_dev) cudaFree(h->staging_dev);
@@ -385,6 +386,46 @@ int rb200_infer_host(rb200_handle h, const float *sigs_host, const int8_t *seqs_
                                    cudaMemcpyDeviceToHost, s));
     RB200_CUDA_TRY(cudaStreamSynchronize(s));
     memcpy(logits_host, p + in_bytes, (size_t)B * h->desc.num_out * 4);
+    return RB200_OK;
+}
+
+int rb200_infer_host_async(rb200_handle h, const float *sigs_pinned, const int8_t *seqs_pinned,
+                           int32_t seq_width, const int16_t *maps_pinned, int32_t map_width,
+                           const int16_t *lens_pinned, int32_t B, int32_t T, float *logits_pinned,
+                           void *stream_v) {
+    RB200_REQUIRE(h, "null handle");
+    RB200_REQUIRE(B >= 0 && T > 0, "bad batch / chunk_len");
+    if (B == 0) return RB200_OK;
+    RB200_REQUIRE(sigs_pinned && seqs_pinned && maps_pinned && lens_pinned && logits_pinned,
+                  "null buffer");
+    DeviceGuard guard(h->device);
+    RB200_REQUIRE(guard.ok, "cannot select device %d", h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream_v);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t n_sig = (size_t)B * T * 4, n_seq = (size_t)B * seq_width,
+                 n_map = (size_t)B * map_width * 2, n_len = (size_t)B * 2,
+                 n_out = (size_t)B * h->desc.num_out * 4;
+    const size_t o_seq = up(n_sig), o_map = o_seq + up(n_seq), o_len = o_map + up(n_map),
+                 o_out = o_len + up(n_len), total = o_out + up(n_out);
+    char *d = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        Workspace &st = h->host_staging[stream_v];
+        int rc = st.ensure(total);
+        if (rc) return rc;
+        d = st.base;
+    }
+    RB200_CUDA_TRY(cudaMemcpyAsync(d, sigs_pinned, n_sig, cudaMemcpyHostToDevice, s));
+    RB200_CUDA_TRY(cudaMemcpyAsync(d + o_seq, seqs_pinned, n_seq, cudaMemcpyHostToDevice, s));
+    RB200_CUDA_TRY(cudaMemcpyAsync(d + o_map, maps_pinned, n_map, cudaMemcpyHostToDevice, s));
+    RB200_CUDA_TRY(cudaMemcpyAsync(d + o_len, lens_pinned, n_len, cudaMemcpyHostToDevice, s));
+    int rc = rb200_forward_compact(h, reinterpret_cast<const float *>(d),
+                                   reinterpret_cast<const int8_t *>(d + o_seq), seq_width,
+                                   reinterpret_cast<const int16_t *>(d + o_map), map_width,
+                                   reinterpret_cast<const int16_t *>(d + o_len), B, T,
+                                   reinterpret_cast<float *>(d + o_out), s);
+    if (rc) return rc;
+    RB200_CUDA_TRY(cudaMemcpyAsync(logits_pinned, d + o_out, n_out, cudaMemcpyDeviceToHost, s));
     return RB200_OK;
 }
 

@@ -79,6 +79,7 @@ struct rb200_model {
     std::vector<rb200::DebugTensor> debug;
     std::mutex mu;
     std::map<void *, rb200::Workspace> workspaces;  // keyed by stream
+    std::map<void *, rb200::Workspace> host_staging;  // device-side input/output staging of rb200_infer_host_async
     rb200::FusedWeights *fused = nullptr;           // non-null when the fused path applies
     // pinned + device staging for rb200_infer_host
     char *pinned = nullptr;

@@ -306,6 +306,26 @@ class B200Model(nn.Module):
         return out
 
 
+    def infer_host_async(self, sigs, sequence, seq_to_sig_map, seq_lens, out, stream=None):
+        """Pipelined host-buffer inference (rb200_infer_host_async): all arguments are PINNED CPU
+        tensors (``torch.Tensor.pin_memory()``), ``out`` a pinned float32 [B, num_out] tensor.  Work is
+        enqueued on ``stream`` (default: current stream) and the call returns immediately; synchronise
+        the stream before reading ``out``."""
+        for t, name in ((sigs, "sigs"), (sequence, "sequence"), (seq_to_sig_map, "seq_to_sig_map"),
+                        (seq_lens, "seq_lens"), (out, "out")):
+            if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.is_pinned()
+                    and t.is_contiguous()):
+                raise RemoraError(f"{name} must be a contiguous pinned CPU tensor")
+        B, T = sigs.shape[0], sigs.shape[-1]
+        if stream is None:
+            stream = torch.cuda.current_stream(self._device)
+        rc = self._lib.rb200_infer_host_async(
+            self._handle, _ptr(sigs), _ptr(sequence), sequence.shape[1], _ptr(seq_to_sig_map),
+            seq_to_sig_map.shape[1], _ptr(seq_lens), B, T, _ptr(out), ctypes.c_void_p(stream.cuda_stream))
+        _native.check(rc, "rb200_infer_host_async")
+        return out
+
+
 def load_torchscript_model(model_filename, device=None, quiet=False, eval_only=False):
     """Same contract as the reference function (model_util.py:532-563)."""
     state_dict, md = _raw_load_torchscript(model_filename)

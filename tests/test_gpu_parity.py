@@ -317,6 +317,28 @@ def test_infer_host_roundtrip(forward_cases):
     assert np.abs(got2 - want[:3]).max() < LOGIT_TOL
 
 
+def test_infer_host_async_pipelined(forward_cases):
+    """rb200_infer_host_async: pinned buffers, two alternating streams, results per slot."""
+    key = "convlstm_s64_k9_hot__n64_T100"
+    model, _ = gpu_model("convlstm_s64_k9_hot")
+    sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+    pins = [torch.from_numpy(a).pin_memory() for a in (sig, seqs, maps, lens)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [torch.zeros((64, 2)).pin_memory() for _ in range(2)]
+    for i in range(6):
+        slot = i & 1
+        streams[slot].synchronize()
+        if i >= 2:
+            assert np.abs(outs[slot].numpy() - want).max() < LOGIT_TOL
+        outs[slot].zero_()
+        model.infer_host_async(*pins, outs[slot], stream=streams[slot])
+    for slot in range(2):
+        streams[slot].synchronize()
+        assert np.abs(outs[slot].numpy() - want).max() < LOGIT_TOL
+    with pytest.raises(RemoraError):  # pageable buffers are refused
+        model.infer_host_async(torch.from_numpy(sig), *pins[1:], outs[0])
+
+
 def test_softmax_ml_kernel():
     import ctypes
     from remora_b200 import _native, util
