@@ -157,6 +157,27 @@ int rb200_infer_host_async(rb200_handle h, const float *sigs_pinned, const int8_
                            const int16_t *lens_pinned, int32_t B, int32_t T, float *logits_pinned,
                            void *stream);
 
+/* On-GPU chunk extraction ("next" row 1): the per-read host loop of
+ * RemoraRead.iter_chunks / extract_chunk (src/remora/data_chunks.py:331-466) and the signal
+ * normalisation (:191-197) as two kernels.  All pointers are device pointers.
+ *   plan: per focus base -> adjusted focus base, chunk centre sample, first overlapping base, number
+ *         of overlapping bases (the caller reads min/max of seq_len to size the arrays and to reject
+ *         reads with an empty chunk, as the reference's Chunk.check would).
+ *   fill: writes signal f32 [n][c0+c1], sequence i8 [n][lmax+kb+ka], mapping i16 [n][lmax+1],
+ *         lens i16 [n] - the layout rb200_forward_compact consumes.
+ * dacs_dtype: 0 = int16, 1 = float32, 2 = float64 (normalisation follows numpy's precision rules for
+ * that dtype so the float32 signal is bit-identical to the reference's). */
+int rb200_chunk_plan(const int32_t *seq_to_sig_map_dev, int32_t n_map, int32_t sig_len,
+                     const int32_t *focus_bases_dev, int32_t n, int32_t chunk_before, int32_t chunk_after,
+                     int32_t base_start_justify, int32_t offset, int32_t *focus_adj_dev,
+                     int32_t *focus_sig_dev, int32_t *seq_start_dev, int32_t *seq_len_dev, void *stream);
+int rb200_chunk_fill(const void *dacs_dev, int32_t dacs_dtype, int32_t sig_len, double shift, double scale,
+                     const int32_t *seq_to_sig_map_dev, int32_t n_map, const int8_t *int_seq_dev,
+                     int32_t n_bases, const int32_t *focus_sig_dev, const int32_t *seq_start_dev,
+                     const int32_t *seq_len_dev, int32_t n, int32_t chunk_before, int32_t chunk_after,
+                     int32_t kmer_before, int32_t kmer_after, int32_t lmax, float *signal_dev,
+                     int8_t *sequence_dev, int16_t *mapping_dev, int16_t *lens_dev, void *stream);
+
 /* Post-processing on device ("next" row 2): softmax over num_out, drop class 0,
  * probs float32 [B][num_out-1] (may be NULL) and ML bytes uint8 [B][num_out-1]
  * = min(floor(p*256), 255)  (src/remora/util.py:182-186, 532-535). */

@@ -429,6 +429,42 @@ int rb200_infer_host_async(rb200_handle h, const float *sigs_pinned, const int8_
     return RB200_OK;
 }
 
+int rb200_chunk_plan(const int32_t *seq_to_sig_map_dev, int32_t n_map, int32_t sig_len,
+                     const int32_t *focus_bases_dev, int32_t n, int32_t chunk_before, int32_t chunk_after,
+                     int32_t base_start_justify, int32_t offset, int32_t *focus_adj_dev,
+                     int32_t *focus_sig_dev, int32_t *seq_start_dev, int32_t *seq_len_dev, void *stream) {
+    RB200_REQUIRE(n >= 0 && n_map >= 2 && sig_len >= 0 && chunk_before >= 0 && chunk_after >= 0 &&
+                      chunk_before + chunk_after > 0,
+                  "bad argument");
+    if (n == 0) return RB200_OK;
+    RB200_REQUIRE(seq_to_sig_map_dev && focus_bases_dev && focus_adj_dev && focus_sig_dev &&
+                      seq_start_dev && seq_len_dev,
+                  "null buffer");
+    return launch_chunk_plan(seq_to_sig_map_dev, n_map, sig_len, focus_bases_dev, n, chunk_before,
+                             chunk_after, base_start_justify, offset, focus_adj_dev, focus_sig_dev,
+                             seq_start_dev, seq_len_dev, static_cast<cudaStream_t>(stream));
+}
+
+int rb200_chunk_fill(const void *dacs_dev, int32_t dacs_dtype, int32_t sig_len, double shift, double scale,
+                     const int32_t *seq_to_sig_map_dev, int32_t n_map, const int8_t *int_seq_dev,
+                     int32_t n_bases, const int32_t *focus_sig_dev, const int32_t *seq_start_dev,
+                     const int32_t *seq_len_dev, int32_t n, int32_t chunk_before, int32_t chunk_after,
+                     int32_t kmer_before, int32_t kmer_after, int32_t lmax, float *signal_dev,
+                     int8_t *sequence_dev, int16_t *mapping_dev, int16_t *lens_dev, void *stream) {
+    RB200_REQUIRE(n >= 0 && dacs_dtype >= 0 && dacs_dtype <= 2 && lmax >= 1 && kmer_before >= 0 &&
+                      kmer_after >= 0 && chunk_before + chunk_after > 0 &&
+                      chunk_before + chunk_after < 32768,
+                  "bad argument");
+    if (n == 0) return RB200_OK;
+    RB200_REQUIRE(dacs_dev && seq_to_sig_map_dev && int_seq_dev && focus_sig_dev && seq_start_dev &&
+                      seq_len_dev && signal_dev && sequence_dev && mapping_dev && lens_dev,
+                  "null buffer");
+    return launch_chunk_fill(dacs_dev, dacs_dtype, sig_len, shift, scale, seq_to_sig_map_dev, n_map,
+                             int_seq_dev, n_bases, focus_sig_dev, seq_start_dev, seq_len_dev, n,
+                             chunk_before, chunk_after, kmer_before, kmer_after, lmax, signal_dev,
+                             sequence_dev, mapping_dev, lens_dev, static_cast<cudaStream_t>(stream));
+}
+
 int rb200_softmax_ml(const float *logits_dev, int32_t B, int32_t num_out, float *probs_dev,
                      uint8_t *ml_dev, void *stream) {
     RB200_REQUIRE(B >= 0 && num_out >= 2, "bad argument");

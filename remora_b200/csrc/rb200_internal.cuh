@@ -109,6 +109,16 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
 int launch_softmax_ml(const float *logits, int B, int num_out, float *probs, uint8_t *ml,
                       cudaStream_t stream);
 
+// rb200_chunks.cu : read -> compact chunk arrays on the device
+int launch_chunk_plan(const int32_t *ssm, int n_map, int sig_len, const int32_t *focus, int n, int c0,
+                      int c1, int bsj, int offset, int32_t *focus_adj, int32_t *focus_sig,
+                      int32_t *seq_start, int32_t *seq_len, cudaStream_t stream);
+int launch_chunk_fill(const void *dacs, int dtype, int sig_len, double shift, double scale,
+                      const int32_t *ssm, int n_map, const int8_t *int_seq, int n_bases,
+                      const int32_t *focus_sig, const int32_t *seq_start, const int32_t *seq_len, int n,
+                      int c0, int c1, int kb, int ka, int lmax, float *signal, int8_t *sequence,
+                      int16_t *mapping, int16_t *lens, cudaStream_t stream);
+
 // rb200_fused.cu : fused sm_100a kernels for ConvLSTM_w_ref size 64
 bool fused_supported(const rb200_model_desc &d);
 int fused_create(rb200_model *m, const float *blob_host);

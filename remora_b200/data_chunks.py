@@ -43,6 +43,29 @@ class ChunkBatch:
 
 
 @dataclasses.dataclass
+class DeviceChunkBatch:
+    """Same compact chunk arrays as :class:`ChunkBatch`, already resident on the GPU (produced by
+    ``RemoraRead.prepare_batches_gpu``); ``labels`` / ``read_focus_bases`` stay on the host."""
+
+    signal: torch.Tensor          # float32 [B, 1, T]   (device)
+    sequence: torch.Tensor        # int8    [B, Lmax + kmer_len - 1]
+    seq_to_sig_map: torch.Tensor  # int16   [B, Lmax + 1]
+    seq_lens: torch.Tensor        # int16   [B]
+    labels: np.ndarray
+    read_focus_bases: np.ndarray
+    kmer_context_bases: tuple
+
+    def __len__(self):
+        return self.seq_lens.shape[0]
+
+    def enc_kmers(self, device):
+        from .encoded_kmers import compute_encoded_kmer_batch_torch
+        return compute_encoded_kmer_batch_torch(
+            self.kmer_context_bases[0], self.kmer_context_bases[1], self.sequence, self.seq_to_sig_map,
+            self.seq_lens, sig_len=self.signal.shape[-1], device=device)
+
+
+@dataclasses.dataclass
 class Chunk:
     """Single chunk, same fields as the reference's ``Chunk`` (data_chunks.py:543-641)."""
 
@@ -289,6 +312,72 @@ class RemoraRead:
                 labels=labels[st:en], read_focus_bases=fb[st:en].astype(np.int64),
                 kmer_context_bases=kmer_context))
 
+    def prepare_batches_gpu(self, model_metadata, batch_size=constants.DEFAULT_BATCH_SIZE, device=None):
+        """``prepare_batches`` with the chunk extraction itself on the GPU ("next" row 1):
+        the read's raw arrays go to the device once (DAC samples, mapping, sequence: a few bytes per
+        sample instead of ~480 B per chunk) and two kernels (``rb200_chunk_plan`` / ``rb200_chunk_fill``)
+        build the compact chunk arrays there, bit-identical to the host path above.  Batches are
+        :class:`DeviceChunkBatch` objects; ``run_model`` consumes them without further copies."""
+        import ctypes
+        from . import _native
+        lib = _native.load_library()
+        self.batches = []
+        self.refine_signal_mapping(model_metadata["sig_map_refiner"])
+        if self.focus_bases is None or len(self.focus_bases) == 0:
+            return
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        c0, c1 = (int(x) for x in model_metadata["chunk_context"])
+        kb, ka = (int(x) for x in model_metadata["kmer_context_bases"])
+        T = c0 + c1
+        if T >= 32768:
+            raise RemoraError("chunk_len does not fit the int16 mapping")
+        dacs = np.ascontiguousarray(self.dacs)
+        if dacs.dtype == np.int16:
+            code = 0
+        elif dacs.dtype == np.float32:
+            code = 1
+        else:  # every other dtype is promoted to float64 by numpy in (dacs - shift) / scale
+            dacs, code = dacs.astype(np.float64), 2
+        ssm = np.ascontiguousarray(self.seq_to_sig_map, dtype=np.int32)
+        focus = np.ascontiguousarray(self.focus_bases, dtype=np.int32)
+        n = focus.size
+        with torch.cuda.device(device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            d_dacs = torch.from_numpy(dacs).to(device)
+            d_ssm = torch.from_numpy(ssm).to(device)
+            d_seq = torch.from_numpy(np.ascontiguousarray(self.int_seq, dtype=np.int8)).to(device)
+            d_focus = torch.from_numpy(focus).to(device)
+            plan = torch.empty((4, n), dtype=torch.int32, device=device)  # focus_adj, focus_sig, start, len
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+            _native.check(lib.rb200_chunk_plan(ptr(d_ssm), ssm.size, dacs.size, ptr(d_focus), n, c0, c1,
+                                               int(bool(model_metadata["base_start_justify"])),
+                                               int(model_metadata["offset"]), ptr(plan[0]), ptr(plan[1]),
+                                               ptr(plan[2]), ptr(plan[3]), stream), "rb200_chunk_plan")
+            lo, hi = int(plan[3].min()), int(plan[3].max())
+            if lo < 1:  # a chunk without sequence: the host path drops the read as well
+                return
+            signal = torch.empty((n, 1, T), dtype=torch.float32, device=device)
+            sequence = torch.empty((n, hi + kb + ka), dtype=torch.int8, device=device)
+            mapping = torch.empty((n, hi + 1), dtype=torch.int16, device=device)
+            lens = torch.empty((n,), dtype=torch.int16, device=device)
+            _native.check(lib.rb200_chunk_fill(ptr(d_dacs), code, dacs.size, float(self.shift),
+                                               float(self.scale), ptr(d_ssm), ssm.size, ptr(d_seq),
+                                               d_seq.numel(), ptr(plan[1]), ptr(plan[2]), ptr(plan[3]), n,
+                                               c0, c1, kb, ka, hi, ptr(signal), ptr(sequence), ptr(mapping),
+                                               ptr(lens), stream), "rb200_chunk_fill")
+            fb = plan[0].cpu().numpy().astype(np.int64)
+        labels = (np.full(n, -1, dtype=np.int64) if self.labels is None
+                  else np.asarray(self.labels)[np.asarray(self.focus_bases)].astype(np.int64))
+        batch_size = max(1, int(batch_size or constants.DEFAULT_BATCH_SIZE))
+        for st in range(0, n, batch_size):
+            en = min(st + batch_size, n)
+            self.batches.append(DeviceChunkBatch(
+                signal=signal[st:en], sequence=sequence[st:en], seq_to_sig_map=mapping[st:en],
+                seq_lens=lens[st:en], labels=labels[st:en], read_focus_bases=fb[st:en],
+                kmer_context_bases=(kb, ka)))
+
     def run_model(self, model):
         """Call modified bases on this read's prepared batches (reference data_chunks.py:516-540).
         Returns (nn_out float32 [N,num_out], labels int64 [N], read positions int64 [N])."""
@@ -296,8 +385,11 @@ class RemoraRead:
         outputs, labels, poss = [], [], []
         compact = hasattr(model, "forward_compact")
         for batch in self.batches:
-            sigs = torch.from_numpy(batch.signal).to(device)
-            if compact:
+            on_device = isinstance(batch, DeviceChunkBatch)
+            sigs = batch.signal.to(device) if on_device else torch.from_numpy(batch.signal).to(device)
+            if compact and on_device:
+                out = model.forward_compact(sigs, batch.sequence, batch.seq_to_sig_map, batch.seq_lens)
+            elif compact:
                 out = model.forward_compact(sigs, torch.from_numpy(batch.sequence),
                                             torch.from_numpy(batch.seq_to_sig_map),
                                             torch.from_numpy(batch.seq_lens))

@@ -9,19 +9,25 @@ from .util import Motif, format_mm_ml_tags, softmax_axis1
 
 
 def call_read_mods(read, model, model_metadata, batch_size=constants.DEFAULT_BATCH_SIZE,
-                   focus_offset=None, return_mm_ml_tags=False, return_mod_probs=False):
+                   focus_offset=None, return_mm_ml_tags=False, return_mod_probs=False,
+                   extract_on_device=False):
     """Call modified bases on a read; same arguments and return forms as the reference
     (inference.py:661-712):
       default               -> (nn_out float32 [N,num_out], labels, positions)
       return_mod_probs      -> (probs float64 [N,num_out-1], labels, positions)
       return_mm_ml_tags     -> (MM string, ML array('B'))
       read without calls    -> three empty arrays
-    Positions come back sorted (the reference returns set-iteration order, util.py:419-426)."""
+    Positions come back sorted (the reference returns set-iteration order, util.py:419-426).
+    ``extract_on_device`` (extension): build the chunk arrays with the GPU extraction kernels
+    (``RemoraRead.prepare_batches_gpu``) instead of on the host; results are identical."""
     if focus_offset is None:
         read.set_motif_focus_bases([Motif(*mot) for mot in model_metadata["motifs"]])
     else:
         read.focus_bases = np.array([focus_offset])
-    read.prepare_batches(model_metadata, batch_size)
+    if extract_on_device:
+        read.prepare_batches_gpu(model_metadata, batch_size, device=next(model.parameters()).device)
+    else:
+        read.prepare_batches(model_metadata, batch_size)
     if len(read.batches) == 0:
         return np.array([]), np.array([]), np.array([])
     nn_out, labels, pos = read.run_model(model)

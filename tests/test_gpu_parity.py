@@ -285,6 +285,51 @@ def test_call_read_mods_matches_reference(read_cases):
         assert diff.max() <= 1 and (diff != 0).mean() <= 0.02
 
 
+def test_gpu_chunk_extraction_is_bit_identical(read_cases):
+    """rb200_chunk_plan / rb200_chunk_fill against the host chunk extraction (itself pinned to the
+    reference's call_read_mods by tests/test_host.py): all four compact arrays bit for bit, for int16,
+    float32 and float64 DAC arrays, short reads with padding on both sides, N bases."""
+    from remora_b200 import util
+    _, md = load_golden_model("convlstm_s64_k9")
+    cases = []
+    for n_bases, seed, dt in ((400, 1, np.int16), (37, 2, np.int16), (8, 3, np.int16),
+                              (250, 4, np.float32), (120, 5, np.float64), (300, 6, np.int32)):
+        dacs, shift, scale, ssm, int_seq = synth_read(n_bases, seed=seed, frac_n=0.02)
+        cases.append((dacs.astype(dt), shift, scale, ssm, int_seq))
+    for dacs, shift, scale, ssm, int_seq in cases:
+        for focus_kind in ("motif", "all"):
+            def fresh():
+                r = data_chunks.RemoraRead(dacs=dacs, shift=shift, scale=scale, seq_to_sig_map=ssm,
+                                           int_seq=int_seq)
+                if focus_kind == "motif":
+                    r.set_motif_focus_bases([util.Motif("C", 0)])
+                else:
+                    r.focus_bases = np.arange(int_seq.size)
+                return r
+            host, dev = fresh(), fresh()
+            host.prepare_batches(md, 64)
+            dev.prepare_batches_gpu(md, 64, device=torch.device("cuda:0"))
+            assert len(host.batches) == len(dev.batches)
+            for hb, db in zip(host.batches, dev.batches):
+                assert np.array_equal(hb.signal, db.signal.cpu().numpy())
+                assert np.array_equal(hb.seq_lens, db.seq_lens.cpu().numpy())
+                assert np.array_equal(hb.seq_to_sig_map, db.seq_to_sig_map.cpu().numpy())
+                assert np.array_equal(hb.sequence, db.sequence.cpu().numpy())
+                assert np.array_equal(hb.read_focus_bases, db.read_focus_bases)
+
+
+def test_call_read_mods_with_device_extraction(read_cases):
+    meta, g = read_cases
+    for i, m in enumerate(meta):
+        model, md = gpu_model(m["model"])
+        read = data_chunks.RemoraRead(dacs=g[f"r{i}_dacs"], shift=m["shift"], scale=m["scale"],
+                                      seq_to_sig_map=g[f"r{i}_ssm"], int_seq=g[f"r{i}_int_seq"])
+        nn_out, labels, pos = inference.call_read_mods(read, model, md, extract_on_device=True)
+        order = np.argsort(g[f"r{i}_pos"])
+        assert np.array_equal(pos, g[f"r{i}_pos"][order])
+        assert np.abs(nn_out - g[f"r{i}_nn_out"][order]).max() < LOGIT_TOL
+
+
 def test_reference_test_read(read_cases):
     """scripts/api_example.py flow: load_model -> RemoraRead.test_read() -> call_read_mods."""
     _, g = read_cases
