@@ -1043,6 +1043,7 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
         // ===================================== MMA issuer ==========================================
         if (lane == 0) {
             constexpr uint32_t idesc_m = idesc_tf32(128, 64);
+            constexpr uint32_t idesc_m128 = idesc_tf32(128, 128);
             constexpr uint32_t idesc_x = idesc_tf32(128, 128);
             int wcount = 0;
             for (int cb = 0; cb < 4; ++cb) {
@@ -1059,12 +1060,25 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
                     const uint32_t b_hi = smem_addr(w_ring + ws * WST_BYTES);
                     const uint32_t b_lo = b_hi + 64 * 128;
                     for (int mt = 0; mt < n_mt; ++mt) {
-                        // per M tile: two main chains (channel blocks {0,1} and {2,3}) + one for the
-                        // correction products: TMEM columns mt*192 + {0, 64, 128}
+                        // TMEM columns of M tile mt: chain 0 (channel blocks 0,1) = [main0 | corrections],
+                        // chain 1 (blocks 2,3) = [main1 | hi*lo of chain 1], 64 columns each.  The weight
+                        // stage holds the 64-row hi tile and the 64-row lo tile back to back, so ONE
+                        // N=128 MMA with the activation hi tile yields a_hi*b_hi and a_hi*b_lo side by
+                        // side; the remaining a_lo*b_hi product (N=64) always adds into chain 0's
+                        // correction columns.  The activation tile is read from shared memory twice per
+                        // K step instead of three times, and the main chains stay short (40 steps).
                         const uint32_t row_off = (uint32_t)(mt_base[mt] + tap) * 128u;
-                        const uint32_t d0 = tmem + mt * 192;
-                        mma3_kblock(d0 + (cb >> 1) * 64, d0 + 128, a_hi + row_off, a_lo + row_off, b_hi,
-                                    b_lo, idesc_m, (cb & 1) == 0 && tap == 0, cb == 0 && tap == 0);
+                        const uint32_t d0 = tmem + mt * 256;
+                        const uint32_t dc = d0 + (cb >= 2 ? 128 : 0);
+                        const uint32_t b_t = smem_addr(w_ring + ws * WST_BYTES);  // [hi (64 rows); lo (64 rows)]
+                        const bool first_chain = (cb & 1) == 0 && tap == 0;
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8) {
+                            const uint32_t o = k8 * 32;
+                            mma_tf32(dc, desc_sw128(a_hi + row_off + o), desc_sw128(b_t + o), idesc_m128,
+                                     (first_chain && k8 == 0) ? 0u : 1u);
+                            mma_tf32(d0 + 64, desc_sw128(a_lo + row_off + o), desc_sw128(b_t + o), idesc_m, 1u);
+                        }
                     }
                     umma_commit(&bars->w_empty[ws]);
                 }
@@ -1125,13 +1139,18 @@ k2tc_kernel(const float *__restrict__ cat_img, const float *__restrict__ wm_tc,
                 const int half = colh;  // 32 channels = one K block of the projection
                 float v[32];
                 {
-                    float v1[32], v2[32];
-                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + mt * 192 + half * 32;
-                    tmem_ld32(t0, v);
-                    tmem_ld32(t0 + 64, v1);
-                    tmem_ld32(t0 + 128, v2);
+                    float v1[32];
+                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + mt * 256 + half * 32;
+                    tmem_ld32(t0, v);         // main chain 0
+                    tmem_ld32(t0 + 128, v1);  // main chain 1
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = (v[i] + v1[i]) + v2[i];
+                    for (int i = 0; i < 32; ++i) v[i] += v1[i];
+                    tmem_ld32(t0 + 64, v1);   // corrections (a_lo*b_hi of both chains + a_hi*b_lo of chain 0)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += v1[i];
+                    tmem_ld32(t0 + 192, v1);  // a_hi*b_lo of chain 1
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += v1[i];
                 }
                 float *t_hi = reinterpret_cast<float *>(m_tiles + ((mt * 2 + half) * 2 + 0) * MT_BYTES);
                 float *t_lo = reinterpret_cast<float *>(m_tiles + ((mt * 2 + half) * 2 + 1) * MT_BYTES);
@@ -1252,28 +1271,46 @@ __device__ __forceinline__ void k1tc_conv(const float *__restrict__ act, int act
                                           int n_mt, int base1, int &kcount, int total_kb, int nw) {
     constexpr int NKB = (KW * 16 + 31) / 32;
     constexpr uint32_t idesc = idesc_tf32(128, 64);
+    constexpr uint32_t idesc128 = idesc_tf32(128, 128);
     const int k0 = kcount;
     kcount += NKB;
     if (threadIdx.x >= 32) {
         // ---------------------------------- tile builders -------------------------------------------
+        // item i = (row r, 16-byte chunk q): source and destination offsets are fixed per conv except
+        // for +32 floats of source per K block, so they are computed once (no divisions in the K loop)
         const int bt = threadIdx.x - 32;
+        constexpr int ITEMS = (256 * 8 + BUILDERS - 1) / BUILDERS;  // R <= 256 rows
+        int src[ITEMS], dst[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int i = bt + k * BUILDERS;
+            const int r = i >> 3, q = i & 7;
+            const int chunk = r / T3, tp = r - chunk * T3;
+            // q >= 4 is the second tap of the K block; bit 30 marks it so the tail K block can zero it
+            src[k] = i < R * 8 ? (chunk * act_stride + (3 * tp + (q >> 2)) * 16 + (q & 3) * 4) | ((q >> 2) << 30)
+                               : -1;
+            dst[k] = r * 32 + ((q ^ (r & 7)) << 2);
+        }
         for (int kbk = 0; kbk < NKB; ++kbk) {
             const int kc = k0 + kbk, st = kc & 1;
             if (kc >= 2) mbar_wait(&bars->a_empty[st], ((kc >> 1) - 1) & 1);
             float *t_hi = reinterpret_cast<float *>(a_stages + st * stage_bytes);
             float *t_lo = t_hi + rpad * 32;
             const bool tap_hi_ok = 2 * kbk + 1 < KW;
-            for (int i = bt; i < R * 8; i += BUILDERS) {
-                const int r = i >> 3, q = i & 7;
-                const int chunk = r / T3, tp = r - chunk * T3;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q < 4 || tap_hi_ok)
-                    v = *reinterpret_cast<const float4 *>(act + chunk * act_stride +
-                                                          (3 * tp + 2 * kbk + (q >> 2)) * 16 + (q & 3) * 4);
-                const int off = r * 32 + ((q ^ (r & 7)) << 2);
-                *reinterpret_cast<float4 *>(t_hi + off) = v;
-                *reinterpret_cast<float4 *>(t_lo + off) =
-                    make_float4(tf32_trunc_lo(v.x), tf32_trunc_lo(v.y), tf32_trunc_lo(v.z), tf32_trunc_lo(v.w));
+            const float *a_k = act + kbk * 32;
+            float4 v[ITEMS];
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src[k] >= 0 && (tap_hi_ok || !(src[k] >> 30)))
+                    v[k] = *reinterpret_cast<const float4 *>(a_k + (src[k] & 0x3FFFFFFF));
+            }
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                if (src[k] < 0) continue;
+                *reinterpret_cast<float4 *>(t_hi + dst[k]) = v[k];
+                *reinterpret_cast<float4 *>(t_lo + dst[k]) = make_float4(
+                    tf32_trunc_lo(v[k].x), tf32_trunc_lo(v[k].y), tf32_trunc_lo(v[k].z), tf32_trunc_lo(v[k].w));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&bars->a_full[st]);
@@ -1286,11 +1323,20 @@ __device__ __forceinline__ void k1tc_conv(const float *__restrict__ act, int act
             mbar_wait(&bars->a_full[st], (kc >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = smem_addr(a_stages + st * stage_bytes), a_lo = a_hi + rpad * 128;
-            const uint32_t b_hi = smem_addr(w_ring + ws * WST_BYTES), b_lo = b_hi + 64 * 128;
+            const uint32_t b_hi = smem_addr(w_ring + ws * WST_BYTES);  // {hi (64 rows); lo (64 rows)}
             for (int mt = 0; mt < n_mt; ++mt) {
+                // TMEM columns [main | corrections] of this M tile: one N=128 MMA with the weight stage's
+                // {hi; lo} tile pair gives a_hi*b_hi and a_hi*b_lo side by side, the N=64 MMA adds
+                // a_lo*b_hi into the correction columns (2 reads of the activation tile per K step, not 3)
                 const uint32_t ro = (uint32_t)(mt ? base1 : 0) * 128u;
-                mma3_kblock(tmem_d + mt * 128, tmem_d + mt * 128 + 64, a_hi + ro, a_lo + ro, b_hi, b_lo, idesc,
-                            kbk == 0, kbk == 0);
+                const uint32_t d = tmem_d + mt * 128;
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8) {
+                    const uint32_t o = k8 * 32;
+                    mma_tf32(d, desc_sw128(a_hi + ro + o), desc_sw128(b_hi + o), idesc128,
+                             (kbk == 0 && k8 == 0) ? 0u : 1u);
+                    mma_tf32(d + 64, desc_sw128(a_lo + ro + o), desc_sw128(b_hi + o), idesc, 1u);
+                }
             }
             umma_commit(&bars->a_empty[st]);
             umma_commit(&bars->w_empty[ws]);
