@@ -63,7 +63,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -99,6 +99,34 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic_bytes(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_name` from the committed
+    `ncu --set full` summary (profiles/, cold-cache capture of the same 1024-chunk step), or None."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_summary_r*.json"))):
+        try:
+            rows = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        for row in rows:
+            if kernel_name not in row.get("Kernel Name", ""):
+                continue
+            total = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                m = re.match(r"([0-9.]+)\s*(\w+)?", row.get(key, ""))
+                if not m:
+                    total = None
+                    break
+                unit = (m.group(2) or "byte").lower()
+                scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+                total += float(m.group(1)) * scale
+            if total is not None:
+                best = (total, os.path.basename(path))
+    return best
 
 
 def make_pool(n_batches, seed):
@@ -273,7 +301,7 @@ def ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)
+        time.sleep(0.6)  # nvidia-smi needs a few hundred ms before its first sample
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -286,7 +314,6 @@ def ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = model.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -331,6 +358,8 @@ def ours(args):
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * e2e_steps / float(t.item())
+    # clock samples cover both timed regions (device-resident loop and the end-to-end loop)
+    clocks = sampler.stop() if rank == 0 else None
     h2d = BATCH * (CHUNK_LEN * 4 + pool["sequence"].shape[1] + pool["sequence_to_signal_mapping"].shape[1] * 2 + 2)
     d2h = BATCH * model.num_out * 4
     # the synchronous single-call form (pageable host buffers, internal pinned staging, blocking)
@@ -358,7 +387,7 @@ def ours(args):
 
     # ---- dense encode kernel alone (the HBM-bound kernel of the path) ------------------------------
     from remora_b200 import encoded_kmers
-    enc_n = 8192
+    enc_n = min(32768, n_pool * BATCH)  # 472 MB of one-hot output per launch
     sl = slice(0, enc_n)
     enc_args = (dev_pool["sequence"][sl], dev_pool["sequence_to_signal_mapping"][sl],
                 dev_pool["sequence_lengths"][sl])
@@ -413,9 +442,9 @@ def ours(args):
             tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0  # dense tf32 = half the measured bf16 GEMM
             tc = impl_used == "fused_tc"
             # algorithmic bytes / MACs per chunk of each fused kernel
-            cat_b = 28 * 128 * 4 * (2 if tc else 1)  # tensor-core path stores cat as TF32 hi + lo images
+            cat_b = 28 * 128 * 4  # cat activations, fp32 (the tensor-core path derives the TF32 lo part on chip)
             kernels = {
-                "k1_front_kernel": {"ms": prof["k1_front_ms"], "bytes": 480 + cat_b,
+                "k1tc_front_kernel" if tc else "k1_front_kernel": {"ms": prof["k1_front_ms"], "bytes": 480 + cat_b,
                                     "mac": 1920 + 29440 + 258048 + 276480 + 372736, "roof": "fp32"},
                 "k2tc_kernel" if tc else "k2_merge_kernel": {
                     "ms": prof["k2_merge_xproj_ms"], "bytes": cat_b + 24 * 256 * 4,
@@ -428,7 +457,8 @@ def ours(args):
             line["roofline"] = {
                 "kernel": name, "bound": "hbm", "achieved": BATCH * dom["bytes"] / dom_s / 1e9,
                 "peak": peak_gbs, "unit": "GB/s", "frac": BATCH * dom["bytes"] / dom_s / 1e9 / peak_gbs,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": (ncu_traffic_bytes(name) or (None, None))[0],
+                "traffic_source": (ncu_traffic_bytes(name) or (None, None))[1], "peak_source": peak_src,
                 "note": "dominant kernel by measured time; it is compute bound, not HBM bound (472 FLOP/B "
                         "at the reference interface; intermediates are L2 resident): the binding roofs are "
                         "in roofline_compute",
@@ -470,7 +500,7 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool-batches", type=int, default=400,
