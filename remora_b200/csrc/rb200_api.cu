@@ -130,7 +130,8 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
     Workspace &ws = m->workspaces[stream_v];
     int impl = m->impl;
     const bool fused_ok =
-        compact && m->fused != nullptr && fused_shape_ok(m, T, seq_width, map_width);
+        m->fused != nullptr && fused_shape_ok(m, T, compact ? seq_width : m->desc.kmer_len,
+                                              compact ? map_width : 2);
     // AUTO prefers the tensor-core variant of the fused path (falls back to FFMA2 inside when the
     // CTA's rows do not fit two M tiles)
     if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_LAYERS;
@@ -139,8 +140,20 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
             set_error("fused kernels not available for this model/shape/input form");
             return RB200_ERR_UNSUPPORTED;
         }
-        return fused_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T,
-                                     logits, stream, impl == RB200_IMPL_FUSED_TC);
+        if (compact)
+            return fused_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T,
+                                         logits, stream, impl == RB200_IMPL_FUSED_TC);
+        // dense interface (the reference's model(sigs, enc_kmers)): dense seq_conv1 kernel + the
+        // tensor-core fused kernels; shapes they cannot take fall through to the layer kernels
+        if (impl == RB200_IMPL_FUSED_TC) {
+            int rc = fused_forward_compact(m, ws, sigs, nullptr, 0, nullptr, 0, nullptr, B, T, logits,
+                                           stream, true, enc);
+            if (rc != RB200_ERR_UNSUPPORTED) return rc;
+        }
+        if (m->impl != RB200_IMPL_AUTO) {
+            set_error("fused kernels not available for the dense interface with this shape");
+            return RB200_ERR_UNSUPPORTED;
+        }
     }
     m->last_impl = RB200_IMPL_LAYERS;
     return layers_forward(m, ws, sigs, enc, seqs, seq_width, maps, map_width, lens, B, T, logits,

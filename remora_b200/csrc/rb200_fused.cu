@@ -442,8 +442,14 @@ __device__ __forceinline__ void k1_stage_inputs(
     const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens, int chunk0, int C,
     int T, int kmer_len, const Geometry &g, const FrontOffsets &fo, uint64_t *bar, const float *wsm,
     float *sig_s, float *s1_s, float *act_s, int16_t *sidx_s, int8_t *seq_s, int16_t *map_s, int *len_s,
-    int s2_stride, int qp) {
+    int s2_stride, int qp, bool dense = false) {
     const int tid = threadIdx.x;
+    if (dense) {  // dense one-hot interface: only the signal is staged, seq_conv1 ran as its own kernel
+        for (int i = tid; i < C * T; i += THREADS) sig_s[i] = sigs[(size_t)chunk0 * T + i];
+        mbar_wait(bar, 0);
+        __syncthreads();
+        return;
+    }
     // ---- stage the compact inputs of this CTA's chunks ------------------------------------------
     for (int i = tid; i < C * T; i += THREADS) {
         sig_s[i] = sigs[(size_t)chunk0 * T + i];
@@ -611,6 +617,65 @@ k1_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seqs,
     // ---- seq_conv2 (16 -> 64, k13, stride 3) -> cat[:, :, 64:128] --------------------------------
     conv16_s3_to_cat<KW_SEQ2>(act_s, g.q1_stride, wsm + fo.w_seq2, wsm + fo.b_seq2, cat_cta,
                               g.cat_stride, SIZE, C, CL, g.NB1, g.T3, tc_rpad);
+}
+
+// =================================================================================================
+// K0 (dense interface only): seq_conv1 + BN + swish on a materialised one-hot tensor
+// =================================================================================================
+// model(sigs, enc_kmers) - the reference's own call form - hands over float32 [B][4k][T].  This
+// kernel is the honest dense convolution (any float input, not only one-hot) producing the same
+// q1 [B][T-4][16] channel-last activations the gather produces on the compact path, so that the rest
+// of the fused pipeline (K1-TC from sig/q1, K2-TC, K3) is shared.  One CTA per chunk: the chunk's
+// [4k x T] tile arrives by one TMA bulk copy, weights [row][tap][16] by another; one thread per output
+// step accumulates 16 channels as 8 FFMA2 pairs.
+__global__ void __launch_bounds__(128)
+k0_dense_seq1_kernel(const float *__restrict__ enc, const float *__restrict__ w, const float *__restrict__ bias,
+                     float *__restrict__ q1, int B, int T, int rows) {
+    extern __shared__ __align__(128) float sm0[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm0);
+    float *x_s = sm0 + 4;                         // [rows][T]
+    float *w_s = x_s + ((rows * T + 3) & ~3);     // [rows][5][16]
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t xb = (uint32_t)rows * T * 4u, wb = (uint32_t)rows * KW_SEQ1 * 16 * 4u;
+        mbar_expect_tx(bar, xb + wb);
+        bulk_g2s(x_s, enc + (size_t)c * rows * T, xb, bar);
+        bulk_g2s(w_s, w, wb, bar);
+    }
+    mbar_wait(bar, 0);
+    const int Q1 = T - (KW_SEQ1 - 1);
+    for (int t = tid; t < Q1; t += blockDim.x) {
+        float2 a[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a[o] = make_float2(bias[2 * o], bias[2 * o + 1]);
+        for (int r = 0; r < rows; ++r) {
+            const float *xr = x_s + r * T + t;
+#pragma unroll
+            for (int j = 0; j < KW_SEQ1; ++j) {
+                const float xv = xr[j];
+                const float4 *wp = reinterpret_cast<const float4 *>(w_s + (r * KW_SEQ1 + j) * 16);
+                const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                a[0] = ffma2(make_float2(w0.x, w0.y), xv, a[0]);
+                a[1] = ffma2(make_float2(w0.z, w0.w), xv, a[1]);
+                a[2] = ffma2(make_float2(w1.x, w1.y), xv, a[2]);
+                a[3] = ffma2(make_float2(w1.z, w1.w), xv, a[3]);
+                a[4] = ffma2(make_float2(w2.x, w2.y), xv, a[4]);
+                a[5] = ffma2(make_float2(w2.z, w2.w), xv, a[5]);
+                a[6] = ffma2(make_float2(w3.x, w3.y), xv, a[6]);
+                a[7] = ffma2(make_float2(w3.z, w3.w), xv, a[7]);
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(q1 + ((size_t)c * Q1 + t) * 16);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            dst[o] = make_float4(swishf_fast(a[2 * o].x), swishf_fast(a[2 * o].y),
+                                 swishf_fast(a[2 * o + 1].x), swishf_fast(a[2 * o + 1].y));
+    }
 }
 
 // =================================================================================================
@@ -1359,7 +1424,7 @@ k1tc_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seq
                   const int16_t *__restrict__ maps, int map_width, const int16_t *__restrict__ lens,
                   const float *__restrict__ wfront, const float *__restrict__ w_tc,
                   float *__restrict__ cat_img, int B, int CPB, int T, int kmer_len, int rpad, int CLs,
-                  int nw, long long *__restrict__ stamps) {
+                  int nw, const float *__restrict__ q1_in, long long *__restrict__ stamps) {
     extern __shared__ __align__(1024) uint8_t smk[];
 #define K1_STAMP(i) do { if (stamps && blockIdx.x == 1 && threadIdx.x == 0) stamps[i] = clock64(); } while (0)
     const Geometry g = make_geometry(T);
@@ -1422,10 +1487,18 @@ k1tc_front_kernel(const float *__restrict__ sigs, const int8_t *__restrict__ seq
     pdl_wait();  // inputs (and the image we overwrite) belong to earlier work in the stream
     K1_STAMP(1);
     k1_stage_inputs(sigs, seqs, seq_width, maps, map_width, lens, chunk0, C, T, kmer_len, g, fo, &bars->wfront,
-                    wsm, sig_s, s1_s, act_s, sidx_s, seq_s, map_s, len_s, lay.act_stride, 16);
+                    wsm, sig_s, s1_s, act_s, sidx_s, seq_s, map_s, len_s, lay.act_stride, 16, q1_in != nullptr);
     // ---- sequence track first: seq_conv1 (two-stage gather; the per-base sums live in the still unused
     // tile stages) -> q1 in act_s -> seq_conv2 on the tensor core, TMEM columns [256, 512) -----------------
-    {
+    if (q1_in != nullptr) {
+        // dense interface: q1 was computed by k0_dense_seq1_kernel; same [chunk][Q1][16] layout as act_s
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)C * g.Q1 * 16 * 4u;
+            mbar_expect_tx(&bars->wfront, bytes);
+            bulk_g2s(act_s, q1_in + (size_t)chunk0 * g.Q1 * 16, bytes, &bars->wfront);
+        }
+        mbar_wait(&bars->wfront, 1);
+    } else {
         float *gs = reinterpret_cast<float *>(a_stages);
         const int LM = map_width - 1;
         if (kmer_len == 9)
@@ -1765,7 +1838,7 @@ __global__ void repack_kernel(const float *__restrict__ src, int64_t chunk_strid
 struct FusedWeights {
     float *dev = nullptr;  // one allocation holding every re-laid-out tensor
     size_t off_front = 0, off_slabs = 0, off_bmerge = 0, off_wih1T = 0, off_b1 = 0, off_whh4 = 0,
-           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0, off_wm_tc = 0, off_wih_tc = 0, off_front_tc = 0, off_w1_tc = 0;
+           off_wih2T = 0, off_b2 = 0, off_fcw = 0, off_fcb = 0, off_wm_tc = 0, off_wih_tc = 0, off_front_tc = 0, off_w1_tc = 0, off_wseq1_dense = 0;
     int kmer_len = 0, num_out = 0;
 };
 
@@ -1911,6 +1984,15 @@ int fused_create(rb200_model *m, const float *blob) {
                 }
         }
 
+    // K0 (dense interface): seq_conv1 weights as [input row][tap][16]
+    fw->off_wseq1_dense = reserve((size_t)4 * K * KW_SEQ1 * 16);
+    {
+        const float *w = blob + d.seq_conv[0].w_off;  // [16][4K][5]
+        for (int row = 0; row < 4 * K; ++row)
+            for (int j = 0; j < KW_SEQ1; ++j)
+                for (int co = 0; co < 16; ++co)
+                    host[fw->off_wseq1_dense + (row * KW_SEQ1 + j) * 16 + co] = w[(co * 4 * K + row) * KW_SEQ1 + j];
+    }
     // K1-TC: stride-3 conv weights as [K block][hi|lo][64][32] tiles, k = (tap - 2*kb)*16 + channel
     fw->off_w1_tc = reserve((size_t)(tc::K1TC_NKB_SIG + tc::K1TC_NKB_SEQ) * 2 * 64 * 32);
     for (int conv = 0; conv < 2; ++conv) {
@@ -1947,6 +2029,7 @@ int fused_create(rb200_model *m, const float *blob) {
     cudaFuncSetAttribute(k3_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES);
     cudaFuncSetAttribute(tc::k2tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(tc::k1tc_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k0_dense_seq1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     m->fused = fw;
     return RB200_OK;
 }
@@ -2009,8 +2092,13 @@ static int pick_cpb(int B, int cmax, int sm_count) {
 
 int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
                           int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
-                          int B, int T, float *logits, cudaStream_t stream, bool want_tc) {
+                          int B, int T, float *logits, cudaStream_t stream, bool want_tc,
+                          const float *enc_dense) {
     const FusedWeights *fw = m->fused;
+    if (enc_dense) {  // dense interface: sizes of the (absent) compact arrays only feed smem layouts
+        seq_width = fw->kmer_len;
+        map_width = 2;
+    }
     const Geometry g = make_geometry(T);
     RB200_REQUIRE(g.ok, "chunk_len %d not supported by the fused kernels", T);
     // tensor-core variants (tcgen05 3xTF32) when requested and the CTA's rows fit two M tiles
@@ -2020,10 +2108,14 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     const int k1_nw =
         tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, 3).total <= 227 * 1024 ? 3 : 2;
     const bool use_tc_k1 =
-        use_tc && !getenv("RB200_NO_K1TC") &&
+        use_tc && (enc_dense != nullptr || !getenv("RB200_NO_K1TC")) &&
         tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, k1_nw).total <= 227 * 1024 &&
         // the per-base gather sums borrow the (not yet used) tile stages
         (size_t)cpb * (map_width - 1) * KW_SEQ1 * GROW * 4 <= (size_t)4 * tc_rpad * 128;
+    if (enc_dense && !use_tc_k1) {
+        set_error("dense fused path not available for this shape");
+        return RB200_ERR_UNSUPPORTED;
+    }
     if (want_tc && !use_tc) {  // fall back to the fp32 kernels with their own best CTA size
         cpb = pick_cpb(B, g.CL, m->sm_count);
         tc_rpad = 0;
@@ -2031,7 +2123,8 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     const int grid = (B + cpb - 1) / cpb;
     const size_t cat_bytes = use_tc ? align256((size_t)grid * 4 * tc_rpad * 32 * 4)
                                     : align256((size_t)B * g.cat_stride * 4);
-    const size_t live_bytes = cat_bytes + align256((size_t)B * g.TM * 256 * 4);
+    const size_t q1_bytes = enc_dense ? align256((size_t)B * g.Q1 * 16 * 4) : 0;
+    const size_t live_bytes = cat_bytes + align256((size_t)B * g.TM * 256 * 4) + q1_bytes;
     const size_t n_cat = (size_t)B * 128 * g.T3, n_xp = (size_t)B * 256 * g.TM;
     size_t need = live_bytes + 1024;
     if (m->keep_debug) need += align256(n_cat * 4) + align256(n_xp * 4);
@@ -2039,6 +2132,8 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     if (rc) return rc;
     float *cat = reinterpret_cast<float *>(ws.base);
     float *xp = reinterpret_cast<float *>(ws.base + cat_bytes);
+    float *q1_buf = enc_dense ? reinterpret_cast<float *>(ws.base + cat_bytes + align256((size_t)B * g.TM * 256 * 4))
+                              : nullptr;
     const K1Smem l1 = k1_smem(g, fw->kmer_len, seq_width, map_width);
     const K2Smem l2 = k2_smem(g);
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -2052,6 +2147,16 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     // with profiling events between the kernels PDL cannot overlap them; launch plainly then
     const bool pdl = !m->profile;
     const int k1_tc = use_tc ? tc_rpad : 0;
+    if (enc_dense) {
+        const int rows = 4 * fw->kmer_len;
+        const size_t smem0 = (4 + ((rows * T + 3) & ~3) + rows * KW_SEQ1 * 16) * sizeof(float);
+        RB200_REQUIRE(smem0 <= 227 * 1024, "chunk_len %d too long for the dense fused path", T);
+        k0_dense_seq1_kernel<<<B, 128, smem0, stream>>>(enc_dense, fw->dev + fw->off_wseq1_dense,
+                                                       fw->dev + fw->off_front_tc + front_offsets(fw->kmer_len, true).b_seq1,
+                                                       q1_buf, B, T, rows);
+        RB200_CUDA_TRY(cudaGetLastError());
+        m->launches += 1;
+    }
     if (use_tc_k1) {
         const int smem1 = tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, k1_nw).total;
         static long long *k1_stamps = nullptr;  // profiling aid: RB200_TC_STAMPS=1
@@ -2062,11 +2167,11 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
                                       seqs, seq_width, maps, map_width, lens,
                                       (const float *)(fw->dev + fw->off_front_tc),
                                       (const float *)(fw->dev + fw->off_w1_tc), cat, B, cpb, T,
-                                      fw->kmer_len, tc_rpad, cpb, k1_nw, k1_stamps));
+                                      fw->kmer_len, tc_rpad, cpb, k1_nw, (const float *)q1_buf, k1_stamps));
         } else {
             tc::k1tc_front_kernel<<<grid, THREADS, smem1, stream>>>(
                 sigs, seqs, seq_width, maps, map_width, lens, fw->dev + fw->off_front_tc,
-                fw->dev + fw->off_w1_tc, cat, B, cpb, T, fw->kmer_len, tc_rpad, cpb, k1_nw, k1_stamps);
+                fw->dev + fw->off_w1_tc, cat, B, cpb, T, fw->kmer_len, tc_rpad, cpb, k1_nw, q1_buf, k1_stamps);
         }
         if (want_k1_stamps) {
             long long h[16];

@@ -127,6 +127,7 @@ bool fused_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
 size_t fused_workspace_bytes(const rb200_model *m, int B, int T);
 int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
                           int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
-                          int B, int T, float *logits, cudaStream_t stream, bool want_tc);
+                          int B, int T, float *logits, cudaStream_t stream, bool want_tc,
+                          const float *enc_dense = nullptr);
 
 }  // namespace rb200
