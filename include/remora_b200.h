@@ -47,10 +47,12 @@ enum rb200_arch {
 };
 
 enum rb200_impl {
-    RB200_IMPL_AUTO = 0,    /* fused kernels when the model/shape qualifies, else layer kernels */
-    RB200_IMPL_LAYERS = 1,  /* one CUDA kernel per layer, any size / kmer_len / chunk_len */
+    RB200_IMPL_AUTO = 0,    /* fused kernels when the model/shape qualifies, else tiled layer kernels */
+    RB200_IMPL_LAYERS = 1,  /* one plain CUDA kernel per layer, any size / kmer_len / chunk_len */
     RB200_IMPL_FUSED = 2,   /* fused sm_100a kernels (ConvLSTM_w_ref, size 64), fp32 FFMA2; error if n/a */
-    RB200_IMPL_FUSED_TC = 3 /* same, merge conv + LSTM input projection on tcgen05 (3xTF32, TMEM) */
+    RB200_IMPL_FUSED_TC = 3, /* same, merge conv + LSTM input projection on tcgen05 (3xTF32, TMEM) */
+    RB200_IMPL_TILED = 4 /* per layer: register-tiled FFMA2 convolutions, gather-form seq_conv1 from the
+                            compact arrays; Conv_w_ref and every shape the fused kernels do not take */
 };
 
 #define RB200_MAX_CONVS 4

@@ -11,7 +11,7 @@ from . import RemoraError
 MAX_CONVS = 4
 ARCH_CONVLSTM_W_REF = 1
 ARCH_CONV_W_REF = 2
-IMPL_AUTO, IMPL_LAYERS, IMPL_FUSED, IMPL_FUSED_TC = 0, 1, 2, 3
+IMPL_AUTO, IMPL_LAYERS, IMPL_FUSED, IMPL_FUSED_TC, IMPL_TILED = 0, 1, 2, 3, 4
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "librb200.so")
 

@@ -134,7 +134,7 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
                                               compact ? map_width : 2);
     // AUTO prefers the tensor-core variant of the fused path (falls back to FFMA2 inside when the
     // CTA's rows do not fit two M tiles)
-    if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_LAYERS;
+    if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_TILED;
     if (impl == RB200_IMPL_FUSED || impl == RB200_IMPL_FUSED_TC) {
         if (!fused_ok) {
             set_error("fused kernels not available for this model/shape/input form");
@@ -155,9 +155,12 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
             return RB200_ERR_UNSUPPORTED;
         }
     }
-    m->last_impl = RB200_IMPL_LAYERS;
+    // layer by layer: the register-tiled FFMA2 kernels (layers without a tiled form use the plain
+    // kernel), or - RB200_IMPL_LAYERS - the plain one-thread-per-output kernels throughout
+    const bool tiled = impl != RB200_IMPL_LAYERS;
+    m->last_impl = tiled ? RB200_IMPL_TILED : RB200_IMPL_LAYERS;
     return layers_forward(m, ws, sigs, enc, seqs, seq_width, maps, map_width, lens, B, T, logits,
-                          stream);
+                          stream, tiled);
 }
 
 }  // namespace rb200
@@ -203,13 +206,13 @@ int rb200_create(const rb200_model_desc *desc, const float *weights_host, int64_
         delete m;
         return RB200_ERR_CUDA;
     }
-    if (fused_supported(m->desc)) {
-        rc = fused_create(m, weights_host);
-        if (rc) {
-            cudaFree(m->blob_dev);
-            delete m;
-            return rc;
-        }
+    rc = tiled_create(m, weights_host);
+    if (rc == RB200_OK && fused_supported(m->desc)) rc = fused_create(m, weights_host);
+    if (rc) {
+        tiled_destroy(m);
+        cudaFree(m->blob_dev);
+        delete m;
+        return rc;
     }
     *out = m;
     return RB200_OK;
@@ -221,6 +224,7 @@ int rb200_destroy(rb200_handle h) {
     cudaDeviceSynchronize();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     fused_destroy(h);
+    tiled_destroy(h);
     for (auto &kv : h->workspaces) kv.second.release();
     for (auto &kv : h->host_staging) kv.second.release();
     if (h->blob_dev) cudaFree(h->blob_dev);
@@ -232,8 +236,8 @@ int rb200_destroy(rb200_handle h) {
 }
 
 int rb200_set_impl(rb200_handle h, int impl) {
-    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_FUSED_TC, "bad argument");
-    if (impl >= RB200_IMPL_FUSED && h->fused == nullptr) {
+    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_TILED, "bad argument");
+    if ((impl == RB200_IMPL_FUSED || impl == RB200_IMPL_FUSED_TC) && h->fused == nullptr) {
         set_error("fused kernels not available for this model");
         return RB200_ERR_UNSUPPORTED;
     }

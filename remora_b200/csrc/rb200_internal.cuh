@@ -63,6 +63,7 @@ struct DebugTensor {
 };
 
 struct FusedWeights;  // rb200_fused.cu
+struct TiledWeights;  // rb200_tiled.cu
 
 }  // namespace rb200
 
@@ -81,6 +82,7 @@ struct rb200_model {
     std::map<void *, rb200::Workspace> workspaces;  // keyed by stream
     std::map<void *, rb200::Workspace> host_staging;  // device-side input/output staging of rb200_infer_host_async
     rb200::FusedWeights *fused = nullptr;           // non-null when the fused path applies
+    rb200::TiledWeights *tiled = nullptr;           // weight layouts of the register-tiled layer kernels
     // pinned + device staging for rb200_infer_host
     char *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -105,7 +107,8 @@ int launch_encode_dense(const int8_t *seqs, int seq_width, const int16_t *maps, 
 size_t layers_workspace_bytes(const rb200_model_desc &d, int B, int T, bool compact);
 int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float *enc,
                    const int8_t *seqs, int seq_width, const int16_t *maps, int map_width,
-                   const int16_t *lens, int B, int T, float *logits, cudaStream_t stream);
+                   const int16_t *lens, int B, int T, float *logits, cudaStream_t stream,
+                   bool tiled);
 int launch_softmax_ml(const float *logits, int B, int num_out, float *probs, uint8_t *ml,
                       cudaStream_t stream);
 
@@ -118,6 +121,19 @@ int launch_chunk_fill(const void *dacs, int dtype, int sig_len, double shift, do
                       const int32_t *focus_sig, const int32_t *seq_start, const int32_t *seq_len, int n,
                       int c0, int c1, int kb, int ka, int lmax, float *signal, int8_t *sequence,
                       int16_t *mapping, int16_t *lens, cudaStream_t stream);
+
+// rb200_tiled.cu : register-tiled FFMA2 layer kernels (Conv_w_ref and every non-fused shape);
+// each returns RB200_ERR_UNSUPPORTED when the layer / shape has no tiled form
+int tiled_create(rb200_model *m, const float *blob_host);
+void tiled_destroy(rb200_model *m);
+int tiled_conv(rb200_model *m, int track, int layer, const rb200_conv_desc &c, const float *x,
+               int64_t x_bstride, int t_in, float *y, int64_t y_bstride, int B, cudaStream_t stream);
+bool tiled_gather_ok(const rb200_model *m, int seq_width, int map_width, int T);
+int tiled_seq1_gather(rb200_model *m, const int8_t *seqs, int seq_width, const int16_t *maps,
+                      int map_width, const int16_t *lens, int B, int T, float *y, int64_t y_bstride,
+                      cudaStream_t stream);
+int tiled_fc(rb200_model *m, const float *x, int64_t bstride, float *logits, int B,
+             cudaStream_t stream);
 
 // rb200_fused.cu : fused sm_100a kernels for ConvLSTM_w_ref size 64
 bool fused_supported(const rb200_model_desc &d);

@@ -6,6 +6,8 @@
 // Activations are channel-first float32 [B][C][T] like the reference tensors.
 #include "rb200_internal.cuh"
 
+#include <algorithm>
+
 namespace rb200 {
 
 // y[b][co][t] = swish(bias[co] + sum_{ci,j} w[co][ci][j] * x[b][ci][t*stride + j])
@@ -167,8 +169,13 @@ size_t layers_workspace_bytes(const rb200_model_desc &d, int B, int T, bool comp
     return total + 1024;
 }
 
-static int run_conv(rb200_model *m, const rb200_conv_desc &c, const float *x, int64_t x_bstride,
-                    int t_in, float *y, int64_t y_bstride, int B, cudaStream_t stream) {
+static int run_conv(rb200_model *m, int track, int layer, bool tiled, const rb200_conv_desc &c,
+                    const float *x, int64_t x_bstride, int t_in, float *y, int64_t y_bstride, int B,
+                    cudaStream_t stream) {
+    if (tiled) {
+        const int rc = tiled_conv(m, track, layer, c, x, x_bstride, t_in, y, y_bstride, B, stream);
+        if (rc != RB200_ERR_UNSUPPORTED) return rc;
+    }
     const int t_out = conv_out_len(t_in, c.kw, c.stride);
     const int64_t total = (int64_t)B * c.c_out * t_out;
     const int threads = 256;
@@ -184,7 +191,8 @@ static int run_conv(rb200_model *m, const rb200_conv_desc &c, const float *x, in
 
 int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float *enc,
                    const int8_t *seqs, int seq_width, const int16_t *maps, int map_width,
-                   const int16_t *lens, int B, int T, float *logits, cudaStream_t stream) {
+                   const int16_t *lens, int B, int T, float *logits, cudaStream_t stream,
+                   bool tiled) {
     const rb200_model_desc &d = m->desc;
     Plan p = make_plan(d, T);
     RB200_REQUIRE(p.ok, "chunk_len %d too short / inconsistent for this architecture", T);
@@ -212,7 +220,10 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
     static const char *seq_names[] = {"seq1", "seq2", "seq3", "seq4"};
     static const char *mrg_names[] = {"merge1", "merge2", "merge3", "merge4"};
 
-    if (compact) {
+    // tiled mode: the first sequence convolution reads the compact arrays itself (gather form)
+    bool gather_seq1 = false;
+    if (compact && tiled) gather_seq1 = tiled_gather_ok(m, seq_width, map_width, T);
+    if (compact && !gather_seq1) {
         float *enc_buf = take((size_t)B * 4 * d.kmer_len * T * 4);
         uint64_t l = 0;
         rc = launch_encode_dense(seqs, seq_width, maps, map_width, lens, B, d.kmer_len, T, enc_buf,
@@ -237,7 +248,7 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
         const bool last = i == d.n_sig_conv - 1;
         float *y = last ? cat : sig_bufs[i];
         const int64_t yb = last ? cat_bstride : (int64_t)d.sig_conv[i].c_out * p.sig_t[i + 1];
-        rc = run_conv(m, d.sig_conv[i], x, xb, p.sig_t[i], y, yb, B, stream);
+        rc = run_conv(m, 0, i, tiled, d.sig_conv[i], x, xb, p.sig_t[i], y, yb, B, stream);
         if (rc) return rc;
         if (!last) keep(sig_names[i], y, d.sig_conv[i].c_out, p.sig_t[i + 1]);
         x = y;
@@ -249,8 +260,14 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
         const bool last = i == d.n_seq_conv - 1;
         float *y = last ? cat + (size_t)d.size * t_cat : seq_bufs[i];
         const int64_t yb = last ? cat_bstride : (int64_t)d.seq_conv[i].c_out * p.seq_t[i + 1];
-        rc = run_conv(m, d.seq_conv[i], x, xb, p.seq_t[i], y, yb, B, stream);
-        if (rc) return rc;
+        if (i == 0 && gather_seq1)
+            rc = tiled_seq1_gather(m, seqs, seq_width, maps, map_width, lens, B, T, y, yb, stream);
+        else
+            rc = run_conv(m, 1, i, tiled, d.seq_conv[i], x, xb, p.seq_t[i], y, yb, B, stream);
+        if (rc) {
+            if (rc == RB200_ERR_UNSUPPORTED) set_error("sequence convolution %d has no kernel", i);
+            return rc;
+        }
         if (!last) keep(seq_names[i], y, d.seq_conv[i].c_out, p.seq_t[i + 1]);
         x = y;
         xb = yb;
@@ -262,7 +279,7 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
     for (int i = 0; i < d.n_merge_conv; ++i) {
         float *y = take((size_t)B * d.merge_conv[i].c_out * p.mrg_t[i + 1] * 4);
         const int64_t yb = (int64_t)d.merge_conv[i].c_out * p.mrg_t[i + 1];
-        rc = run_conv(m, d.merge_conv[i], x, xb, t_cur, y, yb, B, stream);
+        rc = run_conv(m, 2, i, tiled, d.merge_conv[i], x, xb, t_cur, y, yb, B, stream);
         if (rc) return rc;
         keep(mrg_names[i], y, d.merge_conv[i].c_out, p.mrg_t[i + 1]);
         x = y;
@@ -298,6 +315,9 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
                                                        m->blob_dev + d.fc_b_off, logits, B, H,
                                                        d.num_out);
         m->launches++;
+    } else if (tiled) {
+        rc = tiled_fc(m, x, xb, logits, B, stream);
+        if (rc) return rc;
     } else {
         // torch.flatten([B][C][T]) -> feature index c*T + t = channel-first buffer as is
         const int n = B * d.num_out;

@@ -200,12 +200,13 @@ class B200Model(nn.Module):
     # -- controls used by tests / bench ----------------------------------------------------
     def set_impl(self, impl):
         code = {"auto": _native.IMPL_AUTO, "layers": _native.IMPL_LAYERS,
-                "fused": _native.IMPL_FUSED, "fused_tc": _native.IMPL_FUSED_TC}[impl]
+                "fused": _native.IMPL_FUSED, "fused_tc": _native.IMPL_FUSED_TC,
+                "tiled": _native.IMPL_TILED}[impl]
         _native.check(self._lib.rb200_set_impl(self._handle, code), "rb200_set_impl")
 
     @property
     def last_impl(self):
-        return {0: None, 1: "layers", 2: "fused", 3: "fused_tc"}[
+        return {0: None, 1: "layers", 2: "fused", 3: "fused_tc", 4: "tiled"}[
             self._lib.rb200_last_impl(self._handle)]
 
     @property

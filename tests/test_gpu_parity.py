@@ -28,10 +28,10 @@ def gpu_model(name):
 
 
 def impls_for(model):
-    """CUDA paths to check for this model: layer kernels always; for ConvLSTM_w_ref/64 also the fused
-    fp32 FFMA2 kernels and the tcgen05 (3xTF32) variant."""
-    return ["layers", "fused", "fused_tc"] if model.info["arch"] == "ConvLSTM_w_ref" and \
-        model.info["size"] == 64 and fused_available(model) else ["layers"]
+    """CUDA paths to check for this model: the plain and the register-tiled layer kernels always; for
+    ConvLSTM_w_ref/64 also the fused fp32 FFMA2 kernels and the tcgen05 (3xTF32) variant."""
+    return ["layers", "tiled", "fused", "fused_tc"] if model.info["arch"] == "ConvLSTM_w_ref" and \
+        model.info["size"] == 64 and fused_available(model) else ["layers", "tiled"]
 
 
 def fused_available(model):
@@ -153,15 +153,17 @@ def test_per_layer_activations_vs_oracle(forward_cases):
         cat = torch.cat((s3, q2), 1)
         m1 = ro._conv_bn_swish(cat, sd, "merge_conv1", "merge_bn")
         l1 = ro._swish(ro._lstm_forward(m1.permute(2, 0, 1), sd, "lstm1")).permute(1, 2, 0)
-    model.set_impl("layers")
-    model.set_debug(True)
-    model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs), torch.from_numpy(maps),
-                          torch.from_numpy(lens))
-    for name, want in (("sig1", s1), ("sig2", s2), ("seq1", q1), ("cat", cat), ("merge1", m1),
-                       ("lstm1", l1)):
-        got = model.debug_tensor(name).cpu()
-        assert got.shape == want.shape, name
-        assert (got - want).abs().max() < 2e-5, name
+    for impl in ("tiled", "layers"):
+        model.set_impl(impl)
+        model.set_debug(True)
+        model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs), torch.from_numpy(maps),
+                              torch.from_numpy(lens))
+        for name, want in (("sig1", s1), ("sig2", s2), ("seq1", q1), ("cat", cat), ("merge1", m1),
+                           ("lstm1", l1)):
+            got = model.debug_tensor(name).cpu()
+            assert got.shape == want.shape, (impl, name)
+            err, scale = float((got - want).abs().max()), max(1.0, float(want.abs().max()))
+            assert err < 2e-5 * (scale if impl == "tiled" else 1.0), (impl, name, err, scale)
     cat_layers = model.debug_tensor("cat").cpu()
     if "fused" in impls_for(model):
         # intermediates of the fused kernels: cat (K1 output) and the LSTM1 input projection (K2)
@@ -219,6 +221,62 @@ def test_batch_sizes_and_ragged_batches(B):
         again = model.forward_compact(*tail).cpu().numpy()
         assert np.abs(again - outs[impl][B - k:]).max() < 2e-6, impl
     model.set_impl("auto")
+
+
+@pytest.mark.parametrize("name,T,B", [("conv_s64_k9", 100, 1), ("conv_s64_k9", 100, 7),
+                                      ("conv_s64_k9", 100, 1024), ("conv_s64_k9", 100, 4099),
+                                      ("convlstm_s16_k6_o3", 60, 33), ("convlstm_s16_k6_o3", 400, 50),
+                                      ("convlstm_s64_k9_hot", 200, 130),
+                                      ("convlstm_s64_k9_hot", 400, 70)])
+def test_tiled_layer_kernels_match_plain_layer_kernels(name, T, B):
+    """Register-tiled FFMA2 convolutions + gather-form seq_conv1 against the one-thread-per-output
+    kernels, layer by layer (both compact and dense input), over shapes that exercise every tile plan."""
+    model, md = gpu_model(name)
+    ctx = tuple(md["kmer_context_bases"])
+    d = synth_chunks(B, T, ctx, seed=T + B)
+    args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                             "sequence_lengths")]
+    layer_names = ["sig1", "sig2", "sig3", "seq1", "seq2", "seq3", "cat", "merge1", "merge2", "merge3",
+                   "merge4"]
+    kept, logits = {}, {}
+    for impl in ("layers", "tiled"):
+        model.set_impl(impl)
+        model.set_debug(True)
+        logits[impl] = model.forward_compact(*args).cpu()
+        assert model.last_impl == impl
+        kept[impl] = {}
+        for ln in layer_names:
+            try:
+                kept[impl][ln] = model.debug_tensor(ln).cpu()
+            except RemoraError:
+                pass
+    model.set_debug(False)
+    assert set(kept["layers"]) == set(kept["tiled"]) and "cat" in kept["tiled"]
+    for ln, want in kept["layers"].items():
+        scale = max(1.0, float(want.abs().max()))
+        assert float((kept["tiled"][ln] - want).abs().max()) < 2e-5 * scale, ln
+    assert float((logits["tiled"] - logits["layers"]).abs().max()) < 5e-5
+    # dense input through the tiled kernels (no gather form for seq_conv1)
+    enc = torch.from_numpy(ro.encode_kmers_c(ctx[0], ctx[1], d["sequence"],
+                                             d["sequence_to_signal_mapping"],
+                                             d["sequence_lengths"])).cuda()
+    model.set_impl("tiled")
+    dense = model(args[0].cuda(), enc).cpu()
+    model.set_impl("auto")
+    assert float((dense - logits["layers"]).abs().max()) < 5e-5
+
+
+def test_conv_w_ref_auto_is_tiled_and_matches_oracle():
+    model, md = gpu_model("conv_s64_k9")
+    sd, _ = load_golden_model("conv_s64_k9")
+    d = synth_chunks(300, 100, (4, 4), seed=5)
+    args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                             "sequence_lengths")]
+    got = model.forward_compact(*args).cpu().numpy()
+    assert model.last_impl == "tiled"
+    want = ro.oracle_infer_compact(sd, (4, 4), d["signal"], d["sequence"],
+                                   d["sequence_to_signal_mapping"], d["sequence_lengths"])
+    assert np.abs(got - want).max() < LOGIT_TOL
 
 
 def test_empty_batch():
