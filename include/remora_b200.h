@@ -186,6 +186,39 @@ int rb200_chunk_fill(const void *dacs_dev, int32_t dacs_dtype, int32_t sig_len, 
 int rb200_softmax_ml(const float *logits_dev, int32_t B, int32_t num_out, float *probs_dev,
                      uint8_t *ml_dev, void *stream);
 
+/* Signal-mapping refinement on the device ("next" row 4): the banded dynamic programme
+ * of SigMapRefiner.refine_sig_map / refine_signal_mapping (src/remora/refine_signal_map.py:474-499,
+ * 783-840) with the Cython core seq_banded_dp (src/remora/refine_signal_map_core.pyx:403-473:
+ * banded_forward_dp + banded_traceback, both "Viterbi" and "dwell_penalty" steps) for a batch of reads.
+ * Scores, traceback and the returned path are bit-identical to the reference's.
+ *
+ * Layout: reads are concatenated.  Read r owns samples [sig_off[r], sig_off[r+1]) of the signal
+ * (already trimmed to seq_to_sig_map[0]..seq_to_sig_map[-1]), bases [seq_off[r], seq_off[r+1]) of
+ * levels / band_start / band_end (the seq band after adjust_seq_band, signal coordinates relative to
+ * the read: start[0] == 0, both strictly increasing, start[b] <= end[b-1], end[last] == read length),
+ * traceback words [tb_off[r], tb_off[r+1]) with tb_off[r+1]-tb_off[r] = sum(end-start), and
+ * path entries [seq_off[r] + r, seq_off[r+1] + r + 1) (seq_len + 1 values: path[0] = 0, path[b] =
+ * first sample of base b, path[seq_len] = read length).  max_width[r] = widest band of read r;
+ * order (may be NULL) = processing order, longest reads first for load balance.
+ *
+ *   rb200_refine_normalize: signal = (dacs - shift[r]) / scale[r] as float32; dacs_dtype 0 = int16,
+ *     1 = float32 (float32 arithmetic), 2 = float64, 3 = float32 samples in float64 arithmetic (numpy
+ *     float64 shift/scale), following numpy's promotion so the result matches the reference's bits.
+ *   rb200_refine_scratch_bytes: size of wide_scratch_dev (0 when every band fits the shared-memory rows).
+ *   rb200_refine_dp: algo 0 = "Viterbi", 1 = "dwell_penalty" (penalties on the host, <= 16).
+ *     status[r] = 1 when the traceback of read r left its band (undefined behaviour in the reference;
+ *     the path of that read is not usable).  queue_dev: one int32 of device scratch. */
+int rb200_refine_normalize(const void *dacs_dev, int32_t dacs_dtype, const int64_t *sig_off_dev,
+                           const double *shift_dev, const double *scale_dev, int32_t n_reads,
+                           int64_t max_len, float *signal_dev, void *stream);
+int rb200_refine_scratch_bytes(int32_t max_band_width, int64_t *bytes);
+int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const float *levels_dev,
+                    const int32_t *band_start_dev, const int32_t *band_end_dev, const int64_t *seq_off_dev,
+                    const int64_t *tb_off_dev, const int32_t *max_width_dev, const int32_t *order_dev,
+                    int32_t n_reads, const float *dwell_penalty_host, int32_t n_penalty, int32_t algo,
+                    int32_t max_band_width, int32_t *traceback_ws_dev, int32_t *path_dev, float *score_dev,
+                    int32_t *status_dev, int32_t *queue_dev, float *wide_scratch_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

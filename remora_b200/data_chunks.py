@@ -165,8 +165,9 @@ class RemoraRead:
 
     def refine_signal_mapping(self, sig_map_refiner, check_read=False):
         """No-op for an unloaded refiner, like the reference (data_chunks.py:267-269); a loaded
-        refiner (reference object, when the reference package is installed) is applied the same
-        way the reference applies it (data_chunks.py:270-308)."""
+        refiner (``remora_b200.refine_signal_map.SigMapRefiner``: re-scaling on the host, banded DP on
+        the GPU) is applied the same way the reference applies it (data_chunks.py:270-308).  Many
+        reads at once: ``SigMapRefiner.refine_reads`` (one launch for the whole batch)."""
         if not sig_map_refiner.is_loaded:
             return
         if sig_map_refiner.do_rough_rescale:

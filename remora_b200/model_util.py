@@ -16,40 +16,13 @@ from torch import nn
 
 from . import RemoraError, _native, weights
 
-try:  # in a drop-in deployment the reference package is installed next to this one
-    from remora.refine_signal_map import SigMapRefiner as _RefSigMapRefiner  # pragma: no cover
-except Exception:  # noqa: BLE001
-    _RefSigMapRefiner = None
-
-
-class SigMapRefiner:
-    """Placeholder for the reference's signal-mapping refiner (refine_signal_map.py:149-628),
-    which is upstream of the hot path and out of scope for this tier.
-    An unloaded refiner is a no-op exactly like the reference's (data_chunks.py:267-269)."""
-
-    def __init__(self, levels=None, **kwargs):
-        self.levels = levels
-        self.kwargs = kwargs
-        self.is_loaded = levels is not None
-        self.do_rough_rescale = bool(kwargs.get("do_rough_rescale", False))
-        self.scale_iters = int(kwargs.get("scale_iters", -1))
-
-    def _unavailable(self, *a, **k):
-        raise RemoraError(
-            "this model carries a k-mer level table and needs signal-mapping refinement, which "
-            "remora_b200 does not implement; install the reference `remora` package alongside")
-
-    rough_rescale = refine_sig_map = _unavailable
+from .refine_signal_map import SigMapRefiner  # noqa: E402,F401  (same name as the reference exports)
 
 
 def _make_refiner(levels, center_idx, do_rough_rescale, scale_iters, algo, half_bandwidth, sd_arr):
-    if _RefSigMapRefiner is not None:
-        return _RefSigMapRefiner(_levels_array=levels, center_idx=center_idx,
-                                 do_rough_rescale=do_rough_rescale, scale_iters=scale_iters,
-                                 algo=algo, half_bandwidth=half_bandwidth, sd_arr=sd_arr)
-    return SigMapRefiner(levels, center_idx=center_idx, do_rough_rescale=do_rough_rescale,
-                         scale_iters=scale_iters, algo=algo, half_bandwidth=half_bandwidth,
-                         sd_arr=sd_arr)
+    return SigMapRefiner(_levels_array=levels, center_idx=center_idx,
+                         do_rough_rescale=do_rough_rescale, scale_iters=scale_iters, algo=algo,
+                         half_bandwidth=half_bandwidth, sd_arr=sd_arr)
 
 
 def add_derived_metadata(md):
@@ -89,8 +62,7 @@ def add_derived_metadata(md):
             int(md["refine_scale_iters"]), md["refine_algo"], int(md["refine_half_bandwidth"]),
             sd_arr)
     else:  # original models without a refiner (model_util.py:439-443)
-        md["sig_map_refiner"] = (_RefSigMapRefiner() if _RefSigMapRefiner is not None
-                                 else SigMapRefiner())
+        md["sig_map_refiner"] = SigMapRefiner()
         md["base_start_justify"] = False
         md["offset"] = 0
     for key in [k for k in md if k.startswith("refine_")]:
@@ -332,6 +304,7 @@ def load_torchscript_model(model_filename, device=None, quiet=False, eval_only=F
     state_dict, md = _raw_load_torchscript(model_filename)
     add_derived_metadata(md)
     model = B200Model(state_dict, device=device)
+    md["sig_map_refiner"].device = next(model.parameters()).device  # the banded DP runs where the model does
     if eval_only:
         model.eval()
         for param in model.parameters():

@@ -1,0 +1,704 @@
+"""Signal-mapping refinement behind the reference's ``remora.refine_signal_map`` surface
+(src/remora/refine_signal_map.py), "next" row 4 of SURVEY.md 8f.
+
+``SigMapRefiner`` keeps the reference's dataclass fields and methods (``rough_rescale``, ``rescale``,
+``refine_sig_map``, ``extract_levels``, ``load_from_metadata`` ...).  The banded dynamic programme
+(``seq_banded_dp``, refine_signal_map_core.pyx:403-473, >95 % of the reference's time per read) runs on
+the GPU through the C ABI (``rb200_refine_normalize`` / ``rb200_refine_dp``, one warp per read, a whole
+batch of reads per launch: :meth:`SigMapRefiner.refine_reads`); scores, traceback and the returned
+mapping are bit-identical to the reference's.  The cheap per-read set-up stays on the host as vectorised
+numpy: level lookup (core.pyx:87-100), quantile / least-squares re-scaling (:67-122), band construction
+(:634-775, core.pyx:31-69).  There is no CPU fallback for the dynamic programme.
+"""
+import ctypes
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import RemoraError, _native
+
+DEFAULT_REFINE_HBW = 5                                   # constants.py:42
+DEFAULT_REFINE_SHORT_DWELL_PARAMS = (4, 3, 0.5)          # constants.py:233
+REFINE_ALGO_VIT_NAME = "Viterbi"                         # constants.py:234
+REFINE_ALGO_DWELL_PEN_NAME = "dwell_penalty"             # constants.py:235
+REFINE_ALGOS = (REFINE_ALGO_DWELL_PEN_NAME, REFINE_ALGO_VIT_NAME)
+DEFAULT_REFINE_ALGO = REFINE_ALGO_DWELL_PEN_NAME
+ROUGH_RESCALE_LEAST_SQUARES = "least_squares"
+ROUGH_RESCALE_THEIL_SEN = "theil_sen"
+ROUGH_RESCALE_METHODS = (ROUGH_RESCALE_LEAST_SQUARES, ROUGH_RESCALE_THEIL_SEN)
+DEFAULT_ROUGH_RESCALE_METHOD = ROUGH_RESCALE_LEAST_SQUARES
+MAX_POINTS_FOR_THEIL_SEN = 1000                          # constants.py:245
+_ALGO_CODE = {REFINE_ALGO_VIT_NAME: 0, REFINE_ALGO_DWELL_PEN_NAME: 1}
+MAX_DWELL_PENALTIES = 16                                 # rb200_refine_dp limit
+
+
+def compute_dwell_pen_array(target, limit, weight):
+    """refine_signal_map.py:34-41"""
+    if limit > target:
+        limit = target
+    return weight * np.square(np.arange(limit, dtype=np.float32) - target)
+
+
+DEFAULT_REFINE_SHORT_DWELL_PEN = compute_dwell_pen_array(*DEFAULT_REFINE_SHORT_DWELL_PARAMS)
+
+
+# ------------------------------------------------------------------------------------------------
+# re-scaling (host, float64 numpy like the reference)          refine_signal_map.py:54-122
+# ------------------------------------------------------------------------------------------------
+def rescale_lstsq(dacs, levels, shift, scale):
+    norm_sig = (dacs - shift) / scale
+    shift_est, scale_est = np.linalg.lstsq(
+        np.column_stack([np.ones_like(norm_sig), norm_sig]), levels, rcond=None)[0]
+    if scale_est == 0:
+        return shift, scale
+    return shift - (scale * shift_est / scale_est), scale / scale_est
+
+
+def rough_rescale_lstsq(dacs, levels, shift, scale, quants):
+    norm_sig = (dacs - shift) / scale
+    norm_qs = np.quantile(norm_sig, quants)
+    shift_est, scale_est = np.linalg.lstsq(
+        np.column_stack([np.ones_like(norm_qs), norm_qs]), np.quantile(levels, quants),
+        rcond=None)[0]
+    if scale_est == 0:
+        return shift, scale
+    return shift - (scale * shift_est / scale_est), scale / scale_est
+
+
+def compute_slopes(r_event_means, r_model_means):
+    delta_event = r_event_means[:, np.newaxis] - r_event_means
+    delta_model = r_model_means[:, np.newaxis] - r_model_means
+    return delta_model[delta_event > 0] / delta_event[delta_event > 0]
+
+
+def theil_sen(dacs, lvls, shift, scale):
+    slope = np.median(compute_slopes(dacs, lvls))
+    inter = np.median(lvls - (slope * dacs))
+    if slope == 0:
+        raise RemoraError("Read failed sequence-based signal re-scaling parameter estimation.")
+    return shift + (-inter / slope * scale), scale * (1 / slope)
+
+
+def rescale_theil_sen(dacs, levels, shift, scale):
+    norm_sig = (dacs - shift) / scale
+    if levels.shape[0] > MAX_POINTS_FOR_THEIL_SEN:
+        samp_ind = np.random.choice(levels.shape[0], MAX_POINTS_FOR_THEIL_SEN, replace=False)
+        levels = levels[samp_ind]
+        norm_sig = norm_sig[samp_ind]
+    return theil_sen(norm_sig, levels, shift, scale)
+
+
+def rough_rescale_theil_sen(dacs, levels, shift, scale, quants):
+    norm_sig = (dacs - shift) / scale
+    return theil_sen(np.quantile(norm_sig, quants), np.quantile(levels, quants), shift, scale)
+
+
+def index_from_kmer(kmer, alphabet="ACGT"):
+    """refine_signal_map.py:130-146"""
+    return sum(alphabet.find(base) * (len(alphabet) ** kmer_pos)
+               for kmer_pos, base in enumerate(kmer[::-1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# banding (host, integer numpy; same integers as the reference)
+# ------------------------------------------------------------------------------------------------
+def compute_sig_band(bps, levels, bhw=DEFAULT_REFINE_HBW, is_banded=True):
+    """Per signal sample, the range of bases it may be assigned to (refine_signal_map.py:634-688)."""
+    if is_banded and bhw is None:
+        raise RemoraError("Cannot compute band with half width of None.")
+    seq_len = levels.size
+    if bps.size - 1 != seq_len:
+        raise RemoraError("Breakpoints must be one longer than levels.")
+    sig_len = int(bps[-1] - bps[0])
+    seq_indices = np.repeat(np.arange(seq_len), np.diff(bps))
+    band = np.empty((2, sig_len), dtype=np.int32)
+    if is_banded:
+        band[0] = np.maximum(seq_indices - bhw, 0)
+        band[1] = np.minimum(seq_indices + bhw + 1, seq_len)
+    else:
+        band[0] = 0
+        band[1] = seq_len
+    nan_levels = np.isnan(levels)
+    if nan_levels.any():  # bases without a level keep their original samples
+        nan_mask = nan_levels[seq_indices]
+        nan_seq = seq_indices[nan_mask]
+        band[0, nan_mask] = nan_seq
+        band[1, nan_mask] = nan_seq + 1
+    band[0] = np.maximum.accumulate(band[0])
+    band[1] = np.minimum.accumulate(band[1, ::-1])[::-1]
+    return band
+
+
+def convert_to_seq_band(sig_band):
+    """Per base, the range of signal samples it may cover (refine_signal_map.py:743-775)."""
+    sig_len = sig_band.shape[1]
+    seq_len = int(sig_band[1, -1])
+    seq_band = np.zeros((2, seq_len), dtype=np.int32)
+    seq_band[1, :] = sig_len
+    lower_sig_pos = np.nonzero(np.ediff1d(sig_band[1], to_begin=0))[0]
+    seq_band[0, sig_band[1, lower_sig_pos - 1]] = lower_sig_pos
+    seq_band[0] = np.maximum.accumulate(seq_band[0])
+    upper_sig_pos = np.nonzero(np.ediff1d(sig_band[0], to_begin=0))[0]
+    seq_band[1, sig_band[0, upper_sig_pos] - 1] = upper_sig_pos
+    seq_band[1] = np.minimum.accumulate(seq_band[1, ::-1])[::-1]
+    return seq_band
+
+
+def adjust_seq_band(seq_band, min_step=2):
+    """In-place, vectorised form of the reference's sequential loops (refine_signal_map_core.pyx:31-69):
+    every band start (end) at least ``min_step`` below (above) its successor (predecessor), then the
+    first starts / last ends repaired so that they stay strictly increasing from the fixed corner."""
+    st, en = seq_band[0], seq_band[1]
+    n = st.size
+    idx = np.arange(n, dtype=np.int64)
+    band_min = int(st[0])
+    # st[i] = min_{j>=i}(st[j] - min_step*(j-i))
+    st[:] = np.minimum.accumulate((st - min_step * idx)[::-1])[::-1] + min_step * idx
+    st[0] = band_min
+    if n > 1:
+        ok = st[1:] > band_min + idx[:-1]        # first position that already exceeds its predecessor
+        stop = int(np.argmax(ok)) + 1 if ok.any() else n
+        st[1:stop] = band_min + idx[1:stop]
+    band_max = int(en[-1])
+    en[:] = np.maximum.accumulate(en - min_step * idx) + min_step * idx
+    en[-1] = band_max
+    if n > 1:
+        # walking down from n-2 the reference lowers en[pos] to en[pos+1] - 1 while en[pos] >= en[pos+1];
+        # as long as it keeps lowering, en[pos+1] == band_max - dist with dist = n-2-pos
+        dist = np.arange(n - 1, dtype=np.int64)    # 0 for pos n-2, 1 for pos n-3, ...
+        ok = en[:-1][::-1] < band_max - dist       # first position already below its successor
+        stop = int(np.argmax(ok)) if ok.any() else n - 1
+        if stop > 0:
+            en[n - 2 - np.arange(stop)] = band_max - 1 - np.arange(stop)
+    return seq_band
+
+
+def validate_band(band, sig_len=None, seq_len=None, is_sig_band=True):
+    """refine_signal_map.py:691-740"""
+    if band[0, 0] != 0:
+        raise RemoraError("Band does not start with 0 coordinate.")
+    if (band[1] - band[0]).min() <= 0:
+        raise RemoraError("Band contains 0-length region")
+    if band.shape[1] > 1:
+        if np.diff(band[0]).min() < 0:
+            raise RemoraError("Band start positions are not monotonically increasing")
+        if np.diff(band[1]).min() < 0:
+            raise RemoraError("Band end positions are not monotonically increasing")
+    if is_sig_band:
+        if sig_len is not None and band.shape[1] != sig_len:
+            raise RemoraError("Invalid sig_band length")
+        if seq_len is not None and band[1, -1] != seq_len:
+            raise RemoraError("Invalid sig_band end coordinate")
+    else:
+        if sig_len is not None and band[1, -1] != sig_len:
+            raise RemoraError("Invalid seq_band end coordinate")
+        if seq_len is not None and band.shape[1] != seq_len:
+            raise RemoraError("Invalid sig_band length")
+
+
+def _check_dp_preconditions(seq_band):
+    """What the device programme relies on beyond ``validate_band`` (for the reference these cases
+    are out-of-bounds reads): strictly increasing starts and ends, every band reachable from the
+    previous one."""
+    st, en = seq_band[0], seq_band[1]
+    if st.size > 1 and (np.diff(st).min() < 1 or np.diff(en).min() < 1 or (st[1:] > en[:-1]).any()):
+        raise RemoraError("Invalid band for signal mapping refinement")
+
+
+def compute_seq_band(seq_to_sig_map, levels, band_half_width=DEFAULT_REFINE_HBW, adjust_band_min_step=2):
+    """seq band of one read, as ``refine_signal_mapping`` builds it (refine_signal_map.py:814-826);
+    ``seq_to_sig_map`` must start at 0."""
+    seq_to_sig_map = np.asarray(seq_to_sig_map)
+    n = levels.shape[0]
+    if (seq_to_sig_map.size == n + 1 and n > 0 and seq_to_sig_map[-1] > seq_to_sig_map[-2]
+            and not np.isnan(levels).any()):
+        # closed form of compute_sig_band + convert_to_seq_band when every base has a level and the
+        # last base owns a sample: base b may cover the samples of bases b-hbw .. b+hbw; a band end
+        # at sample 0 (leading zero-dwell bases) takes the first positive end, as the reference's
+        # right-to-left minimum does.  O(bases) instead of O(samples); equality with the sample-space
+        # construction is tested on random maps (tests/test_refine.py).
+        b = np.arange(n)
+        seq_band = np.empty((2, n), dtype=np.int32)
+        seq_band[0] = seq_to_sig_map[np.maximum(b - band_half_width, 0)]
+        en = seq_to_sig_map[np.minimum(b + band_half_width + 1, n)]
+        seq_band[1] = np.where(en == 0, en[en > 0][0], en)
+    else:
+        seq_band = convert_to_seq_band(compute_sig_band(seq_to_sig_map, levels, bhw=band_half_width))
+    seq_band = adjust_seq_band(seq_band, min_step=adjust_band_min_step)
+    validate_band(seq_band, sig_len=int(seq_to_sig_map[-1]), seq_len=levels.shape[0], is_sig_band=False)
+    _check_dp_preconditions(seq_band)
+    return seq_band
+
+
+# ------------------------------------------------------------------------------------------------
+# the device programme
+# ------------------------------------------------------------------------------------------------
+def _dacs_code(dacs, shift, scale):
+    """dtype code of rb200_refine_normalize reproducing numpy's promotion of (dacs - shift) / scale."""
+    if dacs.dtype == np.int16:
+        return dacs, 0
+    if dacs.dtype == np.float32:
+        probe = (dacs[:1] - shift) / scale
+        return dacs, (1 if probe.dtype == np.float32 else 3)
+    return dacs.astype(np.float64), 2
+
+
+class DeviceRefineBatch:
+    """A batch of reads resident on the GPU for the banded dynamic programme: ``__init__`` builds the
+    concatenated arrays and uploads them, :meth:`run` enqueues the two kernels
+    (``rb200_refine_normalize`` + ``rb200_refine_dp``) on the current stream, :meth:`paths` reads the
+    result back.  ``banded_dp_batch`` is the one-shot form; benchmarks time :meth:`run` alone."""
+
+    def __init__(self, dacs_list, shifts, scales, levels_list, seq_bands, algo=DEFAULT_REFINE_ALGO,
+                 short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN, device=None):
+        if algo not in _ALGO_CODE:
+            raise RemoraError(f"Invalid core signal mapping refine method: {algo}")
+        self.algo = _ALGO_CODE[algo]
+        self.pen = np.ascontiguousarray(short_dwell_pen, dtype=np.float32)
+        if algo == REFINE_ALGO_DWELL_PEN_NAME and not 1 <= self.pen.size <= MAX_DWELL_PENALTIES:
+            raise RemoraError(f"short dwell penalty array must hold 1..{MAX_DWELL_PENALTIES} values")
+        self.lib = _native.load_library()
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RemoraError("signal mapping refinement needs a CUDA device (no CPU fallback)")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device = torch.device(device)
+        if device.type != "cuda":
+            raise RemoraError("signal mapping refinement needs a CUDA device (no CPU fallback)")
+        self.n_reads = n_reads = len(dacs_list)
+        codes = set()
+        conv = []
+        for d, sh, sc in zip(dacs_list, shifts, scales):
+            d, code = _dacs_code(np.ascontiguousarray(d), sh, sc)
+            conv.append(d)
+            codes.add(code)
+        if len(codes) > 1:  # mixed sample dtypes: float64 reproduces every promotion except pure float32
+            if 1 in codes:
+                raise RemoraError("mixed float32 / other sample dtypes in one refinement batch")
+            conv = [d.astype(np.float64) for d in conv]
+            codes = {2}
+        self.code = codes.pop()
+        sig_lens = np.array([d.size for d in conv], dtype=np.int64)
+        seq_lens = np.array([lv.size for lv in levels_list], dtype=np.int64)
+        self.sig_off = sig_off = np.concatenate([[0], np.cumsum(sig_lens)]).astype(np.int64)
+        self.seq_off = seq_off = np.concatenate([[0], np.cumsum(seq_lens)]).astype(np.int64)
+        widths = [b[1] - b[0] for b in seq_bands]
+        tb_lens = np.array([int(w.sum()) for w in widths], dtype=np.int64)
+        if tb_lens.max() > np.iinfo(np.uint32).max:
+            raise RemoraError("Dynamic programming search space too large. Read likely contains large "
+                              "deletions.")
+        self.tb_off = tb_off = np.concatenate([[0], np.cumsum(tb_lens)]).astype(np.int64)
+        max_w = np.array([int(w.max()) for w in widths], dtype=np.int32)
+        order = np.argsort(-tb_lens, kind="stable").astype(np.int32)
+        for r in range(n_reads):
+            if seq_bands[r].shape[1] != seq_lens[r] or seq_bands[r][1, -1] != sig_lens[r]:
+                raise RemoraError("band does not match read")
+        self.max_sig_len = int(sig_lens.max())
+        self.widest = int(max_w.max())
+        self.cells = int(tb_off[-1])
+        with torch.cuda.device(device):
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)  # noqa: E731
+            self.d_dacs = up(np.concatenate(conv))
+            self.d_sig_off, self.d_seq_off, self.d_tb_off = up(sig_off), up(seq_off), up(tb_off)
+            self.d_shift = up(np.asarray(shifts, dtype=np.float64))
+            self.d_scale = up(np.asarray(scales, dtype=np.float64))
+            self.d_levels = up(np.concatenate([np.asarray(lv, dtype=np.float32) for lv in levels_list]))
+            self.d_st = up(np.concatenate([b[0] for b in seq_bands]).astype(np.int32))
+            self.d_en = up(np.concatenate([b[1] for b in seq_bands]).astype(np.int32))
+            self.d_max_w, self.d_order = up(max_w), up(order)
+            self.d_sig = torch.empty(int(sig_off[-1]), dtype=torch.float32, device=device)
+            self.d_tb = torch.empty(int(tb_off[-1]), dtype=torch.int32, device=device)
+            self.d_path = torch.empty(int(seq_off[-1]) + n_reads, dtype=torch.int32, device=device)
+            self.d_score = torch.empty(n_reads, dtype=torch.float32, device=device)
+            self.d_status = torch.empty(n_reads, dtype=torch.int32, device=device)
+            self.d_queue = torch.zeros(1, dtype=torch.int32, device=device)
+            need = ctypes.c_int64(0)
+            _native.check(self.lib.rb200_refine_scratch_bytes(self.widest, ctypes.byref(need)),
+                          "rb200_refine_scratch_bytes")
+            self.d_wide = (torch.empty(need.value // 4, dtype=torch.float32, device=device)
+                           if need.value else None)
+
+    def run(self):
+        """Enqueue normalisation + banded DP on the current stream of the batch's device."""
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _native.check(self.lib.rb200_refine_normalize(
+                ptr(self.d_dacs), self.code, ptr(self.d_sig_off), ptr(self.d_shift), ptr(self.d_scale),
+                self.n_reads, self.max_sig_len, ptr(self.d_sig), stream), "rb200_refine_normalize")
+            _native.check(self.lib.rb200_refine_dp(
+                ptr(self.d_sig), ptr(self.d_sig_off), ptr(self.d_levels), ptr(self.d_st), ptr(self.d_en),
+                ptr(self.d_seq_off), ptr(self.d_tb_off), ptr(self.d_max_w), ptr(self.d_order), self.n_reads,
+                self.pen.ctypes.data_as(ctypes.c_void_p), self.pen.size, self.algo, self.widest,
+                ptr(self.d_tb), ptr(self.d_path), ptr(self.d_score), ptr(self.d_status), ptr(self.d_queue),
+                ptr(self.d_wide) if self.d_wide is not None else None, stream), "rb200_refine_dp")
+
+    def paths(self, return_scores=False):
+        path = self.d_path.cpu().numpy()
+        status = self.d_status.cpu().numpy()
+        out = []
+        for r in range(self.n_reads):
+            if status[r] != 0:
+                raise RemoraError("signal mapping refinement traceback left the band")
+            out.append(path[self.seq_off[r] + r:self.seq_off[r + 1] + r + 1].copy())
+        return (out, self.d_score.cpu().numpy()) if return_scores else out
+
+
+def banded_dp_batch(dacs_list, shifts, scales, levels_list, seq_bands, algo=DEFAULT_REFINE_ALGO,
+                    short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN, device=None, return_scores=False):
+    """Run the banded dynamic programme for a batch of reads on the GPU.
+
+    dacs_list[r]: un-normalised samples of read r already trimmed to its mapped range;
+    levels_list[r]: float32 levels (NaN allowed); seq_bands[r]: int32 [2, seq_len] from
+    :func:`compute_seq_band`.  Returns the list of paths (int32 [seq_len + 1], path[0] == 0)
+    (and the final forward score per read when ``return_scores``)."""
+    if len(dacs_list) == 0:
+        return ([], np.zeros(0, np.float32)) if return_scores else []
+    batch = DeviceRefineBatch(dacs_list, shifts, scales, levels_list, seq_bands, algo, short_dwell_pen,
+                              device)
+    batch.run()
+    return batch.paths(return_scores)
+
+
+def refine_signal_mapping(signal, seq_to_sig_map, levels, band_half_width=DEFAULT_REFINE_HBW,
+                          refine_algo=DEFAULT_REFINE_ALGO, short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN,
+                          adjust_band_min_step=2, device=None):
+    """Single-read form with the reference's arguments (refine_signal_map.py:783-840); ``signal`` is the
+    normalised signal.  Returns (path, final score, seq_band); the reference additionally returns the
+    full score / traceback arrays, which stay on the device here."""
+    seq_to_sig_map = np.asarray(seq_to_sig_map)
+    start = int(seq_to_sig_map[0])
+    signal = np.asarray(signal)[start:int(seq_to_sig_map[-1])]
+    levels = np.asarray(levels, dtype=np.float32)
+    seq_band = compute_seq_band(seq_to_sig_map - start, levels, band_half_width, adjust_band_min_step)
+    sig32 = np.ascontiguousarray(signal, dtype=np.float32)  # the reference's .astype(np.float32)
+    paths, scores = banded_dp_batch([sig32], [0.0], [1.0], [levels], [seq_band], refine_algo,
+                                    short_dwell_pen, device, return_scores=True)
+    return paths[0] + start, float(scores[0]), seq_band
+
+
+# ------------------------------------------------------------------------------------------------
+# SigMapRefiner
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class SigMapRefiner:
+    """Same fields as the reference dataclass (refine_signal_map.py:149-176) plus ``device``."""
+
+    kmer_model_filename: str = None
+    do_rough_rescale: bool = False
+    scale_iters: int = -1
+    algo: str = DEFAULT_REFINE_ALGO
+    half_bandwidth: int = DEFAULT_REFINE_HBW
+    sd_params: tuple = None
+    do_fix_guage: bool = False
+    rough_rescale_method: str = DEFAULT_ROUGH_RESCALE_METHOD
+    sd_arr: np.ndarray = dataclasses.field(default_factory=lambda: DEFAULT_REFINE_SHORT_DWELL_PEN)
+    _levels_array: np.ndarray = None
+    str_kmer_levels: dict = None
+    kmer_len: int = None
+    kmer_idx_stats = None
+    center_idx: int = -1
+    is_loaded: bool = False
+    device: object = None
+
+    def __post_init__(self):
+        """refine_signal_map.py:276-322"""
+        if self._levels_array is not None and not np.array_equal(self._levels_array, np.array(None)):
+            self.is_loaded = True
+            self._levels_array = np.ascontiguousarray(self._levels_array, dtype=np.float32)
+            self.kmer_len = int(round(np.log(self._levels_array.size) / np.log(4)))
+            if 4 ** self.kmer_len != self._levels_array.size:
+                raise RemoraError("levels array size is not a power of 4")
+        elif self.kmer_model_filename is not None:
+            self.load_kmer_table()
+            self.is_loaded = True
+            self.determine_dominant_pos()
+            if self.do_fix_guage:
+                self.fix_gauge()
+        elif self.str_kmer_levels is not None:
+            self.is_loaded = True
+            self.kmer_len = len(next(iter(self.str_kmer_levels)))
+            self.determine_dominant_pos()
+            if self.do_fix_guage:
+                self.fix_gauge()
+        else:
+            self._levels_array = None
+        if not self.is_loaded and (self.do_rough_rescale or self.scale_iters >= 0):
+            raise RemoraError(
+                "Signal re-scaling is requested without levels table. "
+                f"is_loaded: {self.is_loaded} do_rough_rescale: {self.do_rough_rescale} "
+                f"scale_iters: {self.scale_iters}")
+        if self.sd_params is not None:
+            self.sd_arr = compute_dwell_pen_array(*self.sd_params)
+        if self.rough_rescale_method not in ROUGH_RESCALE_METHODS:
+            raise RemoraError(f"Invalid rough re-scale method: {self.rough_rescale_method}")
+
+    def __repr__(self):
+        if not self.is_loaded:
+            return "No Remora signal refine/map settings loaded"
+        r_str = f"Loaded {self.kmer_len}-mer table with {self.center_idx + 1} central position."
+        if self.do_rough_rescale:
+            r_str += " Rough re-scaling will be executed."
+        if self.scale_iters > 0:
+            r_str += (f" {self.scale_iters} rounds of signal mapping refinement followed by precise "
+                      "re-scaling will be executed.")
+        if self.scale_iters >= 0:
+            r_str += (" Signal mapping refinement will be executed using the "
+                      f"{self.algo} refinement method (band half width: {self.half_bandwidth}).")
+            if self.algo == REFINE_ALGO_DWELL_PEN_NAME:
+                r_str += f" Short dwell penalty array set to {self.sd_arr}."
+        return r_str
+
+    @property
+    def bases_before(self):
+        return self.center_idx
+
+    @property
+    def bases_after(self):
+        return self.kmer_len - self.center_idx - 1
+
+    @property
+    def is_valid(self):
+        if self.is_loaded:
+            return self.do_rough_rescale or self.scale_iters >= 0
+        return not self.do_rough_rescale and self.scale_iters < 0
+
+    # -- level table ---------------------------------------------------------------------------
+    def load_kmer_table(self):
+        """refine_signal_map.py:217-247"""
+        self.str_kmer_levels = {}
+        with open(self.kmer_model_filename) as kmer_fp:
+            for line in kmer_fp:
+                kmer, level = line.split()
+                kmer = kmer.upper()
+                if self.kmer_len is None:
+                    self.kmer_len = len(kmer)
+                if kmer in self.str_kmer_levels:
+                    raise RemoraError(f"K-mer found twice in levels file '{kmer}'.")
+                if self.kmer_len != len(kmer):
+                    raise RemoraError(
+                        f"K-mer lengths not all equal '{len(kmer)} != {self.kmer_len}' for {kmer}.")
+                try:
+                    value = float(level)
+                except ValueError:
+                    raise RemoraError(f"Could not convert level to float '{level}'")
+                self.str_kmer_levels[kmer] = 0 if np.isnan(value) else value
+        if len(self.str_kmer_levels) != 4 ** self.kmer_len:
+            raise RemoraError(
+                f"K-mer table contains fewer entries ({len(self.str_kmer_levels)}) than expected "
+                f"({4 ** self.kmer_len})")
+
+    def determine_dominant_pos(self):
+        """Position in the k-mer whose base orders the levels most (Kruskal-Wallis H statistic per
+        position, refine_signal_map.py:249-274)."""
+        if self.str_kmer_levels is None:
+            return
+        from scipy import stats
+        sorted_kmers = [kmer for _, kmer in sorted((lv, km) for km, lv in self.str_kmer_levels.items())]
+        self.kmer_idx_stats = []
+        for kmer_idx in range(self.kmer_len):
+            col = np.array([kmer[kmer_idx] for kmer in sorted_kmers])
+            groups = [np.nonzero(col == base)[0] for base in "ACGT"]
+            self.kmer_idx_stats.append(stats.kruskal(*groups)[0])
+        self.center_idx = int(np.argmax(self.kmer_idx_stats))
+
+    def fix_gauge(self):
+        """refine_signal_map.py:332-342"""
+        from itertools import product
+        med = np.median(self.levels_array)
+        mad = np.median(np.absolute(self.levels_array - med)) * 1.4826
+        self._levels_array = (self.levels_array - med) / mad
+        self.str_kmer_levels = {"".join(kmer): self._levels_array[index_from_kmer(kmer)]
+                                for kmer in product(*["ACGT"] * self.kmer_len)}
+
+    @property
+    def levels_array(self):
+        if self._levels_array is None:
+            if self.str_kmer_levels is None:
+                return None
+            self._levels_array = np.empty(4 ** self.kmer_len, dtype=np.float32)
+            for kmer, level in self.str_kmer_levels.items():
+                self._levels_array[index_from_kmer(kmer)] = level
+        return self._levels_array
+
+    @property
+    def kmers(self):
+        from itertools import product
+        for kmer in product("ACGT", repeat=self.kmer_len):
+            yield "".join(kmer)
+
+    def write_kmer_table(self, fh):
+        for kmer in self.kmers:
+            fh.write(f"{kmer}\t{self._levels_array[index_from_kmer(kmer)]}\n")
+
+    def extract_levels(self, int_seq):
+        """levels[pos + center_idx] = table[k-mer starting at pos], zero at the read edges
+        (refine_signal_map_core.pyx:87-100), vectorised.  A k-mer containing N (-1) has no defined
+        level in the reference (out-of-range table index); it gets NaN here, which the banding
+        treats as "keep this base's samples" (refine_signal_map.py:673-680)."""
+        int_seq = np.asarray(int_seq).astype(np.int64)
+        table = self.levels_array
+        levels = np.zeros(int_seq.size, dtype=np.float32)
+        k = self.kmer_len
+        if int_seq.size >= k:
+            windows = np.lib.stride_tricks.sliding_window_view(int_seq, k)
+            idx = windows @ (4 ** np.arange(k - 1, -1, -1, dtype=np.int64))
+            has_n = (windows < 0).any(axis=1)
+            vals = table[np.where(has_n, 0, idx)]
+            levels[self.center_idx:self.center_idx + idx.size] = np.where(has_n, np.float32(np.nan), vals)
+        return levels
+
+    # -- re-scaling ----------------------------------------------------------------------------
+    def rough_rescale(self, shift, scale, seq_to_sig_map, int_seq, dacs,
+                      quants=np.arange(0.05, 1, 0.05), clip_bases=10, use_base_center=True):
+        """refine_signal_map.py:390-430"""
+        levels = self.extract_levels(int_seq)
+        if use_base_center:
+            optim_dacs = dacs[(seq_to_sig_map[:-1] + seq_to_sig_map[1:]) // 2]
+            if clip_bases > 0 and levels.size > clip_bases * 2:
+                levels = levels[clip_bases:-clip_bases]
+                optim_dacs = optim_dacs[clip_bases:-clip_bases]
+        else:
+            optim_dacs = dacs[seq_to_sig_map[0]:seq_to_sig_map[-1]]
+        if self.rough_rescale_method == ROUGH_RESCALE_LEAST_SQUARES:
+            return rough_rescale_lstsq(optim_dacs, levels, shift, scale, quants)
+        if self.rough_rescale_method == ROUGH_RESCALE_THEIL_SEN:
+            return rough_rescale_theil_sen(optim_dacs, levels, shift, scale, quants)
+        raise RemoraError(f"Invalid rough re-scale method: {self.rough_rescale_method}")
+
+    def rescale(self, levels, dacs, shift, scale, seq_to_sig_map, dwell_filter_pctls=(10, 90),
+                min_abs_level=0.2, edge_filter_bases=10, min_levels=10):
+        """refine_signal_map.py:432-472"""
+        with np.errstate(invalid="ignore", divide="ignore"):
+            dacs_cumsum = np.empty(dacs.size + 1)
+            dacs_cumsum[0] = 0
+            dacs_cumsum[1:] = np.cumsum(dacs)
+            dwells = np.diff(seq_to_sig_map)
+            dac_means = np.diff(dacs_cumsum[seq_to_sig_map]) / dwells
+        dwell_min, dwell_max = np.percentile(dwells, dwell_filter_pctls)
+        edge_filter = np.full(dwells.size, True, dtype=np.bool_)
+        if edge_filter_bases > 0:
+            edge_filter[:edge_filter_bases] = False
+            edge_filter[-edge_filter_bases:] = False
+        valid_bases = np.logical_and.reduce((
+            dwells > dwell_min, dwells < dwell_max,
+            np.abs(levels - np.mean(levels)) > min_abs_level,
+            np.logical_not(np.isnan(dac_means)), edge_filter))
+        filt_levels = levels[valid_bases]
+        filt_dacs = dac_means[valid_bases]
+        if filt_levels.size < min_levels:
+            raise RemoraError("Too few positions")
+        return rescale_theil_sen(filt_dacs, filt_levels, shift, scale)
+
+    # -- mapping refinement ----------------------------------------------------------------------
+    def refine_sig_maps(self, shifts, scales, seq_to_sig_maps, int_seqs, dacs_list):
+        """Batch form of :meth:`refine_sig_map`: one banded-DP launch per refinement round for all
+        reads.  Returns lists (seq_to_sig_map, shift, scale) per read."""
+        n = len(dacs_list)
+        levels = [self.extract_levels(s) for s in int_seqs]
+        maps = [np.asarray(m) for m in seq_to_sig_maps]
+        sig_st = [int(m[0]) for m in maps]
+        trimmed = [np.asarray(d)[m[0]:m[-1]] for d, m in zip(dacs_list, maps)]
+        rel = [m - st for m, st in zip(maps, sig_st)]
+        shifts, scales = list(shifts), list(scales)
+        active = list(range(n))
+        for _ in range(max(1, self.scale_iters)):  # 0 = one round without re-scaling (:486-487)
+            if not active:
+                break
+            bands = [compute_seq_band(rel[r], levels[r], self.half_bandwidth) for r in active]
+            paths = banded_dp_batch([trimmed[r] for r in active], [shifts[r] for r in active],
+                                    [scales[r] for r in active], [levels[r] for r in active], bands,
+                                    self.algo, self.sd_arr, self.device)
+            for r, path in zip(active, paths):
+                rel[r] = path
+            if self.scale_iters > 0:
+                still = []
+                for r in active:
+                    try:
+                        shifts[r], scales[r] = self.rescale(levels[r], trimmed[r], shifts[r], scales[r],
+                                                            rel[r])
+                        still.append(r)
+                    except RemoraError:  # the reference stops refining this read (:498-500)
+                        pass
+                active = still
+        return [m + st for m, st in zip(rel, sig_st)], shifts, scales
+
+    def refine_sig_map(self, shift, scale, seq_to_sig_map, int_seq, dacs):
+        """Reference signature (refine_signal_map.py:474-502); the dynamic programme runs on the GPU."""
+        maps, shifts, scales = self.refine_sig_maps([shift], [scale], [seq_to_sig_map], [int_seq], [dacs])
+        return maps[0], shifts[0], scales[0]
+
+    def refine_reads(self, reads):
+        """Apply ``RemoraRead.refine_signal_mapping`` (reference data_chunks.py:267-306) to a whole list
+        of reads with ONE banded-DP launch per refinement round: rough re-scaling per read on the host,
+        then the batch on the GPU.  Reads are updated in place (shift, scale, seq_to_sig_map)."""
+        if not self.is_loaded or not reads:
+            return
+        if self.do_rough_rescale:
+            for read in reads:
+                read.shift, read.scale = self.rough_rescale(read.shift, read.scale, read.seq_to_sig_map,
+                                                            read.int_seq, read.dacs)
+                read._sig = None
+        if self.scale_iters >= 0:
+            maps, shifts, scales = self.refine_sig_maps(
+                [r.shift for r in reads], [r.scale for r in reads], [r.seq_to_sig_map for r in reads],
+                [r.int_seq for r in reads], [r.dacs for r in reads])
+            for read, m, sh, sc in zip(reads, maps, shifts, scales):
+                read.seq_to_sig_map, read.shift, read.scale = m, sh, sc
+                read._sig = None
+
+    # -- (de)serialisation -------------------------------------------------------------------------
+    def asdict(self):
+        return {
+            "refine_kmer_levels": self._levels_array,
+            "refine_kmer_center_idx": self.center_idx,
+            "refine_do_rough_rescale": self.do_rough_rescale,
+            "refine_scale_iters": self.scale_iters,
+            "refine_algo": self.algo,
+            "refine_half_bandwidth": self.half_bandwidth,
+            "refine_sd_arr": self.sd_arr,
+            "rough_rescale_method": self.rough_rescale_method,
+        }
+
+    @classmethod
+    def load_from_metadata(cls, metadata, device=None):
+        return cls(
+            _levels_array=metadata.get("refine_kmer_levels"),
+            center_idx=metadata.get("refine_kmer_center_idx"),
+            do_rough_rescale=metadata.get("refine_do_rough_rescale"),
+            scale_iters=metadata.get("refine_scale_iters"),
+            algo=metadata.get("refine_algo"),
+            half_bandwidth=metadata.get("refine_half_bandwidth"),
+            sd_arr=metadata.get("refine_sd_arr"),
+            rough_rescale_method=metadata.get("rough_rescale_method", ROUGH_RESCALE_LEAST_SQUARES),
+            device=device,
+        )
+
+    @classmethod
+    def load_from_dict(cls, data, do_rough_rescale=True, scale_iters=-1, algo=DEFAULT_REFINE_ALGO,
+                       half_bandwidth=DEFAULT_REFINE_HBW, sd_params=None, do_fix_guage=False,
+                       sd_arr=DEFAULT_REFINE_SHORT_DWELL_PEN,
+                       rough_rescale_method=DEFAULT_ROUGH_RESCALE_METHOD, device=None):
+        return cls(do_rough_rescale=do_rough_rescale, scale_iters=scale_iters, algo=algo,
+                   half_bandwidth=half_bandwidth, sd_params=sd_params, do_fix_guage=do_fix_guage,
+                   sd_arr=sd_arr, str_kmer_levels=data, rough_rescale_method=rough_rescale_method,
+                   device=device)
+
+    def __eq__(self, other):
+        """refine_signal_map.py:553-580"""
+        if not isinstance(other, SigMapRefiner):
+            return False
+        if self.do_rough_rescale != other.do_rough_rescale or self.scale_iters != other.scale_iters:
+            return False
+        if not self.do_rough_rescale and self.scale_iters < 0:
+            return True
+        if self.rough_rescale_method != other.rough_rescale_method:
+            return False
+        if (not np.array_equal(self._levels_array, other._levels_array)
+                or self.center_idx != other.center_idx):
+            return False
+        if self.scale_iters < 0:
+            return True
+        return (self.algo == other.algo and self.half_bandwidth == other.half_bandwidth
+                and np.array_equal(self.sd_arr, other.sd_arr))

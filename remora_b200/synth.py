@@ -78,3 +78,49 @@ def synth_read(n_bases=400, seed=0, mean_dwell=10, frac_n=0.0):
     shift, scale = 431.5, 87.25
     dacs = np.round(sig * scale + shift).astype(np.int16)
     return dacs, shift, scale, seq_to_sig_map, int_seq
+
+
+def synth_levels_table(kmer_len=6, seed=0):
+    """Seeded k-mer level table (float32 [4**kmer_len], index = base-4 number of the k-mer, first
+    base most significant, as the reference's ``index_from_int_kmer``,
+    refine_signal_map_core.pyx:76-84).  Roughly unit-variance like a gauge-fixed ONT table."""
+    rng = np.random.default_rng(seed)
+    return rng.normal(0.0, 1.0, size=4 ** kmer_len).astype(np.float32)
+
+
+def synth_refine_read(n_bases=400, table=None, kmer_len=6, center_idx=2, seed=0, mean_dwell=10,
+                      noise=0.25, stride=5, jitter=6, frac_zero_dwell=0.02, frac_stall=0.01,
+                      stall_range=(60, 400), shift=431.5, scale=87.25, scale_error=1.08, shift_error=9.0):
+    """Raw pieces of a synthetic read whose signal follows a k-mer level table, with a deliberately
+    imperfect starting mapping (what a basecaller move table + alignment gives the reference):
+    boundaries snapped to multiples of ``stride`` and jittered, some zero-dwell bases (deletions),
+    some stalls, and shift/scale estimates that are slightly off so rough re-scaling has work to do.
+    Returns (dacs int16, shift, scale, seq_to_sig_map int64, int_seq int64)."""
+    rng = np.random.default_rng(seed)
+    if table is None:
+        table = synth_levels_table(kmer_len, seed=0)
+    int_seq = rng.integers(0, 4, size=n_bases).astype(np.int64)
+    powers = 4 ** np.arange(kmer_len - 1, -1, -1)
+    levels = np.zeros(n_bases, dtype=np.float64)
+    if n_bases >= kmer_len:
+        windows = np.lib.stride_tricks.sliding_window_view(int_seq, kmer_len)
+        levels[center_idx:center_idx + windows.shape[0]] = table[windows @ powers]
+    dwells = rng.integers(max(2, mean_dwell // 3), mean_dwell * 2, size=n_bases)
+    stall = rng.random(n_bases) < frac_stall
+    dwells[stall] = rng.integers(stall_range[0], stall_range[1], size=int(stall.sum()))
+    true_map = np.concatenate([[0], np.cumsum(dwells)]).astype(np.int64)
+    sig_len = int(true_map[-1])
+    sig = np.repeat(levels, dwells) + rng.normal(0.0, noise, size=sig_len)
+    dacs = np.clip(np.round(sig * scale + shift), -32768, 32767).astype(np.int16)
+    # starting map: jitter, snap to the move stride, keep monotone, pin the ends
+    start = true_map + rng.integers(-jitter, jitter + 1, size=true_map.size)
+    start = (np.round(start / stride) * stride).astype(np.int64)
+    start = np.maximum.accumulate(np.clip(start, 0, sig_len))
+    zero = np.nonzero(rng.random(n_bases - 1) < frac_zero_dwell)[0] + 1
+    start[zero] = start[zero - 1]
+    start = np.maximum.accumulate(start)
+    # the last base keeps at least one sample (the reference's rough re-scaling indexes the centre
+    # sample of every base, refine_signal_map.py:415)
+    start = np.minimum(start, sig_len - 1)
+    start[0], start[-1] = 0, sig_len
+    return dacs, shift + shift_error, scale * scale_error, start, int_seq

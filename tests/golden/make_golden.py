@@ -38,7 +38,7 @@ torch.set_num_threads(4)
 
 
 def make_model(arch, size, kmer_context, num_out, chunk_context, motifs, mod_bases, mod_long_names,
-               seed, path, hot=(1.0, 1.0, 1.0)):
+               seed, path, hot=(1.0, 1.0, 1.0), refine=None):
     kmer_len = sum(kmer_context) + 1
     torch.manual_seed(seed)
     model = model_util._load_python_model(
@@ -71,6 +71,8 @@ def make_model(arch, size, kmer_context, num_out, chunk_context, motifs, mod_bas
         "mod_long_names": mod_long_names, "motifs": motifs, "refine_kmer_levels": None,
         "refine_sd_arr": None, "model_version": 3,
     }
+    if refine is not None:  # signal-mapping refiner settings + k-mer level table (make_golden_refine.py)
+        ckpt.update(refine)
     model_util.export_model_torchscript(ckpt, model, path)
 
 
