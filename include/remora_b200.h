@@ -198,24 +198,27 @@ int rb200_softmax_ml(const float *logits_dev, int32_t B, int32_t num_out, float 
  * the read: start[0] == 0, both strictly increasing, start[b] <= end[b-1], end[last] == read length),
  * traceback words [tb_off[r], tb_off[r+1]) with tb_off[r+1]-tb_off[r] = sum(end-start), and
  * path entries [seq_off[r] + r, seq_off[r+1] + r + 1) (seq_len + 1 values: path[0] = 0, path[b] =
- * first sample of base b, path[seq_len] = read length).  max_width[r] = widest band of read r;
- * order (may be NULL) = processing order, longest reads first for load balance.
+ * first sample of base b, path[seq_len] = read length).  order (may be NULL) = processing order,
+ * longest reads first for load balance.
  *
  *   rb200_refine_normalize: signal = (dacs - shift[r]) / scale[r] as float32; dacs_dtype 0 = int16,
  *     1 = float32 (float32 arithmetic), 2 = float64, 3 = float32 samples in float64 arithmetic (numpy
  *     float64 shift/scale), following numpy's promotion so the result matches the reference's bits.
- *   rb200_refine_scratch_bytes: size of wide_scratch_dev (0 when every band fits the shared-memory rows).
+ *   near_cap: capacity (samples) of the per-warp rows kept in shared memory, 64..1024, 0 = chosen from
+ *     max_band_width; bases whose band is wider take their rows from wide_scratch_dev.  A smaller
+ *     capacity lets more warps (reads) share an SM.  max_band_width: widest band of the batch.
+ *   rb200_refine_scratch_bytes: size of wide_scratch_dev (0 when every band fits near_cap).
  *   rb200_refine_dp: algo 0 = "Viterbi", 1 = "dwell_penalty" (penalties on the host, <= 16).
  *     status[r] = 1 when the traceback of read r left its band (undefined behaviour in the reference;
  *     the path of that read is not usable).  queue_dev: one int32 of device scratch. */
 int rb200_refine_normalize(const void *dacs_dev, int32_t dacs_dtype, const int64_t *sig_off_dev,
                            const double *shift_dev, const double *scale_dev, int32_t n_reads,
                            int64_t max_len, float *signal_dev, void *stream);
-int rb200_refine_scratch_bytes(int32_t max_band_width, int64_t *bytes);
+int rb200_refine_scratch_bytes(int32_t near_cap, int32_t max_band_width, int64_t *bytes);
 int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const float *levels_dev,
                     const int32_t *band_start_dev, const int32_t *band_end_dev, const int64_t *seq_off_dev,
-                    const int64_t *tb_off_dev, const int32_t *max_width_dev, const int32_t *order_dev,
-                    int32_t n_reads, const float *dwell_penalty_host, int32_t n_penalty, int32_t algo,
+                    const int64_t *tb_off_dev, const int32_t *order_dev, int32_t n_reads,
+                    const float *dwell_penalty_host, int32_t n_penalty, int32_t algo, int32_t near_cap,
                     int32_t max_band_width, int32_t *traceback_ws_dev, int32_t *path_dev, float *score_dev,
                     int32_t *status_dev, int32_t *queue_dev, float *wide_scratch_dev, void *stream);
 

@@ -85,8 +85,8 @@ def load_library():
     lib.rb200_chunk_fill.argtypes = [vp, i32, i32, ctypes.c_double, ctypes.c_double, vp, i32, vp, i32, vp, vp,
                                      vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.rb200_refine_normalize.argtypes = [vp, i32, vp, vp, vp, i32, i64, vp, vp]
-    lib.rb200_refine_scratch_bytes.argtypes = [i32, ctypes.POINTER(i64)]
-    lib.rb200_refine_dp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp,
+    lib.rb200_refine_scratch_bytes.argtypes = [i32, i32, ctypes.POINTER(i64)]
+    lib.rb200_refine_dp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp,
                                     vp, vp, vp, vp, vp]
     lib.rb200_set_profile.argtypes = [vp, ctypes.c_int]
     lib.rb200_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3),

@@ -510,40 +510,40 @@ int rb200_refine_normalize(const void *dacs_dev, int32_t dacs_dtype, const int64
                                    max_len, signal_dev, static_cast<cudaStream_t>(stream));
 }
 
-int rb200_refine_scratch_bytes(int32_t max_band_width, int64_t *bytes) {
-    RB200_REQUIRE(bytes && max_band_width >= 0, "bad argument");
+int rb200_refine_scratch_bytes(int32_t near_cap, int32_t max_band_width, int64_t *bytes) {
+    RB200_REQUIRE(bytes && max_band_width >= 0 && near_cap >= 0, "bad argument");
     int sms = 0;
     int rc = current_sm_count(&sms);
     if (rc != RB200_OK) return rc;
-    *bytes = (int64_t)refine_wide_scratch_bytes(sms, max_band_width);
+    *bytes = (int64_t)refine_wide_scratch_bytes(sms, near_cap, max_band_width);
     return RB200_OK;
 }
 
 int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const float *levels_dev,
                     const int32_t *band_start_dev, const int32_t *band_end_dev, const int64_t *seq_off_dev,
-                    const int64_t *tb_off_dev, const int32_t *max_width_dev, const int32_t *order_dev,
-                    int32_t n_reads, const float *dwell_penalty_host, int32_t n_penalty, int32_t algo,
+                    const int64_t *tb_off_dev, const int32_t *order_dev, int32_t n_reads,
+                    const float *dwell_penalty_host, int32_t n_penalty, int32_t algo, int32_t near_cap,
                     int32_t max_band_width, int32_t *traceback_ws_dev, int32_t *path_dev, float *score_dev,
                     int32_t *status_dev, int32_t *queue_dev, float *wide_scratch_dev, void *stream) {
-    RB200_REQUIRE(n_reads >= 0 && (algo == 0 || algo == 1) && max_band_width >= 1, "bad argument");
+    RB200_REQUIRE(n_reads >= 0 && (algo == 0 || algo == 1) && max_band_width >= 1 && near_cap >= 0,
+                  "bad argument");
     RB200_REQUIRE(algo == 0 || (n_penalty >= 1 && n_penalty <= 16 && dwell_penalty_host),
                   "the dwell_penalty algorithm needs 1..16 penalties");
     if (n_reads == 0) return RB200_OK;
     RB200_REQUIRE(signal_dev && sig_off_dev && levels_dev && band_start_dev && band_end_dev &&
-                      seq_off_dev && tb_off_dev && max_width_dev && traceback_ws_dev && path_dev &&
-                      score_dev && status_dev && queue_dev,
+                      seq_off_dev && tb_off_dev && traceback_ws_dev && path_dev && score_dev &&
+                      status_dev && queue_dev,
                   "null buffer");
     int sms = 0;
     int rc = current_sm_count(&sms);
     if (rc != RB200_OK) return rc;
-    RB200_REQUIRE(refine_wide_scratch_bytes(sms, max_band_width) == 0 || wide_scratch_dev,
+    RB200_REQUIRE(refine_wide_scratch_bytes(sms, near_cap, max_band_width) == 0 || wide_scratch_dev,
                   "bands wider than the shared-memory rows need wide_scratch_dev "
                   "(rb200_refine_scratch_bytes)");
     return launch_refine_dp(signal_dev, sig_off_dev, levels_dev, band_start_dev, band_end_dev, seq_off_dev,
-                            tb_off_dev, max_width_dev, order_dev, n_reads, dwell_penalty_host,
-                            algo == 1 ? n_penalty : 1, algo, max_band_width, traceback_ws_dev, path_dev,
-                            score_dev, status_dev, queue_dev, wide_scratch_dev, sms,
-                            static_cast<cudaStream_t>(stream));
+                            tb_off_dev, order_dev, n_reads, dwell_penalty_host, algo == 1 ? n_penalty : 1,
+                            algo, near_cap, max_band_width, traceback_ws_dev, path_dev, score_dev, status_dev,
+                            queue_dev, wide_scratch_dev, sms, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

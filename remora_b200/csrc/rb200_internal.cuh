@@ -126,13 +126,12 @@ int launch_chunk_fill(const void *dacs, int dtype, int sig_len, double shift, do
 int launch_refine_normalise(const void *dacs, int dtype, const int64_t *sig_off, const double *shift,
                             const double *scale, int n_reads, int64_t max_len, float *out,
                             cudaStream_t stream);
-size_t refine_wide_scratch_bytes(int sm_count, int max_band_width);
+size_t refine_wide_scratch_bytes(int sm_count, int near_cap, int max_band_width);
 int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *levels, const int32_t *band_st,
                      const int32_t *band_en, const int64_t *seq_off, const int64_t *tb_off,
-                     const int32_t *max_w, const int32_t *order, int n_reads, const float *pen, int n_pen,
-                     int algo, int max_band_width, int32_t *tb, int32_t *path, float *score,
-                     int32_t *status, int32_t *counter, float *wide_scratch, int sm_count,
-                     cudaStream_t stream);
+                     const int32_t *order, int n_reads, const float *pen, int n_pen, int algo, int near_cap,
+                     int max_band_width, int32_t *tb, int32_t *path, float *score, int32_t *status,
+                     int32_t *counter, float *wide_scratch, int sm_count, cudaStream_t stream);
 
 // rb200_tiled.cu : register-tiled FFMA2 layer kernels (Conv_w_ref and every non-fused shape);
 // each returns RB200_ERR_UNSUPPORTED when the layer / shape has no tiled form

@@ -15,19 +15,18 @@ namespace rb200 {
 namespace {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kRowsPerWarp = 6;     // row_a, row_b, unp, utb, bs, mvs
-constexpr int kMaxSmemCap = 1024;   // widest band served from shared memory (24 KB of rows per warp)
+constexpr int kMinNearCap = 64, kMaxNearCap = 1024;  // shared-memory row capacity (samples) per warp
 constexpr size_t kSmemBudget = 220 * 1024;
+constexpr int kWarpExtraWords = 4 + 32;  // slot (padded) + speculation buffer of the traceback
 
-// Shared-memory row capacity for a batch whose widest band is max_w: the smallest of 256/512/1024
-// that holds it (a smaller capacity lets more warps share an SM); reads with still wider bands
-// (long stalls) take their rows from a global scratch area instead.
-inline int pick_cap(int max_w) { return max_w <= 256 ? 256 : (max_w <= 512 ? 512 : kMaxSmemCap); }
-inline size_t warp_words(int cap) { return (size_t)kRowsPerWarp * cap + 4; }  // + slot (padded)
+// Default shared-memory row capacity for a batch whose widest band is max_w (callers that know the
+// distribution of band widths pass a smaller one: bases with wider bands use global scratch rows).
+inline int default_near_cap(int max_w) { return max_w <= 256 ? 256 : (max_w <= 512 ? 512 : kMaxNearCap); }
+inline size_t warp_words(int cap) { return (size_t)refine::kRowsPerWarp * cap + kWarpExtraWords; }
 inline size_t cta_smem_bytes(int cap) { return (size_t)kWarpsPerCta * warp_words(cap) * sizeof(float); }
 inline int ctas_per_sm(int cap) {
     const int by_smem = (int)(kSmemBudget / (cta_smem_bytes(cap) + 1024));
-    return by_smem > 4 ? 4 : (by_smem < 1 ? 1 : by_smem);  // 48 registers x 256 threads: <= 5 CTAs
+    return by_smem > 4 ? 4 : (by_smem < 1 ? 1 : by_smem);  // 62 registers x 256 threads: <= 4 CTAs
 }
 
 enum { DACS_I16 = 0, DACS_F32 = 1, DACS_F64 = 2, DACS_F32_AS_F64 = 3 };
@@ -69,6 +68,15 @@ struct WarpCtx {
     int lane;
     static constexpr int nl = 32;
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ int scan_max(int v) const {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v = max(v, o);
+        }
+        return v;
+    }
+    __device__ __forceinline__ int bcast_last(int v) const { return __shfl_sync(0xffffffffu, v, 31); }
 };
 
 struct RefineArgs {
@@ -79,7 +87,6 @@ struct RefineArgs {
     const int32_t *band_en;    // band end per base
     const int64_t *seq_off;    // [n_reads + 1]
     const int64_t *tb_off;     // [n_reads + 1] offsets into the traceback workspace
-    const int32_t *max_w;      // [n_reads] widest band of the read
     const int32_t *order;      // [n_reads] processing order (longest first) or NULL
     int n_reads;
     int n_pen;
@@ -90,20 +97,24 @@ struct RefineArgs {
     float *score;              // [n_reads] final forward score (all_scores[-1])
     int32_t *status;           // [n_reads]
     int32_t *counter;          // work queue head (zeroed before the launch)
-    float *wide_scratch;       // kRowsPerWarp * wide_w + 4 words per warp of the grid, or NULL
-    int wide_w;                // band capacity of the global scratch rows
-    int cap;                   // band capacity of the shared-memory rows
+    float *wide_scratch;       // kRowsPerWarp * wide_w words per warp of the grid, or NULL
+    int wide_w;                // capacity of the global scratch rows (widest band, multiple of 4)
+    int cap;                   // capacity of the shared-memory rows (multiple of 4)
 };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) refine_dp_kernel(const RefineArgs a) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) refine_dp_kernel(const RefineArgs a) {
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5;
     WarpCtx ctx{(int)(threadIdx.x & 31)};
-    float *sbase = smem + (size_t)warp * ((size_t)kRowsPerWarp * a.cap + 4);
-    float *gbase = a.wide_scratch
-                       ? a.wide_scratch + ((size_t)blockIdx.x * kWarpsPerCta + warp) *
-                                              ((size_t)kRowsPerWarp * a.wide_w + 4)
-                       : nullptr;
+    float *sbase = smem + (size_t)warp * ((size_t)refine::kRowsPerWarp * a.cap + kWarpExtraWords);
+    const refine::Rows near = refine::carve_rows(sbase, (size_t)a.cap);
+    int32_t *slot = reinterpret_cast<int32_t *>(sbase + (size_t)refine::kRowsPerWarp * a.cap);
+    int32_t *spec = slot + 4;
+    refine::Rows far = {};
+    if (a.wide_scratch)
+        far = refine::carve_rows(a.wide_scratch + ((size_t)blockIdx.x * kWarpsPerCta + warp) *
+                                                      ((size_t)refine::kRowsPerWarp * a.wide_w),
+                                 (size_t)a.wide_w);
     for (;;) {
         int q = 0;
         if (ctx.lane == 0) q = atomicAdd(a.counter, 1);
@@ -112,18 +123,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) refine_dp_kernel(const Refi
         const int r = a.order ? a.order[q] : q;
         const int64_t so = a.seq_off[r];
         const int n_bases = (int)(a.seq_off[r + 1] - so);
-        const int w = a.max_w[r];
-        float *base = sbase;
-        int cap = a.cap;
-        if (w > a.cap) {  // rare: a stall wider than the shared-memory rows
-            base = gbase;
-            cap = a.wide_w;
-        }
         refine::refine_read_warp(ctx, a.sig + a.sig_off[r], a.levels + so, a.band_st + so, a.band_en + so,
                                  n_bases, a.pen, a.n_pen, a.algo, a.tb + a.tb_off[r], a.path + so + r,
-                                 a.score + r, a.status + r, base, base + cap, base + 2 * (size_t)cap,
-                                 reinterpret_cast<int32_t *>(base + 3 * (size_t)cap), base + 4 * (size_t)cap,
-                                 base + 5 * (size_t)cap, reinterpret_cast<int32_t *>(base + 6 * (size_t)cap));
+                                 a.score + r, a.status + r, near, a.cap, far, slot, spec);
         __syncwarp();
     }
 }
@@ -140,18 +142,25 @@ int launch_refine_normalise(const void *dacs, int dtype, const int64_t *sig_off,
     return RB200_OK;
 }
 
-size_t refine_wide_scratch_bytes(int sm_count, int max_band_width) {
-    if (max_band_width <= kMaxSmemCap) return 0;
-    const size_t warps = (size_t)sm_count * ctas_per_sm(kMaxSmemCap) * kWarpsPerCta;
-    return warps * warp_words((max_band_width + 3) & ~3) * sizeof(float);
+static int resolve_near_cap(int near_cap, int max_band_width) {
+    if (near_cap <= 0) near_cap = default_near_cap(max_band_width);
+    if (near_cap < kMinNearCap) near_cap = kMinNearCap;
+    if (near_cap > kMaxNearCap) near_cap = kMaxNearCap;
+    return (near_cap + 3) & ~3;
+}
+
+size_t refine_wide_scratch_bytes(int sm_count, int near_cap, int max_band_width) {
+    near_cap = resolve_near_cap(near_cap, max_band_width);
+    if (max_band_width <= near_cap) return 0;
+    const size_t warps = (size_t)sm_count * ctas_per_sm(near_cap) * kWarpsPerCta;
+    return warps * (size_t)refine::kRowsPerWarp * ((max_band_width + 3) & ~3) * sizeof(float);
 }
 
 int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *levels, const int32_t *band_st,
                      const int32_t *band_en, const int64_t *seq_off, const int64_t *tb_off,
-                     const int32_t *max_w, const int32_t *order, int n_reads, const float *pen, int n_pen,
-                     int algo, int max_band_width, int32_t *tb, int32_t *path, float *score,
-                     int32_t *status, int32_t *counter, float *wide_scratch, int sm_count,
-                     cudaStream_t stream) {
+                     const int32_t *order, int n_reads, const float *pen, int n_pen, int algo, int near_cap,
+                     int max_band_width, int32_t *tb, int32_t *path, float *score, int32_t *status,
+                     int32_t *counter, float *wide_scratch, int sm_count, cudaStream_t stream) {
     if (n_reads == 0) return RB200_OK;
     RefineArgs a;
     a.sig = sig;
@@ -161,7 +170,6 @@ int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *leve
     a.band_en = band_en;
     a.seq_off = seq_off;
     a.tb_off = tb_off;
-    a.max_w = max_w;
     a.order = order;
     a.n_reads = n_reads;
     a.n_pen = n_pen;
@@ -172,7 +180,7 @@ int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *leve
     a.score = score;
     a.status = status;
     a.counter = counter;
-    a.cap = pick_cap(max_band_width);
+    a.cap = resolve_near_cap(near_cap, max_band_width);
     a.wide_scratch = max_band_width > a.cap ? wide_scratch : nullptr;
     a.wide_w = (max_band_width + 3) & ~3;  // rows are read in 16-byte groups
     const size_t smem = cta_smem_bytes(a.cap);

@@ -1,0 +1,834 @@
+"""Minimal POD5 and BAM readers and the read object that joins them ("next" row 3),
+behind the parts of the reference's ``remora.io`` surface the inference path touches
+(src/remora/io.py:147-180 helpers, :184-360 ``ReadIndexedBam``, :394-411 ``parse_move_tag``,
+:415-474 POD5 iteration, :1747-2177 ``Read``).
+
+The reference reads both formats through third-party C libraries (``pysam`` / htslib, ``pod5``); neither
+is needed here:
+  * BAM  = BGZF (concatenated raw-deflate blocks, each with its size in a gzip extra field) around
+           length-prefixed binary records; decoded with ``zlib`` + ``struct`` (SAM/BAM specification
+           sections 4.1-4.2).  Records expose the ``pysam.AlignedSegment`` attributes the reference uses.
+  * POD5 = three Arrow IPC files (signal, run-info and reads tables) embedded in one file and located
+           by a FlatBuffers footer; the tables are read with ``pyarrow``, the signal rows
+           ("minknow.vbz": zstd around StreamVByte-16 of zig-zag deltas) are decoded with numpy.
+This is host plumbing that feeds the GPU path; it has no device code.
+"""
+import array
+import dataclasses
+import mmap
+import re
+import struct
+import uuid
+import zlib
+from collections import defaultdict
+
+import numpy as np
+
+from . import RemoraError, util
+from . import data_chunks as DC
+
+PA_TO_NORM_SCALING_FACTOR = 1.4826  # reference constants.py:243
+
+# ------------------------------------------------------------------------------------------------
+# BAM
+# ------------------------------------------------------------------------------------------------
+_SEQ_CODES = "=ACMGRSVTWYHKDBN"
+_SEQ_LUT = np.array([ord(a) for a in _SEQ_CODES for _ in _SEQ_CODES], dtype=np.uint8), \
+    np.array([ord(b) for _ in _SEQ_CODES for b in _SEQ_CODES], dtype=np.uint8)
+_TAG_SCALARS = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I", "f": "<f"}
+_TAG_ARRAYS = {"c": np.int8, "C": np.uint8, "s": "<i2", "S": "<u2", "i": "<i4", "I": "<u4", "f": "<f4"}
+_TAG_ARRAY_CODES = {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i", "I": "I", "f": "f"}
+FLAG_UNMAPPED, FLAG_REVERSE, FLAG_SECONDARY, FLAG_SUPPLEMENTARY = 0x4, 0x10, 0x100, 0x800
+# cigar operations consuming query / reference (reference data_chunks.py:29-35)
+MATCH_OPS = np.array([True, False, False, False, False, False, False, True, True])
+QUERY_OPS = np.array([True, True, False, False, True, False, False, True, True])
+REF_OPS = np.array([True, False, True, True, False, False, False, True, True])
+
+
+def iter_bgzf_blocks(fh):
+    """Yields (file offset, decompressed bytes) of every BGZF block (SAM spec 4.1)."""
+    while True:
+        start = fh.tell()
+        head = fh.read(12)
+        if len(head) == 0:
+            return
+        if len(head) < 12 or head[:4] != b"\x1f\x8b\x08\x04":
+            raise RemoraError("not a BGZF block (is this a BAM file?)")
+        xlen = struct.unpack("<H", head[10:12])[0]
+        extra = fh.read(xlen)
+        bsize = None
+        pos = 0
+        while pos + 4 <= len(extra):
+            si1, si2, slen = extra[pos], extra[pos + 1], struct.unpack("<H", extra[pos + 2:pos + 4])[0]
+            if si1 == 66 and si2 == 67 and slen == 2:
+                bsize = struct.unpack("<H", extra[pos + 4:pos + 6])[0]
+            pos += 4 + slen
+        if bsize is None:
+            raise RemoraError("BGZF block without BC subfield")
+        cdata = fh.read(bsize - xlen - 19)
+        crc, isize = struct.unpack("<II", fh.read(8))
+        data = zlib.decompress(cdata, wbits=-15) if isize else b""
+        if len(data) != isize or (zlib.crc32(data) & 0xFFFFFFFF) != crc:
+            raise RemoraError("corrupt BGZF block")
+        yield start, data
+
+
+class _BgzfStream:
+    """Sequential reader over the decompressed stream that remembers BAM virtual offsets
+    (block file offset << 16 | offset within the block)."""
+
+    def __init__(self, fh):
+        self._blocks = iter_bgzf_blocks(fh)
+        self._buf = b""
+        self._pos = 0
+        self._block_start = 0
+
+    def _fill(self):
+        for start, data in self._blocks:
+            if data:
+                self._block_start, self._buf, self._pos = start, data, 0
+                return True
+        return False
+
+    def tell(self):
+        if self._pos >= len(self._buf) and not self._fill():
+            return None
+        return (self._block_start << 16) | self._pos
+
+    def read(self, n):
+        out = []
+        while n > 0:
+            if self._pos >= len(self._buf) and not self._fill():
+                break
+            chunk = self._buf[self._pos:self._pos + n]
+            self._pos += len(chunk)
+            n -= len(chunk)
+            out.append(chunk)
+        return b"".join(out)
+
+
+@dataclasses.dataclass
+class AlignedSegment:
+    """One BAM record with the ``pysam.AlignedSegment`` attributes the reference's io layer reads."""
+
+    query_name: str
+    flag: int
+    reference_id: int
+    reference_name: str
+    reference_start: int
+    mapping_quality: int
+    cigartuples: list
+    query_sequence: str
+    query_qualities: np.ndarray
+    tags: list  # [(tag, value)]
+    next_reference_id: int = -1
+    next_reference_start: int = -1
+    template_length: int = 0
+
+    @property
+    def is_unmapped(self):
+        return bool(self.flag & FLAG_UNMAPPED)
+
+    @property
+    def is_reverse(self):
+        return bool(self.flag & FLAG_REVERSE)
+
+    @property
+    def is_forward(self):
+        return not self.is_reverse
+
+    @property
+    def is_secondary(self):
+        return bool(self.flag & FLAG_SECONDARY)
+
+    @property
+    def is_supplementary(self):
+        return bool(self.flag & FLAG_SUPPLEMENTARY)
+
+    def has_tag(self, tag):
+        return any(t == tag for t, _ in self.tags)
+
+    def get_tag(self, tag):
+        for t, v in self.tags:
+            if t == tag:
+                return v
+        raise KeyError(f"tag '{tag}' not present")
+
+    def get_reference_sequence(self):
+        """Reference bases under the alignment, rebuilt from the query, CIGAR and MD tag (what
+        ``pysam.AlignedSegment.get_reference_sequence`` does); mismatches come back lower case."""
+        try:
+            md = self.get_tag("MD")
+        except KeyError:
+            raise ValueError("MD tag not present")
+        aligned = []
+        qpos = 0
+        for op, ln in self.cigartuples:
+            if MATCH_OPS[op]:
+                aligned.append(self.query_sequence[qpos:qpos + ln])
+            elif op == 3:
+                raise ValueError("reference skips (N) are not supported")
+            if QUERY_OPS[op]:
+                qpos += ln
+        aligned = "".join(aligned)
+        out = []
+        apos = 0
+        for num, dele, mis in re.findall(r"(\d+)|\^([A-Za-z]+)|([A-Za-z])", md):
+            if num:
+                out.append(aligned[apos:apos + int(num)])
+                apos += int(num)
+            elif dele:
+                out.append(dele.upper())
+            else:
+                out.append(mis.lower())
+                apos += 1
+        if apos != len(aligned):
+            raise ValueError("MD tag discordant with CIGAR")
+        return "".join(out)
+
+    def to_dict(self):
+        return {"name": self.query_name, "flag": str(self.flag), "ref_name": self.reference_name or "*",
+                "ref_pos": str(self.reference_start + 1), "map_quality": str(self.mapping_quality),
+                "cigar": "".join(f"{ln}{DC_CIGAR_CODES[op]}" for op, ln in self.cigartuples) or "*",
+                "seq": self.query_sequence, "tags": [t for t, _ in self.tags]}
+
+
+DC_CIGAR_CODES = "MIDNSHP=X"
+
+
+def _parse_tags(buf, pos, end):
+    tags = []
+    while pos < end:
+        tag = buf[pos:pos + 2].decode("ascii")
+        typ = chr(buf[pos + 2])
+        pos += 3
+        if typ in _TAG_SCALARS:
+            fmt = _TAG_SCALARS[typ]
+            size = struct.calcsize(fmt)
+            val = struct.unpack_from(fmt, buf, pos)[0]
+            pos += size
+        elif typ == "A":
+            val = chr(buf[pos])
+            pos += 1
+        elif typ in "ZH":
+            z = buf.index(b"\x00", pos)
+            val = buf[pos:z].decode("ascii")
+            pos = z + 1
+        elif typ == "B":
+            sub = chr(buf[pos])
+            count = struct.unpack_from("<I", buf, pos + 1)[0]
+            dt = np.dtype(_TAG_ARRAYS[sub])
+            pos += 5
+            # array.array like pysam returns (python-int items, so `mv[0]` is an int, not an int8)
+            val = array.array(_TAG_ARRAY_CODES[sub], bytes(buf[pos:pos + count * dt.itemsize]))
+            pos += count * dt.itemsize
+        else:
+            raise RemoraError(f"unknown BAM tag type '{typ}'")
+        tags.append((tag, val))
+    return tags
+
+
+def _parse_record(buf, ref_names):
+    (ref_id, pos, l_name, mapq, _bin, n_cigar, flag, l_seq, next_ref, next_pos,
+     tlen) = struct.unpack_from("<iiBBHHHIiii", buf, 0)
+    off = 32
+    name = buf[off:off + l_name - 1].decode("ascii")
+    off += l_name
+    cig = np.frombuffer(buf, dtype="<u4", count=n_cigar, offset=off)
+    cigartuples = [(int(c & 0xF), int(c >> 4)) for c in cig]
+    off += 4 * n_cigar
+    packed = np.frombuffer(buf, dtype=np.uint8, count=(l_seq + 1) // 2, offset=off)
+    seq = np.empty(packed.size * 2, dtype=np.uint8)
+    seq[0::2] = _SEQ_LUT[0][packed]
+    seq[1::2] = _SEQ_LUT[1][packed]
+    off += (l_seq + 1) // 2
+    qual = np.frombuffer(buf, dtype=np.uint8, count=l_seq, offset=off)
+    off += l_seq
+    return AlignedSegment(
+        query_name=name, flag=flag, reference_id=ref_id,
+        reference_name=ref_names[ref_id] if 0 <= ref_id < len(ref_names) else None,
+        reference_start=pos, mapping_quality=mapq, cigartuples=cigartuples,
+        query_sequence=seq[:l_seq].tobytes().decode("ascii"), query_qualities=qual,
+        tags=_parse_tags(buf, off, len(buf)), next_reference_id=next_ref, next_reference_start=next_pos,
+        template_length=tlen)
+
+
+class BamReader:
+    """Sequential BAM reader: ``header_text``, ``references`` / ``lengths`` and iteration over
+    :class:`AlignedSegment` records (with their virtual file offsets via :meth:`iter_with_offsets`)."""
+
+    def __init__(self, path):
+        self.path = str(path)
+        self._fh = open(self.path, "rb")
+        self._stream = _BgzfStream(self._fh)
+        if self._stream.read(4) != b"BAM\x01":
+            raise RemoraError(f"{self.path} is not a BAM file")
+        l_text = struct.unpack("<i", self._stream.read(4))[0]
+        self.header_text = self._stream.read(l_text).rstrip(b"\x00").decode("utf-8", errors="replace")
+        n_ref = struct.unpack("<i", self._stream.read(4))[0]
+        self.references, self.lengths = [], []
+        for _ in range(n_ref):
+            l_name = struct.unpack("<i", self._stream.read(4))[0]
+            self.references.append(self._stream.read(l_name)[:-1].decode("ascii"))
+            self.lengths.append(struct.unpack("<i", self._stream.read(4))[0])
+
+    def iter_with_offsets(self):
+        while True:
+            voff = self._stream.tell()
+            if voff is None:
+                return
+            head = self._stream.read(4)
+            if len(head) < 4:
+                return
+            size = struct.unpack("<i", head)[0]
+            buf = self._stream.read(size)
+            if len(buf) < size:
+                raise RemoraError("truncated BAM record")
+            yield voff, _parse_record(buf, self.references)
+
+    def __iter__(self):
+        for _, rec in self.iter_with_offsets():
+            yield rec
+
+    def close(self):
+        self._fh.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def read_is_primary(read):
+    """io.py:147-154"""
+    return not (read.is_supplementary or read.is_secondary)
+
+
+def get_parent_id(bam_read):
+    """Split reads carry their parent's id in the ``pi`` tag (io.py:174-180)."""
+    try:
+        return bam_read.get_tag("pi")
+    except KeyError:
+        return bam_read.query_name
+
+
+@dataclasses.dataclass
+class ReadIndexedBam:
+    """BAM records indexed by (parent) read id, same constructor arguments and query methods as the
+    reference class (io.py:183-360).  Records are parsed once and kept in memory (the reference keeps
+    file pointers and re-reads through htslib)."""
+
+    bam_path: str
+    skip_non_primary: bool = True
+    req_tags: set = None
+    read_id_converter: object = None
+    parent_read_id_subset: set = None
+    child_read_id_subset: set = None
+
+    def __post_init__(self):
+        self.num_reads = None
+        self.num_records = 0
+        self.skip_reasons = defaultdict(int)
+        self._bam_idx = None
+        self.compute_read_index()
+
+    @property
+    def filename(self):
+        return self.bam_path
+
+    reference_filename = filename
+
+    def compute_read_index(self):
+        idx = defaultdict(list)
+        with BamReader(self.bam_path) as bam:
+            self.header_text = bam.header_text
+            self.references = bam.references
+            for read in bam:
+                if self.child_read_id_subset is not None and read.query_name not in self.child_read_id_subset:
+                    self.skip_reasons["Child read ID filtered"] += 1
+                    continue
+                index_read_id = get_parent_id(read)
+                if self.parent_read_id_subset is not None and index_read_id not in self.parent_read_id_subset:
+                    self.skip_reasons["Parent read ID filtered"] += 1
+                    continue
+                if self.read_id_converter is not None:
+                    index_read_id = self.read_id_converter(index_read_id)
+                if self.req_tags is not None and self.req_tags.difference(t for t, _ in read.tags):
+                    self.skip_reasons["Missing BAM tags"] += 1
+                    continue
+                if self.skip_non_primary and not read_is_primary(read):
+                    self.skip_reasons["Non-primary alignment"] += 1
+                    continue
+                self.num_records += 1
+                idx[index_read_id].append(read)
+        self._bam_idx = dict(idx)
+        self.num_reads = len(self._bam_idx)
+
+    def get_alignments(self, read_id):
+        try:
+            yield from self._bam_idx[read_id]
+        except KeyError:
+            raise RemoraError(f"Could not find {read_id} in {self.bam_path}")
+
+    def get_first_alignment(self, read_id):
+        return next(self.get_alignments(read_id))
+
+    def __contains__(self, read_id):
+        return read_id in self._bam_idx
+
+    def __getitem__(self, read_id):
+        return self._bam_idx[read_id]
+
+    @property
+    def read_ids(self):
+        return list(self._bam_idx.keys())
+
+    def __iter__(self):
+        for recs in self._bam_idx.values():
+            yield from recs
+
+
+def parse_move_tag(mv_tag, sig_len, seq_len=None, check=True, reverse_signal=False):
+    """Move table -> first sample of every base (io.py:394-411)."""
+    stride = int(mv_tag[0])
+    mv_table = np.asarray(mv_tag[1:])
+    query_to_signal = np.nonzero(mv_table)[0] * stride
+    query_to_signal = np.concatenate([query_to_signal, [sig_len]])
+    if reverse_signal:
+        query_to_signal = sig_len - query_to_signal[::-1]
+    if check and seq_len is not None and query_to_signal.size - 1 != seq_len:
+        raise RemoraError("Move table discordant with basecalls")
+    if check and mv_table.size != sig_len // stride:
+        raise RemoraError("Move table discordant with signal")
+    return query_to_signal, mv_table, stride
+
+
+def make_sequence_coordinate_mapping(cigar):
+    """Reference position -> (fractional) query position from CIGAR knots (data_chunks.py:77-115)."""
+    cigar = list(cigar)
+    while len(cigar) > 0 and not MATCH_OPS[cigar[-1][0]]:
+        cigar = cigar[:-1]
+    if len(cigar) == 0:
+        raise RemoraError("No match operations found in alignment cigar")
+    ops, lens = map(np.array, zip(*cigar))
+    if ops.min() < 0 or ops.max() > 8:
+        raise RemoraError("Invalid cigar op(s)")
+    if lens.min() < 0:
+        raise RemoraError("Cigar lengths may not be negative")
+    is_match = MATCH_OPS[ops]
+    match_counts = lens[is_match]
+    offsets = np.array([match_counts, np.ones_like(match_counts)])
+    ref_knots = np.cumsum(np.where(REF_OPS[ops], lens, 0))
+    ref_knots = np.concatenate([[0], (ref_knots[is_match] - offsets).T.flatten(), [ref_knots[-1]]])
+    query_knots = np.cumsum(np.where(QUERY_OPS[ops], lens, 0))
+    query_knots = np.concatenate([[0], (query_knots[is_match] - offsets).T.flatten(), [query_knots[-1]]])
+    return np.interp(np.arange(ref_knots[-1] + 1), ref_knots, query_knots)
+
+
+def compute_ref_to_signal(query_to_signal, cigar):
+    """data_chunks.py:60-74, 118-122"""
+    knots = make_sequence_coordinate_mapping(cigar)
+    return np.floor(np.interp(knots, np.arange(query_to_signal.size), query_to_signal)).astype(int)
+
+
+# ------------------------------------------------------------------------------------------------
+# POD5
+# ------------------------------------------------------------------------------------------------
+POD5_SIGNATURE = b"\x8bPOD\r\n\x1a\n"
+
+
+def _fb_table_fields(buf, pos):
+    """FlatBuffers table at ``pos`` -> list of absolute field positions (None = absent)."""
+    vt = pos - struct.unpack_from("<i", buf, pos)[0]
+    vt_size = struct.unpack_from("<H", buf, vt)[0]
+    out = []
+    for o in range(4, vt_size, 2):
+        rel = struct.unpack_from("<H", buf, vt + o)[0]
+        out.append(pos + rel if rel else None)
+    return out
+
+
+def parse_pod5_footer(buf):
+    """Embedded-file list of a POD5 footer (FlatBuffers ``Footer{file_identifier, software,
+    pod5_version, contents:[EmbeddedFile{offset:int64, length:int64, format, content_type}]}``)."""
+    root = struct.unpack_from("<I", buf, 0)[0]
+    fields = _fb_table_fields(buf, root)
+    if len(fields) < 4 or fields[3] is None:
+        raise RemoraError("POD5 footer has no embedded-file list")
+    vec = fields[3] + struct.unpack_from("<I", buf, fields[3])[0]
+    n = struct.unpack_from("<I", buf, vec)[0]
+    files = []
+    for i in range(n):
+        elem = vec + 4 + 4 * i
+        tbl = elem + struct.unpack_from("<I", buf, elem)[0]
+        f = _fb_table_fields(buf, tbl)
+        off = struct.unpack_from("<q", buf, f[0])[0] if len(f) > 0 and f[0] is not None else 0
+        length = struct.unpack_from("<q", buf, f[1])[0] if len(f) > 1 and f[1] is not None else 0
+        ctype = struct.unpack_from("<h", buf, f[3])[0] if len(f) > 3 and f[3] is not None else 0
+        files.append((off, length, ctype))
+    return files
+
+
+def decode_vbz(blob, n_samples):
+    """"minknow.vbz" signal chunk -> int16 samples: zstd frame -> StreamVByte-16 (one key BIT per value,
+    0 = one byte, 1 = two bytes; keys first, then the data bytes) -> zig-zag -> running sum."""
+    import pyarrow as pa
+    if n_samples == 0:
+        return np.zeros(0, dtype=np.int16)
+    blob = bytes(blob)
+    # zstd frame header: content size (always written by the POD5 writers)
+    if blob[:4] != b"\x28\xb5\x2f\xfd":
+        raise RemoraError("signal chunk is not a zstd frame")
+    fhd = blob[4]
+    fcs_flag, single, did = fhd >> 6, (fhd >> 5) & 1, fhd & 3
+    pos = 5 + (0 if single else 1) + (0, 1, 2, 4)[did]
+    fcs_size = (1 if single else 0, 2, 4, 8)[fcs_flag]
+    if fcs_size == 0:
+        raise RemoraError("zstd frame without content size")
+    size = int.from_bytes(blob[pos:pos + fcs_size], "little") + (256 if fcs_size == 2 else 0)
+    raw = np.frombuffer(pa.Codec("zstd").decompress(blob, decompressed_size=size), dtype=np.uint8)
+    n_key = (n_samples + 7) // 8
+    keys = np.unpackbits(raw[:n_key], bitorder="little")[:n_samples].astype(np.int64)
+    data = raw[n_key:]
+    if data.size != n_samples + int(keys.sum()):
+        raise RemoraError("corrupt svb16 signal chunk")
+    off = np.cumsum(1 + keys) - (1 + keys)
+    lo = data[off].astype(np.uint16)
+    hi = np.where(keys == 1, data[np.minimum(off + 1, data.size - 1)], 0).astype(np.uint16)
+    u = lo | (hi << 8)
+    delta = (u >> 1).astype(np.int16) ^ -(u & 1).astype(np.int16)
+    return np.cumsum(delta, dtype=np.int64).astype(np.int16)
+
+
+@dataclasses.dataclass
+class Calibration:
+    offset: float
+    scale: float
+
+
+@dataclasses.dataclass
+class Pod5Read:
+    """The attributes of ``pod5.ReadRecord`` the reference reads (io.py:455-462, 2103-2110)."""
+
+    read_id: uuid.UUID
+    signal: np.ndarray
+    calibration: Calibration
+    num_samples: int
+    read_number: int = 0
+    channel: int = 0
+
+
+class Pod5Reader:
+    """Reads one ``.pod5`` file: ``read_ids`` and ``reads(selection=None)`` like ``pod5.Reader``."""
+
+    def __init__(self, path):
+        import pyarrow as pa
+        import pyarrow.ipc as ipc
+        self.path = str(path)
+        self._fh = open(self.path, "rb")
+        self._mm = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        mm = self._mm
+        if mm[:8] != POD5_SIGNATURE or mm[-8:] != POD5_SIGNATURE:
+            raise RemoraError(f"{self.path} is not a POD5 file")
+        flen = struct.unpack("<q", mm[-32:-24])[0]
+        fstart = len(mm) - 32 - flen
+        if flen <= 0 or fstart < 8:
+            raise RemoraError("corrupt POD5 footer")
+        self._tables = {}
+        for off, length, _ctype in parse_pod5_footer(mm[fstart:fstart + flen]):
+            reader = ipc.open_file(pa.py_buffer(memoryview(mm)[off:off + length]))
+            names = set(reader.schema.names)
+            if "samples" in names and "signal" in names:
+                self._tables["signal"] = reader
+            elif "calibration_offset" in names:
+                self._tables["reads"] = reader
+            elif "acquisition_id" in names:
+                self._tables["run_info"] = reader
+        if "signal" not in self._tables or "reads" not in self._tables:
+            raise RemoraError("POD5 file lacks a signal or reads table")
+        self._reads = self._tables["reads"].read_all()
+        sig = self._tables["signal"]
+        self._sig_batch_rows = np.cumsum([0] + [sig.get_batch(i).num_rows
+                                                for i in range(sig.num_record_batches)])
+        self._sig_vbz = str(sig.schema.field("signal").type) == "large_binary" or \
+            "vbz" in str(sig.schema.field("signal").type)
+        ids = self._reads.column("read_id").to_pylist()
+        self._ids = [uuid.UUID(bytes=bytes(b)) for b in ids]
+        self._row_of = {str(u): i for i, u in enumerate(self._ids)}
+
+    @property
+    def read_ids(self):
+        return [str(u) for u in self._ids]
+
+    @property
+    def num_reads(self):
+        return len(self._ids)
+
+    def _signal_row(self, row):
+        sig = self._tables["signal"]
+        b = int(np.searchsorted(self._sig_batch_rows, row, side="right") - 1)
+        batch = sig.get_batch(b)
+        i = row - int(self._sig_batch_rows[b])
+        n = batch.column(batch.schema.get_field_index("samples"))[i].as_py()
+        cell = batch.column(batch.schema.get_field_index("signal"))[i]
+        if self._sig_vbz:
+            return decode_vbz(cell.as_py(), n)
+        return np.asarray(cell.as_py(), dtype=np.int16)
+
+    def get_read(self, read_id):
+        row = self._row_of.get(str(read_id))
+        if row is None:
+            raise RemoraError(f"read {read_id} not in {self.path}")
+        rec = self._reads.slice(row, 1).to_pylist()[0]
+        parts = [self._signal_row(int(r)) for r in rec["signal"]]
+        signal = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int16)
+        return Pod5Read(read_id=self._ids[row], signal=signal,
+                        calibration=Calibration(rec["calibration_offset"], rec["calibration_scale"]),
+                        num_samples=int(rec["num_samples"]), read_number=int(rec["read_number"]),
+                        channel=int(rec["channel"]))
+
+    def reads(self, selection=None):
+        ids = self.read_ids if selection is None else [str(s) for s in selection]
+        for rid in ids:
+            if rid in self._row_of:
+                yield self.get_read(rid)
+
+    def close(self):
+        self._reads = None
+        self._tables = {}
+        try:
+            self._mm.close()
+        except BufferError:  # arrow buffers still alive; the map is released with them
+            pass
+        self._fh.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def iter_pod5_reads(pod5_path, num_reads=None, read_ids=None):
+    """io.py:415-438"""
+    with Pod5Reader(pod5_path) as reader:
+        for read_num, read in enumerate(reader.reads(selection=read_ids)):
+            if num_reads is not None and read_num >= num_reads:
+                return
+            yield read
+
+
+# ------------------------------------------------------------------------------------------------
+# the joined read
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class RefRegion:
+    """io.py:45-56"""
+
+    ctg: str
+    strand: str
+    start: int
+    end: int = None
+
+    @property
+    def len(self):
+        return self.end - self.start
+
+
+@dataclasses.dataclass
+class Read:
+    """Signal + basecalls + move table + scaling + alignment of one read: the fields and the methods
+    of the reference's ``io.Read`` (io.py:1747-2177) that lead to a ``RemoraRead``."""
+
+    read_id: str
+    dacs: np.ndarray = None
+    seq: str = None
+    stride: int = None
+    mv_table: np.ndarray = None
+    query_to_signal: np.ndarray = None
+    shift_dacs_to_pa: float = None
+    scale_dacs_to_pa: float = None
+    shift_pa_to_norm: float = None
+    scale_pa_to_norm: float = None
+    shift_dacs_to_norm: float = None
+    scale_dacs_to_norm: float = None
+    shift_pa_to_zc_pa: float = None
+    scale_pa_to_zc_pa: float = None
+    ref_seq: str = None
+    ref_reg: RefRegion = None
+    cigar: list = None
+    ref_to_signal: np.ndarray = None
+    full_align: dict = None
+    _child_read_id: str = None
+    _sig_len: int = None
+
+    @property
+    def pa_signal(self):
+        if self.scale_dacs_to_pa is None or self.shift_dacs_to_pa is None:
+            raise RemoraError("pA scaling factors not set")
+        return (self.dacs - self.shift_dacs_to_pa) / self.scale_dacs_to_pa
+
+    @property
+    def norm_signal(self):
+        if self.scale_dacs_to_norm is None or self.shift_dacs_to_norm is None:
+            raise RemoraError("Norm scaling factors not set")
+        return (self.dacs - self.shift_dacs_to_norm) / self.scale_dacs_to_norm
+
+    def compute_pa_to_norm_scaling(self, factor=PA_TO_NORM_SCALING_FACTOR):
+        """median / MAD normalisation when the BAM carries no sm/sd tags (io.py:1851-1856)"""
+        self.shift_pa_to_norm = np.median(self.pa_signal)
+        self.scale_pa_to_norm = max(1.0, np.median(np.abs(self.pa_signal - self.shift_pa_to_norm)) * factor)
+
+    @property
+    def sig_len(self):
+        if self._sig_len is None and self.dacs is not None:
+            self._sig_len = self.dacs.size
+        return self._sig_len
+
+    @property
+    def seq_len(self):
+        if self.query_to_signal is None:
+            return None if self.seq is None else len(self.seq)
+        return self.query_to_signal.size - 1
+
+    @property
+    def child_read_id(self):
+        return self.read_id if self._child_read_id is None else self._child_read_id
+
+    @property
+    def shift_dacs_to_zc_pa(self):
+        if self.shift_dacs_to_pa is None or self.scale_dacs_to_pa is None or self.shift_pa_to_zc_pa is None:
+            raise RemoraError("Zero-centered pA scaling factors not set")
+        return self.shift_dacs_to_pa + (self.scale_dacs_to_pa * self.shift_pa_to_zc_pa)
+
+    @property
+    def scale_dacs_to_zc_pa(self):
+        if self.scale_dacs_to_pa is None or self.scale_pa_to_zc_pa is None:
+            raise RemoraError("Zero-centered pA scaling factors not set")
+        return self.scale_dacs_to_pa * self.scale_pa_to_zc_pa
+
+    def copy(self):
+        return dataclasses.replace(self)
+
+    def add_alignment(self, alignment_record, parse_ref_align=True, reverse_signal=False, pa_scaling=None):
+        """io.py:1972-2084: trim the signal by the sp/ts/ns tags, take basecalls + move table, the
+        sm/sd scaling tags, and (for mapped reads) the reference sequence and base->signal map."""
+        if pa_scaling is not None:
+            self.shift_pa_to_zc_pa, self.scale_pa_to_zc_pa = pa_scaling
+        if alignment_record.reference_name is None and alignment_record.is_reverse:
+            raise RemoraError("Unmapped reads cannot map to reverse strand.")
+        if self.dacs is None:
+            raise RemoraError("Must add signal to io.Read before alignment.")
+        self.full_align = alignment_record.to_dict()
+        tags = dict(alignment_record.tags)
+        if reverse_signal:
+            self.dacs = self.dacs[::-1]
+        self.dacs = self.dacs[tags.get("sp", 0):]
+        self.dacs = self.dacs[tags.get("ts", 0):tags.get("ns", self.dacs.size)]
+        if reverse_signal:
+            self.dacs = self.dacs[::-1]
+        self._sig_len = None
+        parent_read_id = tags.get("pi", None)
+        if parent_read_id is None:
+            if alignment_record.query_name != self.read_id:
+                raise RemoraError("Read IDs mismatch")
+        else:
+            if parent_read_id != self.read_id:
+                raise RemoraError("Split read IDs mismatch")
+            self._child_read_id = alignment_record.query_name
+        self.seq = alignment_record.query_sequence
+        if alignment_record.is_reverse:
+            self.seq = util.revcomp(self.seq)
+        try:
+            self.query_to_signal, self.mv_table, self.stride = parse_move_tag(
+                tags["mv"], sig_len=self.sig_len, seq_len=len(self.seq), reverse_signal=reverse_signal)
+        except KeyError:
+            self.query_to_signal = self.mv_table = self.stride = None
+        try:
+            self.shift_pa_to_norm = tags["sm"]
+            self.scale_pa_to_norm = tags["sd"]
+        except KeyError:
+            self.compute_pa_to_norm_scaling()
+        self.shift_dacs_to_norm = self.shift_dacs_to_pa + (self.scale_dacs_to_pa * self.shift_pa_to_norm)
+        self.scale_dacs_to_norm = self.scale_dacs_to_pa * self.scale_pa_to_norm
+        if not parse_ref_align or alignment_record.is_unmapped:
+            return
+        self.ref_reg = RefRegion(ctg=alignment_record.reference_name,
+                                 strand="-" if alignment_record.is_reverse else "+",
+                                 start=alignment_record.reference_start)
+        try:
+            self.ref_seq = alignment_record.get_reference_sequence().upper()
+        except ValueError:
+            self.ref_seq = None
+        self.cigar = alignment_record.cigartuples
+        if alignment_record.is_reverse:
+            if self.ref_seq is not None:
+                self.ref_seq = util.revcomp(self.ref_seq)
+            self.cigar = self.cigar[::-1]
+        if self.ref_reg.ctg is not None and self.ref_seq is not None and self.query_to_signal is not None:
+            self.ref_to_signal = compute_ref_to_signal(self.query_to_signal, self.cigar)
+            if self.ref_to_signal.size != len(self.ref_seq) + 1:
+                raise RemoraError("Discordant ref seq lengths")
+            self.ref_reg.end = self.ref_reg.start + self.ref_to_signal.size - 1
+
+    @classmethod
+    def from_pod5_and_alignment(cls, pod5_read_record, alignment_record, reverse_signal=False, pa_scaling=None):
+        """io.py:2086-2121; POD5 calibration is pA = (dac + offset) * scale, i.e. shift = -offset,
+        scale = 1 / scale in this class's (x - shift) / scale convention."""
+        dacs = pod5_read_record.signal
+        if reverse_signal:
+            dacs = dacs[::-1]
+        read = cls(read_id=str(pod5_read_record.read_id), dacs=dacs,
+                   shift_dacs_to_pa=-pod5_read_record.calibration.offset,
+                   scale_dacs_to_pa=1 / pod5_read_record.calibration.scale)
+        read.add_alignment(alignment_record, reverse_signal=reverse_signal, pa_scaling=pa_scaling)
+        return read
+
+    def into_remora_read(self, use_reference_anchor):
+        """io.py:2123-2177"""
+        if use_reference_anchor:
+            if self.ref_to_signal is None:
+                if self.cigar is None or self.ref_seq is None:
+                    raise RemoraError("Missing reference alignment")
+                self.ref_to_signal = compute_ref_to_signal(self.query_to_signal, self.cigar)
+                if self.ref_to_signal.size != len(self.ref_seq) + 1:
+                    raise RemoraError("Discordant ref seq lengths")
+            trim_dacs = self.dacs[self.ref_to_signal[0]:self.ref_to_signal[-1]]
+            shift_seq_to_sig = self.ref_to_signal - self.ref_to_signal[0]
+            seq = self.ref_seq
+        else:
+            if self.query_to_signal is None:
+                raise RemoraError("Missing query_to_signal (move table)")
+            trim_dacs = self.dacs[self.query_to_signal[0]:self.query_to_signal[-1]]
+            shift_seq_to_sig = self.query_to_signal - self.query_to_signal[0]
+            seq = self.seq
+        if self.shift_pa_to_zc_pa is None or self.scale_pa_to_zc_pa is None:
+            shift, scale = self.shift_dacs_to_norm, self.scale_dacs_to_norm
+        else:
+            shift, scale = self.shift_dacs_to_zc_pa, self.scale_dacs_to_zc_pa
+        remora_read = DC.RemoraRead(dacs=trim_dacs, shift=shift, scale=scale, seq_to_sig_map=shift_seq_to_sig,
+                                    str_seq=seq, read_id=self.read_id)
+        remora_read.check()
+        return remora_read
+
+
+def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_scaling=None):
+    """(io.Read, error text or None) for every alignment of every POD5 read present in the BAM index:
+    the sequential equivalent of the reference's iter_signal -> extract_alignments workers
+    (io.py:441-511)."""
+    with Pod5Reader(pod5_path) as reader:
+        done = 0
+        for rid in reader.read_ids:
+            if rid not in bam_idx:
+                continue
+            if num_reads is not None and done >= num_reads:
+                return
+            done += 1
+            pod5_read = reader.get_read(rid)
+            for bam_read in bam_idx.get_alignments(rid):
+                try:
+                    yield Read.from_pod5_and_alignment(pod5_read, bam_read, reverse_signal=reverse_signal,
+                                                       pa_scaling=pa_scaling), None
+                except RemoraError as e:
+                    yield Read(read_id=rid), str(e)

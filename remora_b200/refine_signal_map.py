@@ -244,6 +244,22 @@ def _dacs_code(dacs, shift, scale):
     return dacs.astype(np.float64), 2
 
 
+NEAR_CAPS = (128, 192, 256, 384, 512, 768, 1024)
+
+
+def choose_near_cap(band_widths, coverage=0.98):
+    """Capacity of the per-warp shared-memory rows for a batch: the smallest step that holds the bands
+    of ``coverage`` of all DP cells.  The few wider bands (stalls) run from global scratch rows, and the
+    smaller footprint lets more reads share an SM (4 x 8 warps at <= 256 samples)."""
+    w = np.sort(np.asarray(band_widths, dtype=np.int64))
+    cum = np.cumsum(w)
+    need = int(w[np.searchsorted(cum, coverage * cum[-1])])
+    for cap in NEAR_CAPS:
+        if cap >= need:
+            return cap
+    return NEAR_CAPS[-1]
+
+
 class DeviceRefineBatch:
     """A batch of reads resident on the GPU for the banded dynamic programme: ``__init__`` builds the
     concatenated arrays and uploads them, :meth:`run` enqueues the two kernels
@@ -251,7 +267,7 @@ class DeviceRefineBatch:
     result back.  ``banded_dp_batch`` is the one-shot form; benchmarks time :meth:`run` alone."""
 
     def __init__(self, dacs_list, shifts, scales, levels_list, seq_bands, algo=DEFAULT_REFINE_ALGO,
-                 short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN, device=None):
+                 short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN, device=None, near_cap=None):
         if algo not in _ALGO_CODE:
             raise RemoraError(f"Invalid core signal mapping refine method: {algo}")
         self.algo = _ALGO_CODE[algo]
@@ -289,14 +305,15 @@ class DeviceRefineBatch:
             raise RemoraError("Dynamic programming search space too large. Read likely contains large "
                               "deletions.")
         self.tb_off = tb_off = np.concatenate([[0], np.cumsum(tb_lens)]).astype(np.int64)
-        max_w = np.array([int(w.max()) for w in widths], dtype=np.int32)
         order = np.argsort(-tb_lens, kind="stable").astype(np.int32)
         for r in range(n_reads):
             if seq_bands[r].shape[1] != seq_lens[r] or seq_bands[r][1, -1] != sig_lens[r]:
                 raise RemoraError("band does not match read")
         self.max_sig_len = int(sig_lens.max())
-        self.widest = int(max_w.max())
+        all_w = np.concatenate(widths)
+        self.widest = int(all_w.max())
         self.cells = int(tb_off[-1])
+        self.near_cap = near_cap if near_cap else choose_near_cap(all_w)
         with torch.cuda.device(device):
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)  # noqa: E731
             self.d_dacs = up(np.concatenate(conv))
@@ -306,7 +323,7 @@ class DeviceRefineBatch:
             self.d_levels = up(np.concatenate([np.asarray(lv, dtype=np.float32) for lv in levels_list]))
             self.d_st = up(np.concatenate([b[0] for b in seq_bands]).astype(np.int32))
             self.d_en = up(np.concatenate([b[1] for b in seq_bands]).astype(np.int32))
-            self.d_max_w, self.d_order = up(max_w), up(order)
+            self.d_order = up(order)
             self.d_sig = torch.empty(int(sig_off[-1]), dtype=torch.float32, device=device)
             self.d_tb = torch.empty(int(tb_off[-1]), dtype=torch.int32, device=device)
             self.d_path = torch.empty(int(seq_off[-1]) + n_reads, dtype=torch.int32, device=device)
@@ -314,7 +331,7 @@ class DeviceRefineBatch:
             self.d_status = torch.empty(n_reads, dtype=torch.int32, device=device)
             self.d_queue = torch.zeros(1, dtype=torch.int32, device=device)
             need = ctypes.c_int64(0)
-            _native.check(self.lib.rb200_refine_scratch_bytes(self.widest, ctypes.byref(need)),
+            _native.check(self.lib.rb200_refine_scratch_bytes(self.near_cap, self.widest, ctypes.byref(need)),
                           "rb200_refine_scratch_bytes")
             self.d_wide = (torch.empty(need.value // 4, dtype=torch.float32, device=device)
                            if need.value else None)
@@ -329,8 +346,8 @@ class DeviceRefineBatch:
                 self.n_reads, self.max_sig_len, ptr(self.d_sig), stream), "rb200_refine_normalize")
             _native.check(self.lib.rb200_refine_dp(
                 ptr(self.d_sig), ptr(self.d_sig_off), ptr(self.d_levels), ptr(self.d_st), ptr(self.d_en),
-                ptr(self.d_seq_off), ptr(self.d_tb_off), ptr(self.d_max_w), ptr(self.d_order), self.n_reads,
-                self.pen.ctypes.data_as(ctypes.c_void_p), self.pen.size, self.algo, self.widest,
+                ptr(self.d_seq_off), ptr(self.d_tb_off), ptr(self.d_order), self.n_reads,
+                self.pen.ctypes.data_as(ctypes.c_void_p), self.pen.size, self.algo, self.near_cap, self.widest,
                 ptr(self.d_tb), ptr(self.d_path), ptr(self.d_score), ptr(self.d_status), ptr(self.d_queue),
                 ptr(self.d_wide) if self.d_wide is not None else None, stream), "rb200_refine_dp")
 

@@ -46,6 +46,14 @@ def int_to_seq(np_seq, alphabet=CONV_ALPHABET):
     return lut[np_seq].tobytes().decode("ascii")
 
 
+_COMP = str.maketrans("ACGTBVDHKMRY", "TGCAVBHDMKYR")  # same letters as reference util.py:51
+
+
+def revcomp(seq):
+    """Reverse complement, IUPAC aware, upper-cased first (reference util.py:102-106)."""
+    return seq.upper().translate(_COMP)[::-1]
+
+
 def softmax_axis1(x):
     """Row softmax (reference util.py:182-186), same operation order."""
     shifted = x - np.max(x, axis=1, keepdims=True)

@@ -39,7 +39,7 @@ def make_reads(n_reads, n_bases, seed=0, distinct=64):
     return table, [base[i % len(base)] for i in range(n_reads)]
 
 
-def gpu_leg(table, reads, algo, iters=5):
+def gpu_leg(table, reads, algo, iters=5, near_cap=None):
     refiner = rsm.SigMapRefiner(_levels_array=table, center_idx=C, do_rough_rescale=True, scale_iters=0,
                                 algo=algo, device=torch.device("cuda:0"))
     t0 = time.perf_counter()
@@ -50,7 +50,7 @@ def gpu_leg(table, reads, algo, iters=5):
     t0 = time.perf_counter()
     batch = rsm.DeviceRefineBatch([r[0][r[3][0]:r[3][-1]] for r in reads], [x[0] for x in resc],
                                   [x[1] for x in resc], levels, bands, algo, refiner.sd_arr,
-                                  torch.device("cuda:0"))
+                                  torch.device("cuda:0"), near_cap=near_cap)
     torch.cuda.synchronize()
     t_up = time.perf_counter() - t0
     for _ in range(2):
@@ -68,6 +68,7 @@ def gpu_leg(table, reads, algo, iters=5):
     t_down = time.perf_counter() - t0
     n_bases = int(batch.seq_off[-1])
     return dict(algo=algo, reads=len(reads), bases=n_bases, cells=batch.cells, widest_band=batch.widest,
+                near_cap=batch.near_cap,
                 kernel_ms=ms, reads_per_s=len(reads) / ms * 1e3, bases_per_s=n_bases / ms * 1e3,
                 cells_per_s=batch.cells / ms * 1e3, host_setup_s=t_host, upload_s=t_up, readback_s=t_down,
                 e2e_reads_per_s=len(reads) / (t_host + t_up + ms / 1e3 + t_down)), paths, levels, resc, bands
@@ -119,13 +120,14 @@ def main():
     ap.add_argument("--bases", type=int, default=1000)
     ap.add_argument("--json", default=None)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--near-caps", default="", help="comma list: also time these shared-memory row capacities")
     args = ap.parse_args()
     table, reads = make_reads(args.reads, args.bases)
     result = {}
     for algo in ("dwell_penalty", "Viterbi"):
         g, paths, levels, resc, bands = gpu_leg(table, reads, algo)
         print(f"[gpu] {algo}: {g['reads']} reads, {g['bases']} bases, {g['cells'] / 1e6:.1f} M cells, "
-              f"widest band {g['widest_band']}: {g['kernel_ms']:.2f} ms -> {g['reads_per_s'] / 1e3:.1f} k reads/s, "
+              f"widest band {g['widest_band']}, near_cap {g['near_cap']}: {g['kernel_ms']:.2f} ms -> {g['reads_per_s'] / 1e3:.1f} k reads/s, "
               f"{g['bases_per_s'] / 1e6:.1f} M bases/s, {g['cells_per_s'] / 1e9:.2f} G cells/s; "
               f"host set-up {g['host_setup_s']:.2f} s, upload {g['upload_s']:.2f} s, read-back "
               f"{g['readback_s']:.2f} s -> e2e {g['e2e_reads_per_s']:.0f} reads/s", flush=True)
@@ -141,6 +143,11 @@ def main():
             for k, v in c.items():
                 print(f"[cpu] {k}: {v}", flush=True)
             result["cpu"] = c
+    for cap in [int(x) for x in args.near_caps.split(",") if x]:
+        g = gpu_leg(table, reads, "dwell_penalty", near_cap=cap)[0]
+        print(f"[gpu] dwell_penalty near_cap {cap}: {g['kernel_ms']:.2f} ms -> {g['cells_per_s'] / 1e9:.2f} G cells/s",
+              flush=True)
+        result[f"near_cap_{cap}"] = g
     if args.json:
         with open(args.json, "w") as fh:
             json.dump(result, fh, indent=1)

@@ -21,32 +21,57 @@ struct HostCtx {
     int lane;
     int nl;
     pthread_barrier_t *bar;
+    int *xchg;  // nl ints shared by the lanes (what the warp shuffles exchange on the GPU)
     int skip_mod = 0, skip_rem = -1, count = 0;  // negative control: drop every sync with count % mod == rem
     void sync() {
         const int c = count++;
         if (skip_mod > 0 && c % skip_mod == skip_rem) return;
         if (nl > 1) pthread_barrier_wait(bar);
     }
+    void hard_sync() {
+        if (nl > 1) pthread_barrier_wait(bar);
+    }
+    int scan_max(int v) {
+        if (nl == 1) return v;
+        xchg[lane] = v;
+        hard_sync();
+        int m = v;
+        for (int i = 0; i < lane; ++i) m = xchg[i] > m ? xchg[i] : m;
+        hard_sync();
+        return m;
+    }
+    int bcast_last(int v) {
+        if (nl == 1) return v;
+        if (lane == nl - 1) xchg[0] = v;
+        hard_sync();
+        const int out = xchg[0];
+        hard_sync();
+        return out;
+    }
 };
 
 }  // namespace
 
 extern "C" int emul_refine_read(const float *sig, const float *levels, const int32_t *st, const int32_t *en,
-                                int n_bases, const float *pen, int n_pen, int algo, int max_w, int n_lanes,
-                                int32_t *tb, int32_t *path, float *score, int32_t *status) {
-    const int cap = (max_w + 3) & ~3;  // rows are read in 16-byte groups
-    std::vector<float> row_a(cap), row_b(cap), unp(cap), bs(cap), mvs(cap);
-    std::vector<int32_t> utb(cap), slot(4);
+                                int n_bases, const float *pen, int n_pen, int algo, int max_w, int near_cap,
+                                int n_lanes, int32_t *tb, int32_t *path, float *score, int32_t *status) {
+    // "near" rows (shared memory on the GPU) hold bands up to near_cap samples, "far" rows (global
+    // scratch) the wider ones; rows are read in 16-byte groups
+    const size_t ncap = (size_t)((near_cap + 3) & ~3), fcap = (size_t)((max_w + 3) & ~3);
+    std::vector<float> near_buf(rb200::refine::kRowsPerWarp * ncap), far_buf(rb200::refine::kRowsPerWarp * fcap);
+    std::vector<int32_t> slot(4), spec(32);
+    std::vector<int> xchg(32);
+    const rb200::refine::Rows near = rb200::refine::carve_rows(near_buf.data(), ncap);
+    const rb200::refine::Rows far = rb200::refine::carve_rows(far_buf.data(), fcap);
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, nullptr, n_lanes);
     auto body = [&](int lane) {
-        HostCtx ctx{lane, n_lanes, &bar};
+        HostCtx ctx{lane, n_lanes, &bar, xchg.data()};
         if (const char *e = getenv("EMUL_SKIP_SYNC")) {  // "mod,rem" - proves the race detector sees a missing barrier
             sscanf(e, "%d,%d", &ctx.skip_mod, &ctx.skip_rem);
         }
         rb200::refine::refine_read_warp(ctx, sig, levels, st, en, n_bases, pen, n_pen, algo, tb, path, score,
-                                        status, row_a.data(), row_b.data(), unp.data(), utb.data(), bs.data(),
-                                        mvs.data(), slot.data());
+                                        status, near, near_cap, far, slot.data(), spec.data());
     };
     if (n_lanes == 1) {
         body(0);
@@ -62,7 +87,7 @@ extern "C" int emul_refine_read(const float *sig, const float *levels, const int
 #ifdef EMUL_MAIN
 // Standalone form (needed for ThreadSanitizer, which cannot be loaded into a running python):
 //   refine_emul <in.bin> <out.bin>
-// in : int32 {n_bases, sig_len, n_pen, algo, max_w, n_lanes}, float sig[sig_len], float levels[n_bases],
+// in : int32 {n_bases, sig_len, n_pen, algo, max_w, n_lanes, near_cap}, float sig[sig_len], float levels[n_bases],
 //      int32 st[n_bases], int32 en[n_bases], float pen[n_pen]
 // out: int32 path[n_bases+1], float score, int32 status, int32 tb[band_len]
 #include <cstdio>
@@ -70,9 +95,10 @@ int main(int argc, char **argv) {
     if (argc != 3) return 2;
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 2;
-    int32_t h[6];
-    if (fread(h, 4, 6, f) != 6) return 2;
+    int32_t h[7];
+    if (fread(h, 4, 7, f) != 7) return 2;
     const int n_bases = h[0], sig_len = h[1], n_pen = h[2], algo = h[3], max_w = h[4], n_lanes = h[5];
+    const int near_cap = h[6];
     std::vector<float> sig(sig_len), levels(n_bases), pen(n_pen > 0 ? n_pen : 1);
     std::vector<int32_t> st(n_bases), en(n_bases);
     if (fread(sig.data(), 4, sig_len, f) != (size_t)sig_len) return 2;
@@ -87,7 +113,7 @@ int main(int argc, char **argv) {
     float score = 0;
     int32_t status = -1;
     emul_refine_read(sig.data(), levels.data(), st.data(), en.data(), n_bases, pen.data(), n_pen, algo, max_w,
-                     n_lanes, tb.data(), path.data(), &score, &status);
+                     near_cap, n_lanes, tb.data(), path.data(), &score, &status);
     f = fopen(argv[2], "wb");
     if (!f) return 2;
     fwrite(path.data(), 4, path.size(), f);
