@@ -26,7 +26,10 @@ inline size_t warp_words(int cap) { return (size_t)refine::kRowsPerWarp * cap + 
 inline size_t cta_smem_bytes(int cap) { return (size_t)kWarpsPerCta * warp_words(cap) * sizeof(float); }
 inline int ctas_per_sm(int cap) {
     const int by_smem = (int)(kSmemBudget / (cta_smem_bytes(cap) + 1024));
-    return by_smem > 4 ? 4 : (by_smem < 1 ? 1 : by_smem);  // 62 registers x 256 threads: <= 4 CTAs
+    // 126 registers x 256 threads: two CTAs (16 warps) per SM.  Measured on B200: register-capped
+    // variants with 24 / 32 resident warps are no faster (80 registers) or much slower (64 registers:
+    // the chain's shared-memory addresses get rematerialised every step).
+    return by_smem > 2 ? 2 : (by_smem < 1 ? 1 : by_smem);
 }
 
 enum { DACS_I16 = 0, DACS_F32 = 1, DACS_F64 = 2, DACS_F32_AS_F64 = 3 };

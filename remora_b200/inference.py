@@ -1,11 +1,13 @@
 """Single-read and batched inference entry points behind the reference's ``remora.inference``
 surface: ``call_read_mods`` (src/remora/inference.py:661-712) and the device boundary of the
 batched CLI pipeline, ``run_model_batched`` (inference.py:277-316)."""
+import array
+
 import numpy as np
 import torch
 
-from . import constants
-from .util import Motif, format_mm_ml_tags, softmax_axis1
+from . import RemoraError, constants
+from .util import Motif, format_mm_ml_tags, revcomp, softmax_axis1
 
 
 def call_read_mods(read, model, model_metadata, batch_size=constants.DEFAULT_BATCH_SIZE,
@@ -67,3 +69,107 @@ def run_model_batched(batches, models, models_metadata, batch_size):
         dev = devices[can_base]
         nn_out = models[can_base](sigs.to(dev, non_blocking=True), enc.to(dev, non_blocking=True))
         yield can_base, nn_out, b_read_pos, b_reads
+
+
+def mods_tags_to_str(mm_tags, ml_arr):
+    """SAM tag strings of the per-canonical-base MM strings and the joined ML array (reference
+    util.py mods_tags_to_str as used at inference.py:447)."""
+    return [f"MM:Z:{''.join(mm_tags)}", "ML:B:C," + ",".join(str(int(v)) for v in ml_arr)]
+
+
+def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_reads=None,
+                            batch_size=constants.DEFAULT_BATCH_SIZE, reads_per_batch=256, ref_anchored=False,
+                            skip_non_primary=True, extract_on_device=True, return_probs=False):
+    """``remora infer from_pod5_and_bam`` as one function (reference inference.py:462-660 without its
+    process/queue plumbing): POD5 signal + BAM basecalls/move tables -> modified-base calls per read.
+
+    ``models``: ``(model, metadata)`` or ``{can_base: (model, metadata)}`` as ``load_model`` returns them.
+    Reads are handled ``reads_per_batch`` at a time: joined on the host (``remora_b200.io``), their
+    signal mappings refined in ONE banded-DP launch per model (``SigMapRefiner.refine_reads``), chunk
+    arrays built and the network run on the GPU per read.  Returns a list of dicts
+    ``{read_id, mm, ml (array('B')), error}`` (plus ``calls``: ``{can_base: (positions, probs)}`` when
+    ``return_probs``); with ``out_path`` the input records are also written as SAM text with the
+    MM/ML tags attached (previous MM/ML/mv tags dropped), unmapped-style when reference anchored like
+    the reference's output (inference.py:448-456)."""
+    from . import io as rio
+    from .refine_signal_map import SigMapRefiner
+    if isinstance(models, tuple):
+        models = {models[1]["can_base"]: models}
+    rev_sigs = {bool(md["reverse_signal"]) for _, md in models.values()}
+    pa_scalings = {None if md["pa_scaling"] is None else tuple(md["pa_scaling"]) for _, md in models.values()}
+    if len(rev_sigs) != 1 or len(pa_scalings) != 1:
+        raise RemoraError("models disagree on reverse_signal / pa_scaling")
+    reverse_signal, pa_scaling = rev_sigs.pop(), pa_scalings.pop()
+    bam_idx = rio.ReadIndexedBam(in_bam_path, skip_non_primary=skip_non_primary, req_tags={"mv"})
+    results = []
+    out_fh = None
+    if out_path is not None:
+        out_fh = open(out_path, "w")
+        if bam_idx.header_text:
+            out_fh.write(bam_idx.header_text.rstrip("\n") + "\n")
+        out_fh.write("@PG\tID:remora_b200\tPN:remora_b200\n")
+
+    def flush(group):
+        # group: list of io.Read that converted cleanly; one refinement launch per model
+        per_read = [dict(read_id=r.child_read_id, mm=[], ml=array.array("B"), error=None, calls={})
+                    for r in group]
+        for can_base, (model, md) in models.items():
+            rreads = []
+            for io_read, res in zip(group, per_read):
+                try:
+                    rreads.append(io_read.into_remora_read(ref_anchored))
+                except RemoraError as e:
+                    res["error"] = str(e)
+                    rreads.append(None)
+            live = [r for r in rreads if r is not None]
+            refiner = md["sig_map_refiner"]
+            if refiner.is_loaded and live:
+                refiner.refine_reads(live)
+            md_done = dict(md, sig_map_refiner=SigMapRefiner())  # refinement already applied above
+            for rread, res, io_read in zip(rreads, per_read, group):
+                if rread is None or res["error"] is not None:
+                    continue
+                out = call_read_mods(rread, model, md_done, batch_size=batch_size, return_mod_probs=True,
+                                     extract_on_device=extract_on_device)
+                probs, _, pos = out
+                if len(pos) == 0:
+                    continue
+                seq = io_read.ref_seq if ref_anchored else io_read.seq
+                mm, ml = format_mm_ml_tags(seq=seq, poss=pos, probs=probs, mod_bases=md["mod_bases"],
+                                           can_base=can_base)
+                res["mm"].append(mm)
+                res["ml"].extend(ml)
+                if return_probs:
+                    res["calls"][can_base] = (pos, probs)
+        for io_read, res in zip(group, per_read):
+            res["mm"] = "".join(res["mm"])
+            if not return_probs:
+                del res["calls"]
+            results.append(res)
+            rec = io_read.alignment_record
+            if out_fh is not None and res["error"] is None and rec is not None:
+                extra = mods_tags_to_str([res["mm"]], res["ml"])
+                if ref_anchored:
+                    import dataclasses
+                    seq = io_read.ref_seq if io_read.ref_reg.strand == "+" else revcomp(io_read.ref_seq)
+                    rec = dataclasses.replace(rec, cigartuples=[(0, len(io_read.ref_seq))], query_sequence=seq,
+                                              query_qualities=np.zeros(0, dtype=np.uint8))
+                out_fh.write(rec.to_sam(drop_tags=("MM", "ML", "Mm", "Ml", "mv"), extra_tags=extra) + "\n")
+
+    group = []
+    try:
+        for io_read, err in rio.iter_io_reads(pod5_path, bam_idx, num_reads=num_reads,
+                                              reverse_signal=reverse_signal, pa_scaling=pa_scaling):
+            if err is not None:
+                results.append(dict(read_id=io_read.read_id, mm="", ml=array.array("B"), error=err))
+                continue
+            group.append(io_read)
+            if len(group) >= reads_per_batch:
+                flush(group)
+                group = []
+        if group:
+            flush(group)
+    finally:
+        if out_fh is not None:
+            out_fh.close()
+    return results

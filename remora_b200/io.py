@@ -121,9 +121,11 @@ class AlignedSegment:
     query_sequence: str
     query_qualities: np.ndarray
     tags: list  # [(tag, value)]
+    tag_types: dict = None  # tag -> BAM type character ("B" tags: "B" + element type)
     next_reference_id: int = -1
     next_reference_start: int = -1
     template_length: int = 0
+    next_reference_name: str = None
 
     @property
     def is_unmapped(self):
@@ -186,6 +188,34 @@ class AlignedSegment:
             raise ValueError("MD tag discordant with CIGAR")
         return "".join(out)
 
+    def to_sam(self, drop_tags=(), extra_tags=()):
+        """SAM text line; ``extra_tags`` are ready-made ``TAG:TYPE:VALUE`` strings."""
+        if self.next_reference_name is None:
+            rnext = "*"
+        else:
+            rnext = "=" if self.next_reference_name == self.reference_name else self.next_reference_name
+        qual = ("*" if self.query_qualities.size == 0 or self.query_qualities[0] == 0xFF
+                else (self.query_qualities + 33).astype(np.uint8).tobytes().decode("ascii"))
+        fields = [self.query_name, str(self.flag), self.reference_name or "*", str(self.reference_start + 1),
+                  str(self.mapping_quality),
+                  "".join(f"{ln}{DC_CIGAR_CODES[op]}" for op, ln in self.cigartuples) or "*", rnext,
+                  str(self.next_reference_start + 1), str(self.template_length), self.query_sequence or "*", qual]
+        for tag, val in self.tags:
+            if tag in drop_tags:
+                continue
+            typ = (self.tag_types or {}).get(tag, "Z")
+            if typ[0] == "B":
+                fields.append(f"{tag}:B:{typ[1]}," + ",".join(
+                    (repr(float(v)) if typ[1] == "f" else str(int(v))) for v in val))
+            elif typ in "cCsSiI":
+                fields.append(f"{tag}:i:{int(val)}")
+            elif typ == "f":
+                fields.append(f"{tag}:f:{float(val):g}")
+            else:
+                fields.append(f"{tag}:{typ}:{val}")
+        fields.extend(extra_tags)
+        return "\t".join(fields)
+
     def to_dict(self):
         return {"name": self.query_name, "flag": str(self.flag), "ref_name": self.reference_name or "*",
                 "ref_pos": str(self.reference_start + 1), "map_quality": str(self.mapping_quality),
@@ -197,10 +227,11 @@ DC_CIGAR_CODES = "MIDNSHP=X"
 
 
 def _parse_tags(buf, pos, end):
-    tags = []
+    tags, types = [], {}
     while pos < end:
         tag = buf[pos:pos + 2].decode("ascii")
         typ = chr(buf[pos + 2])
+        types[tag] = typ if typ != "B" else "B" + chr(buf[pos + 3])
         pos += 3
         if typ in _TAG_SCALARS:
             fmt = _TAG_SCALARS[typ]
@@ -225,7 +256,7 @@ def _parse_tags(buf, pos, end):
         else:
             raise RemoraError(f"unknown BAM tag type '{typ}'")
         tags.append((tag, val))
-    return tags
+    return tags, types
 
 
 def _parse_record(buf, ref_names):
@@ -244,13 +275,15 @@ def _parse_record(buf, ref_names):
     off += (l_seq + 1) // 2
     qual = np.frombuffer(buf, dtype=np.uint8, count=l_seq, offset=off)
     off += l_seq
+    tags, types = _parse_tags(buf, off, len(buf))
     return AlignedSegment(
         query_name=name, flag=flag, reference_id=ref_id,
         reference_name=ref_names[ref_id] if 0 <= ref_id < len(ref_names) else None,
         reference_start=pos, mapping_quality=mapq, cigartuples=cigartuples,
         query_sequence=seq[:l_seq].tobytes().decode("ascii"), query_qualities=qual,
-        tags=_parse_tags(buf, off, len(buf)), next_reference_id=next_ref, next_reference_start=next_pos,
-        template_length=tlen)
+        tags=tags, tag_types=types, next_reference_id=next_ref, next_reference_start=next_pos,
+        template_length=tlen,
+        next_reference_name=ref_names[next_ref] if 0 <= next_ref < len(ref_names) else None)
 
 
 class BamReader:
@@ -662,6 +695,7 @@ class Read:
     full_align: dict = None
     _child_read_id: str = None
     _sig_len: int = None
+    alignment_record: AlignedSegment = None  # (extension) the BAM record this read was joined with
 
     @property
     def pa_signal(self):
@@ -721,6 +755,8 @@ class Read:
         if self.dacs is None:
             raise RemoraError("Must add signal to io.Read before alignment.")
         self.full_align = alignment_record.to_dict()
+        if isinstance(alignment_record, AlignedSegment):
+            self.alignment_record = alignment_record
         tags = dict(alignment_record.tags)
         if reverse_signal:
             self.dacs = self.dacs[::-1]
@@ -832,3 +868,162 @@ def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_s
                                                        pa_scaling=pa_scaling), None
                 except RemoraError as e:
                     yield Read(read_id=rid), str(e)
+
+
+# ------------------------------------------------------------------------------------------------
+# writers (fixtures, round-trip tests, examples): the same two formats, produced without pysam / pod5
+# ------------------------------------------------------------------------------------------------
+def encode_vbz(signal):
+    """int16 samples -> "minknow.vbz" chunk (inverse of :func:`decode_vbz`)."""
+    import pyarrow as pa
+    signal = np.ascontiguousarray(signal, dtype=np.int16)
+    n = signal.size
+    delta = np.diff(signal.astype(np.int32), prepend=np.int32(0)).astype(np.int16)
+    u = ((delta.astype(np.int32) << 1) ^ (delta.astype(np.int32) >> 15)).astype(np.uint16)
+    keys = (u > 0xFF).astype(np.uint8)
+    key_bytes = np.packbits(keys, bitorder="little")
+    lens = 1 + keys.astype(np.int64)
+    off = np.cumsum(lens) - lens
+    data = np.zeros(int(lens.sum()), dtype=np.uint8)
+    data[off] = (u & 0xFF).astype(np.uint8)
+    two = keys == 1
+    data[off[two] + 1] = (u[two] >> 8).astype(np.uint8)
+    raw = np.concatenate([key_bytes, data]).tobytes()
+    return pa.Codec("zstd").compress(raw, asbytes=True)
+
+
+def _fb_footer(files):
+    """FlatBuffers ``Footer`` with an embedded-file list [(offset, length, content_type)]."""
+    def align(buf, a):
+        buf.extend(b"\x00" * (-len(buf) % a))
+
+    buf = bytearray(4)  # root uoffset, patched below
+    # vtables first (tables refer to them with a positive signed offset)
+    vt_root = len(buf)
+    buf += struct.pack("<HHHHHH", 12, 20, 4, 8, 12, 16)
+    vt_file = len(buf)
+    buf += struct.pack("<HHHHHH", 12, 28, 8, 16, 24, 26)
+    align(buf, 8)
+    root = len(buf)
+    struct.pack_into("<I", buf, 0, root)
+    buf += struct.pack("<i", root - vt_root) + b"\x00" * 16  # 4 uoffsets patched below
+    strings = [b"remora_b200", b"remora_b200", b"0.3.2"]
+    for i, text in enumerate(strings):
+        align(buf, 4)
+        pos = len(buf)
+        struct.pack_into("<I", buf, root + 4 + 4 * i, pos - (root + 4 + 4 * i))
+        buf += struct.pack("<I", len(text)) + text + b"\x00"
+    align(buf, 4)
+    vec = len(buf)
+    struct.pack_into("<I", buf, root + 16, vec - (root + 16))
+    buf += struct.pack("<I", len(files)) + b"\x00" * (4 * len(files))
+    for i, (off, length, ctype) in enumerate(files):
+        align(buf, 8)
+        tbl = len(buf)
+        elem = vec + 4 + 4 * i
+        struct.pack_into("<I", buf, elem, tbl - elem)
+        buf += struct.pack("<i4xqqhh", tbl - vt_file, off, length, 0, ctype)
+    align(buf, 8)
+    return bytes(buf)
+
+
+def write_pod5(path, reads, chunk=102400):
+    """Writes a POD5 file holding ``reads``: iterable of (read_id str, int16 signal, calibration offset,
+    calibration scale).  Signal rows are VBZ chunks of at most ``chunk`` samples like MinKNOW's."""
+    import pyarrow as pa
+    import pyarrow.ipc as ipc
+    sig_ids, sig_blobs, sig_n = [], [], []
+    rows = []
+    for read_id, signal, cal_off, cal_scale in reads:
+        uid = uuid.UUID(str(read_id)).bytes
+        signal = np.ascontiguousarray(signal, dtype=np.int16)
+        idx = []
+        for st in range(0, max(signal.size, 1), chunk):
+            part = signal[st:st + chunk]
+            idx.append(len(sig_blobs))
+            sig_ids.append(uid)
+            sig_blobs.append(encode_vbz(part))
+            sig_n.append(part.size)
+        rows.append((uid, idx, signal.size, float(cal_off), float(cal_scale)))
+    signal_tbl = pa.table({
+        "read_id": pa.array(sig_ids, type=pa.binary(16)),
+        "signal": pa.array(sig_blobs, type=pa.large_binary()),
+        "samples": pa.array(sig_n, type=pa.uint32()),
+    })
+    run_tbl = pa.table({"acquisition_id": pa.array(["remora_b200"]), "sample_rate": pa.array([5000], pa.uint16())})
+    reads_tbl = pa.table({
+        "read_id": pa.array([r[0] for r in rows], type=pa.binary(16)),
+        "signal": pa.array([r[1] for r in rows], type=pa.list_(pa.uint64())),
+        "read_number": pa.array(range(len(rows)), type=pa.uint32()),
+        "num_samples": pa.array([r[2] for r in rows], type=pa.uint64()),
+        "channel": pa.array([1] * len(rows), type=pa.uint16()),
+        "calibration_offset": pa.array([r[3] for r in rows], type=pa.float32()),
+        "calibration_scale": pa.array([r[4] for r in rows], type=pa.float32()),
+    })
+    marker = uuid.uuid4().bytes
+    out = bytearray(POD5_SIGNATURE + marker)
+    files = []
+    for tbl, ctype in ((signal_tbl, 1), (run_tbl, 4), (reads_tbl, 0)):
+        sink = pa.BufferOutputStream()
+        with ipc.new_file(sink, tbl.schema) as writer:
+            writer.write_table(tbl)
+        blob = sink.getvalue().to_pybytes()
+        files.append((len(out), len(blob), ctype))
+        out += blob
+        out += b"\x00" * (-len(out) % 8)
+        out += marker
+    footer = _fb_footer(files)
+    out += b"FOOTER\x00\x00" + footer + struct.pack("<q", len(footer)) + marker + POD5_SIGNATURE
+    with open(path, "wb") as fh:
+        fh.write(out)
+
+
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _bgzf_block(data):
+    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+    cdata = comp.compress(data) + comp.flush()
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00"
+            + struct.pack("<H", len(cdata) + 25) + cdata
+            + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
+def _encode_tag(tag, typ, val):
+    head = tag.encode("ascii")
+    if typ[0] == "B":
+        arr = np.asarray(val, dtype=_TAG_ARRAYS[typ[1]])
+        return head + b"B" + typ[1].encode() + struct.pack("<I", arr.size) + arr.tobytes()
+    if typ in _TAG_SCALARS:
+        return head + typ.encode() + struct.pack(_TAG_SCALARS[typ], val)
+    if typ == "A":
+        return head + b"A" + val.encode("ascii")
+    return head + typ.encode() + val.encode("ascii") + b"\x00"
+
+
+def write_bam(path, header_text, references, records):
+    """Writes an (unsorted, unindexed) BAM.  ``references``: [(name, length)]; ``records``: iterable of
+    dicts with keys query_name, flag, reference_id, reference_start, mapping_quality, cigartuples,
+    query_sequence, tags [(tag, BAM type, value)] (missing keys = unmapped defaults)."""
+    text = header_text.encode()
+    body = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(references)))
+    for name, length in references:
+        body += struct.pack("<i", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<i", length)
+    code = {c: i for i, c in enumerate(_SEQ_CODES)}
+    for rec in records:
+        seq = rec.get("query_sequence", "")
+        name = rec["query_name"].encode() + b"\x00"
+        cigar = rec.get("cigartuples", [])
+        nib = [code.get(c, 15) for c in seq] + ([0] if len(seq) % 2 else [])
+        packed = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+        tags = b"".join(_encode_tag(t, ty, v) for t, ty, v in rec.get("tags", []))
+        core = struct.pack("<iiBBHHHIiii", rec.get("reference_id", -1), rec.get("reference_start", -1),
+                           len(name), rec.get("mapping_quality", 0), 4680, len(cigar), rec.get("flag", 4),
+                           len(seq), -1, -1, 0)
+        blob = (core + name + b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in cigar) + packed
+                + b"\xff" * len(seq) + tags)
+        body += struct.pack("<i", len(blob)) + blob
+    with open(path, "wb") as fh:
+        for st in range(0, len(body), 0xFF00):
+            fh.write(_bgzf_block(bytes(body[st:st + 0xFF00])))
+        fh.write(_BGZF_EOF)

@@ -1,0 +1,317 @@
+"""POD5 / BAM input path.
+
+CPU: format round trips through our own writers (VBZ signal codec incl. extreme values, POD5 container
++ FlatBuffers footer, BGZF/BAM records and tags), reference-sequence reconstruction from MD, the
+move-table / CIGAR coordinate maps; and - when the reference's test files are present (build container)
+- the readers on the real files, checked against tests/golden/io_cases.npz (arrays produced by the
+reference's own io.Read from the same records) and against the live reference classes.
+
+GPU: the golden real reads through load_model -> call_read_mods (with and without signal-mapping
+refinement) against the reference's CPU calls, and infer_from_pod5_and_bam end to end on a synthetic
+POD5 + BAM pair written here.
+"""
+import os
+import uuid
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from remora_b200 import RemoraError, data_chunks, inference, io, model_util
+from remora_b200.synth import synth_levels_table
+
+REF_DATA = "/root/reference/tests/data"
+have_ref_data = os.path.isfile(os.path.join(REF_DATA, "can_reads.pod5"))
+
+
+@pytest.fixture(scope="module")
+def io_cases():
+    return np.load(os.path.join(GOLDEN, "io_cases.npz"))
+
+
+# ---------------------------------------------------------------------------------------------
+# codecs and containers: round trips
+# ---------------------------------------------------------------------------------------------
+def test_vbz_round_trip():
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 1000, 102400):
+        sig = rng.integers(-32768, 32767, size=n).astype(np.int16)
+        if n > 5:
+            sig[:5] = [-32768, 32767, 0, -1, 1]  # deltas that wrap around int16
+        blob = io.encode_vbz(sig)
+        assert np.array_equal(io.decode_vbz(blob, n), sig), n
+    smooth = (np.cumsum(rng.integers(-20, 20, size=50000)) + 900).astype(np.int16)
+    assert len(io.encode_vbz(smooth)) < smooth.nbytes * 0.6  # one byte per sample + zstd
+    with pytest.raises(RemoraError):
+        io.decode_vbz(b"not a zstd frame", 4)
+
+
+def make_ids(n, seed=0):
+    rng = np.random.default_rng(seed)
+    return [str(uuid.UUID(int=int(rng.integers(1, 2 ** 62)))) for _ in range(n)]
+
+
+def test_pod5_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    sig = (np.cumsum(rng.integers(-30, 30, size=250000)) + 900).astype(np.int16)
+    ids = make_ids(3)
+    reads = [(ids[0], sig, -240.0, 0.1755), (ids[1], sig[:1234], 3.0, 0.25), (ids[2], sig[:0], 0.0, 1.0)]
+    path = str(tmp_path / "t.pod5")
+    io.write_pod5(path, reads)
+    with io.Pod5Reader(path) as reader:
+        assert reader.read_ids == ids and reader.num_reads == 3
+        for rid, s, off, sc in reads:
+            got = reader.get_read(rid)
+            assert str(got.read_id) == rid and np.array_equal(got.signal, s) and got.num_samples == s.size
+            assert got.calibration.offset == np.float32(off) and got.calibration.scale == np.float32(sc)
+        assert [str(r.read_id) for r in reader.reads(selection=[ids[1], "missing"])] == [ids[1]]
+        with pytest.raises(RemoraError):
+            reader.get_read("missing")
+    assert [str(r.read_id) for r in io.iter_pod5_reads(path, num_reads=2)] == ids[:2]
+    bad = tmp_path / "bad.pod5"
+    bad.write_bytes(b"x" * 100)
+    with pytest.raises(RemoraError):
+        io.Pod5Reader(str(bad))
+
+
+def test_bam_round_trip(tmp_path):
+    rng = np.random.default_rng(2)
+    ids = make_ids(3, seed=5)
+    mv = np.r_[5, rng.integers(0, 2, size=200)].astype(np.int8)
+    recs = [
+        dict(query_name=ids[0], flag=0, reference_id=0, reference_start=99, mapping_quality=60,
+             cigartuples=[(4, 3), (0, 10), (1, 2), (2, 1), (0, 5)], query_sequence="ACGTNACGTAACCGGTTACG",
+             tags=[("mv", "Bc", mv), ("ts", "i", 10), ("ns", "I", 1010), ("sm", "f", 87.5), ("sd", "f", 26.25),
+                   ("MD", "Z", "10^A5"), ("tp", "A", "P"), ("pi", "Z", ids[1]), ("xs", "s", -7), ("xc", "C", 200),
+                   ("xf", "Bf", np.float32([1.5, -2.25]))]),
+        dict(query_name=ids[1], query_sequence="ACG"),
+        dict(query_name=ids[2], flag=0x900, reference_id=0, reference_start=5, cigartuples=[(0, 4)],
+             query_sequence="ACGT"),
+    ]
+    recs += [dict(query_name=f"bulk{i}", query_sequence="ACGT" * 400) for i in range(120)]  # > one BGZF block
+    path = str(tmp_path / "t.bam")
+    io.write_bam(path, "@HD\tVN:1.6\n@SQ\tSN:chr1\tLN:1000\n", [("chr1", 1000)], recs)
+    with io.BamReader(path) as bam:
+        assert bam.references == ["chr1"] and bam.lengths == [1000] and bam.header_text.startswith("@HD")
+        out = list(bam)
+    assert len(out) == len(recs)
+    a = out[0]
+    assert a.query_name == ids[0] and a.query_sequence == recs[0]["query_sequence"]
+    assert a.cigartuples == recs[0]["cigartuples"] and a.reference_name == "chr1" and a.reference_start == 99
+    assert a.mapping_quality == 60 and not a.is_reverse and not a.is_unmapped
+    assert a.get_tag("ts") == 10 and a.get_tag("ns") == 1010 and a.get_tag("xs") == -7 and a.get_tag("xc") == 200
+    assert list(a.get_tag("mv")) == list(mv) and isinstance(a.get_tag("mv")[0], int)
+    assert a.get_tag("sd") == 26.25 and a.get_tag("tp") == "P" and a.get_tag("pi") == ids[1]
+    assert list(a.get_tag("xf")) == [1.5, -2.25] and a.has_tag("MD") and not a.has_tag("zz")
+    with pytest.raises(KeyError):
+        a.get_tag("zz")
+    # MD + CIGAR -> reference bases: 10 matches, deleted A, 5 matches (the 2-base insertion drops out)
+    assert a.get_reference_sequence() == "TNACGTAACC" + "A" + "TTACG"
+    assert out[1].is_unmapped and out[1].reference_name is None and out[1].query_sequence == "ACG"
+    assert out[2].is_secondary and out[2].is_supplementary and not io.read_is_primary(out[2])
+    sam = a.to_sam(drop_tags=("mv",), extra_tags=["MM:Z:C+m?,1;"]).split("\t")
+    assert sam[:6] == [ids[0], "0", "chr1", "100", "60", "3S10M2I1D5M"] and sam[-1] == "MM:Z:C+m?,1;"
+    assert "ts:i:10" in sam and "sd:f:26.25" in sam and not any(f.startswith("mv:") for f in sam)
+    # the index keys split reads by their parent id and skips non-primary records
+    idx = io.ReadIndexedBam(path)
+    assert ids[1] in idx and idx.get_first_alignment(ids[1]).query_name == ids[0]  # pi tag -> parent id
+    assert ids[2] not in idx and idx.skip_reasons["Non-primary alignment"] == 1
+    assert io.ReadIndexedBam(path, req_tags={"mv"}).num_reads == 1
+    with pytest.raises(RemoraError):
+        next(idx.get_alignments("missing"))
+    not_bam = tmp_path / "plain.bam"
+    not_bam.write_bytes(b"plain text, not BGZF" * 4)
+    with pytest.raises(RemoraError):
+        io.BamReader(str(not_bam))
+
+
+def test_md_mismatches_and_errors():
+    rec = io.AlignedSegment("r", 0, 0, "c", 0, 0, [(0, 6)], "ACGTAC", np.zeros(6, np.uint8), [("MD", "2A3")])
+    assert rec.get_reference_sequence() == "ACaTAC"
+    rec.tags = [("MD", "2A9")]
+    with pytest.raises(ValueError):
+        rec.get_reference_sequence()
+    rec.tags = []
+    with pytest.raises(ValueError):
+        rec.get_reference_sequence()
+
+
+def test_move_table_and_cigar_maps():
+    mv = [5, 1, 0, 1, 1, 0, 0, 1]
+    q2s, table, stride = io.parse_move_tag(mv, sig_len=35, seq_len=4)
+    assert stride == 5 and np.array_equal(q2s, [0, 10, 15, 30, 35]) and table.size == 7
+    rq2s = io.parse_move_tag(mv, sig_len=35, seq_len=4, reverse_signal=True)[0]
+    assert np.array_equal(rq2s, [0, 5, 20, 25, 35])
+    with pytest.raises(RemoraError):
+        io.parse_move_tag(mv, sig_len=35, seq_len=5)
+    with pytest.raises(RemoraError):
+        io.parse_move_tag(mv, sig_len=80, seq_len=4)
+    # 2 matches, 1 inserted query base, 1 match, 1 deleted reference base, 1 match
+    knots = io.make_sequence_coordinate_mapping([(0, 2), (1, 1), (0, 1), (2, 1), (0, 1)])
+    assert np.allclose(knots, [0, 1, 3, 3.5, 4, 5])
+    r2s = io.compute_ref_to_signal(np.array([0, 10, 20, 30, 40, 50]), [(0, 2), (1, 1), (0, 1), (2, 1), (0, 1)])
+    assert np.array_equal(r2s, [0, 10, 30, 35, 40, 50])
+    with pytest.raises(RemoraError):
+        io.make_sequence_coordinate_mapping([(4, 5)])
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's real test files (build container only)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not have_ref_data, reason="reference test data not present")
+def test_real_files_match_golden(io_cases):
+    for stem, rid, n_seq, n_sig, strand in io_cases["index"]:
+        bam_idx = io.ReadIndexedBam(os.path.join(REF_DATA, f"{stem}_mappings.bam"))
+        assert bam_idx.num_reads == 14 and rid in bam_idx
+        with io.Pod5Reader(os.path.join(REF_DATA, f"{stem}_reads.pod5")) as pod5:
+            read = io.Read.from_pod5_and_alignment(pod5.get_read(rid), bam_idx.get_first_alignment(rid))
+        assert len(read.seq) == int(n_seq) and read.dacs.size == int(n_sig) and read.ref_reg.strand == strand
+        k = next(key[: -len("bc_dacs")] for key in io_cases.files if key.startswith(stem) and key.endswith("bc_dacs")
+                 and io_cases[key].size == read.query_to_signal[-1] - read.query_to_signal[0]
+                 and np.array_equal(io_cases[key][:50], read.dacs[read.query_to_signal[0]:][:50]))
+        for anchor, tag in ((False, "bc"), (True, "ref")):
+            rr = read.into_remora_read(anchor)
+            if tag == "bc":
+                assert np.array_equal(rr.dacs, io_cases[k + "bc_dacs"])
+            else:
+                assert [rr.dacs.size, zlib.crc32(rr.dacs.astype(np.int16).tobytes())] == list(io_cases[k + "ref_dacs"])
+            assert np.array_equal(rr.seq_to_sig_map, io_cases[k + tag + "_ssm"])
+            assert np.array_equal(rr.int_seq, io_cases[k + tag + "_int_seq"])
+            assert [rr.shift, rr.scale] == list(io_cases[k + tag + "_shift_scale"])
+
+
+@pytest.mark.skipif(not have_ref_data, reason="reference test data not present")
+def test_read_join_equals_live_reference():
+    import ref_harness
+    ref_harness.import_reference()
+    from remora import io as ref_io
+    for stem in ("can", "mod"):
+        bam_idx = io.ReadIndexedBam(os.path.join(REF_DATA, f"{stem}_mappings.bam"))
+        with io.Pod5Reader(os.path.join(REF_DATA, f"{stem}_reads.pod5")) as pod5:
+            for rid in pod5.read_ids[:6]:
+                rec = bam_idx.get_first_alignment(rid)
+                mine = io.Read.from_pod5_and_alignment(pod5.get_read(rid), rec)
+                theirs = ref_io.Read.from_pod5_and_alignment(pod5.get_read(rid), rec)
+                assert mine.ref_seq == theirs.ref_seq and mine.ref_reg.end == theirs.ref_reg.end
+                for anchor in (False, True):
+                    a, b = mine.into_remora_read(anchor), theirs.into_remora_read(anchor)
+                    assert np.array_equal(a.dacs, b.dacs) and (a.shift, a.scale) == (b.shift, b.scale)
+                    assert np.array_equal(a.seq_to_sig_map, b.seq_to_sig_map) and a.str_seq == b.str_seq
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------
+def golden_reads(io_cases):
+    for key in sorted(k for k in io_cases.files if k.endswith("bc_dacs")):
+        k = key[: -len("bc_dacs")]
+        shift, scale = io_cases[k + "bc_shift_scale"]
+        yield k, dict(dacs=io_cases[k + "bc_dacs"], shift=float(shift), scale=float(scale),
+                      seq_to_sig_map=io_cases[k + "bc_ssm"], int_seq=io_cases[k + "bc_int_seq"].astype(np.int64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["convlstm_s64_k9_hot", "convlstm_s64_k9_refine"])
+def test_gpu_real_reads_match_reference_cpu_calls(io_cases, name):
+    """BASELINE config 5 in miniature: real reads (reference tests/data), mod-call parity against the
+    reference's CPU path, without and with signal-mapping refinement."""
+    dev = torch.device("cuda:0")
+    model, md = model_util.load_model(os.path.join(GOLDEN, name + ".pt"), device=dev, eval_only=True)
+    n = 0
+    for k, kw in golden_reads(io_cases):
+        for on_device in (False, True):
+            read = data_chunks.RemoraRead(**{a: (v.copy() if hasattr(v, "copy") else v) for a, v in kw.items()})
+            nn_out, _, pos = inference.call_read_mods(read, model, md, extract_on_device=on_device)
+            assert np.array_equal(read.seq_to_sig_map, io_cases[k + name + "_ssm"])
+            assert [read.shift, read.scale] == list(io_cases[k + name + "_shift_scale"])
+            order, want = np.argsort(pos), np.argsort(io_cases[k + name + "_pos"])
+            assert np.array_equal(pos[order], io_cases[k + name + "_pos"][want])
+            assert np.abs(nn_out[order] - io_cases[k + name + "_nn_out"][want]).max() < 1e-4
+        read = data_chunks.RemoraRead(**kw)
+        mm, ml = inference.call_read_mods(read, model, md, return_mm_ml_tags=True)
+        assert mm == str(io_cases[k + name + "_mm"])
+        got_ml, want_ml = np.frombuffer(ml, dtype=np.uint8).astype(int), io_cases[k + name + "_ml"].astype(int)
+        assert got_ml.size == want_ml.size and np.abs(got_ml - want_ml).max() <= 1  # bin edges, SURVEY App. D
+        n += 1
+    assert n == 4
+
+
+def write_synthetic_run(tmp_path, n_reads=12, seed=0):
+    """A POD5 + BAM pair whose reads follow the fixture k-mer table: signal from levels, a stride-5 move
+    table, ts trimming, sm/sd scaling tags; returns (pod5, bam, {read_id: RemoraRead pieces})."""
+    rng = np.random.default_rng(seed)
+    table = synth_levels_table(6, 0)
+    ids = make_ids(n_reads, seed=seed + 10)
+    pod5_reads, bam_recs, truth = [], [], {}
+    for i, rid in enumerate(ids):
+        n = int(rng.integers(150, 600))
+        int_seq = rng.integers(0, 4, size=n)
+        levels = np.zeros(n)
+        win = np.lib.stride_tricks.sliding_window_view(int_seq, 6) @ (4 ** np.arange(5, -1, -1))
+        levels[2:2 + win.size] = table[win]
+        dwells = rng.integers(1, 5, size=n) * 5
+        ts = int(rng.integers(0, 4)) * 5
+        pa = np.repeat(levels, dwells) * 26.0 + 88.0 + rng.normal(0, 6.0, size=int(dwells.sum()))
+        cal_off, cal_scale = -240.0, 0.18
+        dacs = np.round(pa / cal_scale - cal_off).astype(np.int16)
+        full = np.concatenate([rng.integers(400, 900, size=ts).astype(np.int16), dacs])
+        mv = np.zeros(dacs.size // 5, dtype=np.int8)
+        mv[(np.cumsum(dwells) - dwells) // 5] = 1
+        seq = "".join("ACGT"[b] for b in int_seq)
+        pod5_reads.append((rid, full, cal_off, cal_scale))
+        bam_recs.append(dict(query_name=rid, flag=4, query_sequence=seq,
+                             tags=[("mv", "Bc", np.r_[5, mv].astype(np.int8)), ("ts", "i", ts),
+                                   ("ns", "i", full.size), ("sm", "f", 88.0), ("sd", "f", 26.0)]))
+        truth[rid] = dict(dacs=dacs, seq=seq, ssm=np.concatenate([np.cumsum(dwells) - dwells, [dacs.size]]),
+                          shift=-cal_off + (1 / np.float32(cal_scale)) * np.float32(88.0),
+                          scale=(1 / np.float32(cal_scale)) * np.float32(26.0))
+    pod5, bam = str(tmp_path / "run.pod5"), str(tmp_path / "run.bam")
+    io.write_pod5(pod5, pod5_reads)
+    io.write_bam(bam, "@HD\tVN:1.6\tSO:unknown\n", [], bam_recs)
+    return pod5, bam, truth
+
+
+def test_synthetic_run_reads_back(tmp_path):
+    pod5, bam, truth = write_synthetic_run(tmp_path, n_reads=4)
+    idx = io.ReadIndexedBam(bam, req_tags={"mv"})
+    got = list(io.iter_io_reads(pod5, idx))
+    assert len(got) == 4 and all(err is None for _, err in got)
+    for read, _ in got:
+        t = truth[read.read_id]
+        rr = read.into_remora_read(False)
+        assert np.array_equal(rr.dacs, t["dacs"]) and rr.str_seq == t["seq"]
+        assert np.array_equal(rr.seq_to_sig_map, t["ssm"])
+        assert np.isclose(rr.shift, t["shift"]) and np.isclose(rr.scale, t["scale"])
+    with pytest.raises(RemoraError):  # unmapped reads cannot be reference anchored
+        got[0][0].into_remora_read(True)
+
+
+@pytest.mark.gpu
+def test_gpu_infer_from_pod5_and_bam(tmp_path):
+    dev = torch.device("cuda:0")
+    pod5, bam, truth = write_synthetic_run(tmp_path, n_reads=12)
+    model, md = model_util.load_model(os.path.join(GOLDEN, "convlstm_s64_k9_refine.pt"), device=dev,
+                                      eval_only=True)
+    out_sam = str(tmp_path / "calls.sam")
+    res = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=out_sam, reads_per_batch=5,
+                                            return_probs=True)
+    assert len(res) == 12 and all(r["error"] is None for r in res)
+    lines = [ln for ln in open(out_sam).read().splitlines() if not ln.startswith("@")]
+    assert len(lines) == 12
+    for r, line in zip(res, lines):
+        t = truth[r["read_id"]]
+        # the same read through the single-read API (refinement batch of one) gives the same calls
+        read = data_chunks.RemoraRead(dacs=t["dacs"].copy(), shift=float(t["shift"]), scale=float(t["scale"]),
+                                      seq_to_sig_map=t["ssm"].copy(), str_seq=t["seq"])
+        probs, _, pos = inference.call_read_mods(read, model, md, return_mod_probs=True)
+        if len(pos) == 0:
+            assert r["mm"] == ""
+            continue
+        got_pos, got_probs = r["calls"]["C"]
+        assert np.array_equal(got_pos, pos) and np.allclose(got_probs, probs, atol=1e-6)
+        fields = line.split("\t")
+        assert fields[0] == r["read_id"] and f"MM:Z:{r['mm']}" in fields
+        assert any(f.startswith("ML:B:C,") for f in fields) and not any(f.startswith("mv:") for f in fields)
+        assert r["mm"].startswith("C+m?,") and len(r["ml"]) == len(pos)
