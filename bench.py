@@ -491,6 +491,12 @@ def ours(args):
         }
         if world == 1:
             line["cpu_baseline"] = run_cpu_sample()
+            try:  # rows of SURVEY.md 8f measured beside the headline (never allowed to break the line)
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                import refine_times
+                line["next_rows"] = {"signal_mapping_refinement": refine_times.refine_bench()}
+            except Exception as e:  # noqa: BLE001
+                line["next_rows"] = {"signal_mapping_refinement": {"error": str(e)[:200]}}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier(device_ids=[local_rank])

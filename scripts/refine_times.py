@@ -114,6 +114,27 @@ def cpu_leg(reads, levels, resc, bands, algo, budget_s=10.0, threads=None):
     return out
 
 
+def refine_bench(n_reads=2048, n_bases=600, cpu_seconds=2.0):
+    """Compact form for bench.py's `next_rows` object: the default (dwell_penalty) refinement of a
+    synthetic batch on the GPU and a bounded sample of the same reads through the reference's DP."""
+    table, reads = make_reads(n_reads, n_bases)
+    g, paths, levels, resc, bands = gpu_leg(table, reads, "dwell_penalty", iters=3)
+    cpu = cpu_leg(reads, levels, resc, bands, "dwell_penalty", budget_s=cpu_seconds)
+    ref = cpu.get("reference_1_thread") or {}
+    port = cpu.get("port_all_threads") or {}
+    return {
+        "kernel": "refine_dp_kernel (+ refine_normalise_kernel)", "unit": "DP cells/s",
+        "workload": f"{g['reads']} synthetic reads, {g['bases']} bases, {g['cells']} band cells, "
+                    f"half bandwidth 5, dwell_penalty, widest band {g['widest_band']} samples",
+        "value": g["cells_per_s"], "ms": g["kernel_ms"], "reads_per_s": g["reads_per_s"],
+        "bases_per_s": g["bases_per_s"], "near_cap": g["near_cap"],
+        "bound": "instruction issue / dependent FADD+FMNMX chain (exact fp32 rounding order forbids a scan)",
+        "cpu_reference_1_thread_cells_per_s": ref.get("cells_per_s"),
+        "cpu_port_threads": port.get("threads"), "cpu_port_cells_per_s": port.get("cells_per_s"),
+        "parity": "paths bit-identical to the reference (tests/test_refine.py)",
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=4096)
