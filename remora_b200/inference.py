@@ -77,6 +77,33 @@ def mods_tags_to_str(mm_tags, ml_arr):
     return [f"MM:Z:{''.join(mm_tags)}", "ML:B:C," + ",".join(str(int(v)) for v in ml_arr)]
 
 
+def _run_merged(model, batches, device, batch_size):
+    """Concatenate the compact chunk arrays of several reads (padding the per-read sequence / mapping
+    widths to the widest; the kernels never read past ``seq_len``) and run the model over them in
+    pieces of ``batch_size`` chunks.  Returns float32 logits [total chunks, num_out] on the host."""
+    import torch.nn.functional as F
+    from .data_chunks import DeviceChunkBatch
+    seq_w = max(b.sequence.shape[1] for b in batches)
+    map_w = max(b.seq_to_sig_map.shape[1] for b in batches)
+    sigs, seqs, maps, lens = [], [], [], []
+    for b in batches:
+        if isinstance(b, DeviceChunkBatch):
+            sig, seq, mp, ln = b.signal, b.sequence, b.seq_to_sig_map, b.seq_lens
+        else:
+            sig, seq, mp, ln = (torch.from_numpy(a) for a in (b.signal, b.sequence, b.seq_to_sig_map,
+                                                                b.seq_lens))
+        sigs.append(sig)
+        seqs.append(F.pad(seq, (0, seq_w - seq.shape[1]), value=-1))
+        maps.append(F.pad(mp, (0, map_w - mp.shape[1]), value=0))
+        lens.append(ln)
+    sig, seq, mp, ln = (torch.cat(x).to(device, non_blocking=True) for x in (sigs, seqs, maps, lens))
+    outs = []
+    for st in range(0, sig.shape[0], batch_size):
+        en = st + batch_size
+        outs.append(model.forward_compact(sig[st:en], seq[st:en], mp[st:en], ln[st:en]))
+    return torch.cat(outs).cpu().numpy()
+
+
 def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_reads=None,
                             batch_size=constants.DEFAULT_BATCH_SIZE, reads_per_batch=256, ref_anchored=False,
                             skip_non_primary=True, extract_on_device=True, return_probs=False):
@@ -86,7 +113,8 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     ``models``: ``(model, metadata)`` or ``{can_base: (model, metadata)}`` as ``load_model`` returns them.
     Reads are handled ``reads_per_batch`` at a time: joined on the host (``remora_b200.io``), their
     signal mappings refined in ONE banded-DP launch per model (``SigMapRefiner.refine_reads``), chunk
-    arrays built and the network run on the GPU per read.  Returns a list of dicts
+    arrays built per read (on the GPU by default) and the network run over the chunks of the whole group
+    in ``batch_size`` pieces.  Returns a list of dicts
     ``{read_id, mm, ml (array('B')), error}`` (plus ``calls``: ``{can_base: (positions, probs)}`` when
     ``return_probs``); with ``out_path`` the input records are also written as SAM text with the
     MM/ML tags attached (previous MM/ML/mv tags dropped), unmapped-style when reference anchored like
@@ -126,21 +154,38 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
             if refiner.is_loaded and live:
                 refiner.refine_reads(live)
             md_done = dict(md, sig_map_refiner=SigMapRefiner())  # refinement already applied above
-            for rread, res, io_read in zip(rreads, per_read, group):
-                if rread is None or res["error"] is not None:
+            device = next(model.parameters()).device
+            motifs = [Motif(*mot) for mot in md["motifs"]]
+            # chunk arrays of every read of the group, then ONE stream of model calls over all of them
+            # (the reference batches chunks across reads the same way, inference.py:185-274)
+            owners, merged = [], []
+            for i, rread in enumerate(rreads):
+                if rread is None or per_read[i]["error"] is not None:
                     continue
-                out = call_read_mods(rread, model, md_done, batch_size=batch_size, return_mod_probs=True,
-                                     extract_on_device=extract_on_device)
-                probs, _, pos = out
-                if len(pos) == 0:
-                    continue
-                seq = io_read.ref_seq if ref_anchored else io_read.seq
-                mm, ml = format_mm_ml_tags(seq=seq, poss=pos, probs=probs, mod_bases=md["mod_bases"],
-                                           can_base=can_base)
-                res["mm"].append(mm)
-                res["ml"].extend(ml)
-                if return_probs:
-                    res["calls"][can_base] = (pos, probs)
+                rread.set_motif_focus_bases(motifs)
+                if extract_on_device:
+                    rread.prepare_batches_gpu(md_done, batch_size=1 << 30, device=device)
+                else:
+                    rread.prepare_batches(md_done, batch_size=1 << 30)
+                for b in rread.batches:
+                    owners.append(i)
+                    merged.append(b)
+            if merged:
+                nn_out = _run_merged(model, merged, device, batch_size)
+                st = 0
+                for i, b in zip(owners, merged):
+                    out = nn_out[st:st + len(b)]
+                    st += len(b)
+                    probs = softmax_axis1(out)[:, 1:].astype(np.float64)
+                    pos = b.read_focus_bases
+                    io_read = group[i]
+                    seq = io_read.ref_seq if ref_anchored else io_read.seq
+                    mm, ml = format_mm_ml_tags(seq=seq, poss=pos, probs=probs, mod_bases=md["mod_bases"],
+                                               can_base=can_base)
+                    per_read[i]["mm"].append(mm)
+                    per_read[i]["ml"].extend(ml)
+                    if return_probs:
+                        per_read[i]["calls"][can_base] = (pos, probs)
         for io_read, res in zip(group, per_read):
             res["mm"] = "".join(res["mm"])
             if not return_probs:

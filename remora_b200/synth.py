@@ -124,3 +124,41 @@ def synth_refine_read(n_bases=400, table=None, kmer_len=6, center_idx=2, seed=0,
     start = np.minimum(start, sig_len - 1)
     start[0], start[-1] = 0, sig_len
     return dacs, shift + shift_error, scale * scale_error, start, int_seq
+
+
+def synth_pod5_bam_run(pod5_path, bam_path, n_reads=12, seed=0, bases=(150, 600), kmer_len=6, center_idx=2):
+    """Writes a POD5 + BAM pair (``remora_b200.io`` writers) whose reads follow the seeded k-mer table:
+    signal from levels, a stride-5 move table, ``ts`` trimming, ``sm``/``sd`` scaling tags, unmapped
+    records.  Returns (pod5_path, bam_path, {read_id: pieces of the RemoraRead the readers must give})."""
+    import uuid
+    from . import io
+    rng = np.random.default_rng(seed)
+    table = synth_levels_table(kmer_len, 0)
+    ids = [str(uuid.UUID(int=int(rng.integers(1, 2 ** 62)))) for _ in range(n_reads)]
+    pod5_reads, bam_recs, truth = [], [], {}
+    powers = 4 ** np.arange(kmer_len - 1, -1, -1)
+    for rid in ids:
+        n = int(rng.integers(bases[0], bases[1]))
+        int_seq = rng.integers(0, 4, size=n)
+        levels = np.zeros(n)
+        win = np.lib.stride_tricks.sliding_window_view(int_seq, kmer_len) @ powers
+        levels[center_idx:center_idx + win.size] = table[win]
+        dwells = rng.integers(1, 5, size=n) * 5
+        ts = int(rng.integers(0, 4)) * 5
+        pa = np.repeat(levels, dwells) * 26.0 + 88.0 + rng.normal(0, 6.0, size=int(dwells.sum()))
+        cal_off, cal_scale = -240.0, 0.18
+        dacs = np.round(pa / cal_scale - cal_off).astype(np.int16)
+        full = np.concatenate([rng.integers(400, 900, size=ts).astype(np.int16), dacs])
+        mv = np.zeros(dacs.size // 5, dtype=np.int8)
+        mv[(np.cumsum(dwells) - dwells) // 5] = 1
+        seq = "".join("ACGT"[b] for b in int_seq)
+        pod5_reads.append((rid, full, cal_off, cal_scale))
+        bam_recs.append(dict(query_name=rid, flag=4, query_sequence=seq,
+                             tags=[("mv", "Bc", np.r_[5, mv].astype(np.int8)), ("ts", "i", ts),
+                                   ("ns", "i", full.size), ("sm", "f", 88.0), ("sd", "f", 26.0)]))
+        truth[rid] = dict(dacs=dacs, seq=seq, ssm=np.concatenate([np.cumsum(dwells) - dwells, [dacs.size]]),
+                          shift=-cal_off + (1 / np.float32(cal_scale)) * np.float32(88.0),
+                          scale=(1 / np.float32(cal_scale)) * np.float32(26.0))
+    io.write_pod5(pod5_path, pod5_reads)
+    io.write_bam(bam_path, "@HD\tVN:1.6\tSO:unknown\n", [], bam_recs)
+    return pod5_path, bam_path, truth

@@ -20,7 +20,7 @@ import torch
 
 from conftest import GOLDEN
 from remora_b200 import RemoraError, data_chunks, inference, io, model_util
-from remora_b200.synth import synth_levels_table
+from remora_b200.synth import synth_pod5_bam_run
 
 REF_DATA = "/root/reference/tests/data"
 have_ref_data = os.path.isfile(os.path.join(REF_DATA, "can_reads.pod5"))
@@ -239,38 +239,7 @@ def test_gpu_real_reads_match_reference_cpu_calls(io_cases, name):
 
 
 def write_synthetic_run(tmp_path, n_reads=12, seed=0):
-    """A POD5 + BAM pair whose reads follow the fixture k-mer table: signal from levels, a stride-5 move
-    table, ts trimming, sm/sd scaling tags; returns (pod5, bam, {read_id: RemoraRead pieces})."""
-    rng = np.random.default_rng(seed)
-    table = synth_levels_table(6, 0)
-    ids = make_ids(n_reads, seed=seed + 10)
-    pod5_reads, bam_recs, truth = [], [], {}
-    for i, rid in enumerate(ids):
-        n = int(rng.integers(150, 600))
-        int_seq = rng.integers(0, 4, size=n)
-        levels = np.zeros(n)
-        win = np.lib.stride_tricks.sliding_window_view(int_seq, 6) @ (4 ** np.arange(5, -1, -1))
-        levels[2:2 + win.size] = table[win]
-        dwells = rng.integers(1, 5, size=n) * 5
-        ts = int(rng.integers(0, 4)) * 5
-        pa = np.repeat(levels, dwells) * 26.0 + 88.0 + rng.normal(0, 6.0, size=int(dwells.sum()))
-        cal_off, cal_scale = -240.0, 0.18
-        dacs = np.round(pa / cal_scale - cal_off).astype(np.int16)
-        full = np.concatenate([rng.integers(400, 900, size=ts).astype(np.int16), dacs])
-        mv = np.zeros(dacs.size // 5, dtype=np.int8)
-        mv[(np.cumsum(dwells) - dwells) // 5] = 1
-        seq = "".join("ACGT"[b] for b in int_seq)
-        pod5_reads.append((rid, full, cal_off, cal_scale))
-        bam_recs.append(dict(query_name=rid, flag=4, query_sequence=seq,
-                             tags=[("mv", "Bc", np.r_[5, mv].astype(np.int8)), ("ts", "i", ts),
-                                   ("ns", "i", full.size), ("sm", "f", 88.0), ("sd", "f", 26.0)]))
-        truth[rid] = dict(dacs=dacs, seq=seq, ssm=np.concatenate([np.cumsum(dwells) - dwells, [dacs.size]]),
-                          shift=-cal_off + (1 / np.float32(cal_scale)) * np.float32(88.0),
-                          scale=(1 / np.float32(cal_scale)) * np.float32(26.0))
-    pod5, bam = str(tmp_path / "run.pod5"), str(tmp_path / "run.bam")
-    io.write_pod5(pod5, pod5_reads)
-    io.write_bam(bam, "@HD\tVN:1.6\tSO:unknown\n", [], bam_recs)
-    return pod5, bam, truth
+    return synth_pod5_bam_run(str(tmp_path / "run.pod5"), str(tmp_path / "run.bam"), n_reads=n_reads, seed=seed)
 
 
 def test_synthetic_run_reads_back(tmp_path):
