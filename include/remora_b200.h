@@ -222,6 +222,18 @@ int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const f
                     int32_t max_band_width, int32_t *traceback_ws_dev, int32_t *path_dev, float *score_dev,
                     int32_t *status_dev, int32_t *queue_dev, float *wide_scratch_dev, void *stream);
 
+/* POD5 signal decode ("next" row 3): the svb16 + zig-zag + delta layers of the
+ * "minknow.vbz" signal rows (the zstd layer is undone on the host) for a batch of rows.  The reference
+ * gets these samples from the pod5 package (pod5.ReadRecord.signal, src/remora/io.py:455-462).
+ * Row i occupies bytes [row_off[i], row_off[i+1]) of packed_dev: ceil(n/8) key bytes (bit k%8 of byte
+ * k/8 set = value k takes two bytes) then the little-endian data bytes; it decodes to row_samples[i]
+ * int16 samples written at out_dev + out_off[i] (offsets that are multiples of 8 samples get 16-byte
+ * stores).  packed_dev must be readable 16 bytes past row_off[n_rows].  status[i] = 1 when the stream
+ * length disagrees with the keys (corrupt row). */
+int rb200_svb16_decode(const uint8_t *packed_dev, const int64_t *row_off_dev, const int32_t *row_samples_dev,
+                       const int64_t *out_off_dev, int32_t n_rows, int16_t *out_dev, int32_t *status_dev,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

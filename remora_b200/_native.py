@@ -21,7 +21,7 @@ EXPORTS = (
     "rb200_last_impl", "rb200_launch_count", "rb200_set_debug", "rb200_debug_tensor",
     "rb200_encode_dense", "rb200_forward_dense", "rb200_forward_compact", "rb200_infer_host",
     "rb200_softmax_ml", "rb200_set_profile", "rb200_get_profile", "rb200_infer_host_async", "rb200_chunk_plan", "rb200_chunk_fill",
-    "rb200_refine_normalize", "rb200_refine_scratch_bytes", "rb200_refine_dp",
+    "rb200_refine_normalize", "rb200_refine_scratch_bytes", "rb200_refine_dp", "rb200_svb16_decode",
 )
 
 
@@ -88,6 +88,7 @@ def load_library():
     lib.rb200_refine_scratch_bytes.argtypes = [i32, i32, ctypes.POINTER(i64)]
     lib.rb200_refine_dp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp,
                                     vp, vp, vp, vp, vp]
+    lib.rb200_svb16_decode.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     lib.rb200_set_profile.argtypes = [vp, ctypes.c_int]
     lib.rb200_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3),
                                       ctypes.POINTER(i32)]

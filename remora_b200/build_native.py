@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librb200.so")
 SOURCES = ["rb200_api.cu", "rb200_encode.cu", "rb200_layers.cu", "rb200_fused.cu", "rb200_chunks.cu",
-           "rb200_tiled.cu", "rb200_refine.cu"]
+           "rb200_tiled.cu", "rb200_refine.cu", "rb200_vbz.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Wno-deprecated-gpu-targets",

@@ -546,4 +546,15 @@ int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const f
                             queue_dev, wide_scratch_dev, sms, static_cast<cudaStream_t>(stream));
 }
 
+int rb200_svb16_decode(const uint8_t *packed_dev, const int64_t *row_off_dev, const int32_t *row_samples_dev,
+                       const int64_t *out_off_dev, int32_t n_rows, int16_t *out_dev, int32_t *status_dev,
+                       void *stream) {
+    RB200_REQUIRE(n_rows >= 0, "bad argument");
+    if (n_rows == 0) return RB200_OK;
+    RB200_REQUIRE(packed_dev && row_off_dev && row_samples_dev && out_off_dev && out_dev && status_dev,
+                  "null buffer");
+    return launch_svb16_decode(packed_dev, row_off_dev, row_samples_dev, out_off_dev, n_rows, out_dev,
+                               status_dev, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

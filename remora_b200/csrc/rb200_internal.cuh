@@ -133,6 +133,11 @@ int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *leve
                      int max_band_width, int32_t *tb, int32_t *path, float *score, int32_t *status,
                      int32_t *counter, float *wide_scratch, int sm_count, cudaStream_t stream);
 
+// rb200_vbz.cu : POD5 signal rows (svb16 + zigzag + delta) -> int16 samples
+int launch_svb16_decode(const uint8_t *packed, const int64_t *row_off, const int32_t *row_samples,
+                        const int64_t *out_off, int n_rows, int16_t *out, int32_t *status,
+                        cudaStream_t stream);
+
 // rb200_tiled.cu : register-tiled FFMA2 layer kernels (Conv_w_ref and every non-fused shape);
 // each returns RB200_ERR_UNSUPPORTED when the layer / shape has no tiled form
 int tiled_create(rb200_model *m, const float *blob_host);

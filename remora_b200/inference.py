@@ -106,12 +106,14 @@ def _run_merged(model, batches, device, batch_size):
 
 def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_reads=None,
                             batch_size=constants.DEFAULT_BATCH_SIZE, reads_per_batch=256, ref_anchored=False,
-                            skip_non_primary=True, extract_on_device=True, return_probs=False):
+                            skip_non_primary=True, extract_on_device=True, return_probs=False,
+                            decode_on_device=True):
     """``remora infer from_pod5_and_bam`` as one function (reference inference.py:462-660 without its
     process/queue plumbing): POD5 signal + BAM basecalls/move tables -> modified-base calls per read.
 
     ``models``: ``(model, metadata)`` or ``{can_base: (model, metadata)}`` as ``load_model`` returns them.
-    Reads are handled ``reads_per_batch`` at a time: joined on the host (``remora_b200.io``), their
+    Reads are handled ``reads_per_batch`` at a time: POD5 signal decoded on the GPU
+    (``rb200_svb16_decode``, ``decode_on_device``), joined with the BAM records on the host, their
     signal mappings refined in ONE banded-DP launch per model (``SigMapRefiner.refine_reads``), chunk
     arrays built per read (on the GPU by default) and the network run over the chunks of the whole group
     in ``batch_size`` pieces.  Returns a list of dicts
@@ -203,8 +205,10 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
 
     group = []
     try:
+        decode_dev = next(next(iter(models.values()))[0].parameters()).device if decode_on_device else None
         for io_read, err in rio.iter_io_reads(pod5_path, bam_idx, num_reads=num_reads,
-                                              reverse_signal=reverse_signal, pa_scaling=pa_scaling):
+                                              reverse_signal=reverse_signal, pa_scaling=pa_scaling,
+                                              device=decode_dev):
             if err is not None:
                 results.append(dict(read_id=io_read.read_id, mm="", ml=array.array("B"), error=err))
                 continue

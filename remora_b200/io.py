@@ -503,14 +503,10 @@ def parse_pod5_footer(buf):
     return files
 
 
-def decode_vbz(blob, n_samples):
-    """"minknow.vbz" signal chunk -> int16 samples: zstd frame -> StreamVByte-16 (one key BIT per value,
-    0 = one byte, 1 = two bytes; keys first, then the data bytes) -> zig-zag -> running sum."""
+def _zstd_frame_content(blob):
+    """zstd-decompress one frame whose header carries the content size (POD5 writers always set it)."""
     import pyarrow as pa
-    if n_samples == 0:
-        return np.zeros(0, dtype=np.int16)
     blob = bytes(blob)
-    # zstd frame header: content size (always written by the POD5 writers)
     if blob[:4] != b"\x28\xb5\x2f\xfd":
         raise RemoraError("signal chunk is not a zstd frame")
     fhd = blob[4]
@@ -520,7 +516,62 @@ def decode_vbz(blob, n_samples):
     if fcs_size == 0:
         raise RemoraError("zstd frame without content size")
     size = int.from_bytes(blob[pos:pos + fcs_size], "little") + (256 if fcs_size == 2 else 0)
-    raw = np.frombuffer(pa.Codec("zstd").decompress(blob, decompressed_size=size), dtype=np.uint8)
+    return pa.Codec("zstd").decompress(blob, decompressed_size=size)
+
+
+def decode_vbz_rows_gpu(blobs, n_samples, device, read_of_row=None):
+    """Decode many "minknow.vbz" rows on the GPU in one launch (``rb200_svb16_decode``): zstd on the host,
+    StreamVByte-16 + zig-zag + running sum on the device.  ``read_of_row`` groups consecutive rows into
+    reads; returns (int16 device tensor, list of (start, length) per read) - every read starts at a
+    multiple of 8 samples so the kernel can use 16-byte stores."""
+    import ctypes
+    import torch
+    from . import _native
+    lib = _native.load_library()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RemoraError("GPU signal decode needs a CUDA device")
+    n_rows = len(blobs)
+    if read_of_row is None:
+        read_of_row = list(range(n_rows))
+    raws = [_zstd_frame_content(b) for b in blobs]
+    row_off = np.zeros(n_rows + 1, dtype=np.int64)
+    row_off[1:] = np.cumsum([r.size for r in raws])
+    packed = np.zeros(int(row_off[-1]) + 16, dtype=np.uint8)
+    for r, raw in enumerate(raws):
+        packed[row_off[r]:row_off[r + 1]] = np.frombuffer(raw, dtype=np.uint8)
+    out_off = np.zeros(n_rows, dtype=np.int64)
+    spans, pos, prev = [], 0, None
+    for r in range(n_rows):
+        if read_of_row[r] != prev:
+            pos = (pos + 7) & ~7
+            spans.append([pos, 0])
+            prev = read_of_row[r]
+        out_off[r] = pos
+        pos += int(n_samples[r])
+        spans[-1][1] += int(n_samples[r])
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    with torch.cuda.device(device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        d_packed = torch.from_numpy(packed).to(device, non_blocking=True)
+        d_row_off = torch.from_numpy(row_off).to(device, non_blocking=True)
+        d_n = torch.from_numpy(np.asarray(n_samples, dtype=np.int32)).to(device, non_blocking=True)
+        d_out_off = torch.from_numpy(out_off).to(device, non_blocking=True)
+        d_out = torch.zeros(max(pos, 1), dtype=torch.int16, device=device)
+        d_status = torch.zeros(max(n_rows, 1), dtype=torch.int32, device=device)
+        _native.check(lib.rb200_svb16_decode(ptr(d_packed), ptr(d_row_off), ptr(d_n), ptr(d_out_off), n_rows,
+                                             ptr(d_out), ptr(d_status), stream), "rb200_svb16_decode")
+        if n_rows and int(d_status.max()) != 0:
+            raise RemoraError("corrupt svb16 signal chunk")
+    return d_out, [tuple(s) for s in spans]
+
+
+def decode_vbz(blob, n_samples):
+    """"minknow.vbz" signal chunk -> int16 samples: zstd frame -> StreamVByte-16 (one key BIT per value,
+    0 = one byte, 1 = two bytes; keys first, then the data bytes) -> zig-zag -> running sum."""
+    if n_samples == 0:
+        return np.zeros(0, dtype=np.int16)
+    raw = np.frombuffer(_zstd_frame_content(blob), dtype=np.uint8)
     n_key = (n_samples + 7) // 8
     keys = np.unpackbits(raw[:n_key], bitorder="little")[:n_samples].astype(np.int64)
     data = raw[n_key:]
@@ -620,6 +671,38 @@ class Pod5Reader:
                         calibration=Calibration(rec["calibration_offset"], rec["calibration_scale"]),
                         num_samples=int(rec["num_samples"]), read_number=int(rec["read_number"]),
                         channel=int(rec["channel"]))
+
+    def get_reads(self, read_ids, device=None):
+        """Several reads at once.  With a CUDA ``device`` all their signal rows are decoded by ONE kernel
+        launch (``decode_vbz_rows_gpu``) and copied back in one transfer; otherwise row by row in numpy."""
+        if device is None or not self._sig_vbz:
+            return [self.get_read(rid) for rid in read_ids]
+        sig = self._tables["signal"]
+        recs, blobs, counts, owner = [], [], [], []
+        for k, rid in enumerate(read_ids):
+            row = self._row_of.get(str(rid))
+            if row is None:
+                raise RemoraError(f"read {rid} not in {self.path}")
+            rec = self._reads.slice(row, 1).to_pylist()[0]
+            recs.append((row, rec))
+            for r in rec["signal"]:
+                b = int(np.searchsorted(self._sig_batch_rows, int(r), side="right") - 1)
+                batch = sig.get_batch(b)
+                i = int(r) - int(self._sig_batch_rows[b])
+                counts.append(batch.column(batch.schema.get_field_index("samples"))[i].as_py())
+                blobs.append(batch.column(batch.schema.get_field_index("signal"))[i].as_py())
+                owner.append(k)
+        d_out, spans = decode_vbz_rows_gpu(blobs, counts, device, owner)
+        host = d_out.cpu().numpy()
+        span_of = dict(zip(sorted(set(owner)), spans))
+        out = []
+        for k, (row, rec) in enumerate(recs):
+            st, ln = span_of.get(k, (0, 0))
+            out.append(Pod5Read(read_id=self._ids[row], signal=host[st:st + ln],
+                                calibration=Calibration(rec["calibration_offset"], rec["calibration_scale"]),
+                                num_samples=int(rec["num_samples"]), read_number=int(rec["read_number"]),
+                                channel=int(rec["channel"])))
+        return out
 
     def reads(self, selection=None):
         ids = self.read_ids if selection is None else [str(s) for s in selection]
@@ -849,25 +932,25 @@ class Read:
         return remora_read
 
 
-def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_scaling=None):
+def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_scaling=None, device=None,
+                  reads_per_decode=64):
     """(io.Read, error text or None) for every alignment of every POD5 read present in the BAM index:
     the sequential equivalent of the reference's iter_signal -> extract_alignments workers
-    (io.py:441-511)."""
+    (io.py:441-511).  With a CUDA ``device`` the signal of ``reads_per_decode`` reads at a time is decoded
+    on the GPU (``Pod5Reader.get_reads``)."""
     with Pod5Reader(pod5_path) as reader:
-        done = 0
-        for rid in reader.read_ids:
-            if rid not in bam_idx:
-                continue
-            if num_reads is not None and done >= num_reads:
-                return
-            done += 1
-            pod5_read = reader.get_read(rid)
-            for bam_read in bam_idx.get_alignments(rid):
-                try:
-                    yield Read.from_pod5_and_alignment(pod5_read, bam_read, reverse_signal=reverse_signal,
-                                                       pa_scaling=pa_scaling), None
-                except RemoraError as e:
-                    yield Read(read_id=rid), str(e)
+        wanted = [rid for rid in reader.read_ids if rid in bam_idx]
+        if num_reads is not None:
+            wanted = wanted[:num_reads]
+        for st in range(0, len(wanted), reads_per_decode):
+            ids = wanted[st:st + reads_per_decode]
+            for rid, pod5_read in zip(ids, reader.get_reads(ids, device=device)):
+                for bam_read in bam_idx.get_alignments(rid):
+                    try:
+                        yield Read.from_pod5_and_alignment(pod5_read, bam_read, reverse_signal=reverse_signal,
+                                                           pa_scaling=pa_scaling), None
+                    except RemoraError as e:
+                        yield Read(read_id=rid), str(e)
 
 
 # ------------------------------------------------------------------------------------------------

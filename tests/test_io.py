@@ -258,6 +258,50 @@ def test_synthetic_run_reads_back(tmp_path):
 
 
 @pytest.mark.gpu
+def test_gpu_svb16_decode_bit_exact(io_cases, tmp_path):
+    """rb200_svb16_decode against the numpy decoder: ragged row lengths around the 32-sample word and
+    8192-sample tile boundaries, int16 extremes (deltas that wrap), empty rows, multi-row reads, real
+    signal statistics (the reference's test reads), and a corrupted row."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    sizes = [0, 1, 5, 31, 32, 33, 255, 256, 257, 8191, 8192, 8193, 16384, 20001, 102400, 70000]
+    rows, owner = [], []
+    for k, n in enumerate(sizes):
+        sig = (np.cumsum(rng.integers(-400, 400, size=n)) + 700).astype(np.int16)
+        if n > 4:
+            sig[1:4] = [-32768, 32767, -1]
+        rows.append(sig)
+        owner.append(k // 2)  # two rows per "read"
+    real = io_cases[sorted(k for k in io_cases.files if k.endswith("bc_dacs"))[0]]
+    rows.append(real)
+    owner.append(99)
+    blobs = [io.encode_vbz(r) for r in rows]
+    d_out, spans = io.decode_vbz_rows_gpu(blobs, [r.size for r in rows], dev, owner)
+    host = d_out.cpu().numpy()
+    assert len(spans) == len(set(owner)) and all(st % 8 == 0 for st, _ in spans)
+    for read_idx, (st, ln) in zip(sorted(set(owner)), spans):
+        want = np.concatenate([r for r, o in zip(rows, owner) if o == read_idx])
+        assert ln == want.size and np.array_equal(host[st:st + ln], want), read_idx
+        for r, blob in zip(rows, blobs):
+            assert np.array_equal(io.decode_vbz(blob, r.size), r)
+    # through the POD5 reader: one launch for several reads
+    ids = make_ids(3, seed=9)
+    path = str(tmp_path / "g.pod5")
+    io.write_pod5(path, [(ids[0], rows[14], -240.0, 0.18), (ids[1], rows[9], 1.0, 0.2), (ids[2], rows[0], 0.0, 1.0)])
+    with io.Pod5Reader(path) as reader:
+        got = reader.get_reads(ids, device=dev)
+        assert [str(g.read_id) for g in got] == ids
+        assert np.array_equal(got[0].signal, rows[14]) and np.array_equal(got[1].signal, rows[9])
+        assert got[2].signal.size == 0
+    # a truncated row is reported, not read past
+    raw = io._zstd_frame_content(blobs[10])
+    import pyarrow as pa
+    bad = pa.Codec("zstd").compress(bytes(raw)[:-5], asbytes=True)
+    with pytest.raises(RemoraError):
+        io.decode_vbz_rows_gpu([bad], [rows[10].size], dev)
+
+
+@pytest.mark.gpu
 def test_gpu_infer_from_pod5_and_bam(tmp_path):
     dev = torch.device("cuda:0")
     pod5, bam, truth = write_synthetic_run(tmp_path, n_reads=12)
