@@ -86,7 +86,8 @@ def load_ref_refine_core():
     path = ref_refine_core_path()
     if not os.path.isfile(path):
         return None
-    if "remora" not in sys.modules:
+    stand_in = "remora" not in sys.modules
+    if stand_in:
         pkg = types.ModuleType("remora")
         pkg.RemoraError = type("RemoraError", (Exception,), {})
         consts = types.ModuleType("remora.constants")
@@ -98,7 +99,12 @@ def load_ref_refine_core():
         sys.modules["remora.constants"] = consts
     spec = importlib.util.spec_from_file_location("remora.refine_signal_map_core", path)
     mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        if stand_in:  # the extension has bound what it needs; do not shadow a later real import
+            sys.modules.pop("remora", None)
+            sys.modules.pop("remora.constants", None)
     return mod
 
 

@@ -568,9 +568,10 @@ class SigMapRefiner:
 
     # -- re-scaling ----------------------------------------------------------------------------
     def rough_rescale(self, shift, scale, seq_to_sig_map, int_seq, dacs,
-                      quants=np.arange(0.05, 1, 0.05), clip_bases=10, use_base_center=True):
-        """refine_signal_map.py:390-430"""
-        levels = self.extract_levels(int_seq)
+                      quants=np.arange(0.05, 1, 0.05), clip_bases=10, use_base_center=True, levels=None):
+        """refine_signal_map.py:390-430 (``levels``: optional pre-computed ``extract_levels(int_seq)``)"""
+        if levels is None:
+            levels = self.extract_levels(int_seq)
         if use_base_center:
             optim_dacs = dacs[(seq_to_sig_map[:-1] + seq_to_sig_map[1:]) // 2]
             if clip_bases > 0 and levels.size > clip_bases * 2:
@@ -609,11 +610,12 @@ class SigMapRefiner:
         return rescale_theil_sen(filt_dacs, filt_levels, shift, scale)
 
     # -- mapping refinement ----------------------------------------------------------------------
-    def refine_sig_maps(self, shifts, scales, seq_to_sig_maps, int_seqs, dacs_list):
+    def refine_sig_maps(self, shifts, scales, seq_to_sig_maps, int_seqs, dacs_list, levels=None):
         """Batch form of :meth:`refine_sig_map`: one banded-DP launch per refinement round for all
         reads.  Returns lists (seq_to_sig_map, shift, scale) per read."""
         n = len(dacs_list)
-        levels = [self.extract_levels(s) for s in int_seqs]
+        if levels is None:
+            levels = [self.extract_levels(s) for s in int_seqs]
         maps = [np.asarray(m) for m in seq_to_sig_maps]
         sig_st = [int(m[0]) for m in maps]
         trimmed = [np.asarray(d)[m[0]:m[-1]] for d, m in zip(dacs_list, maps)]
@@ -652,15 +654,16 @@ class SigMapRefiner:
         then the batch on the GPU.  Reads are updated in place (shift, scale, seq_to_sig_map)."""
         if not self.is_loaded or not reads:
             return
+        levels = [self.extract_levels(read.int_seq) for read in reads]  # once per read, both steps use them
         if self.do_rough_rescale:
-            for read in reads:
+            for read, lv in zip(reads, levels):
                 read.shift, read.scale = self.rough_rescale(read.shift, read.scale, read.seq_to_sig_map,
-                                                            read.int_seq, read.dacs)
+                                                            read.int_seq, read.dacs, levels=lv)
                 read._sig = None
         if self.scale_iters >= 0:
             maps, shifts, scales = self.refine_sig_maps(
                 [r.shift for r in reads], [r.scale for r in reads], [r.seq_to_sig_map for r in reads],
-                [r.int_seq for r in reads], [r.dacs for r in reads])
+                [r.int_seq for r in reads], [r.dacs for r in reads], levels=levels)
             for read, m, sh, sc in zip(reads, maps, shifts, scales):
                 read.seq_to_sig_map, read.shift, read.scale = m, sh, sc
                 read._sig = None

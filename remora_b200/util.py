@@ -157,26 +157,34 @@ def find_focus_bases_in_int_sequence(int_seq, motifs):
 
 
 def format_mm_ml_tags(seq, poss, probs, mod_bases, can_base, strand="+"):
-    """MM string + ML uint8 array for SAM/BAM (reference util.py:485-537).
-    ML byte = floor(p*256) with 256 -> 255 (util.py:532-535)."""
-    per_mod = {mb: [] for mb in mod_bases}
-    for pos, mod_probs in sorted(zip(poss, probs), key=lambda x: x[0]):
-        if mod_probs is None:
-            continue
-        for p, mb in zip(mod_probs, mod_bases):
-            per_mod[mb].append((pos, p))
-    can_count = np.cumsum(np.frombuffer(seq.encode("ascii"), dtype=np.uint8) == ord(can_base))
+    """MM string + ML uint8 array for SAM/BAM (reference util.py:485-537), vectorised: positions sorted
+    (stable, like the reference's sort on position), one MM section per modified base in ``mod_bases``
+    order, gaps counted in canonical bases.  ML byte = floor(p*256) with 256 -> 255 (util.py:532-535).
+    A ``None`` row of ``probs`` skips that position as in the reference."""
     mm_tag, ml_tag = "", array.array("B")
-    for mb, pos_probs in per_mod.items():
-        if not pos_probs:
-            continue
-        pos_probs.sort(key=lambda x: x[0])
-        mod_pos = np.array([pp[0] for pp in pos_probs], dtype=np.int64)
-        p = np.array([pp[1] for pp in pos_probs], dtype=np.float64)
-        can_idx = can_count[mod_pos] - 1
-        gaps = np.diff(np.concatenate([[-1], can_idx])) - 1
-        mm_tag += f"{can_base}{strand}{mb}?," + ",".join(str(int(g)) for g in gaps) + ";"
-        scaled = np.floor(p * 256)
-        scaled[scaled == 256] = 255
-        ml_tag.extend(scaled.astype(np.uint8))
+    poss = np.asarray(poss, dtype=np.int64)
+    if poss.size == 0:
+        return mm_tag, ml_tag
+    if isinstance(probs, np.ndarray) and probs.dtype != object:
+        probs = probs.reshape(poss.size, -1).astype(np.float64)
+    else:
+        keep = np.array([p is not None for p in probs], dtype=bool)
+        poss = poss[keep]
+        probs = np.array([p for p in probs if p is not None], dtype=np.float64).reshape(poss.size, -1)
+        if poss.size == 0:
+            return mm_tag, ml_tag
+    order = np.argsort(poss, kind="stable")
+    mod_pos, probs = poss[order], probs[order]
+    can_count = np.cumsum(np.frombuffer(seq.encode("ascii"), dtype=np.uint8) == ord(can_base))
+    can_idx = can_count[mod_pos] - 1
+    gaps = np.diff(np.concatenate([[-1], can_idx])) - 1
+    gap_txt = ",".join(map(str, gaps.tolist()))
+    scaled = np.floor(probs * 256)
+    scaled[scaled == 256] = 255
+    scaled = scaled.astype(np.uint8)
+    for col, mb in enumerate(mod_bases):
+        if col >= scaled.shape[1]:
+            break
+        mm_tag += f"{can_base}{strand}{mb}?,{gap_txt};"
+        ml_tag.extend(scaled[:, col].tolist())
     return mm_tag, ml_tag
