@@ -118,9 +118,9 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     arrays built per read (on the GPU by default) and the network run over the chunks of the whole group
     in ``batch_size`` pieces.  Returns a list of dicts
     ``{read_id, mm, ml (array('B')), error}`` (plus ``calls``: ``{can_base: (positions, probs)}`` when
-    ``return_probs``); with ``out_path`` the input records are also written as SAM text with the
-    MM/ML tags attached (previous MM/ML/mv tags dropped), unmapped-style when reference anchored like
-    the reference's output (inference.py:448-456)."""
+    ``return_probs``); with ``out_path`` the input records are also written with the MM/ML tags attached
+    (previous MM/ML/mv tags dropped) - as BAM when the name ends in ``.bam``, else as SAM text -
+    unmapped-style when reference anchored like the reference's output (inference.py:448-456)."""
     from . import io as rio
     from .refine_signal_map import SigMapRefiner
     if isinstance(models, tuple):
@@ -133,11 +133,14 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     bam_idx = rio.ReadIndexedBam(in_bam_path, skip_non_primary=skip_non_primary, req_tags={"mv"})
     results = []
     out_fh = None
-    if out_path is not None:
+    out_records = None  # BAM output: records are collected and written at the end
+    header_text = (bam_idx.header_text.rstrip("\n") + "\n" if bam_idx.header_text else "") + \
+        "@PG\tID:remora_b200\tPN:remora_b200\n"
+    if out_path is not None and str(out_path).endswith(".bam"):
+        out_records = []
+    elif out_path is not None:
         out_fh = open(out_path, "w")
-        if bam_idx.header_text:
-            out_fh.write(bam_idx.header_text.rstrip("\n") + "\n")
-        out_fh.write("@PG\tID:remora_b200\tPN:remora_b200\n")
+        out_fh.write(header_text)
 
     def flush(group):
         # group: list of io.Read that converted cleanly; one refinement launch per model
@@ -194,14 +197,19 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
                 del res["calls"]
             results.append(res)
             rec = io_read.alignment_record
-            if out_fh is not None and res["error"] is None and rec is not None:
+            if (out_fh is not None or out_records is not None) and res["error"] is None and rec is not None:
                 extra = mods_tags_to_str([res["mm"]], res["ml"])
                 if ref_anchored:
                     import dataclasses
                     seq = io_read.ref_seq if io_read.ref_reg.strand == "+" else revcomp(io_read.ref_seq)
                     rec = dataclasses.replace(rec, cigartuples=[(0, len(io_read.ref_seq))], query_sequence=seq,
                                               query_qualities=np.zeros(0, dtype=np.uint8))
-                out_fh.write(rec.to_sam(drop_tags=("MM", "ML", "Mm", "Ml", "mv"), extra_tags=extra) + "\n")
+                drop = ("MM", "ML", "Mm", "Ml", "mv")
+                if out_records is not None:
+                    out_records.append(rec.to_record(drop_tags=drop, extra_tags=[
+                        ("MM", "Z", res["mm"]), ("ML", "BC", np.frombuffer(res["ml"], dtype=np.uint8))]))
+                else:
+                    out_fh.write(rec.to_sam(drop_tags=drop, extra_tags=extra) + "\n")
 
     group = []
     try:
@@ -221,4 +229,6 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     finally:
         if out_fh is not None:
             out_fh.close()
+    if out_records is not None:
+        rio.write_bam(out_path, header_text, rio.references_from_header(header_text), out_records)
     return results

@@ -216,6 +216,17 @@ class AlignedSegment:
         fields.extend(extra_tags)
         return "\t".join(fields)
 
+    def to_record(self, drop_tags=(), extra_tags=()):
+        """dict form accepted by :func:`write_bam`; ``extra_tags``: [(tag, BAM type, value)]."""
+        types = self.tag_types or {}
+        tags = [(t, types.get(t, "Z"), v) for t, v in self.tags if t not in drop_tags]
+        return dict(query_name=self.query_name, flag=self.flag, reference_id=self.reference_id,
+                    reference_start=self.reference_start, mapping_quality=self.mapping_quality,
+                    cigartuples=self.cigartuples, query_sequence=self.query_sequence,
+                    query_qualities=self.query_qualities, next_reference_id=self.next_reference_id,
+                    next_reference_start=self.next_reference_start, template_length=self.template_length,
+                    tags=tags + list(extra_tags))
+
     def to_dict(self):
         return {"name": self.query_name, "flag": str(self.flag), "ref_name": self.reference_name or "*",
                 "ref_pos": str(self.reference_start + 1), "map_quality": str(self.mapping_quality),
@@ -1102,11 +1113,25 @@ def write_bam(path, header_text, references, records):
         tags = b"".join(_encode_tag(t, ty, v) for t, ty, v in rec.get("tags", []))
         core = struct.pack("<iiBBHHHIiii", rec.get("reference_id", -1), rec.get("reference_start", -1),
                            len(name), rec.get("mapping_quality", 0), 4680, len(cigar), rec.get("flag", 4),
-                           len(seq), -1, -1, 0)
+                           len(seq), rec.get("next_reference_id", -1), rec.get("next_reference_start", -1),
+                           rec.get("template_length", 0))
+        qual = rec.get("query_qualities")
+        qual = (np.asarray(qual, dtype=np.uint8).tobytes() if qual is not None and len(qual) == len(seq)
+                else b"\xff" * len(seq))
         blob = (core + name + b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in cigar) + packed
-                + b"\xff" * len(seq) + tags)
+                + qual + tags)
         body += struct.pack("<i", len(blob)) + blob
     with open(path, "wb") as fh:
         for st in range(0, len(body), 0xFF00):
             fh.write(_bgzf_block(bytes(body[st:st + 0xFF00])))
         fh.write(_BGZF_EOF)
+
+
+def references_from_header(header_text):
+    """[(name, length)] from the @SQ lines of a SAM header."""
+    refs = []
+    for line in header_text.splitlines():
+        if line.startswith("@SQ"):
+            fields = dict(f.split(":", 1) for f in line.split("\t")[1:] if ":" in f)
+            refs.append((fields.get("SN", "*"), int(fields.get("LN", 0))))
+    return refs

@@ -65,6 +65,11 @@ def main():
                                 k + name + "_shift_scale": np.array([rr.shift, rr.scale]),
                                 k + name + "_mm": np.array(mm), k + name + "_ml": np.frombuffer(ml, dtype=np.uint8)})
                     print(stem, rid, name, "calls", pos.size)
+                # reference-anchored calls (remora infer --reference-anchored): sequence and mapping from
+                # the alignment instead of the basecalls
+                model, md = models["convlstm_s64_k9_hot"]
+                nn_out, _, pos = inference.call_read_mods(io_read.into_remora_read(True), model, md)
+                out.update({k + "ref_nn_out": nn_out.astype(np.float32), k + "ref_pos": pos})
                 index.append([stem, rid, len(io_read.seq), io_read.dacs.size, io_read.ref_reg.strand])
     out["index"] = np.array(index)
     np.savez_compressed(os.path.join(HERE, "io_cases.npz"), **out)

@@ -238,6 +238,35 @@ def test_gpu_real_reads_match_reference_cpu_calls(io_cases, name):
     assert n == 4
 
 
+@pytest.mark.gpu
+def test_gpu_reference_anchored_calls_match_reference(io_cases):
+    """`remora infer --reference-anchored`: reads rebuilt from the golden arrays of the reference's
+    reference-anchored RemoraRead (dacs are a slice of the basecall-anchored samples)."""
+    dev = torch.device("cuda:0")
+    model, md = model_util.load_model(os.path.join(GOLDEN, "convlstm_s64_k9_hot.pt"), device=dev, eval_only=True)
+    n = 0
+    for key in sorted(k for k in io_cases.files if k.endswith("bc_dacs")):
+        k = key[: -len("bc_dacs")]
+        full = io_cases[key]
+        size, crc = (int(v) for v in io_cases[k + "ref_dacs"])
+        ssm = io_cases[k + "ref_ssm"]
+        # locate the slice: the reference-anchored samples start where the first aligned base starts
+        starts = [st for st in range(0, full.size - size + 1)
+                  if zlib.crc32(full[st:st + size].tobytes()) == crc] if size <= full.size else []
+        if not starts:
+            continue
+        shift, scale = io_cases[k + "ref_shift_scale"]
+        read = data_chunks.RemoraRead(dacs=full[starts[0]:starts[0] + size].copy(), shift=float(shift),
+                                      scale=float(scale), seq_to_sig_map=ssm.copy(),
+                                      int_seq=io_cases[k + "ref_int_seq"].astype(np.int64))
+        nn_out, _, pos = inference.call_read_mods(read, model, md)
+        order, want = np.argsort(pos), np.argsort(io_cases[k + "ref_pos"])
+        assert np.array_equal(pos[order], io_cases[k + "ref_pos"][want])
+        assert np.abs(nn_out[order] - io_cases[k + "ref_nn_out"][want]).max() < 1e-4
+        n += 1
+    assert n >= 1
+
+
 def write_synthetic_run(tmp_path, n_reads=12, seed=0):
     return synth_pod5_bam_run(str(tmp_path / "run.pod5"), str(tmp_path / "run.bam"), n_reads=n_reads, seed=seed)
 
@@ -328,3 +357,19 @@ def test_gpu_infer_from_pod5_and_bam(tmp_path):
         assert fields[0] == r["read_id"] and f"MM:Z:{r['mm']}" in fields
         assert any(f.startswith("ML:B:C,") for f in fields) and not any(f.startswith("mv:") for f in fields)
         assert r["mm"].startswith("C+m?,") and len(r["ml"]) == len(pos)
+    # BAM output carries the same tags; two models (one per canonical base) concatenate their sections
+    out_bam = str(tmp_path / "calls.bam")
+    model2, md2 = model_util.load_model(os.path.join(GOLDEN, "convlstm_s64_k9_hot.pt"), device=dev, eval_only=True)
+    md2 = dict(md2, can_base="G", motifs=[("GC", 0)], motif=("GC", 0), mod_bases="x", mod_long_names=["test"])
+    res2 = inference.infer_from_pod5_and_bam(pod5, bam, {"C": (model, md), "G": (model2, md2)}, out_path=out_bam,
+                                             decode_on_device=False, extract_on_device=False)
+    with io.BamReader(out_bam) as reader:
+        recs = {r.query_name: r for r in reader}
+    assert len(recs) == 12
+    for r1, r2 in zip(res, res2):
+        assert r2["read_id"] == r1["read_id"] and r2["mm"].startswith(r1["mm"])  # host paths: same C calls
+        rec = recs[r2["read_id"]]
+        if r2["mm"]:
+            assert rec.get_tag("MM") == r2["mm"] and list(rec.get_tag("ML")) == list(r2["ml"])
+            assert "G+x?," in r2["mm"] or "GC" not in truth[r2["read_id"]]["seq"]
+        assert not rec.has_tag("mv") and rec.query_sequence == truth[r2["read_id"]]["seq"]
