@@ -497,6 +497,20 @@ def ours(args):
                 line["next_rows"] = {"signal_mapping_refinement": refine_times.refine_bench()}
             except Exception as e:  # noqa: BLE001
                 line["next_rows"] = {"signal_mapping_refinement": {"error": str(e)[:200]}}
+            try:
+                import vbz_times
+                v = vbz_times.vbz_bench(n_reads=256, cpu_seconds=1.5, verbose=False)
+                line["next_rows"]["pod5_signal_decode"] = {
+                    "kernel": "svb16_decode_kernel", "unit": "samples/s", "value": v["samples_per_s"],
+                    "ms": v["kernel_ms"], "samples": v["samples"], "packed_bytes_per_sample": v["bytes_per_sample"],
+                    "roofline": {"bound": "hbm", "achieved": v["algorithmic_gb_per_s"], "peak": peak_gbs,
+                                 "unit": "GB/s", "frac": v["algorithmic_gb_per_s"] / peak_gbs,
+                                 "l2": v["l2"]},
+                    "cpu_numpy_1_core_samples_per_s": v["numpy_samples_per_s_1_core"],
+                    "host_zstd_samples_per_s": v["host_zstd_samples_per_s"],
+                    "parity": "bit-exact (tests/test_io.py)"}
+            except Exception as e:  # noqa: BLE001
+                line["next_rows"]["pod5_signal_decode"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier(device_ids=[local_rank])
