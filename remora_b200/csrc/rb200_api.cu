@@ -231,6 +231,9 @@ int rb200_destroy(rb200_handle h) {
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->staging_dev) cudaFree(h->staging_dev);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return RB200_OK;
 }

@@ -89,6 +89,10 @@ struct rb200_model {
     char *staging_dev = nullptr;
     size_t staging_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // tiled layer path: the signal track runs on a side stream next to the sequence track
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int two_tracks = -1;  // -1: decide from RB200_TWO_TRACKS (default on), 0 / 1
     // per-kernel profiling of the fused path
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;  // 4 per profiled forward

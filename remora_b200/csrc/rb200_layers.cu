@@ -6,6 +6,8 @@
 // Activations are channel-first float32 [B][C][T] like the reference tensors.
 #include "rb200_internal.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 namespace rb200 {
@@ -244,11 +246,30 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
     for (int i = 0; i < d.n_seq_conv - 1; ++i)
         seq_bufs.push_back(take((size_t)B * d.seq_conv[i].c_out * p.seq_t[i + 1] * 4));
     float *cat = take((size_t)B * cat_bstride * 4);
+    // The two tracks are independent until the concatenation: in tiled mode the signal track goes to a
+    // side stream (fork / join with events) so that its kernels share the SMs with the sequence track's
+    // (each tiled convolution alone keeps the FMA pipe 54-63 % busy with one 8-warp CTA per SM).
+    if (m->two_tracks < 0) {
+        const char *e = getenv("RB200_TWO_TRACKS");
+        m->two_tracks = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool fork = tiled && m->two_tracks == 1 && !m->keep_debug;
+    cudaStream_t sig_stream = stream;
+    if (fork) {
+        if (!m->side_stream) {
+            RB200_CUDA_TRY(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+            RB200_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+            RB200_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+        }
+        RB200_CUDA_TRY(cudaEventRecord(m->ev_fork, stream));
+        RB200_CUDA_TRY(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
+        sig_stream = m->side_stream;
+    }
     for (int i = 0; i < d.n_sig_conv; ++i) {
         const bool last = i == d.n_sig_conv - 1;
         float *y = last ? cat : sig_bufs[i];
         const int64_t yb = last ? cat_bstride : (int64_t)d.sig_conv[i].c_out * p.sig_t[i + 1];
-        rc = run_conv(m, 0, i, tiled, d.sig_conv[i], x, xb, p.sig_t[i], y, yb, B, stream);
+        rc = run_conv(m, 0, i, tiled, d.sig_conv[i], x, xb, p.sig_t[i], y, yb, B, sig_stream);
         if (rc) return rc;
         if (!last) keep(sig_names[i], y, d.sig_conv[i].c_out, p.sig_t[i + 1]);
         x = y;
@@ -271,6 +292,10 @@ int layers_forward(rb200_model *m, Workspace &ws, const float *sigs, const float
         if (!last) keep(seq_names[i], y, d.seq_conv[i].c_out, p.seq_t[i + 1]);
         x = y;
         xb = yb;
+    }
+    if (fork) {  // join: the merge convolutions read both halves of cat
+        RB200_CUDA_TRY(cudaEventRecord(m->ev_join, m->side_stream));
+        RB200_CUDA_TRY(cudaStreamWaitEvent(stream, m->ev_join, 0));
     }
     keep("cat", cat, 2 * d.size, t_cat);
     x = cat;

@@ -107,7 +107,7 @@ def _run_merged(model, batches, device, batch_size):
 def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_reads=None,
                             batch_size=constants.DEFAULT_BATCH_SIZE, reads_per_batch=256, ref_anchored=False,
                             skip_non_primary=True, extract_on_device=True, return_probs=False,
-                            decode_on_device=True):
+                            decode_on_device=True, rank=0, world_size=1):
     """``remora infer from_pod5_and_bam`` as one function (reference inference.py:462-660 without its
     process/queue plumbing): POD5 signal + BAM basecalls/move tables -> modified-base calls per read.
 
@@ -120,7 +120,9 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     ``{read_id, mm, ml (array('B')), error}`` (plus ``calls``: ``{can_base: (positions, probs)}`` when
     ``return_probs``); with ``out_path`` the input records are also written with the MM/ML tags attached
     (previous MM/ML/mv tags dropped) - as BAM when the name ends in ``.bam``, else as SAM text -
-    unmapped-style when reference anchored like the reference's output (inference.py:448-456)."""
+    unmapped-style when reference anchored like the reference's output (inference.py:448-456).
+    Multi-GPU: one process per GPU calls this with its ``rank`` / ``world_size`` (and its own
+    ``out_path``); reads are split by sequence length (``parallel.shard_by_work``), no collective."""
     from . import io as rio
     from .refine_signal_map import SigMapRefiner
     if isinstance(models, tuple):
@@ -131,6 +133,12 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
         raise RemoraError("models disagree on reverse_signal / pa_scaling")
     reverse_signal, pa_scaling = rev_sigs.pop(), pa_scalings.pop()
     bam_idx = rio.ReadIndexedBam(in_bam_path, skip_non_primary=skip_non_primary, req_tags={"mv"})
+    if world_size > 1:
+        from .parallel import shard_by_work
+        ids = bam_idx.read_ids
+        keep = shard_by_work([sum(len(r.query_sequence) for r in bam_idx[i]) for i in ids], world_size, rank)
+        bam_idx._bam_idx = {ids[i]: bam_idx._bam_idx[ids[i]] for i in keep}
+        bam_idx.num_reads = len(bam_idx._bam_idx)
     results = []
     out_fh = None
     out_records = None  # BAM output: records are collected and written at the end

@@ -65,3 +65,21 @@ class ShardedCaller:
         dist.all_gather(parts, buf, group=self.group)
         out = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
         return (out, None) if async_op else out
+
+
+def shard_by_work(work, world_size, rank):
+    """Indices of the items this rank handles when items carry unequal work (reads of different lengths:
+    the refinement DP and the chunk count both grow with the number of bases).  Longest-first greedy
+    assignment to the least loaded rank; deterministic, every rank computes the same partition, no
+    communication.  Reads are independent, so the file pipeline needs no collective at
+    all: each rank writes the calls of its own reads."""
+    work = [int(w) for w in work]
+    order = sorted(range(len(work)), key=lambda i: (-work[i], i))
+    load = [0] * world_size
+    mine = []
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        load[r] += work[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)

@@ -72,3 +72,45 @@ def test_two_rank_gloo_shard_gather(tmp_path, n_chunks):
     # the CPU oracle picks batch-size dependent oneDNN kernels, so shard-vs-whole is equal only to
     # fp32 rounding; the CUDA kernels are batch-invariant (tests/test_gpu_parity.py checks that)
     assert np.abs(got[0] - single).max() < 2e-6
+
+
+def test_shard_by_work_is_a_balanced_partition():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        work = rng.integers(100, 50000, size=101).tolist()
+        parts = [parallel.shard_by_work(work, world, r) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(101))  # every read exactly once
+        loads = [sum(work[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(work)  # greedy longest-first bound
+    assert parallel.shard_by_work([], 4, 2) == []
+
+
+def _read_shard_worker(rank, world, port, bam, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from remora_b200 import io
+    idx = io.ReadIndexedBam(bam, req_tags={"mv"})
+    ids = idx.read_ids
+    mine = [ids[i] for i in parallel.shard_by_work([len(idx.get_first_alignment(i).query_sequence) for i in ids],
+                                                   world, rank)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "ids.npy"), np.array([len(g) for g in gathered]))
+        flat = sorted(i for g in gathered for i in g)
+        assert flat == sorted(ids) and len(set(flat)) == len(flat)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_read_sharding_of_a_bam(tmp_path):
+    """The file pipeline's multi-GPU form: both ranks index the same BAM and take disjoint read sets
+    whose union is the file (no data-path collective; the gather here is only the test's check)."""
+    from remora_b200.synth import synth_pod5_bam_run
+    _, bam, truth = synth_pod5_bam_run(str(tmp_path / "r.pod5"), str(tmp_path / "r.bam"), n_reads=9,
+                                       bases=(50, 200))
+    mp.spawn(_read_shard_worker, args=(2, _free_port(), bam, str(tmp_path)), nprocs=2, join=True)
+    counts = np.load(tmp_path / "ids.npy")
+    assert counts.sum() == 9 and counts.min() >= 3
