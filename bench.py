@@ -282,19 +282,39 @@ def ours(args):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(device)
 
-    from remora_b200.parallel import ShardedCaller
-    caller = ShardedCaller(None, model.num_out) if distributed else None
+    # The only exchange step the path has: 8 B/chunk of logits gathered to every rank (NCCL all-gather
+    # over NVLink).  Every step's logits are gathered inside the timed region; the steps of a group of G
+    # write into one slot of a double-buffered device ring and ONE asynchronous all-gather ships the group
+    # (G x 8 KB per rank), so the collective's host-side launch cost (tens of microseconds, comparable to a
+    # whole 104 us step) is paid once per group and the transfer overlaps the next group's kernels.
+    G = max(1, args.gather_every)
+    if distributed:
+        local_ring = torch.empty((2, G, BATCH, model.num_out), dtype=torch.float32, device=device)
+        gath_ring = torch.empty((2, world * G * BATCH, model.num_out), dtype=torch.float32, device=device)
+    pending = [None, None]
 
-    def step(i):
-        out = model.forward_compact(*dev_batch(i))
-        if distributed:
-            # the only exchange step the path has: 8 B/chunk of logits gathered to every rank
-            # (NCCL all-gather over NVLink, asynchronous so it overlaps the next step's kernels)
-            return caller.gather(out, world * BATCH, async_op=True)[1]
-        return None
+    def step(i, last=False):
+        if not distributed:
+            model.forward_compact(*dev_batch(i))
+            return
+        slot, k = (i // G) & 1, i % G
+        if k == 0 and pending[slot] is not None:
+            pending[slot].wait()  # stream-side wait: the gather that still reads this slot
+            pending[slot] = None
+        model.forward_compact(*dev_batch(i), out=local_ring[slot, k])
+        if k == G - 1 or last:
+            pending[slot] = dist.all_gather_into_tensor(gath_ring[slot], local_ring[slot].view(G * BATCH, -1),
+                                                        async_op=True)
+
+    def drain():
+        for slot in range(2):
+            if pending[slot] is not None:
+                pending[slot].wait()
+                pending[slot] = None
 
     for i in range(args.warmup):
-        step(i)
+        step(i, last=i == args.warmup - 1)
+    drain()
     barrier()
     impl_used = model.last_impl
     launches0 = model.launch_count
@@ -305,11 +325,9 @@ def ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    work = None
     for i in range(args.steps):
-        work = step(args.warmup + i)
-    if work is not None:
-        work.wait()
+        step(i, last=i == args.steps - 1)
+    drain()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -420,7 +438,8 @@ def ours(args):
                                    "within 1e-4 of the reference CPU forward",
                        "batch_per_gpu": BATCH, "global_batch": world * BATCH,
                        "chunk_len": CHUNK_LEN, "kmer_context": list(KMER_CONTEXT),
-                       "parallelism": f"batch-shard x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"batch-shard x{world}, logits all-gathered (NCCL) in groups of "
+                                       f"{G} steps, asynchronously" if world > 1 else "single GPU"),
                        "impl": impl_used,
                        "l2_policy": f"inputs larger than L2: each step reads a different batch of a "
                                     f"{pool_bytes / 1e6:.0f} MB resident pool ({n_pool} batches)"},
@@ -523,6 +542,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather-every", type=int, default=8,
+                    help="multi-GPU: steps per all-gather of the logits (every step's logits are gathered)")
     ap.add_argument("--pool-batches", type=int, default=400,
                     help="resident batches of compact inputs (400 x 1024 x 480 B = 197 MB > L2)")
     args = ap.parse_args()

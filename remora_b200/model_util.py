@@ -239,11 +239,12 @@ class B200Model(nn.Module):
         _native.check(rc, "rb200_forward_dense")
         return out
 
-    def forward_compact(self, sigs, sequence, seq_to_sig_map, seq_lens):
+    def forward_compact(self, sigs, sequence, seq_to_sig_map, seq_lens, out=None):
         """Fused encode + forward on the reference's compact chunk arrays
         (CoreRemoraDataset._core_dtypes, data_chunks.py:942-948):
         sigs float32 [B,1,T] (or [B,T]), sequence int8 [B,Lmax+k-1], seq_to_sig_map int16 [B,Lmax+1],
-        seq_lens int16 [B] -> float32 [B,num_out]."""
+        seq_lens int16 [B] -> float32 [B,num_out] (written into ``out`` when given: a contiguous float32
+        device tensor of that shape, e.g. a slot of a gather buffer)."""
         sigs = self._prep(sigs, torch.float32, "sigs")
         seqs = self._prep(sequence, torch.int8, "sequence")
         maps = self._prep(seq_to_sig_map, torch.int16, "seq_to_sig_map")
@@ -256,7 +257,11 @@ class B200Model(nn.Module):
             B, T = sigs.shape
         if seqs.shape[0] != B or maps.shape[0] != B or lens.shape[0] != B:
             raise RemoraError("compact arrays disagree on the batch size")
-        out = torch.empty((B, self.num_out), dtype=torch.float32, device=self._device)
+        if out is None:
+            out = torch.empty((B, self.num_out), dtype=torch.float32, device=self._device)
+        elif (out.dtype != torch.float32 or not out.is_contiguous() or out.device != self._device
+              or tuple(out.shape) != (B, self.num_out)):
+            raise RemoraError("out must be a contiguous float32 [B, num_out] tensor on the model's device")
         stream = ctypes.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
         rc = self._lib.rb200_forward_compact(self._handle, _ptr(sigs), _ptr(seqs), seqs.shape[1],
                                              _ptr(maps), maps.shape[1], _ptr(lens), B, T,
