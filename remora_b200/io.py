@@ -78,10 +78,20 @@ class _BgzfStream:
     (block file offset << 16 | offset within the block)."""
 
     def __init__(self, fh):
+        self._fh = fh
         self._blocks = iter_bgzf_blocks(fh)
         self._buf = b""
         self._pos = 0
         self._block_start = 0
+
+    def seek(self, voffset):
+        """Jump to a BAM virtual offset (as returned by :meth:`tell`)."""
+        self._fh.seek(voffset >> 16)
+        self._blocks = iter_bgzf_blocks(self._fh)
+        self._buf, self._pos = b"", 0
+        if not self._fill():
+            raise RemoraError("BAM virtual offset beyond the end of the file")
+        self._pos = voffset & 0xFFFF
 
     def _fill(self):
         for start, data in self._blocks:
@@ -316,6 +326,18 @@ class BamReader:
             self.references.append(self._stream.read(l_name)[:-1].decode("ascii"))
             self.lengths.append(struct.unpack("<i", self._stream.read(4))[0])
 
+    def read_at(self, voffset):
+        """The record that starts at a virtual offset (random access without an index file)."""
+        self._stream.seek(voffset)
+        head = self._stream.read(4)
+        if len(head) < 4:
+            raise RemoraError("truncated BAM record")
+        size = struct.unpack("<i", head)[0]
+        buf = self._stream.read(size)
+        if len(buf) < size:
+            raise RemoraError("truncated BAM record")
+        return _parse_record(buf, self.references)
+
     def iter_with_offsets(self):
         while True:
             voff = self._stream.tell()
@@ -360,8 +382,9 @@ def get_parent_id(bam_read):
 @dataclasses.dataclass
 class ReadIndexedBam:
     """BAM records indexed by (parent) read id, same constructor arguments and query methods as the
-    reference class (io.py:183-360).  Records are parsed once and kept in memory (the reference keeps
-    file pointers and re-reads through htslib)."""
+    reference class (io.py:183-360).  ``in_memory=True`` (default) keeps the parsed records; with
+    ``in_memory=False`` only BAM virtual offsets are kept, like the reference's file pointers
+    (io.py:255-307), and records are re-read on demand - the form for BAM files that do not fit in RAM."""
 
     bam_path: str
     skip_non_primary: bool = True
@@ -369,6 +392,7 @@ class ReadIndexedBam:
     read_id_converter: object = None
     parent_read_id_subset: set = None
     child_read_id_subset: set = None
+    in_memory: bool = True
 
     def __post_init__(self):
         self.num_reads = None
@@ -385,10 +409,11 @@ class ReadIndexedBam:
 
     def compute_read_index(self):
         idx = defaultdict(list)
+        self._reader = None
         with BamReader(self.bam_path) as bam:
             self.header_text = bam.header_text
             self.references = bam.references
-            for read in bam:
+            for voff, read in bam.iter_with_offsets():
                 if self.child_read_id_subset is not None and read.query_name not in self.child_read_id_subset:
                     self.skip_reasons["Child read ID filtered"] += 1
                     continue
@@ -405,15 +430,24 @@ class ReadIndexedBam:
                     self.skip_reasons["Non-primary alignment"] += 1
                     continue
                 self.num_records += 1
-                idx[index_read_id].append(read)
+                idx[index_read_id].append(read if self.in_memory else voff)
         self._bam_idx = dict(idx)
         self.num_reads = len(self._bam_idx)
 
+    def _materialise(self, entry):
+        if self.in_memory:
+            return entry
+        if self._reader is None:
+            self._reader = BamReader(self.bam_path)
+        return self._reader.read_at(entry)
+
     def get_alignments(self, read_id):
         try:
-            yield from self._bam_idx[read_id]
+            entries = self._bam_idx[read_id]
         except KeyError:
             raise RemoraError(f"Could not find {read_id} in {self.bam_path}")
+        for entry in entries:
+            yield self._materialise(entry)
 
     def get_first_alignment(self, read_id):
         return next(self.get_alignments(read_id))
@@ -422,15 +456,21 @@ class ReadIndexedBam:
         return read_id in self._bam_idx
 
     def __getitem__(self, read_id):
-        return self._bam_idx[read_id]
+        return [self._materialise(e) for e in self._bam_idx[read_id]]
 
     @property
     def read_ids(self):
         return list(self._bam_idx.keys())
 
     def __iter__(self):
-        for recs in self._bam_idx.values():
-            yield from recs
+        for entries in self._bam_idx.values():
+            for entry in entries:
+                yield self._materialise(entry)
+
+    def close(self):
+        if self._reader is not None:
+            self._reader.close()
+            self._reader = None
 
 
 def parse_move_tag(mv_tag, sig_len, seq_len=None, check=True, reverse_signal=False):

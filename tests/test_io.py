@@ -121,6 +121,15 @@ def test_bam_round_trip(tmp_path):
     assert io.ReadIndexedBam(path, req_tags={"mv"}).num_reads == 1
     with pytest.raises(RemoraError):
         next(idx.get_alignments("missing"))
+    # pointer index (virtual offsets, records re-read on demand) == in-memory index, also across blocks
+    lazy = io.ReadIndexedBam(path, in_memory=False)
+    assert lazy.read_ids == idx.read_ids and lazy.num_records == idx.num_records
+    for rid in (ids[1], "bulk0", "bulk77", "bulk119"):
+        a_mem, a_lazy = idx.get_first_alignment(rid), lazy.get_first_alignment(rid)
+        assert a_mem.query_name == a_lazy.query_name and a_mem.query_sequence == a_lazy.query_sequence
+        assert a_mem.tags == a_lazy.tags or [t for t, _ in a_mem.tags] == [t for t, _ in a_lazy.tags]
+    assert sum(1 for _ in lazy) == idx.num_records
+    lazy.close()
     not_bam = tmp_path / "plain.bam"
     not_bam.write_bytes(b"plain text, not BGZF" * 4)
     with pytest.raises(RemoraError):
