@@ -156,7 +156,8 @@ size_t refine_wide_scratch_bytes(int sm_count, int near_cap, int max_band_width)
     near_cap = resolve_near_cap(near_cap, max_band_width);
     if (max_band_width <= near_cap) return 0;
     const size_t warps = (size_t)sm_count * ctas_per_sm(near_cap) * kWarpsPerCta;
-    return warps * (size_t)refine::kRowsPerWarp * ((max_band_width + 3) & ~3) * sizeof(float);
+    // + 64 bytes: the chain's look-ahead load reads one 16-byte group past the last row of the last warp
+    return warps * (size_t)refine::kRowsPerWarp * ((max_band_width + 3) & ~3) * sizeof(float) + 64;
 }
 
 int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *levels, const int32_t *band_st,

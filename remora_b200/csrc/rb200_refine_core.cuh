@@ -68,7 +68,8 @@ enum { kStatusOk = 0, kStatusTracebackLeftBand = 1 };
 // Ctx supplies: int lane; int nl (lanes); void sync() (warp barrier with memory ordering);
 // int scan_max(int) (inclusive prefix maximum over the lanes); int bcast_last(int) (value of lane nl-1).
 //
-// Per-warp scratch rows, each 16-byte aligned and holding >= its capacity rounded up to a multiple of 4:
+// Per-warp scratch rows, each 16-byte aligned and holding >= its capacity rounded up to a multiple of 4;
+// the last row (mvs) must be followed by at least 16 readable bytes:
 //   row[2]        penalised scores of the previous / current base (alternating)
 //   unp, utb      un-penalised Viterbi scores and traceback of the current base
 //   bs, mvs       squared errors and move candidates of the current base's band
@@ -145,9 +146,12 @@ RB_HD void base_step(Ctx &ctx, const float *prev, int m, int d, float *__restric
         const int groups = (n + 3) >> 2;
         float x = RB_INF;
         Vec4f e = e4[0], mvv = m4[0];
+        // the fetch of group g+1 runs one group past the row end on the last iteration: rows are followed
+        // by readable scratch (the next row, or the pad after the last one), so no clamp is needed and
+        // the body stays branch-free for the unroller
+#pragma unroll 2
         for (int g = 0; g < groups; ++g) {
-            const int gn = (g + 1 < groups) ? g + 1 : g;
-            const Vec4f en_ = e4[gn], mn_ = m4[gn];
+            const Vec4f en_ = e4[g + 1], mn_ = m4[g + 1];
             Vec4f xo;
             x = fminf(mvv.a, RB_FADD(x, e.a)); xo.a = x;
             x = fminf(mvv.b, RB_FADD(x, e.b)); xo.b = x;

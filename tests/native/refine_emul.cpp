@@ -58,7 +58,8 @@ extern "C" int emul_refine_read(const float *sig, const float *levels, const int
     // "near" rows (shared memory on the GPU) hold bands up to near_cap samples, "far" rows (global
     // scratch) the wider ones; rows are read in 16-byte groups
     const size_t ncap = (size_t)((near_cap + 3) & ~3), fcap = (size_t)((max_w + 3) & ~3);
-    std::vector<float> near_buf(rb200::refine::kRowsPerWarp * ncap), far_buf(rb200::refine::kRowsPerWarp * fcap);
+    // + 4 floats: the chain's look-ahead load reads one group past the last row
+    std::vector<float> near_buf(rb200::refine::kRowsPerWarp * ncap + 4), far_buf(rb200::refine::kRowsPerWarp * fcap + 4);
     std::vector<int32_t> slot(4), spec(32);
     std::vector<int> xchg(32);
     const rb200::refine::Rows near = rb200::refine::carve_rows(near_buf.data(), ncap);
