@@ -61,3 +61,19 @@ def test_sass_has_blackwell_tensor_core_and_tma_paths():
     assert "FFMA2" in k1 and "UBLKCP" in k1
     k3 = next(v for k, v in funcs.items() if "k3_lstm_kernel" in k)
     assert "FFMA2" in k3 and "SHFL" in k3
+
+
+def test_refinement_kernel_has_no_fused_multiply_add():
+    """Bit-exact parity of the banded DP needs every product and sum rounded separately, like the
+    reference's generated C: the kernel's SASS must not contain a single fused multiply-add, and its
+    chain must be the FADD + FMNMX pair the design describes."""
+    import subprocess
+    import pytest
+    out = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    funcs = {f.split("\n", 1)[0]: f for f in out.stdout.split("Function : ")[1:]}
+    kernels = [v for k, v in funcs.items() if "refine_dp_kernel" in k]
+    assert kernels
+    for sass in kernels:
+        assert "FFMA" not in sass and "FMNMX" in sass and "FADD" in sass and "LDS.128" in sass
