@@ -394,8 +394,26 @@ class DeviceRefineBatch:
         return (out, self.d_score.cpu().numpy()) if return_scores else out
 
 
+MAX_CELLS_PER_LAUNCH = 1 << 30  # 4 GiB of traceback workspace per launch
+
+
+def split_by_budget(sizes, budget):
+    """Consecutive index ranges [(start, end)] whose summed ``sizes`` stay within ``budget`` (a single
+    oversized item gets a range of its own)."""
+    spans, start, total = [], 0, 0
+    for i, sz in enumerate(sizes):
+        if i > start and total + sz > budget:
+            spans.append((start, i))
+            start, total = i, 0
+        total += sz
+    if start < len(sizes):
+        spans.append((start, len(sizes)))
+    return spans
+
+
 def banded_dp_batch(dacs_list, shifts, scales, levels_list, seq_bands, algo=DEFAULT_REFINE_ALGO,
-                    short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN, device=None, return_scores=False):
+                    short_dwell_pen=DEFAULT_REFINE_SHORT_DWELL_PEN, device=None, return_scores=False,
+                    max_cells=None):
     """Run the banded dynamic programme for a batch of reads on the GPU.
 
     dacs_list[r]: un-normalised samples of read r already trimmed to its mapped range;
@@ -404,10 +422,20 @@ def banded_dp_batch(dacs_list, shifts, scales, levels_list, seq_bands, algo=DEFA
     (and the final forward score per read when ``return_scores``)."""
     if len(dacs_list) == 0:
         return ([], np.zeros(0, np.float32)) if return_scores else []
-    batch = DeviceRefineBatch(dacs_list, shifts, scales, levels_list, seq_bands, algo, short_dwell_pen,
-                              device)
-    batch.run()
-    return batch.paths(return_scores)
+    # the traceback workspace is 4 bytes per band cell: long reads are handled in several launches
+    cells = [int((b[1] - b[0]).sum()) for b in seq_bands]
+    paths, scores = [], []
+    for st, en in split_by_budget(cells, max_cells or MAX_CELLS_PER_LAUNCH):
+        batch = DeviceRefineBatch(dacs_list[st:en], shifts[st:en], scales[st:en], levels_list[st:en],
+                                  seq_bands[st:en], algo, short_dwell_pen, device)
+        batch.run()
+        out = batch.paths(return_scores)
+        if return_scores:
+            paths.extend(out[0])
+            scores.append(out[1])
+        else:
+            paths.extend(out)
+    return (paths, np.concatenate(scores)) if return_scores else paths
 
 
 def refine_signal_mapping(signal, seq_to_sig_map, levels, band_half_width=DEFAULT_REFINE_HBW,
