@@ -26,7 +26,8 @@ def timed(fn, n=50):
     return e0.elapsed_time(e1) / n
 
 
-for name, T, batches in (("conv_s64_k9", 100, (1024, 4096)), ("convlstm_s16_k6_o3", 100, (1024,))):
+for name, T, batches in (("conv_s64_k9", 100, (1024, 4096)), ("conv_s64_k9_T200", 200, (4096,)),
+                         ("convlstm_s16_k6_o3", 100, (1024,))):
     model, md = model_util.load_model(os.path.join(ROOT, f"tests/golden/{name}.pt"),
                                       device=torch.device("cuda:0"), eval_only=True)
     for B in batches:

@@ -198,3 +198,51 @@ if __name__ == "__main__":
     forward_cases()
     read_cases()
     print("golden vectors written to", HERE)
+
+
+def conv_w_ref_chunk200():
+    """BASELINE config 3 as literally stated (Conv_w_ref at chunk_len 200): the stock model file
+    hard-codes fc = Linear(size * 3) (models/Conv_w_ref.py:42), which only fits chunk_len 100, so the
+    classifier is replaced by Linear(size * 11) (the flattened width at chunk_len 200) before the
+    reference's own exporter scripts the module - SURVEY.md 8d, "C3 (ii)".  Everything else is the
+    reference's code; the logits below come from the exported TorchScript module on CPU."""
+    name = "conv_s64_k9_T200"
+    path = os.path.join(HERE, name + ".pt")
+    torch.manual_seed(7)
+    model = model_util._load_python_model(ref_harness.reference_model_path("Conv_w_ref"), size=64, kmer_len=9,
+                                          num_out=2)
+    model.fc = torch.nn.Linear(64 * 11, 2)
+    gen = torch.Generator().manual_seed(1007)
+    for _, mod in model.named_modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=gen) * 0.5)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=gen) * 1.5 + 0.5)
+            mod.weight.copy_(torch.rand(mod.weight.shape, generator=gen) + 0.5)
+            mod.bias.copy_(torch.randn(mod.bias.shape, generator=gen) * 0.2)
+    for pname, p in model.named_parameters():
+        if "conv" in pname and pname.endswith("weight"):
+            p.mul_(2.5)
+        elif pname.startswith("fc"):
+            p.mul_(8.0)
+    ckpt = {
+        "kmer_context_bases": (4, 4), "chunk_context": (100, 100), "modified_base_labels": True,
+        "mod_bases": "m", "reverse_signal": False, "refine_kmer_center_idx": 0,
+        "refine_do_rough_rescale": False, "refine_scale_iters": -1, "refine_algo": "dwell_penalty",
+        "refine_half_bandwidth": 5, "base_start_justify": False, "offset": 0, "pa_scaling": None,
+        "model_params": {"size": 64, "kmer_len": 9, "num_out": 2}, "mod_long_names": ["5mC"],
+        "motifs": [("CG", 0)], "refine_kmer_levels": None, "refine_sd_arr": None, "model_version": 3,
+    }
+    model_util.export_model_torchscript(ckpt, model, path)
+    model, md = model_util.load_model(path, eval_only=True)
+    out = {}
+    for n, seed in ((33, 70), (1, 71)):
+        d = synth_chunks(n, 200, (4, 4), seed=seed)
+        enc = encoded_kmers.compute_encoded_kmer_batch(4, 4, d["sequence"], d["sequence_to_signal_mapping"],
+                                                       d["sequence_lengths"])
+        logits = model(torch.from_numpy(d["signal"]), torch.from_numpy(enc)).numpy()
+        key = f"n{n}"
+        out.update({key + "_signal": d["signal"], key + "_seqs": d["sequence"],
+                    key + "_maps": d["sequence_to_signal_mapping"], key + "_lens": d["sequence_lengths"],
+                    key + "_logits": logits.astype(np.float32)})
+        print(name, n, "logit range", float(logits.min()), float(logits.max()))
+    np.savez_compressed(os.path.join(HERE, "conv_T200_cases.npz"), **out)

@@ -279,6 +279,32 @@ def test_conv_w_ref_auto_is_tiled_and_matches_oracle():
     assert np.abs(got - want).max() < LOGIT_TOL
 
 
+def test_conv_w_ref_chunk_len_200_matches_reference():
+    """BASELINE config 3 as literally stated: Conv_w_ref at chunk_len 200 (classifier of 64*11 inputs),
+    logits of the reference's TorchScript module on CPU; compact and dense interfaces, plain and tiled
+    layer kernels, batch 33 / 1 / 4096 (the config's batch size: finite and batch-invariant)."""
+    model, md = gpu_model("conv_s64_k9_T200")
+    assert md["chunk_len"] == 200
+    g = np.load(os.path.join(GOLDEN, "conv_T200_cases.npz"))
+    for key in ("n33", "n1"):
+        args = [torch.from_numpy(g[key + k]) for k in ("_signal", "_seqs", "_maps", "_lens")]
+        for impl in ("layers", "tiled", "auto"):
+            model.set_impl(impl)
+            got = model.forward_compact(*args).cpu().numpy()
+            assert np.abs(got - g[key + "_logits"]).max() < LOGIT_TOL, (key, impl)
+        enc = encoded_kmers.compute_encoded_kmer_batch(4, 4, g[key + "_seqs"], g[key + "_maps"], g[key + "_lens"])
+        dense = model(torch.from_numpy(g[key + "_signal"]).cuda(), torch.from_numpy(enc).cuda()).cpu().numpy()
+        assert np.abs(dense - g[key + "_logits"]).max() < LOGIT_TOL
+    d = synth_chunks(4096, 200, (4, 4), seed=77)
+    args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                             "sequence_lengths")]
+    model.set_impl("auto")
+    big = model.forward_compact(*args).cpu().numpy()
+    assert np.isfinite(big).all()
+    part = model.forward_compact(*[a[1000:1033] for a in args]).cpu().numpy()
+    assert np.array_equal(big[1000:1033], part)  # batch-invariant kernels
+
+
 def test_empty_batch():
     model, _ = gpu_model("convlstm_s64_k9")
     out = model.forward_compact(torch.zeros((0, 1, 100)), torch.zeros((0, 28), dtype=torch.int8),

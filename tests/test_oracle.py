@@ -110,3 +110,17 @@ def test_oracle_against_live_reference():
         want = model(torch.from_numpy(d["signal"]), torch.from_numpy(enc)).numpy()
     got = ro.forward_from_state_dict(model.state_dict(), d["signal"], enc).numpy()
     assert np.abs(got - want).max() < 5e-6
+
+
+def test_oracle_conv_w_ref_chunk_len_200():
+    """BASELINE config 3 as stated (Conv_w_ref, chunk_len 200): classifier widened to 64*11 inputs in the
+    reference module before its own exporter scripted it (tests/golden/make_golden.py)."""
+    import remora_oracle as ro
+    from conftest import GOLDEN, load_golden_model
+    sd, md = load_golden_model("conv_s64_k9_T200")
+    assert md["chunk_len"] == 200 and sd["fc.weight"].shape == (2, 704)
+    g = np.load(os.path.join(GOLDEN, "conv_T200_cases.npz"))
+    for key in ("n33", "n1"):
+        enc = ro.encode_kmers_c(4, 4, g[key + "_seqs"], g[key + "_maps"], g[key + "_lens"])
+        out = ro.forward_from_state_dict(sd, g[key + "_signal"], enc).numpy()
+        assert np.abs(out - g[key + "_logits"]).max() < 2e-6
