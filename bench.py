@@ -530,6 +530,11 @@ def ours(args):
                     "parity": "bit-exact (tests/test_io.py)"}
             except Exception as e:  # noqa: BLE001
                 line["next_rows"]["pod5_signal_decode"] = {"error": str(e)[:200]}
+            try:
+                import pipeline_times
+                line["next_rows"]["file_pipeline"] = pipeline_times.pipeline_bench()
+            except Exception as e:  # noqa: BLE001
+                line["next_rows"]["file_pipeline"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier(device_ids=[local_rank])

@@ -19,6 +19,30 @@ from remora_b200 import inference, model_util  # noqa: E402
 from remora_b200.synth import synth_pod5_bam_run  # noqa: E402
 
 
+def pipeline_bench(n_reads=128, n_bases=2000):
+    """Compact form for bench.py's `next_rows`: wall clock of infer_from_pod5_and_bam (refiner-carrying
+    fixture model, BAM output) on a synthetic run written by our own POD5/BAM writers."""
+    dev = torch.device("cuda:0")
+    with tempfile.TemporaryDirectory() as tmp:
+        pod5, bam, truth = synth_pod5_bam_run(os.path.join(tmp, "run.pod5"), os.path.join(tmp, "run.bam"),
+                                              n_reads=n_reads, bases=(n_bases // 2, n_bases * 3 // 2))
+        model, md = model_util.load_model(os.path.join(ROOT, "tests", "golden", "convlstm_s64_k9_refine.pt"),
+                                          device=dev, eval_only=True)
+        inference.infer_from_pod5_and_bam(pod5, bam, (model, md), num_reads=8)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=os.path.join(tmp, "o.bam"))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    calls = sum(len(r["ml"]) for r in res)
+    bases = sum(len(t["seq"]) for t in truth.values())
+    return {"unit": "reads/s", "value": len(res) / dt, "bases_per_s": bases / dt, "calls_per_s": calls / dt,
+            "workload": f"{len(res)} synthetic reads, {bases} bases, {calls} CG calls: POD5 decode (GPU) + BAM join "
+                        "+ rough re-scaling (host) + banded-DP refinement (GPU) + chunk extraction (GPU) + "
+                        "ConvLSTM_w_ref (GPU) + MM/ML tags + BAM output, one process, wall clock",
+            "bound": "host (numpy re-scaling, record parsing, tag formatting); the GPU stages are a few percent"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=256)
