@@ -130,3 +130,36 @@ if __name__ == "__main__":
     torch.set_grad_enabled(False)
     refine_cases()
     refine_model_and_reads()
+    real_read_cases()  # needs tests/golden/io_cases.npz (make_golden_io.py)
+
+
+def real_read_cases():
+    """The reference's own 9-mer level table (tests/data/levels.txt) and two of its real test reads
+    (tests/golden/io_cases.npz: samples, move-table mapping and basecalls as the reference's io.Read
+    gives them): k-mer table statistics, per-base levels, rough re-scaling and the refined mapping from
+    the reference's SigMapRefiner.  The 1 MB table itself is not committed; the per-base levels are."""
+    levels_path = os.path.join(make_golden.ref_harness.REFERENCE_ROOT, "tests", "data", "levels.txt")
+    refiner = ref_rsm.SigMapRefiner(kmer_model_filename=levels_path, do_rough_rescale=True, scale_iters=0,
+                                    algo="dwell_penalty", half_bandwidth=5, sd_arr=SD_ARR)
+    io_cases = np.load(os.path.join(HERE, "io_cases.npz"))
+    out = {"kmer_len": np.array(refiner.kmer_len), "center_idx": np.array(refiner.center_idx),
+           "kmer_idx_stats": np.array(refiner.kmer_idx_stats, dtype=np.float64),
+           "table_head": refiner.levels_array[:4096].copy(),
+           "table_crc": np.array(__import__("zlib").crc32(refiner.levels_array.tobytes()))}
+    keys = sorted(k for k in io_cases.files if k.endswith("bc_dacs"))
+    for idx, key in enumerate((keys[0], keys[2])):
+        k = key[: -len("bc_dacs")]
+        dacs, ssm = io_cases[key], io_cases[k + "bc_ssm"]
+        int_seq = io_cases[k + "bc_int_seq"].astype(np.int64)
+        shift, scale = io_cases[k + "bc_shift_scale"]
+        for algo in ("dwell_penalty", "Viterbi"):
+            refiner.algo = algo
+            read = RemoraRead(dacs.copy(), float(shift), float(scale), ssm.copy(), int_seq.copy())
+            read.refine_signal_mapping(refiner)
+            out[f"real{idx}_{algo}_ssm"] = np.asarray(read.seq_to_sig_map).astype(np.int32)
+            out[f"real{idx}_{algo}_shift_scale"] = np.array([read.shift, read.scale])
+        out[f"real{idx}_key"] = np.array(k)
+        out[f"real{idx}_levels"] = refiner.extract_levels(int_seq)
+        print("real read", k, "bases", int_seq.size, "changed",
+              float((out[f"real{idx}_dwell_penalty_ssm"] != ssm).mean()))
+    np.savez_compressed(os.path.join(HERE, "refine_real_cases.npz"), **out)
