@@ -31,14 +31,15 @@ def pipeline_bench(n_reads=128, n_bases=2000):
         inference.infer_from_pod5_and_bam(pod5, bam, (model, md), num_reads=8)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=os.path.join(tmp, "o.bam"))
+        res = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=os.path.join(tmp, "o.bam"),
+                                                reads_per_batch=256)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     calls = sum(len(r["ml"]) for r in res)
     bases = sum(len(t["seq"]) for t in truth.values())
     return {"unit": "reads/s", "value": len(res) / dt, "bases_per_s": bases / dt, "calls_per_s": calls / dt,
             "workload": f"{len(res)} synthetic reads, {bases} bases, {calls} CG calls: POD5 decode (GPU) + BAM join "
-                        "+ rough re-scaling (host) + banded-DP refinement (GPU) + chunk extraction (GPU) + "
+                        "+ rough re-scaling (host) + banded-DP refinement (GPU) + chunk extraction (host) + "
                         "ConvLSTM_w_ref (GPU) + MM/ML tags + BAM output, one process, wall clock",
             "bound": "host (numpy re-scaling, record parsing, tag formatting); the GPU stages are a few percent"}
 

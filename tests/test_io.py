@@ -347,7 +347,7 @@ def test_gpu_infer_from_pod5_and_bam(tmp_path):
                                       eval_only=True)
     out_sam = str(tmp_path / "calls.sam")
     res = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=out_sam, reads_per_batch=5,
-                                            return_probs=True)
+                                            return_probs=True, extract_on_device=True)
     assert len(res) == 12 and all(r["error"] is None for r in res)
     lines = [ln for ln in open(out_sam).read().splitlines() if not ln.startswith("@")]
     assert len(lines) == 12
