@@ -295,6 +295,70 @@ def test_synthetic_run_reads_back(tmp_path):
         got[0][0].into_remora_read(True)
 
 
+class _OracleModel(torch.nn.Module):
+    """CPU stand-in with the B200Model call surface (tests only): logits from the oracle forward."""
+
+    def __init__(self, name):
+        super().__init__()
+        import remora_oracle as ro
+        from conftest import load_golden_model
+        self.ro = ro
+        self.sd, self.md = load_golden_model(name)
+        self.anchor = torch.nn.Parameter(torch.zeros(1), requires_grad=False)
+
+    def forward_compact(self, sig, seq, mp, ln, out=None):
+        res = self.ro.oracle_infer_compact(self.sd, self.md["kmer_context_bases"], sig.numpy(), seq.numpy(),
+                                           mp.numpy(), ln.numpy())
+        return torch.from_numpy(np.ascontiguousarray(res))
+
+
+def test_pipeline_host_logic_on_cpu(tmp_path):
+    """infer_from_pod5_and_bam with every GPU stage switched off or stubbed (oracle forward, numpy signal
+    decode, host chunk extraction, a model without a refiner): the host plumbing - grouping reads, merging
+    chunk batches of different widths, tags, SAM / BAM output, rank sharding - against per-read calls."""
+    pod5, bam, truth = write_synthetic_run(tmp_path, n_reads=7)
+    model = _OracleModel("convlstm_s16_k6_o3")
+    md = dict(model.md)
+    assert not md["sig_map_refiner"].is_loaded
+    kw = dict(decode_on_device=False, extract_on_device=False)
+    out_bam = str(tmp_path / "cpu.bam")
+    res = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=out_bam, reads_per_batch=3,
+                                            batch_size=50, return_probs=True, **kw)
+    assert [r["read_id"] for r in res] == list(truth) and all(r["error"] is None for r in res)
+    with io.BamReader(out_bam) as reader:
+        recs = {r.query_name: r for r in reader}
+    n_called = 0
+    for r in res:
+        t = truth[r["read_id"]]
+        read = data_chunks.RemoraRead(dacs=t["dacs"].copy(), shift=float(t["shift"]), scale=float(t["scale"]),
+                                      seq_to_sig_map=t["ssm"].copy(), str_seq=t["seq"])
+        probs, _, pos = inference.call_read_mods(read, model, md, return_mod_probs=True)
+        if len(pos) == 0:
+            assert r["mm"] == "" and not r["calls"]
+            continue
+        n_called += 1
+        got_pos, got_probs = r["calls"][md["can_base"]]
+        assert np.array_equal(got_pos, pos) and np.allclose(got_probs, probs, atol=1e-5)
+        assert recs[r["read_id"]].get_tag("MM") == r["mm"]
+        assert list(recs[r["read_id"]].get_tag("ML")) == list(r["ml"])
+        assert len(r["ml"]) == len(pos) * len(md["mod_bases"])  # two modified bases -> two MM sections
+        assert r["mm"].count(";") == len(md["mod_bases"])
+    assert n_called >= 5
+    # two ranks: disjoint shards whose union is the single-process result
+    shards = [inference.infer_from_pod5_and_bam(pod5, bam, (model, md), rank=k, world_size=2, **kw)
+              for k in range(2)]
+    ids = [r["read_id"] for sh in shards for r in sh]
+    assert sorted(ids) == sorted(truth) and len(set(ids)) == len(ids) and min(len(sh) for sh in shards) >= 2
+    by_id = {r["read_id"]: r for sh in shards for r in sh}
+    assert all(by_id[r["read_id"]]["mm"] == r["mm"] and by_id[r["read_id"]]["ml"] == r["ml"] for r in res)
+    # SAM output, num_reads
+    out_sam = str(tmp_path / "cpu.sam")
+    few = inference.infer_from_pod5_and_bam(pod5, bam, (model, md), out_path=out_sam, num_reads=2, **kw)
+    assert len(few) == 2
+    lines = [ln for ln in open(out_sam).read().splitlines() if not ln.startswith("@")]
+    assert len(lines) == 2 and all(ln.split("\t")[0] == r["read_id"] for ln, r in zip(lines, few))
+
+
 @pytest.mark.gpu
 def test_gpu_svb16_decode_bit_exact(io_cases, tmp_path):
     """rb200_svb16_decode against the numpy decoder: ragged row lengths around the 32-sample word and
