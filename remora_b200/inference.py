@@ -163,10 +163,12 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
                 except RemoraError as e:
                     res["error"] = str(e)
                     rreads.append(None)
-            live = [r for r in rreads if r is not None]
+            live_idx = [i for i, r in enumerate(rreads) if r is not None]
             refiner = md["sig_map_refiner"]
-            if refiner.is_loaded and live:
-                refiner.refine_reads(live)
+            if refiner.is_loaded and live_idx:
+                for i, msg in zip(live_idx, refiner.refine_reads([rreads[i] for i in live_idx])):
+                    if msg is not None:  # this read alone fails, like a failed read of the reference's prep worker
+                        per_read[i]["error"] = msg
             md_done = dict(md, sig_map_refiner=SigMapRefiner())  # refinement already applied above
             device = next(model.parameters()).device
             motifs = [Motif(*mot) for mot in md["motifs"]]

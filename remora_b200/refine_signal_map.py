@@ -670,9 +670,12 @@ class SigMapRefiner:
         return rescale_theil_sen(filt_dacs, filt_levels, shift, scale)
 
     # -- mapping refinement ----------------------------------------------------------------------
-    def refine_sig_maps(self, shifts, scales, seq_to_sig_maps, int_seqs, dacs_list, levels=None):
+    def refine_sig_maps(self, shifts, scales, seq_to_sig_maps, int_seqs, dacs_list, levels=None, errors=None):
         """Batch form of :meth:`refine_sig_map`: one banded-DP launch per refinement round for all
-        reads.  Returns lists (seq_to_sig_map, shift, scale) per read."""
+        reads.  Returns lists (seq_to_sig_map, shift, scale) per read.  A read whose band is invalid
+        raises ``RemoraError`` like the reference's ``validate_band`` - unless ``errors`` (a list, one
+        slot per read) is given: then the message is stored there, the read keeps its mapping and the
+        rest of the batch goes on."""
         n = len(dacs_list)
         if levels is None:
             levels = [self.extract_levels(s) for s in int_seqs]
@@ -685,7 +688,18 @@ class SigMapRefiner:
         for _ in range(max(1, self.scale_iters)):  # 0 = one round without re-scaling (:486-487)
             if not active:
                 break
-            bands = [compute_seq_band(rel[r], levels[r], self.half_bandwidth) for r in active]
+            bands, ok = [], []
+            for r in active:
+                try:
+                    bands.append(compute_seq_band(rel[r], levels[r], self.half_bandwidth))
+                    ok.append(r)
+                except RemoraError as e:
+                    if errors is None:
+                        raise
+                    errors[r] = str(e)
+            active = ok
+            if not active:
+                break
             paths = banded_dp_batch([trimmed[r] for r in active], [shifts[r] for r in active],
                                     [scales[r] for r in active], [levels[r] for r in active], bands,
                                     self.algo, self.sd_arr, self.device)
@@ -711,22 +725,36 @@ class SigMapRefiner:
     def refine_reads(self, reads):
         """Apply ``RemoraRead.refine_signal_mapping`` (reference data_chunks.py:267-306) to a whole list
         of reads with ONE banded-DP launch per refinement round: rough re-scaling per read on the host,
-        then the batch on the GPU.  Reads are updated in place (shift, scale, seq_to_sig_map)."""
+        then the batch on the GPU.  Reads are updated in place (shift, scale, seq_to_sig_map).
+        Returns one entry per read: ``None``, or the message of the error that read alone would have
+        raised (index error in the re-scaling of a read whose last base has no sample, invalid band ...);
+        such a read is left as it was and does not stop the batch."""
+        errors = [None] * len(reads)
         if not self.is_loaded or not reads:
-            return
+            return errors
         levels = [self.extract_levels(read.int_seq) for read in reads]  # once per read, both steps use them
         if self.do_rough_rescale:
-            for read, lv in zip(reads, levels):
-                read.shift, read.scale = self.rough_rescale(read.shift, read.scale, read.seq_to_sig_map,
-                                                            read.int_seq, read.dacs, levels=lv)
-                read._sig = None
+            for i, (read, lv) in enumerate(zip(reads, levels)):
+                try:
+                    read.shift, read.scale = self.rough_rescale(read.shift, read.scale, read.seq_to_sig_map,
+                                                                read.int_seq, read.dacs, levels=lv)
+                    read._sig = None
+                except (RemoraError, IndexError, ValueError, np.linalg.LinAlgError) as e:
+                    errors[i] = f"rough re-scaling failed: {e}"
         if self.scale_iters >= 0:
+            live = [i for i in range(len(reads)) if errors[i] is None]
+            sub_err = [None] * len(live)
             maps, shifts, scales = self.refine_sig_maps(
-                [r.shift for r in reads], [r.scale for r in reads], [r.seq_to_sig_map for r in reads],
-                [r.int_seq for r in reads], [r.dacs for r in reads], levels=levels)
-            for read, m, sh, sc in zip(reads, maps, shifts, scales):
-                read.seq_to_sig_map, read.shift, read.scale = m, sh, sc
-                read._sig = None
+                [reads[i].shift for i in live], [reads[i].scale for i in live],
+                [reads[i].seq_to_sig_map for i in live], [reads[i].int_seq for i in live],
+                [reads[i].dacs for i in live], levels=[levels[i] for i in live], errors=sub_err)
+            for k, i in enumerate(live):
+                if sub_err[k] is not None:
+                    errors[i] = sub_err[k]
+                    continue
+                reads[i].seq_to_sig_map, reads[i].shift, reads[i].scale = maps[k], shifts[k], scales[k]
+                reads[i]._sig = None
+        return errors
 
     # -- (de)serialisation -------------------------------------------------------------------------
     def asdict(self):
