@@ -27,3 +27,36 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
                           "--gpus", "2", "--steps", "3"], capture_output=True, text=True, timeout=120,
                          env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_bench_line_has_every_contract_key():
+    """The line the final tree printed on a B200 (profiles/, committed) carries every key the driver's
+    contract names, with consistent arithmetic."""
+    import glob
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = sorted(glob.glob(os.path.join(root, "profiles", "bench_r01_v*.json")),
+                  key=lambda p: int("".join(c for c in os.path.basename(p).split("_v")[1] if c.isdigit()) or 0))
+    path = [p for p in path if "reference" not in p and "_n" not in os.path.basename(p)][-1]
+    d = json.load(open(path))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline",
+                "cpu_baseline"):
+        assert key in d, key
+    assert d["unit"] == "chunks/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic" and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"]
+    batch = d["config"]["global_batch"]
+    assert abs(d["value"] - batch / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in d["e2e"], key
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in d["roofline"], key
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in d["cpu_baseline"], key
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
