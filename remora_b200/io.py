@@ -1061,9 +1061,10 @@ def _fb_footer(files):
     return bytes(buf)
 
 
-def write_pod5(path, reads, chunk=102400):
+def write_pod5(path, reads, chunk=102400, rows_per_batch=None):
     """Writes a POD5 file holding ``reads``: iterable of (read_id str, int16 signal, calibration offset,
-    calibration scale).  Signal rows are VBZ chunks of at most ``chunk`` samples like MinKNOW's."""
+    calibration scale).  Signal rows are VBZ chunks of at most ``chunk`` samples like MinKNOW's;
+    ``rows_per_batch`` splits the Arrow tables into several record batches as real files are."""
     import pyarrow as pa
     import pyarrow.ipc as ipc
     sig_ids, sig_blobs, sig_n = [], [], []
@@ -1100,7 +1101,7 @@ def write_pod5(path, reads, chunk=102400):
     for tbl, ctype in ((signal_tbl, 1), (run_tbl, 4), (reads_tbl, 0)):
         sink = pa.BufferOutputStream()
         with ipc.new_file(sink, tbl.schema) as writer:
-            writer.write_table(tbl)
+            writer.write_table(tbl, max_chunksize=rows_per_batch)
         blob = sink.getvalue().to_pybytes()
         files.append((len(out), len(blob), ctype))
         out += blob

@@ -70,6 +70,13 @@ def test_pod5_round_trip(tmp_path):
         with pytest.raises(RemoraError):
             reader.get_read("missing")
     assert [str(r.read_id) for r in io.iter_pod5_reads(path, num_reads=2)] == ids[:2]
+    # several Arrow record batches and small signal chunks (what files written by MinKNOW look like)
+    many = str(tmp_path / "batches.pod5")
+    io.write_pod5(many, reads, chunk=4096, rows_per_batch=3)
+    with io.Pod5Reader(many) as reader:
+        assert reader._tables["signal"].num_record_batches > 5 and reader.read_ids == ids
+        for rid, s, off, sc in reads:
+            assert np.array_equal(reader.get_read(rid).signal, s)
     bad = tmp_path / "bad.pod5"
     bad.write_bytes(b"x" * 100)
     with pytest.raises(RemoraError):
