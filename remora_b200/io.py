@@ -691,6 +691,16 @@ class Pod5Reader:
         ids = self._reads.column("read_id").to_pylist()
         self._ids = [uuid.UUID(bytes=bytes(b)) for b in ids]
         self._row_of = {str(u): i for i, u in enumerate(self._ids)}
+        # the per-read fields the join needs, pulled out of Arrow once
+        names = set(self._reads.schema.names)
+        col = lambda n, default: (self._reads.column(n).to_pylist() if n in names  # noqa: E731
+                                  else [default] * len(ids))
+        self._rec = {n: col(n, d) for n, d in (("signal", []), ("calibration_offset", 0.0),
+                                               ("calibration_scale", 1.0), ("num_samples", 0),
+                                               ("read_number", 0), ("channel", 0))}
+
+    def _record(self, row):
+        return {n: v[row] for n, v in self._rec.items()}
 
     @property
     def read_ids(self):
@@ -715,7 +725,7 @@ class Pod5Reader:
         row = self._row_of.get(str(read_id))
         if row is None:
             raise RemoraError(f"read {read_id} not in {self.path}")
-        rec = self._reads.slice(row, 1).to_pylist()[0]
+        rec = self._record(row)
         parts = [self._signal_row(int(r)) for r in rec["signal"]]
         signal = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int16)
         return Pod5Read(read_id=self._ids[row], signal=signal,
@@ -734,7 +744,7 @@ class Pod5Reader:
             row = self._row_of.get(str(rid))
             if row is None:
                 raise RemoraError(f"read {rid} not in {self.path}")
-            rec = self._reads.slice(row, 1).to_pylist()[0]
+            rec = self._record(row)
             recs.append((row, rec))
             for r in rec["signal"]:
                 b = int(np.searchsorted(self._sig_batch_rows, int(r), side="right") - 1)
