@@ -245,6 +245,119 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# the second bar of SURVEY.md 2.2 / BASELINE.md 3.5: the reference's STOCK GPU path on the same B200
+# ------------------------------------------------------------------------------------------------
+def gpu_stock_baseline(device, steps, warmup):
+    """The reference's own GPU path: its TorchScript module moved to the B200 and called with dense
+    inputs already resident in HBM, `models[can_base](sigs, enc_kmers)` (src/remora/inference.py:311-314,
+    data_chunks.py:528-533) - every op is a cuDNN / cuBLAS / ATen library kernel, none of this repo's.
+    Dense inputs come from the oracle's C encoder (untimed).  fp32 under three TF32 settings: torch's
+    defaults (what `remora infer --device N` gets), TF32 off everywhere, TF32 on everywhere."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import remora_oracle as ro
+    n_b = 16  # 16 x 1024 x 14.8 KB = 242 MB of dense inputs: larger than L2
+    pool = make_pool(n_b, seed=7)
+    enc = ro.encode_kmers_c(KMER_CONTEXT[0], KMER_CONTEXT[1], pool["sequence"],
+                            pool["sequence_to_signal_mapping"], pool["sequence_lengths"])
+    sigs_d = torch.from_numpy(pool["signal"]).to(device)
+    enc_d = torch.from_numpy(np.asarray(enc)).to(device)
+    module = torch.jit.load(MODEL_PT, map_location=device).eval()
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {"what": "reference TorchScript module on this GPU via cuDNN/cuBLAS/ATen, dense (sigs, enc_kmers) "
+                   "resident in HBM (src/remora/inference.py:311-314 semantics), batch 1024, chunk_len 100",
+           "unit": "chunks/s", "steps": steps, "warmup": max(warmup, 8),
+           "torch_default_tf32": {"cudnn": bool(saved[0]), "matmul": bool(saved[1])}}
+    try:
+        with torch.no_grad():
+            for name, tf in (("torch_defaults", saved), ("tf32_off", (False, False)), ("tf32_on", (True, True))):
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+                for i in range(max(warmup, 8)):  # includes the TorchScript profiling runs
+                    sl = slice((i % n_b) * BATCH, (i % n_b + 1) * BATCH)
+                    module(sigs_d[sl], enc_d[sl])
+                torch.cuda.synchronize(device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    sl = slice((i % n_b) * BATCH, (i % n_b + 1) * BATCH)
+                    res = module(sigs_d[sl], enc_d[sl])
+                e1.record()
+                torch.cuda.synchronize(device)
+                ms = e0.elapsed_time(e1)
+                out[name] = {"value": steps * BATCH / (ms * 1e-3), "ms_per_step": ms / steps}
+            out["finite"] = bool(torch.isfinite(res).all())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
+
+
+def config_legs(device, hot_model):
+    """Driver-visible numbers for the other BASELINE.json configs (parity of each is in tests/):
+    config 3 = Conv_w_ref at batch 4096 (stock chunk_len 100 and the chunk_len-200 / 704-input-classifier
+    variant SURVEY.md 8d prescribes), and the reference's dense call form model(sigs, enc_kmers)."""
+    import torch
+    from remora_b200 import model_util
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import remora_oracle as ro
+    from remora_b200.synth import synth_chunks
+    legs = {}
+
+    def timed(fn, n_items, steps=30, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": n_items / (ms * 1e-3), "unit": "chunks/s", "ms_per_step": ms, "steps": steps}
+
+    for name, pt, T in (("conv_w_ref_b4096_T100", "conv_s64_k9.pt", 100),
+                        ("conv_w_ref_b4096_T200_fc704", "conv_s64_k9_T200.pt", 200)):
+        try:
+            model, md = model_util.load_model(os.path.join(ROOT, "tests", "golden", pt), device=device,
+                                              eval_only=True)
+            B = 4096
+            # 8 different batches (8 x 4096 x ~0.5-0.9 KB); activations between layers dominate traffic
+            ds = [synth_chunks(B, T, KMER_CONTEXT, seed=50 + k) for k in range(4)]
+            dev = [[torch.from_numpy(d[k]).to(device) for k in
+                    ("signal", "sequence", "sequence_to_signal_mapping", "sequence_lengths")] for d in ds]
+            it = [0]
+
+            def fn():
+                it[0] += 1
+                model.forward_compact(*dev[it[0] % len(dev)])
+            l0 = model.launch_count
+            legs[name] = timed(fn, B)
+            legs[name].update({"impl": model.last_impl, "batch": B, "chunk_len": T, "dtype": "f32",
+                               "launches_per_step": (model.launch_count - l0) / (legs[name]["steps"] + 5)})
+            del model, dev
+        except Exception as e:  # noqa: BLE001
+            legs[name] = {"error": str(e)[:200]}
+    try:
+        d = make_pool(8, seed=11)
+        enc = ro.encode_kmers_c(KMER_CONTEXT[0], KMER_CONTEXT[1], d["sequence"],
+                                d["sequence_to_signal_mapping"], d["sequence_lengths"])
+        sig_d, enc_d = torch.from_numpy(d["signal"]).to(device), torch.from_numpy(np.asarray(enc)).to(device)
+        it = [0]
+
+        def fn_dense():
+            it[0] += 1
+            sl = slice((it[0] % 8) * BATCH, (it[0] % 8 + 1) * BATCH)
+            hot_model(sig_d[sl], enc_d[sl])
+        legs["dense_interface_b1024_T100"] = timed(fn_dense, BATCH, steps=100)
+        legs["dense_interface_b1024_T100"].update({
+            "impl": hot_model.last_impl, "what": "model(sigs, enc_kmers) with the materialised one-hot, the "
+            "reference's own call form (14.8 KB/chunk read from HBM)"})
+    except Exception as e:  # noqa: BLE001
+        legs["dense_interface_b1024_T100"] = {"error": str(e)[:200]}
+    return legs
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -312,6 +425,12 @@ def ours(args):
                 pending[slot].wait()
                 pending[slot] = None
 
+    # untimed settle phase: touch the whole resident pool once (first-touch page faults, TLB fill, L2
+    # state, PDL ramp), i.e. >= 200 forwards, so that a short --steps window reads the steady state;
+    # the --warmup steps follow as usual
+    for i in range(max(n_pool, 200)):
+        model.forward_compact(*dev_batch(i))
+    torch.cuda.synchronize(device)
     for i in range(args.warmup):
         step(i, last=i == args.warmup - 1)
     drain()
@@ -332,6 +451,35 @@ def ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = model.launch_count - launches0
+
+    # ---- untimed check of the exchange step (N > 1): the gathered ring slot holds, for every rank in
+    # rank order and every step of the group in step order, exactly the logits a single GPU computes for
+    # the same chunks (bitwise: the kernels are batch-invariant).  Every rank ships the compact inputs of
+    # its last group to everybody (bytes over NCCL), recomputes all of them locally and compares.
+    gather_verified = None
+    if distributed:
+        first = ((args.steps - 1) // G) * G           # first step of the last (possibly partial) group
+        n_in_group = args.steps - first
+        slot = (first // G) & 1
+        ok = True
+        for k in range(n_in_group):
+            parts = []
+            for t in dev_batch(first + k):
+                mine = t.contiguous().view(torch.uint8).reshape(-1)
+                everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(everyone, mine)
+                parts.append(everyone.view(world, -1))
+            for r in range(world):
+                shapes = [(BATCH, 1, CHUNK_LEN), dev_pool["sequence"][:BATCH].shape,
+                          dev_pool["sequence_to_signal_mapping"][:BATCH].shape, (BATCH,)]
+                dts = [torch.float32, torch.int8, torch.int16, torch.int16]
+                args_r = [p[r].view(dt).reshape(tuple(sh)) for p, dt, sh in zip(parts, dts, shapes)]
+                want = model.forward_compact(*args_r)
+                got = gath_ring[slot].view(world, G, BATCH, -1)[r, k]
+                ok = ok and bool(torch.equal(got, want))
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_verified = bool(flag.item())
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -454,7 +602,10 @@ def ours(args):
                                                  "this rank only"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "settle": f"{max(n_pool, 200)} untimed forwards over the whole pool before the {args.warmup} warm-up steps",
         }
+        if gather_verified is not None:
+            line["gather_verified"] = gather_verified
         if prof is not None:
             sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
             fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # FFMA2 issue peak at the sampled clock
@@ -509,6 +660,23 @@ def ours(args):
             "chunks": enc_n, "ms": enc_ms, "l2": "flushed between launches",
         }
         if world == 1:
+            try:
+                line["gpu_stock_baseline"] = gpu_stock_baseline(device, steps=min(args.steps, 200),
+                                                                warmup=args.warmup)
+                best = max(v["value"] for k, v in line["gpu_stock_baseline"].items()
+                           if isinstance(v, dict) and "value" in v)
+                line["gpu_stock_baseline"]["ours_over_best_stock"] = value / best
+            except Exception as e:  # noqa: BLE001
+                line["gpu_stock_baseline"] = {"error": str(e)[:300]}
+            try:
+                line["configs"] = config_legs(device, model)
+                stock = line["gpu_stock_baseline"]
+                if "torch_defaults" in stock and "value" in line["configs"].get("dense_interface_b1024_T100", {}):
+                    line["configs"]["dense_interface_b1024_T100"]["over_stock_cudnn_same_interface"] = (
+                        line["configs"]["dense_interface_b1024_T100"]["value"] /
+                        max(stock[k]["value"] for k in ("torch_defaults", "tf32_off", "tf32_on")))
+            except Exception as e:  # noqa: BLE001
+                line["configs"] = {"error": str(e)[:300]}
             line["cpu_baseline"] = run_cpu_sample()
             try:  # rows of SURVEY.md 8f measured beside the headline (never allowed to break the line)
                 sys.path.insert(0, os.path.join(ROOT, "scripts"))

@@ -51,8 +51,13 @@ enum rb200_impl {
     RB200_IMPL_LAYERS = 1,  /* one plain CUDA kernel per layer, any size / kmer_len / chunk_len */
     RB200_IMPL_FUSED = 2,   /* fused sm_100a kernels (ConvLSTM_w_ref, size 64), fp32 FFMA2; error if n/a */
     RB200_IMPL_FUSED_TC = 3, /* same, merge conv + LSTM input projection on tcgen05 (3xTF32, TMEM) */
-    RB200_IMPL_TILED = 4 /* per layer: register-tiled FFMA2 convolutions, gather-form seq_conv1 from the
-                            compact arrays; Conv_w_ref and every shape the fused kernels do not take */
+    RB200_IMPL_TILED = 4, /* per layer: register-tiled FFMA2 convolutions, gather-form seq_conv1 from the
+                             compact arrays; Conv_w_ref and every shape the fused kernels do not take */
+    RB200_IMPL_FUSED_MEGA = 5, /* ConvLSTM_w_ref size 64, chunk_len <= 100: ONE kernel per batch, every
+                                  GEMM-shaped layer on tcgen05 with fp16 hi/lo split operands (three
+                                  products, fp32 TMEM accumulators): fp32 parity (1e-4).  AUTO picks it */
+    RB200_IMPL_FUSED_BF16 = 6  /* the same kernel with single-pass bf16 operands (BASELINE configs[1]
+                                  "bf16"): fp32 accumulate and gates, its own tolerance; never picked by AUTO */
 };
 
 #define RB200_MAX_CONVS 4
@@ -105,6 +110,12 @@ int rb200_set_debug(rb200_handle h, int keep); /* keep layer outputs of the next
  * sig3 seq1 seq2 seq3 merge1..merge4 lstm1 lstm2.  *n_floats receives the element count. */
 int rb200_debug_tensor(rb200_handle h, const char *name, float *dst_dev, int64_t capacity,
                        int64_t *n_floats, int32_t *channels, int32_t *steps, void *stream);
+
+/* Sticky diagnostics of the fp16-split single-kernel path: *flags bit 0 is set once an intermediate
+ * activation left the fp16 range (|x| >= 65504; it was saturated, results of that call are not to be
+ * trusted - rerun with RB200_IMPL_FUSED_TC, whose operands are fp32-ranged).  Synchronises the device;
+ * clear != 0 resets the flags. */
+int rb200_get_flags(rb200_handle h, int32_t *flags, int clear);
 
 /* Per-kernel device timing of the fused path (CUDA events recorded on the caller's stream between
  * K1/K2/K3).  rb200_set_profile(h, 1) enables it and zeroes the accumulators;

@@ -11,7 +11,7 @@ from . import RemoraError
 MAX_CONVS = 4
 ARCH_CONVLSTM_W_REF = 1
 ARCH_CONV_W_REF = 2
-IMPL_AUTO, IMPL_LAYERS, IMPL_FUSED, IMPL_FUSED_TC, IMPL_TILED = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_LAYERS, IMPL_FUSED, IMPL_FUSED_TC, IMPL_TILED, IMPL_FUSED_MEGA, IMPL_FUSED_BF16 = 0, 1, 2, 3, 4, 5, 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "librb200.so")
 
@@ -22,6 +22,7 @@ EXPORTS = (
     "rb200_encode_dense", "rb200_forward_dense", "rb200_forward_compact", "rb200_infer_host",
     "rb200_softmax_ml", "rb200_set_profile", "rb200_get_profile", "rb200_infer_host_async", "rb200_chunk_plan", "rb200_chunk_fill",
     "rb200_refine_normalize", "rb200_refine_scratch_bytes", "rb200_refine_dp", "rb200_svb16_decode",
+    "rb200_get_flags",
 )
 
 
@@ -89,6 +90,7 @@ def load_library():
     lib.rb200_refine_dp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp,
                                     vp, vp, vp, vp, vp]
     lib.rb200_svb16_decode.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.rb200_get_flags.argtypes = [vp, ctypes.POINTER(i32), ctypes.c_int]
     lib.rb200_set_profile.argtypes = [vp, ctypes.c_int]
     lib.rb200_get_profile.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 3),
                                       ctypes.POINTER(i32)]

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librb200.so")
 SOURCES = ["rb200_api.cu", "rb200_encode.cu", "rb200_layers.cu", "rb200_fused.cu", "rb200_chunks.cu",
-           "rb200_tiled.cu", "rb200_refine.cu", "rb200_vbz.cu"]
+           "rb200_tiled.cu", "rb200_refine.cu", "rb200_vbz.cu", "rb200_mega.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Wno-deprecated-gpu-targets",
@@ -25,7 +25,8 @@ NVCC_FLAGS = [
 
 def _digest():
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + [os.path.join(ROOT, "include", "remora_b200.h")]
+    files = sorted(n for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h"))) + \
+        [os.path.join(ROOT, "include", "remora_b200.h")]
     for name in files:
         path = name if os.path.isabs(name) else os.path.join(CSRC, name)
         with open(path, "rb") as fh:

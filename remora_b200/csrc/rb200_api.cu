@@ -132,9 +132,20 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
     const bool fused_ok =
         m->fused != nullptr && fused_shape_ok(m, T, compact ? seq_width : m->desc.kmer_len,
                                               compact ? map_width : 2);
-    // AUTO prefers the tensor-core variant of the fused path (falls back to FFMA2 inside when the
-    // CTA's rows do not fit two M tiles)
-    if (impl == RB200_IMPL_AUTO) impl = fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_TILED;
+    // AUTO: the single-kernel path when the shape qualifies (compact arrays, chunk_len <= 100), else the
+    // three-kernel tensor-core path (falls back to FFMA2 inside when the CTA's rows do not fit two M
+    // tiles), else the tiled layer kernels
+    const bool mega_ok = compact && mega_shape_ok(m, T, seq_width, map_width);
+    if (impl == RB200_IMPL_AUTO)
+        impl = mega_ok ? RB200_IMPL_FUSED_MEGA : fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_TILED;
+    if (impl == RB200_IMPL_FUSED_MEGA || impl == RB200_IMPL_FUSED_BF16) {
+        if (!mega_ok) {
+            set_error("single-kernel path not available for this model/shape/input form");
+            return RB200_ERR_UNSUPPORTED;
+        }
+        return mega_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T, logits, stream,
+                                    impl == RB200_IMPL_FUSED_BF16 ? 1 : 0);
+    }
     if (impl == RB200_IMPL_FUSED || impl == RB200_IMPL_FUSED_TC) {
         if (!fused_ok) {
             set_error("fused kernels not available for this model/shape/input form");
@@ -208,7 +219,10 @@ int rb200_create(const rb200_model_desc *desc, const float *weights_host, int64_
     }
     rc = tiled_create(m, weights_host);
     if (rc == RB200_OK && fused_supported(m->desc)) rc = fused_create(m, weights_host);
+    if (rc == RB200_OK && mega_supported(m->desc)) rc = mega_create(m, weights_host);
     if (rc) {
+        fused_destroy(m);
+        mega_destroy(m);
         tiled_destroy(m);
         cudaFree(m->blob_dev);
         delete m;
@@ -224,6 +238,7 @@ int rb200_destroy(rb200_handle h) {
     cudaDeviceSynchronize();
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     fused_destroy(h);
+    mega_destroy(h);
     tiled_destroy(h);
     for (auto &kv : h->workspaces) kv.second.release();
     for (auto &kv : h->host_staging) kv.second.release();
@@ -239,9 +254,13 @@ int rb200_destroy(rb200_handle h) {
 }
 
 int rb200_set_impl(rb200_handle h, int impl) {
-    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_TILED, "bad argument");
+    RB200_REQUIRE(h && impl >= RB200_IMPL_AUTO && impl <= RB200_IMPL_FUSED_BF16, "bad argument");
     if ((impl == RB200_IMPL_FUSED || impl == RB200_IMPL_FUSED_TC) && h->fused == nullptr) {
         set_error("fused kernels not available for this model");
+        return RB200_ERR_UNSUPPORTED;
+    }
+    if ((impl == RB200_IMPL_FUSED_MEGA || impl == RB200_IMPL_FUSED_BF16) && h->mega == nullptr) {
+        set_error("single-kernel path not available for this model");
         return RB200_ERR_UNSUPPORTED;
     }
     h->impl = impl;
@@ -249,6 +268,16 @@ int rb200_set_impl(rb200_handle h, int impl) {
 }
 
 int rb200_last_impl(rb200_handle h) { return h ? h->last_impl : 0; }
+
+int rb200_get_flags(rb200_handle h, int32_t *flags, int clear) {
+    RB200_REQUIRE(h && flags, "null argument");
+    DeviceGuard guard(h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    int v = 0;
+    int rc = mega_read_flags(h, &v, clear != 0);
+    *flags = v;
+    return rc;
+}
 
 uint64_t rb200_launch_count(rb200_handle h) { return h ? h->launches.load() : 0; }
 

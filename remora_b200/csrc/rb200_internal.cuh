@@ -64,6 +64,7 @@ struct DebugTensor {
 
 struct FusedWeights;  // rb200_fused.cu
 struct TiledWeights;  // rb200_tiled.cu
+struct MegaWeights;   // rb200_mega.cu
 
 }  // namespace rb200
 
@@ -83,6 +84,7 @@ struct rb200_model {
     std::map<void *, rb200::Workspace> host_staging;  // device-side input/output staging of rb200_infer_host_async
     rb200::FusedWeights *fused = nullptr;           // non-null when the fused path applies
     rb200::TiledWeights *tiled = nullptr;           // weight layouts of the register-tiled layer kernels
+    rb200::MegaWeights *mega = nullptr;             // single-kernel path (rb200_mega.cu)
     // pinned + device staging for rb200_infer_host
     char *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -165,5 +167,15 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
                           int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
                           int B, int T, float *logits, cudaStream_t stream, bool want_tc,
                           const float *enc_dense = nullptr);
+
+// rb200_mega.cu : ConvLSTM_w_ref size 64 as one kernel per batch (fp16 hi/lo split or bf16 operands)
+bool mega_supported(const rb200_model_desc &d);
+int mega_create(rb200_model *m, const float *blob_host);
+void mega_destroy(rb200_model *m);
+bool mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
+int mega_read_flags(rb200_model *m, int *out, bool clear);
+int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
+                         const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
+                         cudaStream_t stream, int mode);
 
 }  // namespace rb200

@@ -1,0 +1,1150 @@
+// ConvLSTM_w_ref (size 64) as ONE sm_100a kernel per batch: compact chunk arrays in, logits out,
+// nothing but 8 B/chunk of logits ever leaves the SM.
+//
+// Reference semantics: models/ConvLSTM_w_ref.py:39-58 (eval BatchNorm folded into the convolutions),
+// k-mer one-hot of src/remora/encoded_kmers.pyx:13-45 fused into seq_conv1 as a gather-add.
+//
+// Shape of the kernel:
+//   * a CTA owns G = 4 chunks; its activations live in shared memory as MMA-ready tiles whose row index is
+//     chunk * 32 + t (28 valid output steps + 4 rows of slack per chunk), i.e. exactly one M = 128 tile.
+//     113 KB of shared memory, 256 TMEM columns and 256 threads x 128 registers per CTA, so TWO CTAs share
+//     an SM: while one walks the 24-step LSTM chain (latency bound, FFMA2) the other one runs its
+//     convolutions on the tensor cores - the hardware interleaves the two dependency chains.
+//   * every GEMM-shaped layer (sig_conv3, seq_conv2, merge_conv1, LSTM1 input projection) is a
+//     tcgen05.mma kind::f16 with fp32 accumulators in TMEM.  Operand tiles are K-major WITHOUT swizzle,
+//     stored [16-byte K chunk][row]: an 8-row core matrix is 128 contiguous bytes (SBO = 128 B), K chunks
+//     are LBO = rows * 16 B apart, and a descriptor whose start address is advanced by i * 16 B reads the
+//     tile shifted down by i rows.  A stride-1 convolution tap is therefore a descriptor shift (no
+//     im2col); for the two stride-3 convolutions the producing layer writes its output de-interleaved by
+//     t mod 3 into three tiles, which turns tap j = 3 i + r into "tile r shifted by i rows".
+//   * fp32 parity (1e-4 on the logits) with half-precision tensor-core operands: MODE 0 splits every
+//     operand into fp16 hi + lo (22 significant bits, weights pre-scaled by a power of two per layer so
+//     their lo parts stay normal) and issues a*b ~= ah*bh + ah*bl + al*bh.  ah*[bh;bl] is ONE N = 128
+//     MMA (the weight tile stacks hi and lo rows), al*bh an N = 64 MMA into the correction columns.
+//     Compared with 3xTF32 the operand bytes and the instruction count halve.  MODE 1 is the bf16 variant
+//     (BASELINE.json configs[1]): one pass, bf16 operands, fp32 accumulate, fp32 gates.
+//   * weights stream from L2 through a 4-stage ring of 8 KB TMA bulk copies (mbarrier full/empty,
+//     tcgen05.commit frees a stage); one elected thread issues TMA and MMA.
+//   * the recurrence keeps W_hh in registers (thread = 4 gate rows x 16 k, transposing shuffle butterfly),
+//     reads the input projection from shared memory ([t][chunk][256], drained from TMEM once), then does
+//     the single needed step of the reversed LSTM2 and the classifier.
+//   * consecutive batches overlap: the kernel triggers its dependents at once (PDL) and only orders its
+//     final 8 B/chunk store after the previous grid (griddepcontrol.wait), it has no global scratch.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "rb200_internal.cuh"
+
+namespace rb200 {
+namespace mega {
+
+constexpr int SIZE = 64;
+constexpr int G = 4;                 // chunks per CTA
+constexpr int U = 32;                // tile rows per chunk
+constexpr int MROWS = G * U;         // 128 = MMA M
+constexpr int RP = MROWS + 8;        // rows stored per K chunk (tap shifts read up to 4 rows past row 127)
+constexpr int LBO_A = RP * 16;       // byte distance between K chunks of an activation tile (2176)
+constexpr int THREADS = 256;
+constexpr int KW_SIG1 = 5, KW_SIG2 = 5, KW_SIG3 = 9, KW_SEQ1 = 5, KW_SEQ2 = 13, KW_MRG = 5;
+constexpr int GROW = 20;             // floats per gather-table row (16 + 4 pad)
+constexpr int STAGE_BYTES = 8192;    // one weight stage
+constexpr int RING = 4;
+constexpr int TMEM_COLS = 256;
+constexpr int HG = 16 * G + 4;       // floats per k-group of h
+constexpr int XPS = G * 256 + 4;     // floats per time step of the staged input projection
+constexpr int MAX_T3 = U - (KW_MRG - 1);  // 28
+constexpr int MAX_TM = MAX_T3 - (KW_MRG - 1);  // 24
+
+// ---- constants blob (floats), copied to shared memory once per CTA ------------------------------------
+constexpr int C_WSIG1 = 0;      // [j][co]            20
+constexpr int C_BSIG1 = 20;     //                     4
+constexpr int C_WSIG2 = 24;     // [j][ci][co]       320
+constexpr int C_BSIG2 = 344;    //                    16
+constexpr int C_BSEQ1 = 360;    //                    16
+constexpr int C_BSIG3 = 376;    //                    64
+constexpr int C_BSEQ2 = 440;    //                    64
+constexpr int C_BMRG = 504;     //                    64
+constexpr int C_SCALE = 568;    // inverse weight scales: seq2, sig3, merge, xproj (+4 pad)
+constexpr int C_B1 = 576;       // LSTM1 bias        256
+constexpr int CONST_FLOATS = 832;
+constexpr int CONST_BYTES = CONST_FLOATS * 4;  // 3328
+
+// ---- shared memory map (bytes) ------------------------------------------------------------------------
+constexpr int OFF_BARS = 0;
+constexpr int OFF_CONST = 256;
+constexpr int OFF_TILES = 3840;                          // h, g, y of the recurrence
+constexpr int TILES_BYTES = (4 * HG + G * 256 + G * SIZE) * 4;  // 6208
+constexpr int OFF_RING = 10112;
+constexpr int OFF_A = OFF_RING + RING * STAGE_BYTES;     // 42880
+constexpr int XT_BYTES = 2 * LBO_A;                      // one residue tile, one of hi/lo: 2 K chunks
+constexpr int XSET_BYTES = 6 * XT_BYTES;                 // 3 residues x {hi, lo} = 26112
+constexpr int CAT_HALF = 16 * LBO_A;                     // 34816: 128 channels, hi (or lo)
+constexpr int M_HALF = 8 * LBO_A;                        // 17408
+constexpr int A_BYTES = 2 * CAT_HALF;                    // 69632
+constexpr int A_GS = 0, GS_CAP = 32768;                  // per-base gather sums
+constexpr int A_XS = 0;                                  // signal-track tiles (over the dead gather sums)
+constexpr int A_TAB = 32768, TAB_CAP = XSET_BYTES;       // gather table, then the sequence-track tiles
+constexpr int A_XQ = 32768;
+constexpr int A_S1 = A_TAB + TAB_CAP;                    // 58880: sig_conv1 output [G][T1][4] fp32
+constexpr int A_STG = A_S1 + G * 96 * 16;                // 65024: staged compact inputs
+constexpr int STG_SIG = 0, STG_SIDX = 1600, STG_SEQ = 2400, STG_MAP = 3040, STG_LEN = 4080;
+constexpr int MAX_T = 100, MAX_SEQ_W = 160, MAX_MAP_W = 130;
+constexpr int SMEM_BYTES = OFF_A + A_BYTES;              // 112512  (two CTAs per SM: <= 115712)
+static_assert(OFF_TILES + TILES_BYTES <= OFF_RING, "tiles overlap the ring");
+static_assert(A_STG + STG_LEN + 16 <= A_BYTES, "staging does not fit region A");
+static_assert(OFF_RING + MAX_TM * XPS * 4 <= SMEM_BYTES, "staged projection does not fit");
+static_assert(SMEM_BYTES <= 115712, "two CTAs per SM need <= 113 KB each");
+
+struct Bars {
+    uint64_t w_full[RING], w_empty[RING], front, seq_done, conv_done, mrg_done, xp_done;
+    uint32_t tmem_base;
+};
+
+struct Params {
+    const float *sigs;
+    const int8_t *seqs;
+    const int16_t *maps;
+    const int16_t *lens;
+    int seq_width, map_width, B, T, kmer_len, num_out;
+    const float *consts;     // CONST_FLOATS
+    const float *gtab;       // seq_conv1 gather table [tap][kmer pos][base][GROW] + one zero row
+    int gtab_bytes;
+    const uint8_t *wstream;  // weight stages in execution order
+    const float4 *whh4;      // W_hh1 in the register layout of the recurrence
+    const float *wih2T, *b2, *fcw, *fcb;
+    float *logits;
+    float *dbg_cat, *dbg_m, *dbg_xp;  // optional canonical [B][C][T] copies of the intermediates
+    int *flags;                       // [0] != 0: an activation left the fp16 range (MODE 0)
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float2 ffma2(float2 a, float b, float2 c) { return __ffma2_rn(a, make_float2(b, b), c); }
+
+// K-major, no swizzle: start address, LBO = distance between 16-byte K chunks, SBO = 128 B (8 rows x 16 B)
+__device__ __forceinline__ uint64_t desc_ns(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// D = f32; A, B = f16 (0) or bf16 (1), both K-major; N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t idesc_h(int M, int N, int bf16) {
+    return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_h(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void nbar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// ---- fp32 -> operand conversion: 8 consecutive channels = one 16-byte K chunk --------------------------
+// MODE 0: hi = rn_f16(a) (saturating), lo = rn_f16(a - hi); MODE 1: bf16(a), no lo tile.
+template <int MODE>
+__device__ __forceinline__ uint32_t pack2(float a0, float a1) {
+    uint32_t r;
+    if (MODE == 0)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a1), "f"(a0));
+    else
+        asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a1), "f"(a0));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t r) {
+    __half2 h;
+    memcpy(&h, &r, 4);
+    return __half22float2(h);
+}
+template <int MODE>
+__device__ __forceinline__ void store_chunk8(uint8_t *tile_hi, uint8_t *tile_lo, int off, const float (&v)[8]) {
+    uint32_t hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hi[e] = pack2<MODE>(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4 *>(tile_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (MODE == 0) {
+        uint32_t lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 h = unpack_h2(hi[e]);
+            lo[e] = pack2<0>(v[2 * e] - h.x, v[2 * e + 1] - h.y);
+        }
+        *reinterpret_cast<uint4 *>(tile_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---- weight stream geometry ----------------------------------------------------------------------------
+// MODE 0: B tiles stack hi rows then lo rows (N = 128; projection: separate hi / lo stages of N = 256).
+// MODE 1: N = 64 (projection 256), twice the K extent per 8 KB stage.
+template <int MODE>
+struct Cfg {
+    static constexpr int NB = MODE == 0 ? 128 : 64;                // rows of a conv / merge B tile
+    static constexpr int B_LBO = NB * 16;                          // K-chunk distance in those tiles
+    static constexpr int TAPS = STAGE_BYTES / (2 * B_LBO);         // stride-3 conv taps per stage: 2 | 4
+    static constexpr int NS_SEQ = (KW_SEQ2 + TAPS - 1) / TAPS;     // 7 | 4
+    static constexpr int NS_SIG = (KW_SIG3 + TAPS - 1) / TAPS;     // 5 | 3
+    static constexpr int MRG_KC = STAGE_BYTES / B_LBO;             // K chunks (8 channels) per merge stage: 4 | 8
+    static constexpr int NS_MRG = KW_MRG * (16 / MRG_KC);          // 20 | 10
+    static constexpr int NS_XP = MODE == 0 ? 8 : 4;                // projection: k16 x {hi, lo} | k16
+    static constexpr int NS_TOTAL = NS_SEQ + NS_SIG + NS_MRG + NS_XP;
+};
+
+__device__ __forceinline__ void load_stage(int s, int total, const uint8_t *wstream, uint8_t *ring, Bars *bars) {
+    if (s >= total) return;
+    const int slot = s & (RING - 1);
+    if (s >= RING) mbar_wait(&bars->w_empty[slot], ((s >> 2) - 1) & 1);
+    mbar_expect_tx(&bars->w_full[slot], STAGE_BYTES);
+    bulk_g2s(ring + slot * STAGE_BYTES, wstream + (size_t)s * STAGE_BYTES, STAGE_BYTES, &bars->w_full[slot]);
+}
+
+// one stride-3 convolution (16 input channels): tap j = 3 i + r reads residue tile r shifted by i rows
+template <int MODE, int KW>
+__device__ __forceinline__ void issue_conv3(uint32_t xset, uint32_t d_tmem, int &s, const uint8_t *wstream,
+                                            uint8_t *ring, Bars *bars) {
+    using C = Cfg<MODE>;
+    constexpr int NS = (KW + C::TAPS - 1) / C::TAPS;
+    constexpr uint32_t id_main = idesc_h(128, C::NB, MODE), id_corr = idesc_h(128, 64, MODE);
+    for (int st = 0; st < NS; ++st, ++s) {
+        const int slot = s & (RING - 1);
+        mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
+        tc_fence_after();
+        const uint32_t b0 = smem_addr(ring + slot * STAGE_BYTES);
+#pragma unroll
+        for (int tp = 0; tp < C::TAPS; ++tp) {
+            const int j = st * C::TAPS + tp;
+            if (j < KW) {
+                const int r = j % 3, i = j / 3;
+                const uint32_t a_hi = xset + (2 * r) * XT_BYTES + i * 16;
+                const uint32_t b = b0 + tp * 2 * C::B_LBO;
+                mma_h(d_tmem, desc_ns(a_hi, LBO_A), desc_ns(b, C::B_LBO), id_main, j ? 1u : 0u);
+                if (MODE == 0)
+                    mma_h(d_tmem + 64, desc_ns(a_hi + XT_BYTES, LBO_A), desc_ns(b, C::B_LBO), id_corr, 1u);
+            }
+        }
+        umma_commit(&bars->w_empty[slot]);
+        load_stage(s + RING - 1, C::NS_TOTAL, wstream, ring, bars);
+    }
+}
+
+// ---- recurrence helpers (same scheme as rb200_fused.cu K3, one half-batch of 4 chunks) ------------------
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int mask) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+}
+__device__ __forceinline__ float2 sel2(bool take_a, float2 a, float2 b) {
+    return make_float2(take_a ? a.x : b.x, take_a ? a.y : b.y);
+}
+// gate pre-activations: g[c][r] = xin[c] + sum_k W_hh[r][k] h[k][c]; thread (rb = tid >> 2, kg = tid & 3) holds
+// W_hh[4 rb .. 4 rb + 3][16 kg .. 16 kg + 15]; two-round transposing butterfly leaves row tid in this thread
+__device__ __forceinline__ void lstm_matvec(const float (&w)[4][16], const float *__restrict__ hk,
+                                            const float (&xin)[G], float *__restrict__ g_s, int r, bool hi2,
+                                            bool hi1) {
+    float2 a[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i][0] = a[i][1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int kl = 0; kl < 16; ++kl) {
+        const float4 hv = *reinterpret_cast<const float4 *>(hk + kl * G);
+        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i][0] = ffma2(h01, w[i][kl], a[i][0]);
+            a[i][1] = ffma2(h23, w[i][kl], a[i][1]);
+        }
+    }
+    float2 rA[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const float2 send = sel2(hi2, a[j][p], a[2 + j][p]);
+            const float2 keep = sel2(hi2, a[2 + j][p], a[j][p]);
+            rA[j][p] = __fadd2_rn(keep, shfl_xor2(send, 2));
+        }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const float2 send = sel2(hi1, rA[0][p], rA[1][p]);
+        const float2 keep = sel2(hi1, rA[1][p], rA[0][p]);
+        const float2 g2 = __fadd2_rn(keep, shfl_xor2(send, 1));
+        g_s[(2 * p) * 256 + r] = g2.x + xin[2 * p];
+        g_s[(2 * p + 1) * 256 + r] = g2.y + xin[2 * p + 1];
+    }
+}
+
+// =========================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant__ Params p) {
+    using CF = Cfg<MODE>;
+    extern __shared__ __align__(128) uint8_t sm[];
+    Bars *bars = reinterpret_cast<Bars *>(sm + OFF_BARS);
+    float *cst = reinterpret_cast<float *>(sm + OFF_CONST);
+    float *h_s = reinterpret_cast<float *>(sm + OFF_TILES);
+    float *g_s = h_s + 4 * HG;
+    float *y_s = g_s + G * 256;
+    uint8_t *ring = sm + OFF_RING;
+    uint8_t *ra = sm + OFF_A;
+    float *xp_s = reinterpret_cast<float *>(sm + OFF_RING);  // recurrence phase: over the ring and region A
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk0 = blockIdx.x * G;
+    const int C = min(G, p.B - chunk0);
+    const int T = p.T, T1 = T - (KW_SIG1 - 1), T2 = T1 - (KW_SIG2 - 1), Q1 = T - (KW_SEQ1 - 1);
+    const int T3 = (T2 - KW_SIG3) / 3 + 1, TM = T3 - (KW_MRG - 1);
+    const int seq_width = p.seq_width, map_width = p.map_width, K = p.kmer_len;
+
+    pdl_launch_dependents();  // the next batch may start as soon as SM resources free up
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(&bars->w_full[i], 1);
+            mbar_init(&bars->w_empty[i], 1);
+        }
+        mbar_init(&bars->front, 1);
+        mbar_init(&bars->seq_done, 1);
+        mbar_init(&bars->conv_done, 1);
+        mbar_init(&bars->mrg_done, 1);
+        mbar_init(&bars->xp_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_addr(&bars->tmem_base)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) {
+        mbar_expect_tx(&bars->front, CONST_BYTES + p.gtab_bytes);
+        bulk_g2s(cst, p.consts, CONST_BYTES, &bars->front);
+        bulk_g2s(ra + A_TAB, p.gtab, p.gtab_bytes, &bars->front);
+        for (int s = 0; s < RING - 1; ++s) load_stage(s, CF::NS_TOTAL, p.wstream, ring, bars);
+    }
+
+    // ---- P0: stage the compact inputs, move-table expansion ------------------------------------------------
+    float *sig_s = reinterpret_cast<float *>(ra + A_STG + STG_SIG);
+    int16_t *sidx_s = reinterpret_cast<int16_t *>(ra + A_STG + STG_SIDX);
+    int8_t *seq_s = reinterpret_cast<int8_t *>(ra + A_STG + STG_SEQ);
+    int16_t *map_s = reinterpret_cast<int16_t *>(ra + A_STG + STG_MAP);
+    int *len_s = reinterpret_cast<int *>(ra + A_STG + STG_LEN);
+    for (int i = tid; i < C * T; i += THREADS) {
+        sig_s[i] = p.sigs[(size_t)chunk0 * T + i];
+        sidx_s[i] = -1;
+    }
+    if (tid < C) {
+        int L = p.lens[chunk0 + tid];
+        L = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
+        len_s[tid] = L;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * seq_width; i += THREADS) {
+        const int c = i / seq_width, s = i - c * seq_width;
+        // padding past seq_len + kmer_len - 1 is uninitialised in the reference's arrays: never read
+        seq_s[i] = s < len_s[c] + K - 1 ? p.seqs[(size_t)(chunk0 + c) * seq_width + s] : (int8_t)-1;
+    }
+    for (int i = tid; i < C * map_width; i += THREADS) {
+        const int c = i / map_width, s = i - c * map_width;
+        map_s[i] = s <= len_s[c] ? p.maps[(size_t)(chunk0 + c) * map_width + s] : (int16_t)0;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * (map_width - 1); i += THREADS) {
+        const int c = i / (map_width - 1), s = i - c * (map_width - 1);
+        if (s < len_s[c]) {
+            const int st = max((int)map_s[c * map_width + s], 0);
+            const int en = min((int)map_s[c * map_width + s + 1], T);
+            for (int t = st; t < en; ++t) sidx_s[c * T + t] = (int16_t)s;
+        }
+    }
+    mbar_wait(&bars->front, 0);  // constants and the gather table have landed
+    __syncthreads();
+
+    // ---- P1: seq_conv1 on the (virtual) one-hot = gather-add of weight columns -> residue tiles ------------
+    const int LM = map_width - 1;
+    const bool two_stage = C * LM * KW_SEQ1 * GROW * 4 <= GS_CAP;
+    uint8_t *xq = ra + (two_stage ? A_XQ : A_XS);
+    {
+        const float *gt = reinterpret_cast<const float *>(ra + A_TAB);
+        const int zero_off = KW_SEQ1 * K * 4 * GROW;  // all-zero row: N bases contribute nothing
+        float *gs = reinterpret_cast<float *>(ra + A_GS);
+        if (two_stage) {
+            // every sample covered by the same base shares its k-mer: sum the k columns once per (base, tap)
+            for (int i = tid; i < C * LM * KW_SEQ1; i += THREADS) {
+                const int j = i % KW_SEQ1;
+                const int cs = i / KW_SEQ1;
+                const int c = cs / LM, sb = cs - c * LM;
+                if (sb >= len_s[c]) continue;
+                float2 a[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) a[o] = make_float2(0.f, 0.f);
+                const int8_t *sp = seq_s + c * seq_width + sb;
+                const int joff = j * K * 4 * GROW;
+                for (int pp = 0; pp < K; ++pp) {
+                    const int base = sp[pp];
+                    const int off = (base >= 0 && base <= 3) ? joff + (pp * 4 + base) * GROW : zero_off;
+                    const float4 *wv = reinterpret_cast<const float4 *>(gt + off);
+                    const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
+                    a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+                    a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+                    a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+                    a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+                    a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+                    a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+                    a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+                    a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+                }
+                float4 *dst = reinterpret_cast<float4 *>(gs + (size_t)i * GROW);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) dst[o] = make_float4(a[2 * o].x, a[2 * o].y, a[2 * o + 1].x, a[2 * o + 1].y);
+            }
+            __syncthreads();  // sums complete; the table is dead: the sequence tiles may overwrite it
+        }
+        const float *b = cst + C_BSEQ1;
+        for (int i = tid; i < C * Q1; i += THREADS) {
+            const int c = i / Q1, t = i - c * Q1;
+            float2 a[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
+#pragma unroll
+            for (int j = 0; j < KW_SEQ1; ++j) {
+                const int sb = sidx_s[c * T + t + j];
+                if (sb < 0) continue;  // sample not covered by any base: no one-hot entries
+                if (two_stage) {
+                    const float4 *gv =
+                        reinterpret_cast<const float4 *>(gs + ((size_t)(c * LM + sb) * KW_SEQ1 + j) * GROW);
+                    const float4 v0 = gv[0], v1 = gv[1], v2 = gv[2], v3 = gv[3];
+                    a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+                    a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+                    a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+                    a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+                    a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+                    a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+                    a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+                    a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+                } else {
+                    const int8_t *sp = seq_s + c * seq_width + sb;
+                    const int joff = j * K * 4 * GROW;
+                    for (int pp = 0; pp < K; ++pp) {
+                        const int base = sp[pp];
+                        const int off = (base >= 0 && base <= 3) ? joff + (pp * 4 + base) * GROW : zero_off;
+                        const float4 *wv = reinterpret_cast<const float4 *>(gt + off);
+                        const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
+                        a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+                        a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+                        a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+                        a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+                        a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+                        a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+                        a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+                        a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+                    }
+                }
+            }
+            const int r = t % 3, u = t / 3;
+            uint8_t *t_hi = xq + (2 * r) * XT_BYTES;
+            const int off = (c * U + u) * 16;
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[2 * e] = swishf_fast(a[4 * kc + e].x);
+                    v[2 * e + 1] = swishf_fast(a[4 * kc + e].y);
+                }
+                store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, kc * LBO_A + off, v);
+            }
+        }
+    }
+    fence_async_smem();  // generic-proxy tile writes -> tensor-core (async proxy) reads
+    __syncthreads();
+
+    // ---- M1 (warp 0) || P2 (warps 1..7): seq_conv2 on the tensor core under sig_conv1 / sig_conv2 ----------
+    int s_next = 0;  // weight stage counter of the issuing thread
+    if (warp == 0) {
+        if (lane == 0) {
+            issue_conv3<MODE, KW_SEQ2>(smem_addr(xq), tmem, s_next, p.wstream, ring, bars);
+            umma_commit(&bars->seq_done);
+        }
+        __syncwarp();
+    } else {
+        const int wt = tid - 32, NW = THREADS - 32;
+        float *s1_s = reinterpret_cast<float *>(ra + A_S1);
+        {
+            const float *w = cst + C_WSIG1, *bb = cst + C_BSIG1;
+            for (int i = wt; i < C * T1; i += NW) {
+                const int c = i / T1, t = i - c * T1;
+                const float *x = sig_s + c * T + t;
+                float4 a = *reinterpret_cast<const float4 *>(bb);
+#pragma unroll
+                for (int j = 0; j < KW_SIG1; ++j) {
+                    const float xv = x[j];
+                    const float4 wv = *reinterpret_cast<const float4 *>(w + 4 * j);
+                    a.x = fmaf(wv.x, xv, a.x);
+                    a.y = fmaf(wv.y, xv, a.y);
+                    a.z = fmaf(wv.z, xv, a.z);
+                    a.w = fmaf(wv.w, xv, a.w);
+                }
+                *reinterpret_cast<float4 *>(s1_s + (size_t)i * 4) =
+                    make_float4(swishf_fast(a.x), swishf_fast(a.y), swishf_fast(a.z), swishf_fast(a.w));
+            }
+        }
+        nbar_sync(1, NW);
+        // the signal tiles reuse the gather sums' space; without gather sums (direct gather) that space holds
+        // the sequence tiles, which the tensor core must have finished reading
+        if (!two_stage) mbar_wait(&bars->seq_done, 0);
+        {
+            const float *w = cst + C_WSIG2, *bb = cst + C_BSIG2;
+            uint8_t *xs = ra + A_XS;
+            for (int i = wt; i < C * T2 * 2; i += NW) {
+                const int half = i & 1;
+                const int ct = i >> 1;
+                const int c = ct / T2, t = ct - c * T2;
+                float acc[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = bb[half * 8 + o];
+#pragma unroll
+                for (int j = 0; j < KW_SIG2; ++j) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(s1_s + (size_t)(c * T1 + t + j) * 4);
+                    const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const float4 *wp = reinterpret_cast<const float4 *>(w + (j * 4 + ci) * 16 + half * 8);
+                        const float4 wa = wp[0], wb = wp[1];
+                        acc[0] = fmaf(wa.x, xs4[ci], acc[0]);
+                        acc[1] = fmaf(wa.y, xs4[ci], acc[1]);
+                        acc[2] = fmaf(wa.z, xs4[ci], acc[2]);
+                        acc[3] = fmaf(wa.w, xs4[ci], acc[3]);
+                        acc[4] = fmaf(wb.x, xs4[ci], acc[4]);
+                        acc[5] = fmaf(wb.y, xs4[ci], acc[5]);
+                        acc[6] = fmaf(wb.z, xs4[ci], acc[6]);
+                        acc[7] = fmaf(wb.w, xs4[ci], acc[7]);
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = swishf_fast(acc[o]);
+                const int r = t % 3, u = t / 3;
+                uint8_t *t_hi = xs + (2 * r) * XT_BYTES;
+                store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, half * LBO_A + (c * U + u) * 16, acc);
+            }
+        }
+        fence_async_smem();
+    }
+    __syncthreads();
+
+    // ---- M2: sig_conv3; E1: both accumulators -> bias + swish -> cat tile (hi / lo) -------------------------
+    if (tid == 0) {
+        s_next = CF::NS_SEQ;
+        issue_conv3<MODE, KW_SIG3>(smem_addr(ra + A_XS), tmem + 128, s_next, p.wstream, ring, bars);
+        umma_commit(&bars->conv_done);
+    }
+    __syncwarp();
+    mbar_wait(&bars->conv_done, 0);
+    tc_fence_after();
+    const int q = warp & 3;           // TMEM lane quarter of this warp = chunk q of the CTA
+    const int wh = warp >> 2;         // which half of the columns this warp drains
+    const int row = q * U + lane;     // tile row = (chunk q, step lane)
+    const bool row_ok = q < C;
+    bool overflow = false;
+    {
+        const int trk = wh;  // 0: sig_conv3 (TMEM columns 128..255) -> channels 0..63; 1: seq_conv2 -> 64..127
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (trk ? 0 : 128);
+        const float *bias = cst + (trk ? C_BSEQ2 : C_BSIG3);
+        const float inv = cst[C_SCALE + (trk ? 0 : 1)];
+        uint8_t *cat_hi = ra, *cat_lo = ra + CAT_HALF;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            float v[32];
+            tmem_ld32(tb + 32 * h, v);
+            if (MODE == 0) {
+                float v2[32];
+                tmem_ld32(tb + 64 + 32 * h, v2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += v2[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = swishf_fast(fmaf(v[8 * j + e], inv, bias[32 * h + 8 * j + e]));
+                    if (MODE == 0 && row_ok && lane < T3 && !(fabsf(o[e]) < 65504.f)) overflow = true;
+                }
+                const int kc = trk * 8 + 4 * h + j;
+                store_chunk8<MODE>(cat_hi, cat_lo, kc * LBO_A + row * 16, o);
+                if (p.dbg_cat && row_ok && lane < T3) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        p.dbg_cat[((size_t)(chunk0 + q) * 128 + kc * 8 + e) * T3 + lane] = o[e];
+                }
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- M3: merge_conv1 (K = 5 taps x 128 channels), tap = descriptor shift; E2 -> m tiles -----------------
+    if (tid == 0) {
+        int s = CF::NS_SEQ + CF::NS_SIG;
+        constexpr uint32_t id_main = idesc_h(128, CF::NB, MODE), id_corr = idesc_h(128, 64, MODE);
+        const uint32_t cat_hi = smem_addr(ra), cat_lo = cat_hi + CAT_HALF;
+        constexpr int KBLKS = 16 / CF::MRG_KC;  // channel blocks per tap
+        for (int st = 0; st < CF::NS_MRG; ++st, ++s) {
+            const int kb = st / KW_MRG, tap = st - kb * KW_MRG;
+            const int slot = s & (RING - 1);
+            mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
+            tc_fence_after();
+            const uint32_t b0 = smem_addr(ring + slot * STAGE_BYTES);
+#pragma unroll
+            for (int k16 = 0; k16 < CF::MRG_KC / 2; ++k16) {
+                const uint32_t aoff = (kb * CF::MRG_KC + 2 * k16) * LBO_A + tap * 16;
+                const uint32_t b = b0 + k16 * 2 * CF::B_LBO;
+                mma_h(tmem, desc_ns(cat_hi + aoff, LBO_A), desc_ns(b, CF::B_LBO), id_main, (st | k16) ? 1u : 0u);
+                if (MODE == 0) mma_h(tmem + 64, desc_ns(cat_lo + aoff, LBO_A), desc_ns(b, CF::B_LBO), id_corr, 1u);
+            }
+            umma_commit(&bars->w_empty[slot]);
+            load_stage(s + RING - 1, CF::NS_TOTAL, p.wstream, ring, bars);
+        }
+        (void)KBLKS;
+        umma_commit(&bars->mrg_done);
+    }
+    __syncwarp();
+    mbar_wait(&bars->mrg_done, 0);
+    tc_fence_after();
+    {
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + 32 * wh;  // channels 32 wh .. 32 wh + 31
+        const float *bias = cst + C_BMRG + 32 * wh;
+        const float inv = cst[C_SCALE + 2];
+        uint8_t *m_hi = ra, *m_lo = ra + M_HALF;
+        float v[32];
+        tmem_ld32(tb, v);
+        if (MODE == 0) {
+            float v2[32];
+            tmem_ld32(tb + 64, v2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                o[e] = swishf_fast(fmaf(v[8 * j + e], inv, bias[8 * j + e]));
+                if (MODE == 0 && row_ok && lane < TM && !(fabsf(o[e]) < 65504.f)) overflow = true;
+            }
+            const int kc = 4 * wh + j;
+            store_chunk8<MODE>(m_hi, m_lo, kc * LBO_A + row * 16, o);
+            if (p.dbg_m && row_ok && lane < TM) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) p.dbg_m[((size_t)(chunk0 + q) * SIZE + kc * 8 + e) * TM + lane] = o[e];
+            }
+        }
+    }
+    if (MODE == 0 && overflow && p.flags) atomicOr(p.flags, 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- M4: LSTM1 input projection (N = 256 gate rows, K = 64); E3 -> xp_s[t][chunk][256] ------------------
+    if (tid == 0) {
+        int s = CF::NS_SEQ + CF::NS_SIG + CF::NS_MRG;
+        constexpr uint32_t id_x = idesc_h(128, 256, MODE);
+        const uint32_t m_hi = smem_addr(ra), m_lo = m_hi + M_HALF;
+        for (int st = 0; st < CF::NS_XP; ++st, ++s) {
+            const int slot = s & (RING - 1);
+            mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
+            tc_fence_after();
+            const uint32_t b = smem_addr(ring + slot * STAGE_BYTES);
+            if (MODE == 0) {
+                const int k16 = st >> 1, lo_stage = st & 1;
+                const uint32_t aoff = 2 * k16 * LBO_A;
+                if (!lo_stage) {  // W_hi: m_hi * W_hi, m_lo * W_hi
+                    mma_h(tmem, desc_ns(m_hi + aoff, LBO_A), desc_ns(b, 4096), id_x, st ? 1u : 0u);
+                    mma_h(tmem, desc_ns(m_lo + aoff, LBO_A), desc_ns(b, 4096), id_x, 1u);
+                } else {  // W_lo: m_hi * W_lo
+                    mma_h(tmem, desc_ns(m_hi + aoff, LBO_A), desc_ns(b, 4096), id_x, 1u);
+                }
+            } else {
+                mma_h(tmem, desc_ns(m_hi + 2 * st * LBO_A, LBO_A), desc_ns(b, 4096), id_x, st ? 1u : 0u);
+            }
+            umma_commit(&bars->w_empty[slot]);
+            load_stage(s + RING - 1, CF::NS_TOTAL, p.wstream, ring, bars);
+        }
+        umma_commit(&bars->xp_done);
+    }
+    __syncwarp();
+    mbar_wait(&bars->xp_done, 0);  // every MMA has completed: ring, tiles and region A are dead
+    tc_fence_after();
+    {
+        const float inv = cst[C_SCALE + 3];
+        const float *b1 = cst + C_B1 + 128 * wh;
+        float *dst = xp_s + lane * XPS + q * 256 + 128 * wh;
+#pragma unroll 1
+        for (int cq = 0; cq < 4; ++cq) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 * wh + 32 * cq, v);
+            if (lane < TM) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(b1 + 32 * cq + 4 * c4);
+                    *reinterpret_cast<float4 *>(dst + 32 * cq + 4 * c4) =
+                        make_float4(fmaf(v[4 * c4], inv, bb.x), fmaf(v[4 * c4 + 1], inv, bb.y),
+                                    fmaf(v[4 * c4 + 2], inv, bb.z), fmaf(v[4 * c4 + 3], inv, bb.w));
+                }
+                if (p.dbg_xp && row_ok) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        p.dbg_xp[((size_t)(chunk0 + q) * 256 + 128 * wh + 32 * cq + e) * TM + lane] =
+                            fmaf(v[e], inv, b1[32 * cq + e]);
+                }
+            }
+        }
+    }
+    for (int i = tid; i < 4 * HG; i += THREADS) h_s[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+
+    // ---- R: LSTM1 recurrence, W_hh in registers ---------------------------------------------------------------
+    const int kg = lane & 3;
+    float w[4][16];
+#pragma unroll
+    for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 v = p.whh4[q4 * 256 + tid];
+        w[q4 >> 2][(q4 & 3) * 4 + 0] = v.x;
+        w[q4 >> 2][(q4 & 3) * 4 + 1] = v.y;
+        w[q4 >> 2][(q4 & 3) * 4 + 2] = v.z;
+        w[q4 >> 2][(q4 & 3) * 4 + 3] = v.w;
+    }
+    const float *hk = h_s + kg * HG;
+    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+    const int u0 = tid & 63, cq = tid >> 6;             // cell (unit u0, chunk cq) owned in the update phase
+    const int hu = (u0 >> 4) * HG + (u0 & 15) * G;
+    float cstate = 0.f, hval = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < TM; ++t) {
+        float xin[G];
+#pragma unroll
+        for (int c = 0; c < G; ++c) xin[c] = xp_s[t * XPS + c * 256 + tid];
+        lstm_matvec(w, hk, xin, g_s, tid, hi2, hi1);
+        __syncthreads();
+        {
+            const float *g = g_s + cq * 256;
+            const float ig = sigmoidf_fast(g[u0]), fg = sigmoidf_fast(g[64 + u0]);
+            const float gg = tanhf_fast(g[128 + u0]), og = sigmoidf_fast(g[192 + u0]);
+            cstate = fg * cstate + ig * gg;
+            hval = og * tanhf_fast(cstate);
+            h_s[hu + cq] = hval;
+        }
+        __syncthreads();
+    }
+    // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54) ----------------
+    h_s[hu + cq] = swishf(hval);
+    __syncthreads();
+    {
+        float a2[G];
+        const float bias = p.b2[tid];
+#pragma unroll
+        for (int c = 0; c < G; ++c) a2[c] = bias;
+#pragma unroll 8
+        for (int k = 0; k < SIZE; ++k) {
+            const float wv = p.wih2T[k * 256 + tid];
+            const float4 hv = *reinterpret_cast<const float4 *>(h_s + (k >> 4) * HG + (k & 15) * G);
+            a2[0] = fmaf(wv, hv.x, a2[0]);
+            a2[1] = fmaf(wv, hv.y, a2[1]);
+            a2[2] = fmaf(wv, hv.z, a2[2]);
+            a2[3] = fmaf(wv, hv.w, a2[3]);
+        }
+#pragma unroll
+        for (int c = 0; c < G; ++c) g_s[c * 256 + tid] = a2[c];
+    }
+    __syncthreads();
+    {
+        const float *g = g_s + cq * 256;
+        const float c2 = sigmoidf_acc(g[u0]) * tanhf(g[128 + u0]);
+        const float h2 = sigmoidf_acc(g[192 + u0]) * tanhf(c2);
+        y_s[cq * SIZE + u0] = swishf(h2);
+    }
+    __syncthreads();
+    pdl_wait();  // order our only global writes after the previous grid in the stream (output buffer reuse)
+    if (warp < C) {
+        for (int o = 0; o < p.num_out; ++o) {
+            float part = p.fcw[o * SIZE + lane] * y_s[warp * SIZE + lane] +
+                         p.fcw[o * SIZE + lane + 32] * y_s[warp * SIZE + lane + 32];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (lane == 0) p.logits[(size_t)(chunk0 + warp) * p.num_out + o] = part + p.fcb[o];
+        }
+    }
+}
+
+}  // namespace mega
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+struct MegaWeights {
+    float *dev = nullptr;
+    size_t off_consts[2] = {0, 0}, off_gtab = 0, off_stream[2] = {0, 0}, off_whh4 = 0, off_wih2T = 0, off_b2 = 0,
+           off_fcw = 0, off_fcb = 0;
+    int gtab_bytes = 0, kmer_len = 0, num_out = 0;
+    int *flags = nullptr;
+};
+
+bool mega_supported(const rb200_model_desc &d) {
+    using namespace mega;
+    if (d.arch != RB200_ARCH_CONVLSTM_W_REF || d.size != SIZE) return false;
+    if (d.n_sig_conv != 3 || d.n_seq_conv != 2 || d.n_merge_conv != 1 || d.n_lstm != 2) return false;
+    auto is = [](const rb200_conv_desc &c, int ci, int co, int kw, int st) {
+        return c.c_in == ci && c.c_out == co && c.kw == kw && c.stride == st;
+    };
+    if (d.kmer_len > 16) return false;
+    if ((KW_SEQ1 * d.kmer_len * 4 + 1) * GROW * 4 > TAB_CAP) return false;
+    return is(d.sig_conv[0], 1, 4, KW_SIG1, 1) && is(d.sig_conv[1], 4, 16, KW_SIG2, 1) &&
+           is(d.sig_conv[2], 16, SIZE, KW_SIG3, 3) && is(d.seq_conv[0], 4 * d.kmer_len, 16, KW_SEQ1, 1) &&
+           is(d.seq_conv[1], 16, SIZE, KW_SEQ2, 3) && is(d.merge_conv[0], 2 * SIZE, SIZE, KW_MRG, 1);
+}
+
+bool mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width) {
+    using namespace mega;
+    if (m->mega == nullptr) return false;
+    if (T > MAX_T || seq_width > MAX_SEQ_W || map_width > MAX_MAP_W || map_width < 2) return false;
+    const int T2 = T - 8, Q1 = T - 4;
+    if (T2 < KW_SIG3 || Q1 < KW_SEQ2) return false;
+    const int T3 = (T2 - KW_SIG3) / 3 + 1, q2 = (Q1 - KW_SEQ2) / 3 + 1;
+    return T3 == q2 && T3 <= MAX_T3 && T3 - (KW_MRG - 1) >= 1;
+}
+
+namespace {
+uint16_t f2h(float x) {
+    __half h = __float2half_rn(x);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+float h2f(uint16_t u) {
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
+}
+uint16_t f2bf(float x) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+// power-of-two scale that brings the largest |w| just under 2^15: the fp16 lo parts stay normal numbers
+float pow2_scale(const float *w, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+    int e = 0;
+    frexpf(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+    int s = 15 - e;
+    if (s > 24) s = 24;
+    if (s < -24) s = -24;
+    return ldexpf(1.f, s);
+}
+}  // namespace
+
+int mega_create(rb200_model *m, const float *blob) {
+    using namespace mega;
+    const rb200_model_desc &d = m->desc;
+    const int K = d.kmer_len;
+    MegaWeights *mw = new MegaWeights();
+    mw->kmer_len = K;
+    mw->num_out = d.num_out;
+    std::vector<float> host;
+    auto reserve = [&](size_t n_floats) {
+        size_t at = host.size();
+        host.resize(at + ((n_floats + 31) & ~(size_t)31), 0.f);
+        return at;
+    };
+    const float *w_seq2 = blob + d.seq_conv[1].w_off, *w_sig3 = blob + d.sig_conv[2].w_off,
+                *w_mrg = blob + d.merge_conv[0].w_off, *w_ih = blob + d.lstm_w_ih_off[0];
+    const float sc[4] = {pow2_scale(w_seq2, (size_t)SIZE * 16 * KW_SEQ2), pow2_scale(w_sig3, (size_t)SIZE * 16 * KW_SIG3),
+                         pow2_scale(w_mrg, (size_t)SIZE * 128 * KW_MRG), pow2_scale(w_ih, (size_t)256 * SIZE)};
+    // ---- constants (one blob per mode: only the inverse scales differ) ----
+    for (int mode = 0; mode < 2; ++mode) {
+        mw->off_consts[mode] = reserve(CONST_FLOATS);
+        float *f = host.data() + mw->off_consts[mode];
+        const float *w = blob + d.sig_conv[0].w_off;  // [4][1][5]
+        for (int j = 0; j < KW_SIG1; ++j)
+            for (int co = 0; co < 4; ++co) f[C_WSIG1 + j * 4 + co] = w[co * KW_SIG1 + j];
+        memcpy(f + C_BSIG1, blob + d.sig_conv[0].b_off, 4 * sizeof(float));
+        w = blob + d.sig_conv[1].w_off;  // [16][4][5]
+        for (int j = 0; j < KW_SIG2; ++j)
+            for (int ci = 0; ci < 4; ++ci)
+                for (int co = 0; co < 16; ++co) f[C_WSIG2 + (j * 4 + ci) * 16 + co] = w[(co * 4 + ci) * KW_SIG2 + j];
+        memcpy(f + C_BSIG2, blob + d.sig_conv[1].b_off, 16 * sizeof(float));
+        memcpy(f + C_BSEQ1, blob + d.seq_conv[0].b_off, 16 * sizeof(float));
+        memcpy(f + C_BSIG3, blob + d.sig_conv[2].b_off, SIZE * sizeof(float));
+        memcpy(f + C_BSEQ2, blob + d.seq_conv[1].b_off, SIZE * sizeof(float));
+        memcpy(f + C_BMRG, blob + d.merge_conv[0].b_off, SIZE * sizeof(float));
+        for (int i = 0; i < 4; ++i) f[C_SCALE + i] = mode == 0 ? 1.f / sc[i] : 1.f;
+        memcpy(f + C_B1, blob + d.lstm_b_off[0], 256 * sizeof(float));
+    }
+    // ---- gather table [tap][kmer pos][base][GROW] + zero row ----
+    {
+        const int rows = KW_SEQ1 * K * 4 + 1;
+        mw->gtab_bytes = ((rows * GROW * 4) + 15) & ~15;
+        mw->off_gtab = reserve((size_t)rows * GROW);
+        const float *w = blob + d.seq_conv[0].w_off;  // [16][4K][5], input row = 4 p + base
+        for (int j = 0; j < KW_SEQ1; ++j)
+            for (int rw = 0; rw < 4 * K; ++rw)
+                for (int co = 0; co < 16; ++co)
+                    host[mw->off_gtab + (size_t)(j * 4 * K + rw) * GROW + co] = w[(co * 4 * K + rw) * KW_SEQ1 + j];
+    }
+    // ---- weight streams ----
+    for (int mode = 0; mode < 2; ++mode) {
+        const int NB = mode == 0 ? 128 : 64, B_LBO = NB * 16, TAPS = STAGE_BYTES / (2 * B_LBO),
+                  MRG_KC = STAGE_BYTES / B_LBO;
+        const int ns_seq = (KW_SEQ2 + TAPS - 1) / TAPS, ns_sig = (KW_SIG3 + TAPS - 1) / TAPS,
+                  ns_mrg = KW_MRG * (16 / MRG_KC), ns_xp = mode == 0 ? 8 : 4;
+        const int total = ns_seq + ns_sig + ns_mrg + ns_xp;
+        mw->off_stream[mode] = reserve((size_t)total * STAGE_BYTES / 4);
+        uint8_t *st0 = reinterpret_cast<uint8_t *>(host.data() + mw->off_stream[mode]);
+        // element (row n, k) of a [K chunk][rows][8] tile at `base` with K-chunk distance lbo
+        auto put = [&](uint8_t *base, int lbo, int n, int k, uint16_t v) {
+            memcpy(base + (size_t)(k >> 3) * lbo + (size_t)n * 16 + (k & 7) * 2, &v, 2);
+        };
+        auto put_w = [&](uint8_t *base, int lbo, int n, int k, float wv, float scale) {
+            if (mode == 0) {
+                const uint16_t hi = f2h(wv * scale);
+                put(base, lbo, n, k, hi);
+                put(base, lbo, n + NB / 2, k, f2h(wv * scale - h2f(hi)));
+            } else {
+                put(base, lbo, n, k, f2bf(wv));
+            }
+        };
+        int s = 0;
+        for (int conv = 0; conv < 2; ++conv) {  // stream order = execution order: seq_conv2, then sig_conv3
+            const int KW = conv == 0 ? KW_SEQ2 : KW_SIG3;
+            const float *w = conv == 0 ? w_seq2 : w_sig3;  // [64][16][KW]
+            const float scale = sc[conv];
+            const int ns = conv == 0 ? ns_seq : ns_sig;
+            for (int st = 0; st < ns; ++st, ++s)
+                for (int tp = 0; tp < TAPS; ++tp) {
+                    const int j = st * TAPS + tp;
+                    if (j >= KW) continue;
+                    uint8_t *base = st0 + (size_t)s * STAGE_BYTES + (size_t)tp * 2 * B_LBO;
+                    for (int n = 0; n < SIZE; ++n)
+                        for (int k = 0; k < 16; ++k) put_w(base, B_LBO, n, k, w[(n * 16 + k) * KW + j], scale);
+                }
+        }
+        for (int st = 0; st < ns_mrg; ++st, ++s) {  // merge: stage = (channel block kb, tap)
+            const int kb = st / KW_MRG, tap = st - kb * KW_MRG;
+            uint8_t *base = st0 + (size_t)s * STAGE_BYTES;
+            for (int n = 0; n < SIZE; ++n)
+                for (int k = 0; k < MRG_KC * 8; ++k)
+                    put_w(base, B_LBO, n, k, w_mrg[(n * 128 + kb * MRG_KC * 8 + k) * KW_MRG + tap], sc[2]);
+        }
+        for (int st = 0; st < ns_xp; ++st, ++s) {  // projection: [K chunk (2)][256 gate rows][8]
+            uint8_t *base = st0 + (size_t)s * STAGE_BYTES;
+            const int k16 = mode == 0 ? st >> 1 : st;
+            for (int n = 0; n < 256; ++n)
+                for (int k = 0; k < 16; ++k) {
+                    const float wv = w_ih[n * SIZE + k16 * 16 + k];
+                    if (mode == 0) {
+                        const uint16_t hi = f2h(wv * sc[3]);
+                        put(base, 4096, n, k, (st & 1) ? f2h(wv * sc[3] - h2f(hi)) : hi);
+                    } else {
+                        put(base, 4096, n, k, f2bf(wv));
+                    }
+                }
+        }
+    }
+    // ---- recurrence / tail weights (same layouts as rb200_fused.cu K3) ----
+    mw->off_whh4 = reserve(SIZE * 256);
+    for (int q = 0; q < 16; ++q)
+        for (int tid = 0; tid < 256; ++tid)
+            for (int e = 0; e < 4; ++e) {
+                const int i = q >> 2, kl = (q & 3) * 4 + e;
+                const int row = 4 * (tid >> 2) + i, k = 16 * (tid & 3) + kl;
+                host[mw->off_whh4 + (q * 256 + tid) * 4 + e] = blob[d.lstm_w_hh_off[0] + row * SIZE + k];
+            }
+    mw->off_wih2T = reserve(SIZE * 256);
+    for (int k = 0; k < SIZE; ++k)
+        for (int r = 0; r < 256; ++r) host[mw->off_wih2T + k * 256 + r] = blob[d.lstm_w_ih_off[1] + r * SIZE + k];
+    mw->off_b2 = reserve(256);
+    memcpy(host.data() + mw->off_b2, blob + d.lstm_b_off[1], 256 * sizeof(float));
+    mw->off_fcw = reserve((size_t)d.num_out * SIZE);
+    memcpy(host.data() + mw->off_fcw, blob + d.fc_w_off, (size_t)d.num_out * SIZE * sizeof(float));
+    mw->off_fcb = reserve(d.num_out);
+    memcpy(host.data() + mw->off_fcb, blob + d.fc_b_off, d.num_out * sizeof(float));
+
+    cudaError_t e = cudaMalloc(&mw->dev, host.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(mw->dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&mw->flags, 16);
+    if (e == cudaSuccess) e = cudaMemset(mw->flags, 0, 16);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mega_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mega_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("single-kernel path set-up failed: %s", cudaGetErrorString(e));
+        if (mw->dev) cudaFree(mw->dev);
+        if (mw->flags) cudaFree(mw->flags);
+        delete mw;
+        return RB200_ERR_CUDA;
+    }
+    m->mega = mw;
+    return RB200_OK;
+}
+
+void mega_destroy(rb200_model *m) {
+    if (!m->mega) return;
+    if (m->mega->dev) cudaFree(m->mega->dev);
+    if (m->mega->flags) cudaFree(m->mega->flags);
+    delete m->mega;
+    m->mega = nullptr;
+}
+
+int mega_read_flags(rb200_model *m, int *out, bool clear) {
+    *out = 0;
+    if (!m->mega) return RB200_OK;
+    RB200_CUDA_TRY(cudaDeviceSynchronize());
+    RB200_CUDA_TRY(cudaMemcpy(out, m->mega->flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (clear) RB200_CUDA_TRY(cudaMemset(m->mega->flags, 0, sizeof(int)));
+    return RB200_OK;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
+                         const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
+                         cudaStream_t stream, int mode) {
+    using namespace mega;
+    const MegaWeights *mw = m->mega;
+    RB200_REQUIRE(mega_shape_ok(m, T, seq_width, map_width), "chunk shape not supported by the single-kernel path");
+    const int T3 = (T - 8 - KW_SIG3) / 3 + 1, TM = T3 - (KW_MRG - 1);
+    Params p;
+    p.sigs = sigs;
+    p.seqs = seqs;
+    p.maps = maps;
+    p.lens = lens;
+    p.seq_width = seq_width;
+    p.map_width = map_width;
+    p.B = B;
+    p.T = T;
+    p.kmer_len = mw->kmer_len;
+    p.num_out = mw->num_out;
+    p.consts = mw->dev + mw->off_consts[mode];
+    p.gtab = mw->dev + mw->off_gtab;
+    p.gtab_bytes = mw->gtab_bytes;
+    p.wstream = reinterpret_cast<const uint8_t *>(mw->dev + mw->off_stream[mode]);
+    p.whh4 = reinterpret_cast<const float4 *>(mw->dev + mw->off_whh4);
+    p.wih2T = mw->dev + mw->off_wih2T;
+    p.b2 = mw->dev + mw->off_b2;
+    p.fcw = mw->dev + mw->off_fcw;
+    p.fcb = mw->dev + mw->off_fcb;
+    p.logits = logits;
+    p.dbg_cat = p.dbg_m = p.dbg_xp = nullptr;
+    p.flags = mw->flags;
+    if (m->keep_debug) {
+        const size_t n_cat = (size_t)B * 128 * T3, n_m = (size_t)B * SIZE * TM, n_xp = (size_t)B * 256 * TM;
+        int rc = ws.ensure(align256(n_cat * 4) + align256(n_m * 4) + align256(n_xp * 4));
+        if (rc) return rc;
+        p.dbg_cat = reinterpret_cast<float *>(ws.base);
+        p.dbg_m = reinterpret_cast<float *>(ws.base + align256(n_cat * 4));
+        p.dbg_xp = reinterpret_cast<float *>(ws.base + align256(n_cat * 4) + align256(n_m * 4));
+        m->debug.clear();
+        m->debug.push_back({"cat", p.dbg_cat, B, 128, T3});
+        m->debug.push_back({"merge1", p.dbg_m, B, SIZE, TM});
+        m->debug.push_back({"xproj", p.dbg_xp, B, 256, TM});
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((B + G - 1) / G);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = m->keep_debug || m->profile ? 0 : 1;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (m->profile) {
+        for (int i = 0; i < 4; ++i) RB200_CUDA_TRY(cudaEventCreate(&ev[i]));
+        RB200_CUDA_TRY(cudaEventRecord(ev[0], stream));
+    }
+    if (mode == 0)
+        RB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mega_kernel<0>, p));
+    else
+        RB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, mega_kernel<1>, p));
+    if (m->profile) {
+        // the per-kernel profile has three slots (K1, K2, K3 of the three-kernel path): the single kernel
+        // reports its whole time in the first one
+        for (int i = 1; i < 4; ++i) RB200_CUDA_TRY(cudaEventRecord(ev[i], stream));
+        for (int i = 0; i < 4; ++i) m->prof_events.push_back(ev[i]);
+    }
+    m->launches += 1;
+    m->last_impl = mode == 0 ? RB200_IMPL_FUSED_MEGA : RB200_IMPL_FUSED_BF16;
+    return RB200_OK;
+}
+
+}  // namespace rb200

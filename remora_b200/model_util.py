@@ -173,13 +173,22 @@ class B200Model(nn.Module):
     def set_impl(self, impl):
         code = {"auto": _native.IMPL_AUTO, "layers": _native.IMPL_LAYERS,
                 "fused": _native.IMPL_FUSED, "fused_tc": _native.IMPL_FUSED_TC,
-                "tiled": _native.IMPL_TILED}[impl]
+                "tiled": _native.IMPL_TILED, "fused_mega": _native.IMPL_FUSED_MEGA,
+                "fused_bf16": _native.IMPL_FUSED_BF16}[impl]
         _native.check(self._lib.rb200_set_impl(self._handle, code), "rb200_set_impl")
 
     @property
     def last_impl(self):
-        return {0: None, 1: "layers", 2: "fused", 3: "fused_tc", 4: "tiled"}[
-            self._lib.rb200_last_impl(self._handle)]
+        return {0: None, 1: "layers", 2: "fused", 3: "fused_tc", 4: "tiled", 5: "fused_mega",
+                6: "fused_bf16"}[self._lib.rb200_last_impl(self._handle)]
+
+    def get_flags(self, clear=False):
+        """Sticky diagnostics of the single-kernel fp16-split path (rb200_get_flags): bit 0 = an
+        intermediate activation left the fp16 range and was saturated.  Synchronises the device."""
+        flags = ctypes.c_int32()
+        _native.check(self._lib.rb200_get_flags(self._handle, ctypes.byref(flags), int(clear)),
+                      "rb200_get_flags")
+        return int(flags.value)
 
     @property
     def launch_count(self):

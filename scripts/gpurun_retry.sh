@@ -1,0 +1,11 @@
+#!/bin/bash
+# gpurun with retries while the pod answers "busy" (exit code 3, nothing charged).
+# usage: scripts/gpurun_retry.sh [gpurun options] -- '<command>'
+for attempt in $(seq 1 30); do
+    /usr/local/graft/bin/gpurun "$@"
+    rc=$?
+    if [ $rc -ne 3 ]; then exit $rc; fi
+    echo "[retry] pod busy (attempt $attempt), sleeping 60 s" >&2
+    sleep 60
+done
+exit 3

@@ -27,11 +27,13 @@ def gpu_model(name):
     return _MODELS[name]
 
 
-def impls_for(model):
+def impls_for(model, T=100):
     """CUDA paths to check for this model: the plain and the register-tiled layer kernels always; for
-    ConvLSTM_w_ref/64 also the fused fp32 FFMA2 kernels and the tcgen05 (3xTF32) variant."""
-    return ["layers", "tiled", "fused", "fused_tc"] if model.info["arch"] == "ConvLSTM_w_ref" and \
-        model.info["size"] == 64 and fused_available(model) else ["layers", "tiled"]
+    ConvLSTM_w_ref/64 also the fused fp32 FFMA2 kernels, the tcgen05 (3xTF32) variant and - for
+    chunk_len <= 100 - the single-kernel path (fp16 hi/lo split operands on tcgen05, fp32 parity)."""
+    if not (model.info["arch"] == "ConvLSTM_w_ref" and model.info["size"] == 64 and fused_available(model)):
+        return ["layers", "tiled"]
+    return ["layers", "tiled", "fused", "fused_tc"] + (["fused_mega"] if T <= 100 else [])
 
 
 def fused_available(model):
@@ -113,14 +115,18 @@ def test_forward_compact_vs_reference_logits(forward_cases):
         key = str(key)
         model, md = gpu_model(key.split("__")[0])
         sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
-        for impl in impls_for(model):
+        for impl in impls_for(model, sig.shape[-1]):
             model.set_impl(impl)
             got = model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
                                         torch.from_numpy(maps), torch.from_numpy(lens))
-            assert model.last_impl in (impl, "fused") if impl == "fused_tc" else model.last_impl == impl
+            # the implementation that RAN is the one requested: every golden shape (T = 100 / 200 / 400)
+            # fits the tensor-core kernels, so a silent FFMA2 fallback would fail here
+            assert model.last_impl == impl, (key, impl, model.last_impl)
             err = np.abs(got.cpu().numpy() - want).max()
             assert err < LOGIT_TOL, f"{key} [{impl}] max-abs err {err}"
         model.set_impl("auto")
+        if "fused_mega" in impls_for(model, sig.shape[-1]):
+            assert model.get_flags(clear=True) == 0, "an activation left the fp16 range"
 
 
 def test_forward_dense_vs_reference_logits(forward_cases):
@@ -188,8 +194,55 @@ def test_per_layer_activations_vs_oracle(forward_cases):
         got_xp = model.debug_tensor("xproj").cpu()
         err = float((got_xp - want_xp).abs().max())
         assert err < 1e-5 * scale + 1e-5, f"tcgen05 convs + projection: err {err:.3e} at scale {scale:.1f}"
+    if "fused_mega" in impls_for(model):
+        # intermediates of the single-kernel path: cat (both stride-3 convs on tcgen05), merge conv
+        # output, LSTM1 input projection - fp16 hi/lo split operands, fp32 accumulate
+        model.set_impl("fused_mega")
+        model.set_debug(True)
+        model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs),
+                              torch.from_numpy(maps), torch.from_numpy(lens))
+        assert model.last_impl == "fused_mega"
+        got_cat = model.debug_tensor("cat").cpu()
+        assert got_cat.shape == cat.shape
+        assert (got_cat[:, :64] - cat[:, :64]).abs().max() < 2e-5, "single kernel: sig track"
+        assert (got_cat[:, 64:] - cat[:, 64:]).abs().max() < 2e-5, "single kernel: seq track"
+        got_m = model.debug_tensor("merge1").cpu()
+        assert got_m.shape == m1.shape and (got_m - m1).abs().max() < 2e-5 * max(1.0, float(m1.abs().max()))
+        got_xp = model.debug_tensor("xproj").cpu()
+        err = float((got_xp - want_xp).abs().max())
+        assert err < 1e-5 * scale + 1e-5, f"single kernel projection: err {err:.3e} at scale {scale:.1f}"
     model.set_debug(False)
     model.set_impl("auto")
+
+
+def test_bf16_variant_tolerance(forward_cases):
+    """BASELINE configs[1] names a bf16 ConvLSTM_w_ref: the single kernel with one-pass bf16 tensor-core
+    operands (activations and weights of the four GEMM-shaped layers rounded to bf16, fp32 accumulate,
+    fp32 signal convs / gates / classifier).  Its own stated tolerance against the reference's fp32 CPU
+    logits on the hot fixture (logits span +-4): max-abs logit error < 0.15, max-abs probability error
+    < 0.03, ML-byte mismatch (|delta| > 1) rate < 15 %, never selected by AUTO."""
+    model, md = gpu_model("convlstm_s64_k9_hot")
+    worst_logit = worst_prob = 0.0
+    n = n_ml_bad = 0
+    for key in forward_cases["index"]:
+        key = str(key)
+        if not key.startswith("convlstm_s64_k9_hot__") or not key.endswith("T100"):
+            continue
+        sig, seqs, maps, lens, want = _case_inputs(forward_cases, key)
+        model.set_impl("fused_bf16")
+        got = model.forward_compact(torch.from_numpy(sig), torch.from_numpy(seqs), torch.from_numpy(maps),
+                                    torch.from_numpy(lens)).cpu().numpy()
+        assert model.last_impl == "fused_bf16" and np.isfinite(got).all()
+        from remora_b200 import util
+        pg, pw = util.softmax_axis1(got)[:, 1:], util.softmax_axis1(want)[:, 1:]
+        worst_logit = max(worst_logit, float(np.abs(got - want).max()))
+        worst_prob = max(worst_prob, float(np.abs(pg - pw).max()))
+        n_ml_bad += int((np.abs(ro.ml_bytes(pg).astype(int) - ro.ml_bytes(pw).astype(int)) > 1).sum())
+        n += pg.size
+    model.set_impl("auto")
+    print(f"bf16 variant: max|dlogit| {worst_logit:.4f} max|dprob| {worst_prob:.4f} "
+          f"ML bytes off by >1: {n_ml_bad}/{n}")
+    assert n > 0 and worst_logit < 0.15 and worst_prob < 0.03 and n_ml_bad / n < 0.15
 
 
 @pytest.mark.parametrize("B", [1, 2, 63, 64, 65, 1024, 4096])
@@ -220,6 +273,26 @@ def test_batch_sizes_and_ragged_batches(B):
         model.set_impl(impl)
         again = model.forward_compact(*tail).cpu().numpy()
         assert np.abs(again - outs[impl][B - k:]).max() < 2e-6, impl
+    model.set_impl("auto")
+
+
+def test_full_baseline_batch_against_oracle():
+    """The whole BASELINE batch (1024 chunks, T=100) against the oracle (the reference's arithmetic on
+    CPU), every chunk, for every CUDA implementation - not a prefix and not another CUDA path."""
+    model, md = gpu_model("convlstm_s64_k9_hot")
+    sd, _ = load_golden_model("convlstm_s64_k9_hot")
+    d = synth_chunks(1024, 100, (4, 4), seed=20261017)
+    args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                             "sequence_lengths")]
+    want = ro.oracle_infer_compact(sd, (4, 4), d["signal"], d["sequence"],
+                                   d["sequence_to_signal_mapping"], d["sequence_lengths"])
+    assert want.shape == (1024, 2) and float(np.abs(want).max()) > 1.0  # logits span several units
+    for impl in impls_for(model):
+        model.set_impl(impl)
+        got = model.forward_compact(*args).cpu().numpy()
+        assert model.last_impl == impl
+        err = float(np.abs(got - want).max())
+        assert err < LOGIT_TOL, f"[{impl}] max-abs err {err:.3e} over 1024 chunks"
     model.set_impl("auto")
 
 
@@ -533,5 +606,9 @@ def test_full_size_batch_properties():
             assert (out - ref).abs().max() < LOGIT_TOL  # two fp32 paths, both within tolerance of the oracle
             model.set_impl("fused_tc")
             out_tc = model.forward_compact(*args)
-            model.set_impl("auto")
             assert (out_tc - ref).abs().max() < LOGIT_TOL  # tensor-core (3xTF32) path
+            model.set_impl("fused_mega")
+            out_mega = model.forward_compact(*args)
+            model.set_impl("auto")
+            assert model.last_impl == "fused_mega"
+            assert (out_mega - ref).abs().max() < LOGIT_TOL  # single kernel, fp16 hi/lo split operands

@@ -53,6 +53,38 @@ def make_ids(n, seed=0):
     return [str(uuid.UUID(int=int(rng.integers(1, 2 ** 62)))) for _ in range(n)]
 
 
+# Known-answer vector built BY HAND from the published "minknow.vbz" / svb16 format description (POD5
+# format spec: delta -> zig-zag -> StreamVByte-16 with one key bit per value, keys first, little-endian
+# data, then a zstd frame), independent of this package's encoder:
+#   samples  10, 12, 9, 300, -200, -200, 32767, -32768, 0
+#   deltas   10,  2, -3, 291, -500,   0, 32967->(wraps mod 2^16: -32569), -65535->(+1), 32768->(-32768)
+#   zig-zag  20,  4,  5, 582,  999,   0, 65137, 2, 65535
+#   key bits (1 = two bytes): values 3, 4, 6, 8 -> byte0 = 0b01011000 = 0x58, byte1 = 0b00000001
+SVB16_KAT_SAMPLES = np.array([10, 12, 9, 300, -200, -200, 32767, -32768, 0], dtype=np.int16)
+SVB16_KAT_STREAM = bytes([0x58, 0x01,
+                          0x14, 0x04, 0x05, 0x46, 0x02, 0xE7, 0x03, 0x00, 0x71, 0xFE, 0x02, 0xFF, 0xFF])
+
+
+def _kat_blob():
+    import pyarrow as pa
+    return pa.Codec("zstd").compress(SVB16_KAT_STREAM, asbytes=True)
+
+
+def test_svb16_known_answer_numpy():
+    assert np.array_equal(io.decode_vbz(_kat_blob(), SVB16_KAT_SAMPLES.size), SVB16_KAT_SAMPLES)
+    # and the package's own encoder produces exactly this stream
+    assert bytes(io._zstd_frame_content(io.encode_vbz(SVB16_KAT_SAMPLES))) == SVB16_KAT_STREAM
+
+
+@pytest.mark.gpu
+def test_svb16_known_answer_gpu():
+    dev = torch.device("cuda:0")
+    d_out, spans = io.decode_vbz_rows_gpu([_kat_blob()], [SVB16_KAT_SAMPLES.size], dev)
+    st, ln = spans[0]
+    assert ln == SVB16_KAT_SAMPLES.size
+    assert np.array_equal(d_out[st:st + ln].cpu().numpy(), SVB16_KAT_SAMPLES)
+
+
 def test_pod5_round_trip(tmp_path):
     rng = np.random.default_rng(1)
     sig = (np.cumsum(rng.integers(-30, 30, size=250000)) + 900).astype(np.int16)
