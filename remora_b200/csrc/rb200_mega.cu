@@ -120,6 +120,7 @@ struct Params {
     float *logits;
     float *dbg_cat, *dbg_m, *dbg_xp;  // optional canonical [B][C][T] copies of the intermediates
     int *flags;                       // [0] != 0: an activation left the fp16 range (MODE 0)
+    long long *stamps;                // optional phase timestamps of CTA 0 (profiling aid)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------
@@ -353,6 +354,8 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     const int T3 = (T2 - KW_SIG3) / 3 + 1, TM = T3 - (KW_MRG - 1);
     const int seq_width = p.seq_width, map_width = p.map_width, K = p.kmer_len;
 
+#define MG_STAMP(i) do { if (p.stamps && blockIdx.x == 0 && tid == 0) p.stamps[i] = clock64(); } while (0)
+    MG_STAMP(0);
     pdl_launch_dependents();  // the next batch may start as soon as SM resources free up
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) {
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         for (int s = 0; s < RING - 1; ++s) load_stage(s, CF::NS_TOTAL, p.wstream, ring, bars);
     }
 
+    MG_STAMP(1);
     // ---- P0: stage the compact inputs, move-table expansion ------------------------------------------------
     float *sig_s = reinterpret_cast<float *>(ra + A_STG + STG_SIG);
     int16_t *sidx_s = reinterpret_cast<int16_t *>(ra + A_STG + STG_SIDX);
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     }
     mbar_wait(&bars->front, 0);  // constants and the gather table have landed
     __syncthreads();
+    MG_STAMP(2);
 
     // ---- P1: seq_conv1 on the (virtual) one-hot = gather-add of weight columns -> residue tiles ------------
     const int LM = map_width - 1;
@@ -518,6 +523,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     }
     fence_async_smem();  // generic-proxy tile writes -> tensor-core (async proxy) reads
     __syncthreads();
+    MG_STAMP(3);
 
     // ---- M1 (warp 0) || P2 (warps 1..7): seq_conv2 on the tensor core under sig_conv1 / sig_conv2 ----------
     int s_next = 0;  // weight stage counter of the issuing thread
@@ -591,6 +597,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         fence_async_smem();
     }
     __syncthreads();
+    MG_STAMP(4);
 
     // ---- M2: sig_conv3; E1: both accumulators -> bias + swish -> cat tile (hi / lo) -------------------------
     if (tid == 0) {
@@ -601,6 +608,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     __syncwarp();
     mbar_wait(&bars->conv_done, 0);
     tc_fence_after();
+    MG_STAMP(5);
     const int q = warp & 3;           // TMEM lane quarter of this warp = chunk q of the CTA
     const int wh = warp >> 2;         // which half of the columns this warp drains
     const int row = q * U + lane;     // tile row = (chunk q, step lane)
@@ -645,6 +653,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
 
+    MG_STAMP(6);
     // ---- M3: merge_conv1 (K = 5 taps x 128 channels), tap = descriptor shift; E2 -> m tiles -----------------
     if (tid == 0) {
         int s = CF::NS_SEQ + CF::NS_SIG;
@@ -673,6 +682,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     __syncwarp();
     mbar_wait(&bars->mrg_done, 0);
     tc_fence_after();
+    MG_STAMP(7);
     {
         const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + 32 * wh;  // channels 32 wh .. 32 wh + 31
         const float *bias = cst + C_BMRG + 32 * wh;
@@ -708,6 +718,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
 
+    MG_STAMP(8);
     // ---- M4: LSTM1 input projection (N = 256 gate rows, K = 64); E3 -> xp_s[t][chunk][256] ------------------
     if (tid == 0) {
         int s = CF::NS_SEQ + CF::NS_SIG + CF::NS_MRG;
@@ -738,6 +749,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     __syncwarp();
     mbar_wait(&bars->xp_done, 0);  // every MMA has completed: ring, tiles and region A are dead
     tc_fence_after();
+    MG_STAMP(9);
     {
         const float inv = cst[C_SCALE + 3];
         const float *b1 = cst + C_B1 + 128 * wh;
@@ -769,6 +781,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 
+    MG_STAMP(10);
     // ---- R: LSTM1 recurrence, W_hh in registers ---------------------------------------------------------------
     const int kg = lane & 3;
     float w[4][16];
@@ -782,6 +795,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     }
     const float *hk = h_s + kg * HG;
     const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+    MG_STAMP(11);
     const int u0 = tid & 63, cq = tid >> 6;             // cell (unit u0, chunk cq) owned in the update phase
     const int hu = (u0 >> 4) * HG + (u0 & 15) * G;
     float cstate = 0.f, hval = 0.f;
@@ -802,6 +816,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         }
         __syncthreads();
     }
+    MG_STAMP(12);
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54) ----------------
     h_s[hu + cq] = swishf(hval);
     __syncthreads();
@@ -810,14 +825,22 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         const float bias = p.b2[tid];
 #pragma unroll
         for (int c = 0; c < G; ++c) a2[c] = bias;
-#pragma unroll 8
-        for (int k = 0; k < SIZE; ++k) {
-            const float wv = p.wih2T[k * 256 + tid];
-            const float4 hv = *reinterpret_cast<const float4 *>(h_s + (k >> 4) * HG + (k & 15) * G);
-            a2[0] = fmaf(wv, hv.x, a2[0]);
-            a2[1] = fmaf(wv, hv.y, a2[1]);
-            a2[2] = fmaf(wv, hv.z, a2[2]);
-            a2[3] = fmaf(wv, hv.w, a2[3]);
+        // W_ih2^T comes straight from L2 (coalesced, read once): all loads of a half are issued before the
+        // first use so that the kernel pays two L2 round trips here, not one per unrolled group
+#pragma unroll 1
+        for (int k0 = 0; k0 < SIZE; k0 += 32) {
+            float wv[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) wv[k] = __ldg(p.wih2T + (k0 + k) * 256 + tid);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float4 hv =
+                    *reinterpret_cast<const float4 *>(h_s + ((k0 + k) >> 4) * HG + ((k0 + k) & 15) * G);
+                a2[0] = fmaf(wv[k], hv.x, a2[0]);
+                a2[1] = fmaf(wv[k], hv.y, a2[1]);
+                a2[2] = fmaf(wv[k], hv.z, a2[2]);
+                a2[3] = fmaf(wv[k], hv.w, a2[3]);
+            }
         }
 #pragma unroll
         for (int c = 0; c < G; ++c) g_s[c * 256 + tid] = a2[c];
@@ -830,7 +853,9 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         y_s[cq * SIZE + u0] = swishf(h2);
     }
     __syncthreads();
+    MG_STAMP(13);
     pdl_wait();  // order our only global writes after the previous grid in the stream (output buffer reuse)
+    MG_STAMP(14);
     if (warp < C) {
         for (int o = 0; o < p.num_out; ++o) {
             float part = p.fcw[o * SIZE + lane] * y_s[warp * SIZE + lane] +
@@ -840,6 +865,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             if (lane == 0) p.logits[(size_t)(chunk0 + warp) * p.num_out + o] = part + p.fcb[o];
         }
     }
+#undef MG_STAMP
 }
 
 }  // namespace mega
@@ -1105,6 +1131,13 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     p.logits = logits;
     p.dbg_cat = p.dbg_m = p.dbg_xp = nullptr;
     p.flags = mw->flags;
+    p.stamps = nullptr;
+    static const bool want_stamps = getenv("RB200_MEGA_STAMPS") != nullptr;  // profiling aid
+    static long long *stamps_dev = nullptr;
+    if (want_stamps) {
+        if (!stamps_dev) cudaMalloc(&stamps_dev, 16 * sizeof(long long));
+        p.stamps = stamps_dev;
+    }
     if (m->keep_debug) {
         const size_t n_cat = (size_t)B * 128 * T3, n_m = (size_t)B * SIZE * TM, n_xp = (size_t)B * 256 * TM;
         int rc = ws.ensure(align256(n_cat * 4) + align256(n_m * 4) + align256(n_xp * 4));
@@ -1141,6 +1174,17 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
         // reports its whole time in the first one
         for (int i = 1; i < 4; ++i) RB200_CUDA_TRY(cudaEventRecord(ev[i], stream));
         for (int i = 0; i < 4; ++i) m->prof_events.push_back(ev[i]);
+    }
+    if (want_stamps) {
+        long long h[16];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, stamps_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        static const char *names[14] = {"prologue", "stage+sidx", "gather", "seq2||sig12", "sig3 mma", "E1 cat",
+                                        "merge mma", "E2 m", "xproj mma", "E3 xp", "whh load", "recurrence",
+                                        "lstm2", "pdl_wait"};
+        fprintf(stderr, "[mega stamps, cycles]");
+        for (int i = 0; i < 14; ++i) fprintf(stderr, " %s %lld |", names[i], h[i + 1] - h[i]);
+        fprintf(stderr, " total %lld\n", h[14] - h[0]);
     }
     m->launches += 1;
     m->last_impl = mode == 0 ? RB200_IMPL_FUSED_MEGA : RB200_IMPL_FUSED_BF16;

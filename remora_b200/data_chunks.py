@@ -379,9 +379,10 @@ class RemoraRead:
                 seq_lens=lens[st:en], labels=labels[st:en], read_focus_bases=fb[st:en],
                 kmer_context_bases=(kb, ka)))
 
-    def run_model(self, model):
+    def run_model(self, model, keep_on_device=False):
         """Call modified bases on this read's prepared batches (reference data_chunks.py:516-540).
-        Returns (nn_out float32 [N,num_out], labels int64 [N], read positions int64 [N])."""
+        Returns (nn_out float32 [N,num_out], labels int64 [N], read positions int64 [N]);
+        ``keep_on_device`` (extension) leaves nn_out as one device tensor for device post-processing."""
         device = next(model.parameters()).device
         outputs, labels, poss = [], [], []
         compact = hasattr(model, "forward_compact")
@@ -396,7 +397,8 @@ class RemoraRead:
                                             torch.from_numpy(batch.seq_lens))
             else:
                 out = model(sigs, batch.enc_kmers(device))
-            outputs.append(out.detach().cpu().numpy())
+            outputs.append(out.detach() if keep_on_device else out.detach().cpu().numpy())
             labels.append(batch.labels)
             poss.append(batch.read_focus_bases)
-        return np.concatenate(outputs, axis=0), np.concatenate(labels), np.concatenate(poss)
+        nn_out = torch.cat(outputs, dim=0) if keep_on_device else np.concatenate(outputs, axis=0)
+        return nn_out, np.concatenate(labels), np.concatenate(poss)

@@ -32,9 +32,19 @@ def call_read_mods(read, model, model_metadata, batch_size=constants.DEFAULT_BAT
         read.prepare_batches(model_metadata, batch_size)
     if len(read.batches) == 0:
         return np.array([]), np.array([]), np.array([])
-    nn_out, labels, pos = read.run_model(model)
     if not return_mod_probs and not return_mm_ml_tags:
-        return nn_out, labels, pos
+        return read.run_model(model)
+    if hasattr(model, "softmax_ml"):
+        # post-processing on the device: softmax, class 0 dropped, ML bytes; only
+        # the float32 probabilities / uint8 ML bytes come back, the logits never leave the GPU
+        nn_dev, labels, pos = read.run_model(model, keep_on_device=True)
+        probs_dev, ml_dev = model.softmax_ml(nn_dev, want_probs=not return_mm_ml_tags)
+        if return_mm_ml_tags:
+            return format_mm_ml_tags(seq=read.str_seq, poss=pos, probs=None, ml_bytes=ml_dev.cpu().numpy(),
+                                     mod_bases=model_metadata["mod_bases"],
+                                     can_base=model_metadata["can_base"])
+        return probs_dev.cpu().numpy().astype(np.float64), labels, pos
+    nn_out, labels, pos = read.run_model(model)
     probs = softmax_axis1(nn_out)[:, 1:].astype(np.float64)
     if return_mm_ml_tags:
         return format_mm_ml_tags(seq=read.str_seq, poss=pos, probs=probs,
@@ -80,7 +90,7 @@ def mods_tags_to_str(mm_tags, ml_arr):
 def _run_merged(model, batches, device, batch_size):
     """Concatenate the compact chunk arrays of several reads (padding the per-read sequence / mapping
     widths to the widest; the kernels never read past ``seq_len``) and run the model over them in
-    pieces of ``batch_size`` chunks.  Returns float32 logits [total chunks, num_out] on the host."""
+    pieces of ``batch_size`` chunks.  Returns float32 logits [total chunks, num_out] on the device."""
     import torch.nn.functional as F
     from .data_chunks import DeviceChunkBatch
     seq_w = max(b.sequence.shape[1] for b in batches)
@@ -101,13 +111,14 @@ def _run_merged(model, batches, device, batch_size):
     for st in range(0, sig.shape[0], batch_size):
         en = st + batch_size
         outs.append(model.forward_compact(sig[st:en], seq[st:en], mp[st:en], ln[st:en]))
-    return torch.cat(outs).cpu().numpy()
+    return torch.cat(outs)
 
 
 def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_reads=None,
                             batch_size=constants.DEFAULT_BATCH_SIZE, reads_per_batch=256, ref_anchored=False,
                             skip_non_primary=True, extract_on_device=False, return_probs=False,
-                            decode_on_device=True, rank=0, world_size=1):
+                            decode_on_device=True, rank=0, world_size=1, drop_move_tag=False, out_format=None,
+                            bam_in_memory=False):
     """``remora infer from_pod5_and_bam`` as one function (reference inference.py:462-660 without its
     process/queue plumbing): POD5 signal + BAM basecalls/move tables -> modified-base calls per read.
 
@@ -119,11 +130,16 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     launches and transfers of ``extract_on_device``, 1.4 k vs 0.8 k reads/s measured) and the network run
     over the chunks of the whole group in ``batch_size`` pieces.  Returns a list of dicts
     ``{read_id, mm, ml (array('B')), error}`` (plus ``calls``: ``{can_base: (positions, probs)}`` when
-    ``return_probs``); with ``out_path`` the input records are also written with the MM/ML tags attached
-    (previous MM/ML/mv tags dropped) - as BAM when the name ends in ``.bam``, else as SAM text -
-    unmapped-style when reference anchored like the reference's output (inference.py:448-456).
+    ``return_probs``); with ``out_path`` EVERY input record of the processed reads is written, like the
+    reference's main loop does (inference.py:609-625): called reads with the MM/ML tags attached
+    (previous MM/ML dropped), reads that failed (join, refinement, chunking) unchanged without new tags.
+    The move table is kept unless ``drop_move_tag`` (the reference keeps it, ``prune(drop_move_tag=False)``).
+    Format: ``out_format`` "bam" / "sam", default by the name (``*.bam`` -> BAM, else SAM text);
+    reference-anchored calls are written unmapped-style like the reference's (inference.py:448-456).
+    The BAM is indexed by file offsets (``bam_in_memory=False``), as the reference does (io.py:255-307).
     Multi-GPU: one process per GPU calls this with its ``rank`` / ``world_size`` (and its own
-    ``out_path``); reads are split by sequence length (``parallel.shard_by_work``), no collective."""
+    ``out_path``); ``num_reads`` selects the reads of the run FIRST, then they are split by sequence
+    length (``parallel.shard_by_work``, lengths recorded while indexing), no collective."""
     from . import io as rio
     from .refine_signal_map import SigMapRefiner
     if isinstance(models, tuple):
@@ -133,23 +149,48 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     if len(rev_sigs) != 1 or len(pa_scalings) != 1:
         raise RemoraError("models disagree on reverse_signal / pa_scaling")
     reverse_signal, pa_scaling = rev_sigs.pop(), pa_scalings.pop()
-    bam_idx = rio.ReadIndexedBam(in_bam_path, skip_non_primary=skip_non_primary, req_tags={"mv"})
+    bam_idx = rio.ReadIndexedBam(in_bam_path, skip_non_primary=skip_non_primary, req_tags={"mv"},
+                                 in_memory=bam_in_memory)
+    shard_ids = None
     if world_size > 1:
         from .parallel import shard_by_work
-        ids = bam_idx.read_ids
-        keep = shard_by_work([sum(len(r.query_sequence) for r in bam_idx[i]) for i in ids], world_size, rank)
-        bam_idx._bam_idx = {ids[i]: bam_idx._bam_idx[ids[i]] for i in keep}
-        bam_idx.num_reads = len(bam_idx._bam_idx)
+        with rio.Pod5Reader(pod5_path) as reader:  # the run = POD5 order, truncated by num_reads, THEN sharded
+            ids = [rid for rid in reader.read_ids if rid in bam_idx]
+        if num_reads is not None:
+            ids = ids[:num_reads]
+        shard_ids = [ids[i] for i in shard_by_work([bam_idx.seq_lens[i] for i in ids], world_size, rank)]
     results = []
     out_fh = None
     out_records = None  # BAM output: records are collected and written at the end
     header_text = (bam_idx.header_text.rstrip("\n") + "\n" if bam_idx.header_text else "") + \
         "@PG\tID:remora_b200\tPN:remora_b200\n"
-    if out_path is not None and str(out_path).endswith(".bam"):
+    if out_format is None:
+        out_format = "bam" if str(out_path).endswith(".bam") else "sam"
+    if out_format not in ("bam", "sam"):
+        raise RemoraError(f"unknown output format {out_format!r} (bam or sam)")
+    if out_path is not None and out_format == "bam":
         out_records = []
     elif out_path is not None:
         out_fh = open(out_path, "w")
         out_fh.write(header_text)
+    drop = ("MM", "ML", "Mm", "Ml") + (("mv",) if drop_move_tag else ())
+
+    def emit(rec, res, io_read=None):
+        """One output record: the input record, plus MM/ML when the read was called."""
+        if rec is None or (out_fh is None and out_records is None):
+            return
+        called = res["error"] is None
+        if called and ref_anchored and io_read is not None:
+            import dataclasses
+            seq = io_read.ref_seq if io_read.ref_reg.strand == "+" else revcomp(io_read.ref_seq)
+            rec = dataclasses.replace(rec, cigartuples=[(0, len(io_read.ref_seq))], query_sequence=seq,
+                                      query_qualities=np.zeros(0, dtype=np.uint8))
+        if out_records is not None:
+            extra = [("MM", "Z", res["mm"]), ("ML", "BC", np.frombuffer(res["ml"], dtype=np.uint8))] if called else []
+            out_records.append(rec.to_record(drop_tags=drop if called else (), extra_tags=extra))
+        else:
+            extra = mods_tags_to_str([res["mm"]], res["ml"]) if called else []
+            out_fh.write(rec.to_sam(drop_tags=drop if called else (), extra_tags=extra) + "\n")
 
     def flush(group):
         # group: list of io.Read that converted cleanly; one refinement launch per model
@@ -187,17 +228,22 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
                     owners.append(i)
                     merged.append(b)
             if merged:
-                nn_out = _run_merged(model, merged, device, batch_size)
+                # softmax + ML-byte quantisation on the device for the chunks of the whole group
+                # (rb200_softmax_ml; reference inference.py:429-459 does this per read in numpy)
+                probs_dev, ml_dev = model.softmax_ml(_run_merged(model, merged, device, batch_size),
+                                                     want_probs=return_probs)
+                ml_all = ml_dev.cpu().numpy()
+                probs_all = probs_dev.cpu().numpy().astype(np.float64) if return_probs else None
                 st = 0
                 for i, b in zip(owners, merged):
-                    out = nn_out[st:st + len(b)]
+                    ml_b = ml_all[st:st + len(b)]
+                    probs = probs_all[st:st + len(b)] if return_probs else None
                     st += len(b)
-                    probs = softmax_axis1(out)[:, 1:].astype(np.float64)
                     pos = b.read_focus_bases
                     io_read = group[i]
                     seq = io_read.ref_seq if ref_anchored else io_read.seq
-                    mm, ml = format_mm_ml_tags(seq=seq, poss=pos, probs=probs, mod_bases=md["mod_bases"],
-                                               can_base=can_base)
+                    mm, ml = format_mm_ml_tags(seq=seq, poss=pos, probs=None, ml_bytes=ml_b,
+                                               mod_bases=md["mod_bases"], can_base=can_base)
                     per_read[i]["mm"].append(mm)
                     per_read[i]["ml"].extend(ml)
                     if return_probs:
@@ -207,29 +253,21 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
             if not return_probs:
                 del res["calls"]
             results.append(res)
-            rec = io_read.alignment_record
-            if (out_fh is not None or out_records is not None) and res["error"] is None and rec is not None:
-                extra = mods_tags_to_str([res["mm"]], res["ml"])
-                if ref_anchored:
-                    import dataclasses
-                    seq = io_read.ref_seq if io_read.ref_reg.strand == "+" else revcomp(io_read.ref_seq)
-                    rec = dataclasses.replace(rec, cigartuples=[(0, len(io_read.ref_seq))], query_sequence=seq,
-                                              query_qualities=np.zeros(0, dtype=np.uint8))
-                drop = ("MM", "ML", "Mm", "Ml", "mv")
-                if out_records is not None:
-                    out_records.append(rec.to_record(drop_tags=drop, extra_tags=[
-                        ("MM", "Z", res["mm"]), ("ML", "BC", np.frombuffer(res["ml"], dtype=np.uint8))]))
-                else:
-                    out_fh.write(rec.to_sam(drop_tags=drop, extra_tags=extra) + "\n")
+            emit(io_read.alignment_record, res, io_read)
 
     group = []
     try:
         decode_dev = next(next(iter(models.values()))[0].parameters()).device if decode_on_device else None
         for io_read, err in rio.iter_io_reads(pod5_path, bam_idx, num_reads=num_reads,
                                               reverse_signal=reverse_signal, pa_scaling=pa_scaling,
-                                              device=decode_dev):
+                                              device=decode_dev, read_ids=shard_ids):
             if err is not None:
-                results.append(dict(read_id=io_read.read_id, mm="", ml=array.array("B"), error=err))
+                if group:  # keep the output in input order
+                    flush(group)
+                    group = []
+                res = dict(read_id=io_read.child_read_id, mm="", ml=array.array("B"), error=err)
+                results.append(res)
+                emit(io_read.alignment_record, res)
                 continue
             group.append(io_read)
             if len(group) >= reads_per_batch:
@@ -240,6 +278,9 @@ def infer_from_pod5_and_bam(pod5_path, in_bam_path, models, out_path=None, num_r
     finally:
         if out_fh is not None:
             out_fh.close()
+        bam_idx.close()
     if out_records is not None:
-        rio.write_bam(out_path, header_text, rio.references_from_header(header_text), out_records)
+        # the binary reference dictionary of the input (present even when the text header has no @SQ lines)
+        refs = list(zip(bam_idx.references, bam_idx.ref_lengths)) or rio.references_from_header(header_text)
+        rio.write_bam(out_path, header_text, refs, out_records)
     return results

@@ -410,9 +410,12 @@ class ReadIndexedBam:
     def compute_read_index(self):
         idx = defaultdict(list)
         self._reader = None
+        self.seq_lens = {}  # (extension) total basecall length per indexed read id: sharding work estimate
+        self.ref_lengths = []
         with BamReader(self.bam_path) as bam:
             self.header_text = bam.header_text
             self.references = bam.references
+            self.ref_lengths = list(bam.lengths)  # binary reference dictionary (may exist without @SQ lines)
             for voff, read in bam.iter_with_offsets():
                 if self.child_read_id_subset is not None and read.query_name not in self.child_read_id_subset:
                     self.skip_reasons["Child read ID filtered"] += 1
@@ -431,6 +434,7 @@ class ReadIndexedBam:
                     continue
                 self.num_records += 1
                 idx[index_read_id].append(read if self.in_memory else voff)
+                self.seq_lens[index_read_id] = self.seq_lens.get(index_read_id, 0) + len(read.query_sequence)
         self._bam_idx = dict(idx)
         self.num_reads = len(self._bam_idx)
 
@@ -994,7 +998,7 @@ class Read:
 
 
 def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_scaling=None, device=None,
-                  reads_per_decode=64):
+                  reads_per_decode=64, read_ids=None):
     """(io.Read, error text or None) for every alignment of every POD5 read present in the BAM index:
     the sequential equivalent of the reference's iter_signal -> extract_alignments workers
     (io.py:441-511).  With a CUDA ``device`` the signal of ``reads_per_decode`` reads at a time is decoded
@@ -1003,6 +1007,9 @@ def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_s
         wanted = [rid for rid in reader.read_ids if rid in bam_idx]
         if num_reads is not None:
             wanted = wanted[:num_reads]
+        if read_ids is not None:  # a rank's shard of the (already truncated) run
+            keep = set(read_ids)
+            wanted = [rid for rid in wanted if rid in keep]
         for st in range(0, len(wanted), reads_per_decode):
             ids = wanted[st:st + reads_per_decode]
             for rid, pod5_read in zip(ids, reader.get_reads(ids, device=device)):
@@ -1010,8 +1017,8 @@ def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_s
                     try:
                         yield Read.from_pod5_and_alignment(pod5_read, bam_read, reverse_signal=reverse_signal,
                                                            pa_scaling=pa_scaling), None
-                    except RemoraError as e:
-                        yield Read(read_id=rid), str(e)
+                    except RemoraError as e:  # the record still reaches the output, without new tags
+                        yield Read(read_id=rid, _child_read_id=bam_read.query_name, alignment_record=bam_read), str(e)
 
 
 # ------------------------------------------------------------------------------------------------

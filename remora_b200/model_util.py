@@ -278,6 +278,23 @@ class B200Model(nn.Module):
         _native.check(rc, "rb200_forward_compact")
         return out
 
+    def softmax_ml(self, logits, want_probs=True):
+        """Post-processing on the device (``rb200_softmax_ml``): row softmax of float32 logits
+        [N, num_out], class 0 dropped -> (probs float32 [N, num_out-1] or None, ML bytes uint8
+        [N, num_out-1] = min(floor(p*256), 255)), both device tensors
+        (reference util.py:182-186, 532-535 as used at inference.py:429-459)."""
+        logits = self._prep(logits, torch.float32, "logits")
+        if logits.dim() != 2 or logits.shape[1] != self.num_out:
+            raise RemoraError(f"logits must be [N,{self.num_out}] (got {tuple(logits.shape)})")
+        n = logits.shape[0]
+        probs = torch.empty((n, self.num_out - 1), dtype=torch.float32, device=self._device) if want_probs else None
+        ml = torch.empty((n, self.num_out - 1), dtype=torch.uint8, device=self._device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        rc = self._lib.rb200_softmax_ml(_ptr(logits), n, self.num_out,
+                                        _ptr(probs) if want_probs else None, _ptr(ml), stream)
+        _native.check(rc, "rb200_softmax_ml")
+        return probs, ml
+
     def infer_host(self, sigs, sequence, seq_to_sig_map, seq_lens):
         """numpy in / numpy out through rb200_infer_host (H2D, kernels, D2H, sync)."""
         sigs = np.ascontiguousarray(sigs, dtype=np.float32)

@@ -156,16 +156,20 @@ def find_focus_bases_in_int_sequence(int_seq, motifs):
     return np.unique(np.concatenate(hits)).astype(int)
 
 
-def format_mm_ml_tags(seq, poss, probs, mod_bases, can_base, strand="+"):
+def format_mm_ml_tags(seq, poss, probs, mod_bases, can_base, strand="+", ml_bytes=None):
     """MM string + ML uint8 array for SAM/BAM (reference util.py:485-537), vectorised: positions sorted
     (stable, like the reference's sort on position), one MM section per modified base in ``mod_bases``
     order, gaps counted in canonical bases.  ML byte = floor(p*256) with 256 -> 255 (util.py:532-535).
-    A ``None`` row of ``probs`` skips that position as in the reference."""
+    A ``None`` row of ``probs`` skips that position as in the reference.  ``ml_bytes`` (extension):
+    uint8 [N, n_mods] already quantised on the device (``B200Model.softmax_ml``); ``probs`` is then
+    not needed."""
     mm_tag, ml_tag = "", array.array("B")
     poss = np.asarray(poss, dtype=np.int64)
     if poss.size == 0:
         return mm_tag, ml_tag
-    if isinstance(probs, np.ndarray) and probs.dtype != object:
+    if ml_bytes is not None:
+        probs = np.asarray(ml_bytes).reshape(poss.size, -1)
+    elif isinstance(probs, np.ndarray) and probs.dtype != object:
         probs = probs.reshape(poss.size, -1).astype(np.float64)
     else:
         keep = np.array([p is not None for p in probs], dtype=bool)
@@ -179,9 +183,12 @@ def format_mm_ml_tags(seq, poss, probs, mod_bases, can_base, strand="+"):
     can_idx = can_count[mod_pos] - 1
     gaps = np.diff(np.concatenate([[-1], can_idx])) - 1
     gap_txt = ",".join(map(str, gaps.tolist()))
-    scaled = np.floor(probs * 256)
-    scaled[scaled == 256] = 255
-    scaled = scaled.astype(np.uint8)
+    if ml_bytes is not None:
+        scaled = probs.astype(np.uint8)
+    else:
+        scaled = np.floor(probs * 256)
+        scaled[scaled == 256] = 255
+        scaled = scaled.astype(np.uint8)
     for col, mb in enumerate(mod_bases):
         if col >= scaled.shape[1]:
             break

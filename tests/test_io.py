@@ -350,6 +350,12 @@ class _OracleModel(torch.nn.Module):
                                            mp.numpy(), ln.numpy())
         return torch.from_numpy(np.ascontiguousarray(res))
 
+    def softmax_ml(self, logits, want_probs=True):
+        from remora_b200 import util
+        probs = util.softmax_axis1(logits.numpy())[:, 1:]
+        ml = torch.from_numpy(self.ro.ml_bytes(probs))
+        return (torch.from_numpy(probs.astype(np.float32)) if want_probs else None), ml
+
 
 def test_pipeline_host_logic_on_cpu(tmp_path):
     """infer_from_pod5_and_bam with every GPU stage switched off or stubbed (oracle forward, numpy signal
