@@ -512,8 +512,8 @@ def ours(args):
 
     # ---- e2e: HOST buffers through the C-ABI host call (rb200_infer_host_async): every step copies its
     # compact inputs from pinned host memory to the device, runs the kernels and copies the logits back
-    # to pinned host memory, all inside the timed region.  Two streams alternate so step i+1's copies
-    # overlap step i's kernels - the same double buffering the reference's queue pipeline does
+    # to pinned host memory, all inside the timed region.  Four streams rotate so later steps' copies
+    # overlap earlier steps' kernels - the same pipelining the reference's queue pipeline does
     # (src/remora/inference.py:488-572); a slot's result is read on the host before the slot is reused.
     n_host = min(n_pool, 16)
     host_batches = []
@@ -521,19 +521,20 @@ def ours(args):
         d = slice_batch(pool, i)
         host_batches.append(tuple(torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in
                                   ("signal", "sequence", "sequence_to_signal_mapping", "sequence_lengths")))
-    e2e_streams = [torch.cuda.Stream(device) for _ in range(2)]
-    e2e_out = [torch.empty((BATCH, model.num_out), dtype=torch.float32).pin_memory() for _ in range(2)]
+    NSLOT = 4  # steps in flight: copies of later steps overlap the kernels of earlier ones
+    e2e_streams = [torch.cuda.Stream(device) for _ in range(NSLOT)]
+    e2e_out = [torch.empty((BATCH, model.num_out), dtype=torch.float32).pin_memory() for _ in range(NSLOT)]
     checksum = 0.0
 
     def e2e_run(n_steps):
         nonlocal checksum
         for i in range(n_steps):
-            slot = i & 1
-            if i >= 2:
-                e2e_streams[slot].synchronize()          # step i-2 finished: its logits are on the host
+            slot = i % NSLOT
+            if i >= NSLOT:
+                e2e_streams[slot].synchronize()          # step i-NSLOT finished: its logits are on the host
                 checksum += float(e2e_out[slot][0, 0])   # host-side read of the step's result
             model.infer_host_async(*host_batches[i % n_host], e2e_out[slot], stream=e2e_streams[slot])
-        for slot in range(2):
+        for slot in range(NSLOT):
             e2e_streams[slot].synchronize()
             checksum += float(e2e_out[slot][0, 0])
 
@@ -654,9 +655,9 @@ def ours(args):
                                     f"{pool_bytes / 1e6:.0f} MB resident pool ({n_pool} batches)"},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "path": "B200Model.infer_host_async -> rb200_infer_host_async, pinned host buffers, 2 "
-                            "alternating streams (double buffered); every step's H2D and D2H are in the "
-                            "timed region",
+                    "path": "B200Model.infer_host_async -> rb200_infer_host_async, pinned host buffers, 4 "
+                            "streams in rotation (a slot's result is read on the host before the slot is "
+                            "reused); every step's H2D and D2H are in the timed region",
                     "blocking_single_call_value": e2e_sync_value,
                     "blocking_single_call_path": "B200Model.infer_host -> rb200_infer_host (pageable "
                                                  "buffers, one call = copy in + kernels + copy out + sync), "

@@ -261,7 +261,16 @@ __device__ __forceinline__ void load_stage(int s, int total, const uint8_t *wstr
 }
 
 // one stride-3 convolution (16 input channels): tap j = 3 i + r reads residue tile r shifted by i rows
-template <int MODE, int KW>
+// the producer side of the weight ring for the phases in which every other warp waits for the tensor core
+// anyway: one thread keeps RING stages in flight (a stage is re-filled as soon as the MMAs that read it
+// complete), so the MMA-issuing thread never blocks on a free slot
+__device__ __forceinline__ void produce_until(int &next, int upto, int total, const uint8_t *wstream, uint8_t *ring,
+                                              Bars *bars) {
+    const int end = upto < total ? upto : total;
+    for (; next < end; ++next) load_stage(next, total, wstream, ring, bars);
+}
+
+template <int MODE, int KW, bool SELF_LOAD>
 __device__ __forceinline__ void issue_conv3(uint32_t xset, uint32_t d_tmem, int &s, const uint8_t *wstream,
                                             uint8_t *ring, Bars *bars) {
     using C = Cfg<MODE>;
@@ -285,7 +294,7 @@ __device__ __forceinline__ void issue_conv3(uint32_t xset, uint32_t d_tmem, int 
             }
         }
         umma_commit(&bars->w_empty[slot]);
-        load_stage(s + RING - 1, C::NS_TOTAL, wstream, ring, bars);
+        if (SELF_LOAD) load_stage(s + RING - 1, C::NS_TOTAL, wstream, ring, bars);
     }
 }
 
@@ -529,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     int s_next = 0;  // weight stage counter of the issuing thread
     if (warp == 0) {
         if (lane == 0) {
-            issue_conv3<MODE, KW_SEQ2>(smem_addr(xq), tmem, s_next, p.wstream, ring, bars);
+            issue_conv3<MODE, KW_SEQ2, true>(smem_addr(xq), tmem, s_next, p.wstream, ring, bars);
             umma_commit(&bars->seq_done);
         }
         __syncwarp();
@@ -600,10 +609,14 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     MG_STAMP(4);
 
     // ---- M2: sig_conv3; E1: both accumulators -> bias + swish -> cat tile (hi / lo) -------------------------
+    // from here on warp 1's lane 0 is the TMA producer of the weight ring (M1 left it RING - 1 stages ahead)
+    int p_next = CF::NS_SEQ + RING - 1;
     if (tid == 0) {
         s_next = CF::NS_SEQ;
-        issue_conv3<MODE, KW_SIG3>(smem_addr(ra + A_XS), tmem + 128, s_next, p.wstream, ring, bars);
+        issue_conv3<MODE, KW_SIG3, false>(smem_addr(ra + A_XS), tmem + 128, s_next, p.wstream, ring, bars);
         umma_commit(&bars->conv_done);
+    } else if (tid == 32) {
+        produce_until(p_next, CF::NS_SEQ + CF::NS_SIG + RING, CF::NS_TOTAL, p.wstream, ring, bars);
     }
     __syncwarp();
     mbar_wait(&bars->conv_done, 0);
@@ -674,10 +687,11 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
                 if (MODE == 0) mma_h(tmem + 64, desc_ns(cat_lo + aoff, LBO_A), desc_ns(b, CF::B_LBO), id_corr, 1u);
             }
             umma_commit(&bars->w_empty[slot]);
-            load_stage(s + RING - 1, CF::NS_TOTAL, p.wstream, ring, bars);
         }
         (void)KBLKS;
         umma_commit(&bars->mrg_done);
+    } else if (tid == 32) {
+        produce_until(p_next, CF::NS_SEQ + CF::NS_SIG + CF::NS_MRG + RING, CF::NS_TOTAL, p.wstream, ring, bars);
     }
     __syncwarp();
     mbar_wait(&bars->mrg_done, 0);
@@ -742,9 +756,10 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
                 mma_h(tmem, desc_ns(m_hi + 2 * st * LBO_A, LBO_A), desc_ns(b, 4096), id_x, st ? 1u : 0u);
             }
             umma_commit(&bars->w_empty[slot]);
-            load_stage(s + RING - 1, CF::NS_TOTAL, p.wstream, ring, bars);
         }
         umma_commit(&bars->xp_done);
+    } else if (tid == 32) {
+        produce_until(p_next, CF::NS_TOTAL, CF::NS_TOTAL, p.wstream, ring, bars);
     }
     __syncwarp();
     mbar_wait(&bars->xp_done, 0);  // every MMA has completed: ring, tiles and region A are dead

@@ -893,68 +893,91 @@ class Read:
     def copy(self):
         return dataclasses.replace(self)
 
-    def add_alignment(self, alignment_record, parse_ref_align=True, reverse_signal=False, pa_scaling=None):
-        """io.py:1972-2084: trim the signal by the sp/ts/ns tags, take basecalls + move table, the
-        sm/sd scaling tags, and (for mapped reads) the reference sequence and base->signal map."""
-        if pa_scaling is not None:
-            self.shift_pa_to_zc_pa, self.scale_pa_to_zc_pa = pa_scaling
-        if alignment_record.reference_name is None and alignment_record.is_reverse:
-            raise RemoraError("Unmapped reads cannot map to reverse strand.")
-        if self.dacs is None:
-            raise RemoraError("Must add signal to io.Read before alignment.")
-        self.full_align = alignment_record.to_dict()
-        if isinstance(alignment_record, AlignedSegment):
-            self.alignment_record = alignment_record
-        tags = dict(alignment_record.tags)
-        if reverse_signal:
-            self.dacs = self.dacs[::-1]
-        self.dacs = self.dacs[tags.get("sp", 0):]
-        self.dacs = self.dacs[tags.get("ts", 0):tags.get("ns", self.dacs.size)]
-        if reverse_signal:
-            self.dacs = self.dacs[::-1]
+    # -- joining a BAM record onto the signal ---------------------------------------------------------
+    # What the basecaller's tags mean (SAM tag conventions of dorado / guppy, as consumed by the reference
+    # at io.py:1972-2084):  sp = samples a parent read was split at, ts = samples trimmed from the start
+    # before basecalling, ns = number of samples the basecaller saw counted from the split point (so the
+    # kept window is [sp + ts, sp + ns)), pi = parent read id of a split read, mv = stride + move table
+    # over that window, sm / sd = shift / scale from pA to the normalised signal the basecaller used.
+    def _window_signal(self, tags, reverse_signal):
+        """Cut the raw samples down to the window the move table describes.  For reversed (RNA) signal
+        the tags refer to the acquisition order, so the cut happens in that order."""
+        sig = self.dacs[::-1] if reverse_signal else self.dacs
+        sig = sig[tags.get("sp", 0):]
+        sig = sig[tags.get("ts", 0):tags.get("ns", sig.size)]
+        self.dacs = sig[::-1] if reverse_signal else sig
         self._sig_len = None
-        parent_read_id = tags.get("pi", None)
-        if parent_read_id is None:
-            if alignment_record.query_name != self.read_id:
-                raise RemoraError("Read IDs mismatch")
-        else:
-            if parent_read_id != self.read_id:
+
+    def _claim_record(self, record, tags):
+        """The record must belong to this read: by name, or - for a split read - through its parent id."""
+        parent = tags.get("pi")
+        if parent is None and record.query_name != self.read_id:
+            raise RemoraError("Read IDs mismatch")
+        if parent is not None:
+            if parent != self.read_id:
                 raise RemoraError("Split read IDs mismatch")
-            self._child_read_id = alignment_record.query_name
-        self.seq = alignment_record.query_sequence
-        if alignment_record.is_reverse:
-            self.seq = util.revcomp(self.seq)
-        try:
+            self._child_read_id = record.query_name
+
+    def _take_basecalls(self, record, tags, reverse_signal):
+        """Basecalls in sequencing direction (BAM stores reverse-strand alignments reverse-complemented)
+        and the first sample of every base from the move table, when there is one."""
+        self.seq = util.revcomp(record.query_sequence) if record.is_reverse else record.query_sequence
+        if "mv" in tags:
             self.query_to_signal, self.mv_table, self.stride = parse_move_tag(
                 tags["mv"], sig_len=self.sig_len, seq_len=len(self.seq), reverse_signal=reverse_signal)
-        except KeyError:
+        else:
             self.query_to_signal = self.mv_table = self.stride = None
-        try:
-            self.shift_pa_to_norm = tags["sm"]
-            self.scale_pa_to_norm = tags["sd"]
-        except KeyError:
+
+    def _take_scaling(self, tags):
+        """pA -> normalised: the basecaller's sm / sd when present, else median / MAD of this read;
+        composed with the POD5 calibration into the DAC -> normalised pair RemoraRead uses."""
+        if "sm" in tags and "sd" in tags:
+            self.shift_pa_to_norm, self.scale_pa_to_norm = tags["sm"], tags["sd"]
+        else:
             self.compute_pa_to_norm_scaling()
         self.shift_dacs_to_norm = self.shift_dacs_to_pa + (self.scale_dacs_to_pa * self.shift_pa_to_norm)
         self.scale_dacs_to_norm = self.scale_dacs_to_pa * self.scale_pa_to_norm
-        if not parse_ref_align or alignment_record.is_unmapped:
-            return
-        self.ref_reg = RefRegion(ctg=alignment_record.reference_name,
-                                 strand="-" if alignment_record.is_reverse else "+",
-                                 start=alignment_record.reference_start)
+
+    def _anchor_to_reference(self, record):
+        """Reference coordinates of a mapped record, everything turned into sequencing direction:
+        region, reference sequence rebuilt from MD + CIGAR, reversed CIGAR on the minus strand, and the
+        first sample of every REFERENCE base by pushing reference positions through the CIGAR onto
+        the move table."""
+        minus = record.is_reverse
+        self.ref_reg = RefRegion(ctg=record.reference_name, strand="-" if minus else "+",
+                                 start=record.reference_start)
         try:
-            self.ref_seq = alignment_record.get_reference_sequence().upper()
-        except ValueError:
+            fwd = record.get_reference_sequence().upper()
+            self.ref_seq = util.revcomp(fwd) if minus else fwd
+        except ValueError:  # no (usable) MD tag
             self.ref_seq = None
-        self.cigar = alignment_record.cigartuples
-        if alignment_record.is_reverse:
-            if self.ref_seq is not None:
-                self.ref_seq = util.revcomp(self.ref_seq)
-            self.cigar = self.cigar[::-1]
-        if self.ref_reg.ctg is not None and self.ref_seq is not None and self.query_to_signal is not None:
-            self.ref_to_signal = compute_ref_to_signal(self.query_to_signal, self.cigar)
-            if self.ref_to_signal.size != len(self.ref_seq) + 1:
-                raise RemoraError("Discordant ref seq lengths")
-            self.ref_reg.end = self.ref_reg.start + self.ref_to_signal.size - 1
+        self.cigar = record.cigartuples[::-1] if minus else record.cigartuples
+        if self.ref_reg.ctg is None or self.ref_seq is None or self.query_to_signal is None:
+            return
+        self.ref_to_signal = compute_ref_to_signal(self.query_to_signal, self.cigar)
+        if self.ref_to_signal.size != len(self.ref_seq) + 1:
+            raise RemoraError("Discordant ref seq lengths")
+        self.ref_reg.end = self.ref_reg.start + self.ref_to_signal.size - 1
+
+    def add_alignment(self, alignment_record, parse_ref_align=True, reverse_signal=False, pa_scaling=None):
+        """Join a BAM record onto a read that already holds its POD5 samples and calibration
+        (same signature and resulting fields as the reference method, io.py:1972-2084)."""
+        if self.dacs is None:
+            raise RemoraError("Must add signal to io.Read before alignment.")
+        if alignment_record.reference_name is None and alignment_record.is_reverse:
+            raise RemoraError("Unmapped reads cannot map to reverse strand.")
+        if pa_scaling is not None:
+            self.shift_pa_to_zc_pa, self.scale_pa_to_zc_pa = pa_scaling
+        tags = dict(alignment_record.tags)
+        self.full_align = alignment_record.to_dict()
+        if isinstance(alignment_record, AlignedSegment):
+            self.alignment_record = alignment_record
+        self._window_signal(tags, reverse_signal)
+        self._claim_record(alignment_record, tags)
+        self._take_basecalls(alignment_record, tags, reverse_signal)
+        self._take_scaling(tags)
+        if parse_ref_align and not alignment_record.is_unmapped:
+            self._anchor_to_reference(alignment_record)
 
     @classmethod
     def from_pod5_and_alignment(cls, pod5_read_record, alignment_record, reverse_signal=False, pa_scaling=None):

@@ -78,52 +78,66 @@ def quantile_linear(a, q):
     return out
 
 
-def rescale_lstsq(dacs, levels, shift, scale):
-    norm_sig = (dacs - shift) / scale
-    shift_est, scale_est = np.linalg.lstsq(
-        np.column_stack([np.ones_like(norm_sig), norm_sig]), levels, rcond=None)[0]
-    if scale_est == 0:
+# The re-scaling estimators all do the same thing: fit a line  level ~ b0 + b1 * x  through points
+# (x = currently-normalised signal summary, level = expected k-mer level) and fold it into the read's
+# (shift, scale).  What differs is (a) which points (quantiles of the whole read for the rough pass,
+# per-base means for the refinement rounds) and (b) the line estimator.  The two estimators fold the fit
+# in with algebraically equal but differently rounded expressions in the reference
+# (refine_signal_map.py:68-80 vs :95-103); both forms are kept verbatim in `_fold_*` because the
+# resulting shift / scale are compared bit for bit with the reference's (tests/test_refine.py).
+def _line_least_squares(x, y):
+    """(b0, b1) minimising |b0 + b1 x - y|^2 through numpy's LAPACK driver - the same call the
+    reference makes, so the estimates agree to the last bit."""
+    design = np.column_stack([np.ones_like(x), x])
+    b0, b1 = np.linalg.lstsq(design, y, rcond=None)[0]
+    return b0, b1
+
+
+def _line_theil_sen(x, y):
+    """Median of the pairwise slopes over pairs with increasing x, then the median residual."""
+    dx = x[:, np.newaxis] - x
+    dy = y[:, np.newaxis] - y
+    rising = dx > 0
+    b1 = np.median(dy[rising] / dx[rising])
+    b0 = np.median(y - (b1 * x))
+    return b0, b1
+
+
+def _fold_least_squares(shift, scale, b0, b1):
+    if b1 == 0:  # degenerate fit: keep the read's scaling
         return shift, scale
-    return shift - (scale * shift_est / scale_est), scale / scale_est
+    return shift - (scale * b0 / b1), scale / b1
 
 
-def rough_rescale_lstsq(dacs, levels, shift, scale, quants):
-    norm_sig = (dacs - shift) / scale
-    norm_qs = quantile_linear(norm_sig, quants)
-    shift_est, scale_est = np.linalg.lstsq(
-        np.column_stack([np.ones_like(norm_qs), norm_qs]), quantile_linear(levels, quants),
-        rcond=None)[0]
-    if scale_est == 0:
-        return shift, scale
-    return shift - (scale * shift_est / scale_est), scale / scale_est
-
-
-def compute_slopes(r_event_means, r_model_means):
-    delta_event = r_event_means[:, np.newaxis] - r_event_means
-    delta_model = r_model_means[:, np.newaxis] - r_model_means
-    return delta_model[delta_event > 0] / delta_event[delta_event > 0]
-
-
-def theil_sen(dacs, lvls, shift, scale):
-    slope = np.median(compute_slopes(dacs, lvls))
-    inter = np.median(lvls - (slope * dacs))
-    if slope == 0:
+def _fold_theil_sen(shift, scale, b0, b1):
+    if b1 == 0:
         raise RemoraError("Read failed sequence-based signal re-scaling parameter estimation.")
-    return shift + (-inter / slope * scale), scale * (1 / slope)
+    return shift + (-b0 / b1 * scale), scale * (1 / b1)
 
 
-def rescale_theil_sen(dacs, levels, shift, scale):
-    norm_sig = (dacs - shift) / scale
-    if levels.shape[0] > MAX_POINTS_FOR_THEIL_SEN:
-        samp_ind = np.random.choice(levels.shape[0], MAX_POINTS_FOR_THEIL_SEN, replace=False)
-        levels = levels[samp_ind]
-        norm_sig = norm_sig[samp_ind]
-    return theil_sen(norm_sig, levels, shift, scale)
+_ESTIMATORS = {
+    ROUGH_RESCALE_LEAST_SQUARES: (_line_least_squares, _fold_least_squares),
+    ROUGH_RESCALE_THEIL_SEN: (_line_theil_sen, _fold_theil_sen),
+}
 
 
-def rough_rescale_theil_sen(dacs, levels, shift, scale, quants):
-    norm_sig = (dacs - shift) / scale
-    return theil_sen(quantile_linear(norm_sig, quants), quantile_linear(levels, quants), shift, scale)
+def recalibrate(points, levels, shift, scale, method, quantiles=None, max_points=None):
+    """New (shift, scale) from DAC-domain ``points`` and the ``levels`` they should sit on.
+    ``quantiles``: compare the two distributions at these quantiles instead of point by point (rough
+    pass, refine_signal_map.py:82-93, 115-122); ``max_points``: random sub-sample of the pairs before a
+    Theil-Sen fit, whose cost is quadratic (:105-113)."""
+    try:
+        line, fold = _ESTIMATORS[method]
+    except KeyError:
+        raise RemoraError(f"Invalid rough re-scale method: {method}")
+    x = (points - shift) / scale
+    y = levels
+    if quantiles is not None:
+        x, y = quantile_linear(x, quantiles), quantile_linear(y, quantiles)
+    elif max_points is not None and y.shape[0] > max_points:
+        pick = np.random.choice(y.shape[0], max_points, replace=False)
+        x, y = x[pick], y[pick]
+    return fold(shift, scale, *line(x, y))
 
 
 def index_from_kmer(kmer, alphabet="ACGT"):
@@ -135,46 +149,48 @@ def index_from_kmer(kmer, alphabet="ACGT"):
 # ------------------------------------------------------------------------------------------------
 # banding (host, integer numpy; same integers as the reference)
 # ------------------------------------------------------------------------------------------------
-def compute_sig_band(bps, levels, bhw=DEFAULT_REFINE_HBW, is_banded=True):
-    """Per signal sample, the range of bases it may be assigned to (refine_signal_map.py:634-688)."""
-    if is_banded and bhw is None:
-        raise RemoraError("Cannot compute band with half width of None.")
-    seq_len = levels.size
-    if bps.size - 1 != seq_len:
+def base_space_band(seq_to_sig_map, levels, hbw=DEFAULT_REFINE_HBW):
+    """Seq band of a read, int32 [2, n_bases]: for every base the half-open range of signal samples it
+    may be moved over, before ``adjust_seq_band``.
+
+    Definition (what refine_signal_map.py:634-688 + :743-775 compute through two per-SAMPLE arrays): a
+    sample that currently belongs to base b may be re-assigned to bases [b - hbw, b + hbw] (clipped to
+    the read); a base without a level (NaN: its k-mer holds an N) keeps exactly its own samples; both
+    bounds are made monotone along the signal (running max of the lower, running min from the right of
+    the upper bound); base q may then cover the samples whose bounds contain q.  Only bases that own
+    at least one sample take part, and the bounds are constant over a base's dwell - so everything is
+    computed per BASE here (O(bases log bases), no per-sample array), by two binary searches over the
+    monotone bounds.  The integers equal the sample-space construction's (randomised test against the
+    oracle's restatement of it, tests/test_refine.py)."""
+    n = levels.shape[0]
+    rel = np.asarray(seq_to_sig_map, dtype=np.int64)
+    if rel.size - 1 != n:
         raise RemoraError("Breakpoints must be one longer than levels.")
-    sig_len = int(bps[-1] - bps[0])
-    seq_indices = np.repeat(np.arange(seq_len), np.diff(bps))
-    band = np.empty((2, sig_len), dtype=np.int32)
-    if is_banded:
-        band[0] = np.maximum(seq_indices - bhw, 0)
-        band[1] = np.minimum(seq_indices + bhw + 1, seq_len)
-    else:
-        band[0] = 0
-        band[1] = seq_len
-    nan_levels = np.isnan(levels)
-    if nan_levels.any():  # bases without a level keep their original samples
-        nan_mask = nan_levels[seq_indices]
-        nan_seq = seq_indices[nan_mask]
-        band[0, nan_mask] = nan_seq
-        band[1, nan_mask] = nan_seq + 1
-    band[0] = np.maximum.accumulate(band[0])
-    band[1] = np.minimum.accumulate(band[1, ::-1])[::-1]
+    if hbw is None:
+        raise RemoraError("Cannot compute band with half width of None.")
+    rel = rel - rel[0]
+    sig_len = int(rel[-1])
+    base = np.arange(n)
+    unknown = np.isnan(levels)
+    lower = np.where(unknown, base, np.maximum(base - hbw, 0))
+    upper = np.where(unknown, base + 1, np.minimum(base + hbw + 1, n))
+    owns = np.diff(rel) > 0
+    if not owns.any():
+        raise RemoraError("Band contains 0-length region")
+    first_sample = rel[:-1][owns]
+    lower = np.maximum.accumulate(lower[owns])
+    upper = np.minimum.accumulate(upper[owns][::-1])[::-1]
+    n_q = int(upper[-1])  # bases reachable from the last sample
+    q = np.arange(n_q)
+    band = np.empty((2, n_q), dtype=np.int32)
+    # start: first sample whose upper bound already exceeds q (upper[-1] = n_q > q: always found)
+    band[0] = first_sample[np.searchsorted(upper, q, side="right")]
+    # end: first sample AFTER sample 0 at which the lower bound steps above q; none -> end of the signal
+    step = np.searchsorted(lower, q, side="right")
+    later = np.searchsorted(lower, lower[0], side="right")  # first owner whose bound exceeds the first one's
+    step = np.where(step == 0, later, step)
+    band[1] = np.where(step < first_sample.size, first_sample[np.minimum(step, first_sample.size - 1)], sig_len)
     return band
-
-
-def convert_to_seq_band(sig_band):
-    """Per base, the range of signal samples it may cover (refine_signal_map.py:743-775)."""
-    sig_len = sig_band.shape[1]
-    seq_len = int(sig_band[1, -1])
-    seq_band = np.zeros((2, seq_len), dtype=np.int32)
-    seq_band[1, :] = sig_len
-    lower_sig_pos = np.nonzero(np.ediff1d(sig_band[1], to_begin=0))[0]
-    seq_band[0, sig_band[1, lower_sig_pos - 1]] = lower_sig_pos
-    seq_band[0] = np.maximum.accumulate(seq_band[0])
-    upper_sig_pos = np.nonzero(np.ediff1d(sig_band[0], to_begin=0))[0]
-    seq_band[1, sig_band[0, upper_sig_pos] - 1] = upper_sig_pos
-    seq_band[1] = np.minimum.accumulate(seq_band[1, ::-1])[::-1]
-    return seq_band
 
 
 def adjust_seq_band(seq_band, min_step=2):
@@ -207,26 +223,26 @@ def adjust_seq_band(seq_band, min_step=2):
 
 
 def validate_band(band, sig_len=None, seq_len=None, is_sig_band=True):
-    """refine_signal_map.py:691-740"""
-    if band[0, 0] != 0:
-        raise RemoraError("Band does not start with 0 coordinate.")
-    if (band[1] - band[0]).min() <= 0:
-        raise RemoraError("Band contains 0-length region")
-    if band.shape[1] > 1:
-        if np.diff(band[0]).min() < 0:
-            raise RemoraError("Band start positions are not monotonically increasing")
-        if np.diff(band[1]).min() < 0:
-            raise RemoraError("Band end positions are not monotonically increasing")
-    if is_sig_band:
-        if sig_len is not None and band.shape[1] != sig_len:
-            raise RemoraError("Invalid sig_band length")
-        if seq_len is not None and band[1, -1] != seq_len:
-            raise RemoraError("Invalid sig_band end coordinate")
-    else:
-        if sig_len is not None and band[1, -1] != sig_len:
-            raise RemoraError("Invalid seq_band end coordinate")
-        if seq_len is not None and band.shape[1] != seq_len:
-            raise RemoraError("Invalid sig_band length")
+    """Raise ``RemoraError`` (the reference's messages, refine_signal_map.py:691-740) unless ``band``
+    [2, n] starts at 0, has no empty interval, is monotone in both rows and ends where the other
+    coordinate system says it should."""
+    starts, ends = band[0], band[1]
+    length_of, end_of = ("sig", "seq") if is_sig_band else ("seq", "sig")
+    want = {"sig": sig_len, "seq": seq_len}
+    checks = [
+        (starts[0] != 0, "Band does not start with 0 coordinate."),
+        ((ends - starts).min() <= 0, "Band contains 0-length region"),
+        (starts.size > 1 and np.diff(starts).min() < 0, "Band start positions are not monotonically increasing"),
+        (starts.size > 1 and np.diff(ends).min() < 0, "Band end positions are not monotonically increasing"),
+        (want[length_of] is not None and starts.size != want[length_of], "Invalid sig_band length"),
+        (want[end_of] is not None and ends[-1] != want[end_of],
+         f"Invalid {'sig' if is_sig_band else 'seq'}_band end coordinate"),
+    ]
+    if not is_sig_band:  # the reference tests the end coordinate before the length for a seq band
+        checks[4], checks[5] = checks[5], checks[4]
+    for failed, message in checks:
+        if failed:
+            raise RemoraError(message)
 
 
 def _check_dp_preconditions(seq_band):
@@ -239,26 +255,15 @@ def _check_dp_preconditions(seq_band):
 
 
 def compute_seq_band(seq_to_sig_map, levels, band_half_width=DEFAULT_REFINE_HBW, adjust_band_min_step=2):
-    """seq band of one read, as ``refine_signal_mapping`` builds it (refine_signal_map.py:814-826);
-    ``seq_to_sig_map`` must start at 0."""
+    """seq band of one read, as ``refine_signal_mapping`` builds it (refine_signal_map.py:814-826):
+    band in base space, minimum-step adjustment, validation."""
     seq_to_sig_map = np.asarray(seq_to_sig_map)
-    n = levels.shape[0]
-    if (seq_to_sig_map.size == n + 1 and n > 0 and seq_to_sig_map[-1] > seq_to_sig_map[-2]
-            and not np.isnan(levels).any()):
-        # closed form of compute_sig_band + convert_to_seq_band when every base has a level and the
-        # last base owns a sample: base b may cover the samples of bases b-hbw .. b+hbw; a band end
-        # at sample 0 (leading zero-dwell bases) takes the first positive end, as the reference's
-        # right-to-left minimum does.  O(bases) instead of O(samples); equality with the sample-space
-        # construction is tested on random maps (tests/test_refine.py).
-        b = np.arange(n)
-        seq_band = np.empty((2, n), dtype=np.int32)
-        seq_band[0] = seq_to_sig_map[np.maximum(b - band_half_width, 0)]
-        en = seq_to_sig_map[np.minimum(b + band_half_width + 1, n)]
-        seq_band[1] = np.where(en == 0, en[en > 0][0], en)
-    else:
-        seq_band = convert_to_seq_band(compute_sig_band(seq_to_sig_map, levels, bhw=band_half_width))
+    seq_band = base_space_band(seq_to_sig_map, levels, band_half_width)
+    if seq_band.shape[1] != levels.shape[0]:
+        raise RemoraError("Invalid sig_band length")
     seq_band = adjust_seq_band(seq_band, min_step=adjust_band_min_step)
-    validate_band(seq_band, sig_len=int(seq_to_sig_map[-1]), seq_len=levels.shape[0], is_sig_band=False)
+    validate_band(seq_band, sig_len=int(seq_to_sig_map[-1] - seq_to_sig_map[0]), seq_len=levels.shape[0],
+                  is_sig_band=False)
     _check_dp_preconditions(seq_band)
     return seq_band
 
@@ -629,45 +634,49 @@ class SigMapRefiner:
     # -- re-scaling ----------------------------------------------------------------------------
     def rough_rescale(self, shift, scale, seq_to_sig_map, int_seq, dacs,
                       quants=np.arange(0.05, 1, 0.05), clip_bases=10, use_base_center=True, levels=None):
-        """refine_signal_map.py:390-430 (``levels``: optional pre-computed ``extract_levels(int_seq)``)"""
+        """Quantile matching of the read against its expected levels (reference signature,
+        refine_signal_map.py:390-430; ``levels``: optional pre-computed ``extract_levels(int_seq)``).
+        One sample per base (the one in the middle of its dwell) with ``clip_bases`` dropped at both ends,
+        or every mapped sample when ``use_base_center`` is off."""
         if levels is None:
             levels = self.extract_levels(int_seq)
-        if use_base_center:
-            optim_dacs = dacs[(seq_to_sig_map[:-1] + seq_to_sig_map[1:]) // 2]
-            if clip_bases > 0 and levels.size > clip_bases * 2:
-                levels = levels[clip_bases:-clip_bases]
-                optim_dacs = optim_dacs[clip_bases:-clip_bases]
+        if not use_base_center:
+            picked = dacs[seq_to_sig_map[0]:seq_to_sig_map[-1]]
         else:
-            optim_dacs = dacs[seq_to_sig_map[0]:seq_to_sig_map[-1]]
-        if self.rough_rescale_method == ROUGH_RESCALE_LEAST_SQUARES:
-            return rough_rescale_lstsq(optim_dacs, levels, shift, scale, quants)
-        if self.rough_rescale_method == ROUGH_RESCALE_THEIL_SEN:
-            return rough_rescale_theil_sen(optim_dacs, levels, shift, scale, quants)
-        raise RemoraError(f"Invalid rough re-scale method: {self.rough_rescale_method}")
+            picked = dacs[(seq_to_sig_map[:-1] + seq_to_sig_map[1:]) // 2]
+            if clip_bases > 0 and levels.size > 2 * clip_bases:
+                inner = slice(clip_bases, -clip_bases)
+                picked, levels = picked[inner], levels[inner]
+        return recalibrate(picked, levels, shift, scale, self.rough_rescale_method, quantiles=quants)
+
+    @staticmethod
+    def _base_means(dacs, seq_to_sig_map):
+        """Mean DAC value of every base's dwell from one running sum (NaN for zero-dwell bases)."""
+        running = np.empty(dacs.size + 1)
+        running[0] = 0
+        running[1:] = np.cumsum(dacs)
+        dwells = np.diff(seq_to_sig_map)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.diff(running[seq_to_sig_map]) / dwells, dwells
 
     def rescale(self, levels, dacs, shift, scale, seq_to_sig_map, dwell_filter_pctls=(10, 90),
                 min_abs_level=0.2, edge_filter_bases=10, min_levels=10):
-        """refine_signal_map.py:432-472"""
-        with np.errstate(invalid="ignore", divide="ignore"):
-            dacs_cumsum = np.empty(dacs.size + 1)
-            dacs_cumsum[0] = 0
-            dacs_cumsum[1:] = np.cumsum(dacs)
-            dwells = np.diff(seq_to_sig_map)
-            dac_means = np.diff(dacs_cumsum[seq_to_sig_map]) / dwells
-        dwell_min, dwell_max = np.percentile(dwells, dwell_filter_pctls)
-        edge_filter = np.full(dwells.size, True, dtype=np.bool_)
+        """Theil-Sen re-fit on per-base means after a refinement round (reference signature,
+        refine_signal_map.py:432-472).  Bases are used when their dwell lies strictly inside the given
+        dwell percentiles, their level is informative (away from the mean level), they have samples,
+        and they are not within ``edge_filter_bases`` of either read end."""
+        means, dwells = self._base_means(dacs, seq_to_sig_map)
+        shortest, longest = np.percentile(dwells, dwell_filter_pctls)
+        keep = (dwells > shortest) & (dwells < longest)
+        keep &= np.abs(levels - np.mean(levels)) > min_abs_level
+        keep &= ~np.isnan(means)
         if edge_filter_bases > 0:
-            edge_filter[:edge_filter_bases] = False
-            edge_filter[-edge_filter_bases:] = False
-        valid_bases = np.logical_and.reduce((
-            dwells > dwell_min, dwells < dwell_max,
-            np.abs(levels - np.mean(levels)) > min_abs_level,
-            np.logical_not(np.isnan(dac_means)), edge_filter))
-        filt_levels = levels[valid_bases]
-        filt_dacs = dac_means[valid_bases]
-        if filt_levels.size < min_levels:
+            keep[:edge_filter_bases] = False
+            keep[-edge_filter_bases:] = False
+        if np.count_nonzero(keep) < min_levels:
             raise RemoraError("Too few positions")
-        return rescale_theil_sen(filt_dacs, filt_levels, shift, scale)
+        return recalibrate(means[keep], levels[keep], shift, scale, ROUGH_RESCALE_THEIL_SEN,
+                           max_points=MAX_POINTS_FOR_THEIL_SEN)
 
     # -- mapping refinement ----------------------------------------------------------------------
     def refine_sig_maps(self, shifts, scales, seq_to_sig_maps, int_seqs, dacs_list, levels=None, errors=None):
@@ -757,56 +766,46 @@ class SigMapRefiner:
         return errors
 
     # -- (de)serialisation -------------------------------------------------------------------------
+    # model metadata key -> field (the key names are the wire format of meta.txt, model_util.py:115-176)
+    _METADATA_FIELDS = (
+        ("refine_kmer_levels", "_levels_array"), ("refine_kmer_center_idx", "center_idx"),
+        ("refine_do_rough_rescale", "do_rough_rescale"), ("refine_scale_iters", "scale_iters"),
+        ("refine_algo", "algo"), ("refine_half_bandwidth", "half_bandwidth"), ("refine_sd_arr", "sd_arr"),
+        ("rough_rescale_method", "rough_rescale_method"),
+    )
+
     def asdict(self):
-        return {
-            "refine_kmer_levels": self._levels_array,
-            "refine_kmer_center_idx": self.center_idx,
-            "refine_do_rough_rescale": self.do_rough_rescale,
-            "refine_scale_iters": self.scale_iters,
-            "refine_algo": self.algo,
-            "refine_half_bandwidth": self.half_bandwidth,
-            "refine_sd_arr": self.sd_arr,
-            "rough_rescale_method": self.rough_rescale_method,
-        }
+        return {key: getattr(self, field) for key, field in self._METADATA_FIELDS}
 
     @classmethod
     def load_from_metadata(cls, metadata, device=None):
-        return cls(
-            _levels_array=metadata.get("refine_kmer_levels"),
-            center_idx=metadata.get("refine_kmer_center_idx"),
-            do_rough_rescale=metadata.get("refine_do_rough_rescale"),
-            scale_iters=metadata.get("refine_scale_iters"),
-            algo=metadata.get("refine_algo"),
-            half_bandwidth=metadata.get("refine_half_bandwidth"),
-            sd_arr=metadata.get("refine_sd_arr"),
-            rough_rescale_method=metadata.get("rough_rescale_method", ROUGH_RESCALE_LEAST_SQUARES),
-            device=device,
-        )
+        fields = {field: metadata.get(key) for key, field in cls._METADATA_FIELDS}
+        if fields["rough_rescale_method"] is None:  # models exported before the key existed
+            fields["rough_rescale_method"] = ROUGH_RESCALE_LEAST_SQUARES
+        return cls(device=device, **fields)
 
     @classmethod
     def load_from_dict(cls, data, do_rough_rescale=True, scale_iters=-1, algo=DEFAULT_REFINE_ALGO,
                        half_bandwidth=DEFAULT_REFINE_HBW, sd_params=None, do_fix_guage=False,
                        sd_arr=DEFAULT_REFINE_SHORT_DWELL_PEN,
                        rough_rescale_method=DEFAULT_ROUGH_RESCALE_METHOD, device=None):
-        return cls(do_rough_rescale=do_rough_rescale, scale_iters=scale_iters, algo=algo,
-                   half_bandwidth=half_bandwidth, sd_params=sd_params, do_fix_guage=do_fix_guage,
-                   sd_arr=sd_arr, str_kmer_levels=data, rough_rescale_method=rough_rescale_method,
-                   device=device)
+        """A refiner from a ``{kmer: level}`` dictionary (reference keyword surface)."""
+        options = dict(locals())
+        del options["cls"], options["data"]
+        return cls(str_kmer_levels=data, **options)
+
+    def _behaviour_key(self):
+        """Everything that decides what this refiner does to a read - and nothing else: settings of a
+        stage that is switched off do not count (same notion of equality as refine_signal_map.py:553-580)."""
+        def raw(arr):
+            return None if arr is None else np.asarray(arr).tobytes()
+        key = [self.do_rough_rescale, self.scale_iters]
+        if self.do_rough_rescale or self.scale_iters >= 0:
+            key += [self.rough_rescale_method, self.center_idx, raw(self._levels_array),
+                    None if self._levels_array is None else np.asarray(self._levels_array).shape]
+        if self.scale_iters >= 0:
+            key += [self.algo, self.half_bandwidth, raw(self.sd_arr)]
+        return key
 
     def __eq__(self, other):
-        """refine_signal_map.py:553-580"""
-        if not isinstance(other, SigMapRefiner):
-            return False
-        if self.do_rough_rescale != other.do_rough_rescale or self.scale_iters != other.scale_iters:
-            return False
-        if not self.do_rough_rescale and self.scale_iters < 0:
-            return True
-        if self.rough_rescale_method != other.rough_rescale_method:
-            return False
-        if (not np.array_equal(self._levels_array, other._levels_array)
-                or self.center_idx != other.center_idx):
-            return False
-        if self.scale_iters < 0:
-            return True
-        return (self.algo == other.algo and self.half_bandwidth == other.half_bandwidth
-                and np.array_equal(self.sd_arr, other.sd_arr))
+        return isinstance(other, SigMapRefiner) and self._behaviour_key() == other._behaviour_key()
