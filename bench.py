@@ -425,7 +425,27 @@ def ours(args):
     # (G x 8 KB per rank), so the collective's host-side launch cost (tens of microseconds, comparable to a
     # whole 104 us step) is paid once per group and the transfer overlaps the next group's kernels.
     G = max(1, args.gather_every)
+    peer_ring, gather_mode = None, None
     if distributed:
+        gather_mode = args.gather
+        if gather_mode == "p2p":
+            # the exchange fused into the kernel: the classifier epilogue stores into every rank's ring over
+            # NVLink (symmetric memory), no collective launch at all; NCCL stays as the fallback
+            try:
+                from remora_b200.parallel import PeerLogitRing
+                peer_ring = PeerLogitRing(model, slots=2, steps=G, batch=BATCH, multicast=args.multicast)
+                model.forward_compact(*dev_batch(0))
+                if model.last_impl not in ("fused_mega", "fused_bf16"):
+                    raise RuntimeError("single-kernel path not selected")
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] p2p gather unavailable ({str(e)[:200]}); using NCCL all-gather", file=sys.stderr)
+                peer_ring, gather_mode = None, "nccl"
+            # every rank must take the same path
+            agree = torch.tensor([1 if peer_ring is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 0:
+                peer_ring, gather_mode = None, "nccl"
         local_ring = torch.empty((2, G, BATCH, model.num_out), dtype=torch.float32, device=device)
         gath_ring = torch.empty((2, world * G * BATCH, model.num_out), dtype=torch.float32, device=device)
     pending = [None, None]
@@ -435,6 +455,9 @@ def ours(args):
             model.forward_compact(*dev_batch(i))
             return
         slot, k = (i // G) & 1, i % G
+        if peer_ring is not None:
+            peer_ring.forward(model, dev_batch(i), slot, k, signal=args.signal)
+            return
         if k == 0 and pending[slot] is not None:
             pending[slot].wait()  # stream-side wait: the gather that still reads this slot
             pending[slot] = None
@@ -482,6 +505,8 @@ def ours(args):
     # its last group to everybody (bytes over NCCL), recomputes all of them locally and compares.
     gather_verified = None
     if distributed:
+        if peer_ring is not None:
+            peer_ring.barrier()                       # every rank's kernels (and their peer stores) are done
         first = ((args.steps - 1) // G) * G           # first step of the last (possibly partial) group
         n_in_group = args.steps - first
         slot = (first // G) & 1
@@ -499,7 +524,8 @@ def ours(args):
                 dts = [torch.float32, torch.int8, torch.int16, torch.int16]
                 args_r = [p[r].view(dt).reshape(tuple(sh)) for p, dt, sh in zip(parts, dts, shapes)]
                 want = model.forward_compact(*args_r)
-                got = gath_ring[slot].view(world, G, BATCH, -1)[r, k]
+                got = (peer_ring.block(slot)[r, k] if peer_ring is not None
+                       else gath_ring[slot].view(world, G, BATCH, -1)[r, k])
                 ok = ok and bool(torch.equal(got, want))
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -648,8 +674,14 @@ def ours(args):
                                    "variant the config names is timed in `variants`",
                        "batch_per_gpu": BATCH, "global_batch": world * BATCH,
                        "chunk_len": CHUNK_LEN, "kmer_context": list(KMER_CONTEXT),
-                       "parallelism": (f"batch-shard x{world}, logits all-gathered (NCCL) in groups of "
-                                       f"{G} steps, asynchronously" if world > 1 else "single GPU"),
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"batch-shard x{world}; exchange fused into the kernel: the classifier "
+                                       f"epilogue stores every step's logits into every rank's ring over NVLink "
+                                       f"(symmetric memory{', NVLS multicast' if peer_ring.multicast_ptr else ''}), "
+                                       f"no collective launch" if peer_ring is not None else
+                                       f"batch-shard x{world}, logits all-gathered (NCCL) in groups of "
+                                       f"{G} steps, asynchronously"),
+                       "gather": gather_mode,
                        "impl": impl_used,
                        "l2_policy": f"inputs larger than L2: each step reads a different batch of a "
                                     f"{pool_bytes / 1e6:.0f} MB resident pool ({n_pool} batches)"},
@@ -835,6 +867,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gather-every", type=int, default=8,
                     help="multi-GPU: steps per all-gather of the logits (every step's logits are gathered)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange of the logits: fused peer stores from the kernel (default) or NCCL")
+    ap.add_argument("--multicast", action="store_true", help="p2p gather through the NVLS multicast address")
+    ap.add_argument("--signal", action="store_true",
+                    help="p2p gather: also bump the per-step arrival counters on every rank (system-scope fence "
+                         "per thread block); the bench reads the ring only after a barrier and leaves it off")
     ap.add_argument("--pool-batches", type=int, default=400,
                     help="resident batches of compact inputs (400 x 1024 x 480 B = 197 MB > L2)")
     args = ap.parse_args()

@@ -151,6 +151,27 @@ int rb200_forward_compact(rb200_handle h, const float *sigs_dev, const int8_t *s
                           const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
                           void *stream);
 
+/* Fused compute + exchange for the multi-GPU form of the path: rb200_forward_compact whose
+ * classifier epilogue stores every chunk's logits straight into the logits buffer of EVERY rank over
+ * NVLink / NVSwitch, instead of a separate collective after the kernel (the reference has no multi-device
+ * mode; its order contract for gathered batches is src/remora/inference.py:331-367).
+ *   peer_bases_dev : device array of n_peers float* (n_peers <= 32): the base of each rank's buffer as mapped
+ *                    into THIS process (CUDA IPC / torch symmetric memory `buffer_ptrs_dev`), own rank included
+ *   dst_offset     : float offset inside every buffer of this call's [B][num_out] block
+ *   multicast_base : NVLS multicast alias of the same buffers (symmetric memory `multicast_ptr`), or NULL;
+ *                    when given, ONE multimem.st per value reaches all ranks through the switch
+ *   flag_word      : >= 0: index (in 4-byte words from the buffer base) of a uint32 arrival counter that
+ *                    every CTA increments on every rank after its stores are visible system-wide; the block
+ *                    is complete on a rank when the counter has advanced by ceil(B / 4).  -1: no counter
+ *   logits_dev     : optional local copy of the logits (may be NULL)
+ * Only the single-kernel path provides it (RB200_ERR_UNSUPPORTED otherwise: use rb200_forward_compact and a
+ * collective). */
+int rb200_forward_compact_gather(rb200_handle h, const float *sigs_dev, const int8_t *seqs_dev,
+                                 int32_t seq_width, const int16_t *maps_dev, int32_t map_width,
+                                 const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
+                                 void *const *peer_bases_dev, int32_t n_peers, int64_t dst_offset,
+                                 void *multicast_base, int64_t flag_word, void *stream);
+
 /* End-to-end convenience for host callers (the bench's e2e leg and non-torch hosts): copies the
  * compact arrays host->device through pinned staging, runs rb200_forward_compact, copies the
  * logits back and synchronises.  Host buffers may be pageable. */
@@ -239,11 +260,15 @@ int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const f
  * Row i occupies bytes [row_off[i], row_off[i+1]) of packed_dev: ceil(n/8) key bytes (bit k%8 of byte
  * k/8 set = value k takes two bytes) then the little-endian data bytes; it decodes to row_samples[i]
  * int16 samples written at out_dev + out_off[i] (offsets that are multiples of 8 samples get 16-byte
- * stores).  packed_dev must be readable 16 bytes past row_off[n_rows].  status[i] = 1 when the stream
- * length disagrees with the keys (corrupt row). */
+ * stores).  packed_dev must be readable 16 bytes past row_off[n_rows].  max_row_samples >= every
+ * row_samples[i] sizes the launch: one thread block per 8192-sample tile of every row, so rows are decoded
+ * in parallel WITHIN a row too; scratch_dev (rb200_svb16_scratch_bytes, 4 B per tile) carries the running
+ * sums between the tiles of a row.  status[i] = 1 when the stream length disagrees with the keys or the
+ * sample count cannot fit the row's bytes (corrupt row; nothing is read past the row). */
+int rb200_svb16_scratch_bytes(int32_t n_rows, int32_t max_row_samples, int64_t *bytes);
 int rb200_svb16_decode(const uint8_t *packed_dev, const int64_t *row_off_dev, const int32_t *row_samples_dev,
-                       const int64_t *out_off_dev, int32_t n_rows, int16_t *out_dev, int32_t *status_dev,
-                       void *stream);
+                       const int64_t *out_off_dev, int32_t n_rows, int32_t max_row_samples, int16_t *out_dev,
+                       int32_t *status_dev, void *scratch_dev, void *stream);
 
 #ifdef __cplusplus
 }

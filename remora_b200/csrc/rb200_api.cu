@@ -383,6 +383,37 @@ int rb200_forward_compact(rb200_handle h, const float *sigs_dev, const int8_t *s
                           B, T, logits_dev, stream);
 }
 
+int rb200_forward_compact_gather(rb200_handle h, const float *sigs_dev, const int8_t *seqs_dev,
+                                 int32_t seq_width, const int16_t *maps_dev, int32_t map_width,
+                                 const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
+                                 void *const *peer_bases_dev, int32_t n_peers, int64_t dst_offset,
+                                 void *multicast_base, int64_t flag_word, void *stream_v) {
+    RB200_REQUIRE(h != nullptr, "null handle");
+    RB200_REQUIRE(B >= 0 && T > 0, "bad batch (%d) / chunk_len (%d)", B, T);
+    if (B == 0) return RB200_OK;
+    RB200_REQUIRE(sigs_dev && seqs_dev && maps_dev && lens_dev && peer_bases_dev, "null buffer");
+    RB200_REQUIRE(n_peers >= 1 && n_peers <= 32 && dst_offset >= 0, "bad gather target");
+    RB200_REQUIRE(map_width >= 2 && seq_width >= h->desc.kmer_len, "compact arrays too narrow");
+    DeviceGuard guard(h->device);
+    RB200_REQUIRE(guard.ok, "cannot select device %d", h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    const int impl = h->impl;
+    if (!(impl == RB200_IMPL_AUTO || impl == RB200_IMPL_FUSED_MEGA || impl == RB200_IMPL_FUSED_BF16) ||
+        !mega_shape_ok(h, T, seq_width, map_width)) {
+        set_error("the fused exchange needs the single-kernel path (model / shape / selected implementation)");
+        return RB200_ERR_UNSUPPORTED;
+    }
+    GatherTarget g;
+    g.peers_dev = reinterpret_cast<float *const *>(peer_bases_dev);
+    g.n_peers = n_peers;
+    g.dst_offset = dst_offset;
+    g.multicast_base = static_cast<float *>(multicast_base);
+    g.flag_offset = flag_word;
+    return mega_forward_compact(h, h->workspaces[stream_v], sigs_dev, seqs_dev, seq_width, maps_dev, map_width,
+                                lens_dev, B, T, logits_dev, static_cast<cudaStream_t>(stream_v),
+                                impl == RB200_IMPL_FUSED_BF16 ? 1 : 0, &g);
+}
+
 int rb200_infer_host(rb200_handle h, const float *sigs_host, const int8_t *seqs_host,
                      int32_t seq_width, const int16_t *maps_host, int32_t map_width,
                      const int16_t *lens_host, int32_t B, int32_t T, float *logits_host) {
@@ -578,15 +609,22 @@ int rb200_refine_dp(const float *signal_dev, const int64_t *sig_off_dev, const f
                             queue_dev, wide_scratch_dev, sms, static_cast<cudaStream_t>(stream));
 }
 
+int rb200_svb16_scratch_bytes(int32_t n_rows, int32_t max_row_samples, int64_t *bytes) {
+    RB200_REQUIRE(bytes && n_rows >= 0 && max_row_samples >= 0, "bad argument");
+    *bytes = (int64_t)svb16_scratch_bytes(n_rows, max_row_samples);
+    return RB200_OK;
+}
+
 int rb200_svb16_decode(const uint8_t *packed_dev, const int64_t *row_off_dev, const int32_t *row_samples_dev,
-                       const int64_t *out_off_dev, int32_t n_rows, int16_t *out_dev, int32_t *status_dev,
-                       void *stream) {
-    RB200_REQUIRE(n_rows >= 0, "bad argument");
+                       const int64_t *out_off_dev, int32_t n_rows, int32_t max_row_samples, int16_t *out_dev,
+                       int32_t *status_dev, void *scratch_dev, void *stream) {
+    RB200_REQUIRE(n_rows >= 0 && max_row_samples >= 0, "bad argument");
     if (n_rows == 0) return RB200_OK;
-    RB200_REQUIRE(packed_dev && row_off_dev && row_samples_dev && out_off_dev && out_dev && status_dev,
+    RB200_REQUIRE(packed_dev && row_off_dev && row_samples_dev && out_off_dev && out_dev && status_dev &&
+                      scratch_dev,
                   "null buffer");
-    return launch_svb16_decode(packed_dev, row_off_dev, row_samples_dev, out_off_dev, n_rows, out_dev,
-                               status_dev, static_cast<cudaStream_t>(stream));
+    return launch_svb16_decode(packed_dev, row_off_dev, row_samples_dev, out_off_dev, n_rows, max_row_samples,
+                               out_dev, status_dev, scratch_dev, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

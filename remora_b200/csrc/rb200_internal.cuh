@@ -140,9 +140,10 @@ int launch_refine_dp(const float *sig, const int64_t *sig_off, const float *leve
                      int32_t *counter, float *wide_scratch, int sm_count, cudaStream_t stream);
 
 // rb200_vbz.cu : POD5 signal rows (svb16 + zigzag + delta) -> int16 samples
+size_t svb16_scratch_bytes(int n_rows, int max_row_samples);
 int launch_svb16_decode(const uint8_t *packed, const int64_t *row_off, const int32_t *row_samples,
-                        const int64_t *out_off, int n_rows, int16_t *out, int32_t *status,
-                        cudaStream_t stream);
+                        const int64_t *out_off, int n_rows, int max_row_samples, int16_t *out, int32_t *status,
+                        void *scratch, cudaStream_t stream);
 
 // rb200_tiled.cu : register-tiled FFMA2 layer kernels (Conv_w_ref and every non-fused shape);
 // each returns RB200_ERR_UNSUPPORTED when the layer / shape has no tiled form
@@ -174,8 +175,15 @@ int mega_create(rb200_model *m, const float *blob_host);
 void mega_destroy(rb200_model *m);
 bool mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
 int mega_read_flags(rb200_model *m, int *out, bool clear);
+struct GatherTarget {            // rb200_forward_compact_gather: where the classifier epilogue stores
+    float *const *peers_dev;     // device array of n_peers buffer base pointers (peer mapped)
+    int n_peers;
+    long long dst_offset;        // float offset of the [B][num_out] block inside every buffer
+    float *multicast_base;       // NVLS multicast alias of the buffers, or null
+    long long flag_offset;       // uint32 word index of the arrival counter inside every buffer, or -1
+};
 int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
                          const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
-                         cudaStream_t stream, int mode);
+                         cudaStream_t stream, int mode, const GatherTarget *gather = nullptr);
 
 }  // namespace rb200

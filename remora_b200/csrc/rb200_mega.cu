@@ -121,6 +121,12 @@ struct Params {
     float *dbg_cat, *dbg_m, *dbg_xp;  // optional canonical [B][C][T] copies of the intermediates
     int *flags;                       // [0] != 0: an activation left the fp16 range (MODE 0)
     long long *stamps;                // optional phase timestamps of CTA 0 (profiling aid)
+    // fused exchange step (multi-GPU): the classifier epilogue stores the logits into every rank's buffer
+    float *const *peers;              // n_peers base pointers (peer-mapped over NVLink), or null
+    int n_peers;
+    long long peer_off;               // float offset of this call's [B][num_out] block in every buffer
+    float *mc_base;                   // NVLS multicast alias of the same buffers (one store reaches all), or null
+    long long flag_off;               // >= 0: uint32 slot (counted in 4-byte words) incremented once per CTA
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------
@@ -877,8 +883,29 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
                          p.fcw[o * SIZE + lane + 32] * y_s[warp * SIZE + lane + 32];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-            if (lane == 0) p.logits[(size_t)(chunk0 + warp) * p.num_out + o] = part + p.fcb[o];
+            const float val = part + p.fcb[o];  // every lane holds the sum
+            const size_t idx = (size_t)(chunk0 + warp) * p.num_out + o;
+            if (p.logits != nullptr && lane == 0) p.logits[idx] = val;
+            if (p.n_peers > 0) {
+                // the exchange step of the path, fused into the producing kernel: lane r stores into rank
+                // r's buffer through its peer mapping (NVLink / NVSwitch), or one multimem store reaches
+                // every rank through the switch
+                if (p.mc_base != nullptr) {
+                    if (lane == 0)
+                        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.mc_base + p.peer_off + idx),
+                                     "f"(val)
+                                     : "memory");
+                } else if (lane < p.n_peers) {
+                    p.peers[lane][p.peer_off + idx] = val;
+                }
+            }
         }
+    }
+    if (p.n_peers > 0 && p.flag_off >= 0) {  // arrival counter per destination: complete when it reaches gridDim.x
+        __threadfence_system();
+        __syncthreads();
+        if (tid < p.n_peers)
+            atomicAdd_system(reinterpret_cast<unsigned int *>(p.peers[tid]) + p.flag_off, 1u);
     }
 #undef MG_STAMP
 }
@@ -1118,7 +1145,7 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
                          const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
-                         cudaStream_t stream, int mode) {
+                         cudaStream_t stream, int mode, const GatherTarget *gather) {
     using namespace mega;
     const MegaWeights *mw = m->mega;
     RB200_REQUIRE(mega_shape_ok(m, T, seq_width, map_width), "chunk shape not supported by the single-kernel path");
@@ -1147,6 +1174,20 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     p.dbg_cat = p.dbg_m = p.dbg_xp = nullptr;
     p.flags = mw->flags;
     p.stamps = nullptr;
+    p.peers = nullptr;
+    p.n_peers = 0;
+    p.peer_off = 0;
+    p.mc_base = nullptr;
+    p.flag_off = -1;
+    if (gather != nullptr) {
+        RB200_REQUIRE(gather->n_peers >= 1 && gather->n_peers <= 32 && gather->peers_dev != nullptr,
+                      "gather target needs 1..32 peer buffers");
+        p.peers = gather->peers_dev;
+        p.n_peers = gather->n_peers;
+        p.peer_off = gather->dst_offset;
+        p.mc_base = gather->multicast_base;
+        p.flag_off = gather->flag_offset;
+    }
     static const bool want_stamps = getenv("RB200_MEGA_STAMPS") != nullptr;  // profiling aid
     static long long *stamps_dev = nullptr;
     if (want_stamps) {

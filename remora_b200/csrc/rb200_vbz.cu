@@ -10,15 +10,23 @@
 // src/remora/io.py:455); the output is bit-identical to remora_b200.io.decode_vbz and to the samples
 // the reference's test files hold.
 //
-// One CTA per row, tiles of 8192 samples:
+// One CTA per TILE of 8192 samples (grid = tiles x rows), so a batch of rows fills the machine and the
+// kernel streams at HBM speed instead of walking each row serially:
+//   0  where the tile's data bytes start: one byte per earlier sample of the row + one per earlier
+//      two-byte value = popcount of the row's earlier key bytes (re-read by the row's later tiles: 1 KB per
+//      tile, L2 hits), CTA reduction - no dependence on other CTAs
 //   1  256 key words (32 samples each) -> popcounts -> CTA exclusive scan = data offset of every word
 //   2  the tile's data bytes staged into shared memory with aligned 32-bit loads (coalesced)
 //   3  interleaved decode: thread j takes samples j, j+256, ... so neighbouring threads read neighbouring
 //      bytes; a sample's byte offset = index + popcount of the key bits before it; deltas go to an
 //      int16 [256][34] array (row pitch 17 words: conflict-free for the row-wise reads of step 4)
-//   4  blocked running sums: thread t sums row t (32 consecutive samples), CTA scan of the row totals plus
-//      the carry of the previous tile, 64 contiguous output bytes per thread
-// Byte/integer work bound by HBM (about 1.1 B read + 2 B written per sample) and barrier latency.
+//   4  blocked running sums: thread t sums row t (32 consecutive samples), CTA scan of the row totals
+//   5  the running sum carried in from the row's earlier tiles: every tile publishes the sum of ITS deltas
+//      (flag + 16-bit sum in one word) as soon as step 4 is done, and reads its predecessors' words -
+//      aggregates, not prefixes, so no tile waits on a chain; predecessors have lower block indices and
+//      are resident or finished (dispatch order), so the spin cannot deadlock
+//   6  64 contiguous output bytes per thread
+// Byte/integer work bound by HBM: about 1.17 B read + 2 B written per sample.
 #include "rb200_internal.cuh"
 
 namespace rb200 {
@@ -50,115 +58,175 @@ __device__ __forceinline__ int cta_exclusive_scan(int v, int *warp_tot, int *tot
     return base + inc - v;
 }
 
+__device__ __forceinline__ int cta_sum(int v, int *warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) warp_tot[warp] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) tot += warp_tot[w];
+    __syncthreads();
+    return tot;
+}
+
+constexpr uint32_t kAggFlag = 0x80000000u;
+
 __global__ void __launch_bounds__(kThreads)
 svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict__ row_off,
                     const int32_t *__restrict__ row_samples, const int64_t *__restrict__ out_off,
-                    int16_t *__restrict__ out, int32_t *__restrict__ status) {
+                    int16_t *__restrict__ out, int32_t *__restrict__ status, uint32_t *__restrict__ agg,
+                    int tiles_per_row) {
     __shared__ uint32_t s_key[kThreads];
     __shared__ int s_pref[kThreads];
     __shared__ int s_warp[kThreads / 32];
     __shared__ __align__(16) uint32_t s_data[(2 * kTile + 16) / 4];
     __shared__ int16_t s_delta[kThreads * 34];
 
-    const int row = blockIdx.x;
+    const int row = blockIdx.y, tile = blockIdx.x;
     const int n = row_samples[row];
-    const uint8_t *base = packed + row_off[row];
+    const int t0 = tile * kTile;
+    const int j = threadIdx.x;
     const int64_t row_bytes = row_off[row + 1] - row_off[row];
-    const int nk = (n + 7) >> 3;
+    const int64_t nk = ((int64_t)n + 7) >> 3;
+    // the sample count is untrusted input: a row must at least hold its keys and one byte per sample
+    const bool sane = n >= 0 && nk + n <= row_bytes && (int64_t)n <= (int64_t)tiles_per_row * kTile;
+    if (!sane) {
+        if (j == 0 && tile == 0) status[row] = 1;
+        if (n <= 0 || t0 >= n) return;
+    } else if (t0 >= n) {
+        if (tile == 0 && j == 0 && row_bytes != 0) status[row] = 1;  // empty row with bytes
+        return;
+    }
+    uint32_t *my_agg = agg + (size_t)row * tiles_per_row + tile;
+    if (!sane) {  // later tiles of the row must not wait for this one
+        if (j == 0) atomicExch(my_agg, kAggFlag);
+        return;
+    }
+    const uint8_t *base = packed + row_off[row];
     const uint8_t *data = base + nk;
     int16_t *dst = out + out_off[row];
-    const int j = threadIdx.x;
-    int64_t data_pos = 0;  // data bytes consumed by the previous tiles
-    int carry = 0;         // running sum at the end of the previous tile
 
-    for (int t0 = 0; t0 < n; t0 += kTile) {
-        // ---- 1: key word of 32 samples per thread, bits past the row end cleared
-        const int kb = (t0 >> 3) + 4 * j;  // first key byte of this thread's word
-        uint32_t key = 0;
+    // ---- 0: data bytes consumed by the row's earlier tiles
+    int prior = 0;
+    for (int k = j; k < tile * (kTile / 8); k += kThreads) prior += __popc((uint32_t)base[k]);
+    const int64_t data_pos = (int64_t)t0 + cta_sum(prior, s_warp);
+
+    // ---- 1: key word of 32 samples per thread, bits past the row end cleared
+    const int64_t kb = (t0 >> 3) + 4 * j;  // first key byte of this thread's word
+    uint32_t key = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (kb + b < nk) key |= (uint32_t)base[kb + b] << (8 * b);
-        const int first = t0 + 32 * j;  // first sample of this thread's word
-        const int valid = n - first;    // samples of the word inside the row
-        if (valid < 32) key = valid > 0 ? (key & ((1u << valid) - 1u)) : 0u;
-        const int in_word = valid >= 32 ? 32 : (valid > 0 ? valid : 0);
-        int tile_bytes;
-        const int pref = cta_exclusive_scan(in_word + __popc(key), s_warp, &tile_bytes);
-        if (tile_bytes > row_bytes - nk - data_pos) {  // truncated row: never read past it
-            if (j == 0) status[row] = 1;
-            return;
+    for (int b = 0; b < 4; ++b)
+        if (kb + b < nk) key |= (uint32_t)base[kb + b] << (8 * b);
+    const int first = t0 + 32 * j;  // first sample of this thread's word
+    const int valid = n - first;    // samples of the word inside the row
+    if (valid < 32) key = valid > 0 ? (key & ((1u << valid) - 1u)) : 0u;
+    const int in_word = valid >= 32 ? 32 : (valid > 0 ? valid : 0);
+    int tile_bytes;
+    const int pref = cta_exclusive_scan(in_word + __popc(key), s_warp, &tile_bytes);
+    if (tile_bytes > row_bytes - nk - data_pos) {  // truncated row: never read past it
+        if (j == 0) {
+            status[row] = 1;
+            atomicExch(my_agg, kAggFlag);
         }
-        s_key[j] = key;
-        s_pref[j] = pref - 32 * j;  // popcount of the key bits before this word (+0 for full words)
-        // ---- 2: stage the tile's data bytes (aligned words; the buffer is padded by the caller)
-        const uint8_t *src = data + data_pos;
-        const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
-        const uint32_t *src_w = reinterpret_cast<const uint32_t *>(src - mis);
-        const int words = (mis + tile_bytes + 3) >> 2;
-        for (int k = j; k < words; k += kThreads) s_data[k] = src_w[k];
-        __syncthreads();
-        // ---- 3: interleaved decode into the padded delta array
-        const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data) + mis;
-        const int tile_n = min(kTile, n - t0);
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            const int i = r * kThreads + j;  // sample within the tile
-            const int w = i >> 5, bit = i & 31;
-            int delta = 0;
-            if (i < tile_n) {
-                const uint32_t kw = s_key[w];
-                // bytes before sample i: one per earlier sample of the tile + one per earlier 2-byte value
-                const int off = i + s_pref[w] + __popc(kw & ((1u << bit) - 1u));
-                uint32_t u = sb[off];
-                if ((kw >> bit) & 1u) u |= (uint32_t)sb[off + 1] << 8;
-                delta = (int)(int16_t)((u >> 1) ^ (0u - (u & 1u)));
-            }
-            s_delta[w * 34 + bit] = (int16_t)delta;
-        }
-        __syncthreads();
-        // ---- 4: blocked running sums, 32 consecutive samples per thread
-        int vals[32];
-        int sum = 0;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            sum += s_delta[j * 34 + c];
-            vals[c] = sum;
-        }
-        int tile_sum;
-        const int before = cta_exclusive_scan(sum, s_warp, &tile_sum) + carry;
-        const int o0 = t0 + 32 * j;
-        if (o0 + 32 <= n && ((reinterpret_cast<uintptr_t>(dst + o0) & 15) == 0)) {
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst + o0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t lo = (uint32_t)(vals[q * 8 + 2 * e] + before) & 0xFFFFu;
-                    const uint32_t hi = (uint32_t)(vals[q * 8 + 2 * e + 1] + before) & 0xFFFFu;
-                    w[e] = lo | (hi << 16);
-                }
-                d4[q] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (o0 + c < n) dst[o0 + c] = (int16_t)(uint16_t)((uint32_t)(vals[c] + before) & 0xFFFFu);
-        }
-        carry += tile_sum;
-        data_pos += tile_bytes;
-        __syncthreads();  // shared arrays reused by the next tile
+        return;
     }
-    if (j == 0) status[row] = (data_pos + nk == row_bytes) ? 0 : 1;  // 1: stream length disagrees with the keys
+    s_key[j] = key;
+    s_pref[j] = pref - 32 * j;  // popcount of the key bits before this word (+0 for full words)
+    // ---- 2: stage the tile's data bytes (aligned words; the buffer is padded by the caller)
+    const uint8_t *src = data + data_pos;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
+    const uint32_t *src_w = reinterpret_cast<const uint32_t *>(src - mis);
+    const int words = (mis + tile_bytes + 3) >> 2;
+    for (int k = j; k < words; k += kThreads) s_data[k] = src_w[k];
+    __syncthreads();
+    // ---- 3: interleaved decode into the padded delta array
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data) + mis;
+    const int tile_n = min(kTile, n - t0);
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+        const int i = r * kThreads + j;  // sample within the tile
+        const int w = i >> 5, bit = i & 31;
+        int delta = 0;
+        if (i < tile_n) {
+            const uint32_t kw = s_key[w];
+            // bytes before sample i: one per earlier sample of the tile + one per earlier 2-byte value
+            const int off = i + s_pref[w] + __popc(kw & ((1u << bit) - 1u));
+            uint32_t u = sb[off];
+            if ((kw >> bit) & 1u) u |= (uint32_t)sb[off + 1] << 8;
+            delta = (int)(int16_t)((u >> 1) ^ (0u - (u & 1u)));
+        }
+        s_delta[w * 34 + bit] = (int16_t)delta;
+    }
+    __syncthreads();
+    // ---- 4: blocked running sums, 32 consecutive samples per thread
+    int vals[32];
+    int sum = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        sum += s_delta[j * 34 + c];
+        vals[c] = sum;
+    }
+    int tile_sum;
+    int before = cta_exclusive_scan(sum, s_warp, &tile_sum);
+    // ---- 5: publish this tile's aggregate, collect the predecessors' (sums are taken modulo 2^16)
+    if (j == 0) {
+        __threadfence();
+        atomicExch(my_agg, kAggFlag | ((uint32_t)tile_sum & 0xFFFFu));
+    }
+    int carry = 0;
+    for (int k = j; k < tile; k += kThreads) {
+        const volatile uint32_t *pa = agg + (size_t)row * tiles_per_row + k;
+        uint32_t v;
+        do {
+            v = *pa;
+        } while (!(v & kAggFlag));
+        carry += (int)(v & 0xFFFFu);
+    }
+    if (tile > 0) before += cta_sum(carry, s_warp);
+    // ---- 6: store
+    const int o0 = t0 + 32 * j;
+    if (o0 + 32 <= n && ((reinterpret_cast<uintptr_t>(dst + o0) & 15) == 0)) {
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + o0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t lo = (uint32_t)(vals[q * 8 + 2 * e] + before) & 0xFFFFu;
+                const uint32_t hi = (uint32_t)(vals[q * 8 + 2 * e + 1] + before) & 0xFFFFu;
+                w[e] = lo | (hi << 16);
+            }
+            d4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (o0 + c < n) dst[o0 + c] = (int16_t)(uint16_t)((uint32_t)(vals[c] + before) & 0xFFFFu);
+    }
+    // the row's last tile knows where the stream ends: 1 = its length disagrees with the keys
+    if (j == 0 && t0 + kTile >= n && data_pos + tile_bytes + nk != row_bytes) status[row] = 1;
 }
 
 }  // namespace
 
+size_t svb16_scratch_bytes(int n_rows, int max_row_samples) {
+    const size_t tiles = (size_t)((max_row_samples + kTile - 1) / kTile);
+    return (size_t)n_rows * (tiles > 0 ? tiles : 1) * sizeof(uint32_t);
+}
+
 int launch_svb16_decode(const uint8_t *packed, const int64_t *row_off, const int32_t *row_samples,
-                        const int64_t *out_off, int n_rows, int16_t *out, int32_t *status,
-                        cudaStream_t stream) {
+                        const int64_t *out_off, int n_rows, int max_row_samples, int16_t *out, int32_t *status,
+                        void *scratch, cudaStream_t stream) {
     if (n_rows == 0) return RB200_OK;
-    svb16_decode_kernel<<<n_rows, kThreads, 0, stream>>>(packed, row_off, row_samples, out_off, out, status);
+    const int tiles = max_row_samples > 0 ? (max_row_samples + kTile - 1) / kTile : 1;
+    RB200_REQUIRE(n_rows <= 65535, "at most 65535 rows per call");
+    RB200_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)n_rows * sizeof(int32_t), stream));
+    RB200_CUDA_TRY(cudaMemsetAsync(scratch, 0, svb16_scratch_bytes(n_rows, max_row_samples), stream));
+    svb16_decode_kernel<<<dim3(tiles, n_rows), kThreads, 0, stream>>>(packed, row_off, row_samples, out_off, out,
+                                                                        status, static_cast<uint32_t *>(scratch),
+                                                                        tiles);
     RB200_CUDA_TRY(cudaGetLastError());
     return RB200_OK;
 }

@@ -614,8 +614,13 @@ def decode_vbz_rows_gpu(blobs, n_samples, device, read_of_row=None):
         d_out_off = torch.from_numpy(out_off).to(device, non_blocking=True)
         d_out = torch.zeros(max(pos, 1), dtype=torch.int16, device=device)
         d_status = torch.zeros(max(n_rows, 1), dtype=torch.int32, device=device)
+        max_n = int(max(n_samples)) if n_rows else 0
+        need = ctypes.c_int64()
+        _native.check(lib.rb200_svb16_scratch_bytes(n_rows, max_n, ctypes.byref(need)), "rb200_svb16_scratch_bytes")
+        d_scratch = torch.empty(max(int(need.value), 4), dtype=torch.uint8, device=device)
         _native.check(lib.rb200_svb16_decode(ptr(d_packed), ptr(d_row_off), ptr(d_n), ptr(d_out_off), n_rows,
-                                             ptr(d_out), ptr(d_status), stream), "rb200_svb16_decode")
+                                             max_n, ptr(d_out), ptr(d_status), ptr(d_scratch), stream),
+                      "rb200_svb16_decode")
         if n_rows and int(d_status.max()) != 0:
             raise RemoraError("corrupt svb16 signal chunk")
     return d_out, [tuple(s) for s in spans]

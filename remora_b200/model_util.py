@@ -278,6 +278,25 @@ class B200Model(nn.Module):
         _native.check(rc, "rb200_forward_compact")
         return out
 
+    def forward_compact_gather(self, sigs, sequence, seq_to_sig_map, seq_lens, peer_bases_dev, n_peers,
+                               dst_offset, multicast_ptr=0, flag_word=-1, out=None):
+        """``forward_compact`` fused with the exchange step of the multi-GPU path
+        (``rb200_forward_compact_gather``): the kernel's classifier epilogue stores the [B, num_out]
+        logits at float offset ``dst_offset`` of every rank's buffer (``peer_bases_dev``: device pointer
+        to the array of ``n_peers`` peer-mapped base pointers, e.g. symmetric memory ``buffer_ptrs_dev``)."""
+        sigs = self._prep(sigs, torch.float32, "sigs")
+        seqs = self._prep(sequence, torch.int8, "sequence")
+        maps = self._prep(seq_to_sig_map, torch.int16, "seq_to_sig_map")
+        lens = self._prep(seq_lens, torch.int16, "seq_lens")
+        B, T = sigs.shape[0], sigs.shape[-1]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        rc = self._lib.rb200_forward_compact_gather(
+            self._handle, _ptr(sigs), _ptr(seqs), seqs.shape[1], _ptr(maps), maps.shape[1], _ptr(lens), B, T,
+            _ptr(out) if out is not None else None, ctypes.c_void_p(int(peer_bases_dev)), int(n_peers),
+            int(dst_offset), ctypes.c_void_p(int(multicast_ptr)) if multicast_ptr else None, int(flag_word),
+            stream)
+        _native.check(rc, "rb200_forward_compact_gather")
+
     def softmax_ml(self, logits, want_probs=True):
         """Post-processing on the device (``rb200_softmax_ml``): row softmax of float32 logits
         [N, num_out], class 0 dropped -> (probs float32 [N, num_out-1] or None, ML bytes uint8

@@ -83,3 +83,62 @@ def shard_by_work(work, world_size, rank):
         if r == rank:
             mine.append(i)
     return sorted(mine)
+
+
+class PeerLogitRing:
+    """The exchange step without a collective call: a ring of logits blocks in symmetric memory
+    (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into every process over
+    NVLink / NVSwitch) that the forward kernel itself writes into on ALL ranks
+    (``B200Model.forward_compact_gather`` -> ``rb200_forward_compact_gather``).
+
+    Layout of every rank's buffer: float32 [slots][world][steps][batch][num_out], then one uint32 arrival
+    counter per (slot, step, source rank).  ``forward(model, arrays, slot, step)`` runs this rank's
+    batch and lands its logits in block [slot][rank][step] everywhere; ``block(slot)`` is the local view
+    [world, steps, batch, num_out] in rank order - the same tensor an all-gather would have produced.
+    The NCCL path (``ShardedCaller.gather``) stays as the checked fallback."""
+
+    def __init__(self, model, slots, steps, batch, group=None, multicast=False):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.slots, self.steps, self.batch, self.num_out = slots, steps, batch, model.num_out
+        self.block_floats = batch * model.num_out
+        self.n_data = slots * self.world * steps * self.block_floats
+        self.n_flags = slots * steps * self.world
+        self.buf = symm_mem.empty(self.n_data + self.n_flags, dtype=torch.float32, device=model.device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.peers_dev = int(self.handle.buffer_ptrs_dev)
+        self.multicast_ptr = 0
+        if multicast and getattr(self.handle, "has_multicast_support", False):
+            self.multicast_ptr = int(self.handle.multicast_ptr or 0)
+        self.handle.barrier()
+
+    def offset(self, slot, step, rank=None):
+        rank = self.rank if rank is None else rank
+        return ((slot * self.world + rank) * self.steps + step) * self.block_floats
+
+    def flag_word(self, slot, step, rank=None):
+        rank = self.rank if rank is None else rank
+        return self.n_data + (slot * self.steps + step) * self.world + rank
+
+    def forward(self, model, arrays, slot, step, signal=True):
+        """``signal``: also bump the per-(slot, step, source) arrival counters on every rank (one
+        system-scope fence + atomic per thread block); consumers that only read after a stream / group
+        synchronisation can switch it off."""
+        model.forward_compact_gather(*arrays, self.peers_dev, self.world, self.offset(slot, step),
+                                     multicast_ptr=self.multicast_ptr,
+                                     flag_word=self.flag_word(slot, step) if signal else -1)
+
+    def block(self, slot):
+        n = self.world * self.steps * self.block_floats
+        return self.buf[slot * n:(slot + 1) * n].view(self.world, self.steps, self.batch, self.num_out)
+
+    def arrivals(self, slot):
+        """uint32 arrival counters [steps, world] of a slot (CTAs that have delivered, cumulative)."""
+        st = self.n_data + slot * self.steps * self.world
+        return self.buf[st:st + self.steps * self.world].view(torch.int32).view(self.steps, self.world)
+
+    def barrier(self):
+        self.handle.barrier()

@@ -76,8 +76,13 @@ def vbz_bench(n_reads=512, n_samples=100000, cpu_seconds=3.0, verbose=True):
     d_status = torch.zeros(len(raws), dtype=torch.int32, device=dev)
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    max_n = int(max(counts))
+    need = ctypes.c_int64()
+    _native.check(lib.rb200_svb16_scratch_bytes(len(raws), max_n, ctypes.byref(need)), "svb16 scratch")
+    d_scratch = torch.empty(max(int(need.value), 4), dtype=torch.uint8, device=dev)
     run = lambda: _native.check(lib.rb200_svb16_decode(ptr(d_packed), ptr(d_row_off), ptr(d_n), ptr(d_out_off),  # noqa: E731
-                                                       len(raws), ptr(d_o), ptr(d_status), stream), "svb16")
+                                                       len(raws), max_n, ptr(d_o), ptr(d_status), ptr(d_scratch),
+                                                       stream), "svb16")
     for _ in range(3):
         run()
     torch.cuda.synchronize()

@@ -473,14 +473,15 @@ def test_gpu_infer_from_pod5_and_bam(tmp_path):
         assert np.array_equal(got_pos, pos) and np.allclose(got_probs, probs, atol=1e-6)
         fields = line.split("\t")
         assert fields[0] == r["read_id"] and f"MM:Z:{r['mm']}" in fields
-        assert any(f.startswith("ML:B:C,") for f in fields) and not any(f.startswith("mv:") for f in fields)
+        assert any(f.startswith("ML:B:C,") for f in fields)
+        assert any(f.startswith("mv:B:c,") for f in fields)  # the move table is kept, as the reference keeps it
         assert r["mm"].startswith("C+m?,") and len(r["ml"]) == len(pos)
     # BAM output carries the same tags; two models (one per canonical base) concatenate their sections
     out_bam = str(tmp_path / "calls.bam")
     model2, md2 = model_util.load_model(os.path.join(GOLDEN, "convlstm_s64_k9_hot.pt"), device=dev, eval_only=True)
     md2 = dict(md2, can_base="G", motifs=[("GC", 0)], motif=("GC", 0), mod_bases="x", mod_long_names=["test"])
     res2 = inference.infer_from_pod5_and_bam(pod5, bam, {"C": (model, md), "G": (model2, md2)}, out_path=out_bam,
-                                             decode_on_device=False, extract_on_device=False)
+                                             decode_on_device=False, extract_on_device=False, drop_move_tag=True)
     with io.BamReader(out_bam) as reader:
         recs = {r.query_name: r for r in reader}
     assert len(recs) == 12
