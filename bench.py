@@ -472,22 +472,21 @@ def ours(args):
                 pending[slot].wait()
                 pending[slot] = None
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.6)  # nvidia-smi needs a few hundred ms before its first sample (GPU idle: before warm-up)
     # untimed settle phase: touch the whole resident pool once (first-touch page faults, TLB fill, L2
-    # state, PDL ramp), i.e. >= 200 forwards, so that a short --steps window reads the steady state;
-    # the --warmup steps follow as usual
+    # state, clocks back up after the idle wait above), i.e. >= 200 forwards, so that a short --steps
+    # window reads the steady state; the --warmup steps follow and lead straight into the timed region
     for i in range(max(n_pool, 200)):
         model.forward_compact(*dev_batch(i))
     torch.cuda.synchronize(device)
     for i in range(args.warmup):
         step(i, last=i == args.warmup - 1)
     drain()
-    barrier()
     impl_used = model.last_impl
     launches0 = model.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.6)  # nvidia-smi needs a few hundred ms before its first sample
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

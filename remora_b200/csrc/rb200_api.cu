@@ -135,9 +135,12 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
     // AUTO: the single-kernel path when the shape qualifies (compact arrays, chunk_len <= 100), else the
     // three-kernel tensor-core path (falls back to FFMA2 inside when the CTA's rows do not fit two M
     // tiles), else the tiled layer kernels
+    const bool conv_mega_ok = compact && conv_mega_shape_ok(m, T, seq_width, map_width);
     const bool mega_ok = compact && mega_shape_ok(m, T, seq_width, map_width);
     if (impl == RB200_IMPL_AUTO)
-        impl = mega_ok ? RB200_IMPL_FUSED_MEGA : fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_TILED;
+        impl = (mega_ok || conv_mega_ok) ? RB200_IMPL_FUSED_MEGA : fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_TILED;
+    if (impl == RB200_IMPL_FUSED_MEGA && conv_mega_ok)  // Conv_w_ref: its own single kernel
+        return conv_mega_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T, logits, stream);
     if (impl == RB200_IMPL_FUSED_MEGA || impl == RB200_IMPL_FUSED_BF16) {
         if (!mega_ok) {
             set_error("single-kernel path not available for this model/shape/input form");
@@ -220,9 +223,11 @@ int rb200_create(const rb200_model_desc *desc, const float *weights_host, int64_
     rc = tiled_create(m, weights_host);
     if (rc == RB200_OK && fused_supported(m->desc)) rc = fused_create(m, weights_host);
     if (rc == RB200_OK && mega_supported(m->desc)) rc = mega_create(m, weights_host);
+    if (rc == RB200_OK && conv_mega_supported(m->desc)) rc = conv_mega_create(m, weights_host);
     if (rc) {
         fused_destroy(m);
         mega_destroy(m);
+        conv_mega_destroy(m);
         tiled_destroy(m);
         cudaFree(m->blob_dev);
         delete m;
@@ -239,6 +244,7 @@ int rb200_destroy(rb200_handle h) {
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     fused_destroy(h);
     mega_destroy(h);
+    conv_mega_destroy(h);
     tiled_destroy(h);
     for (auto &kv : h->workspaces) kv.second.release();
     for (auto &kv : h->host_staging) kv.second.release();
@@ -259,7 +265,8 @@ int rb200_set_impl(rb200_handle h, int impl) {
         set_error("fused kernels not available for this model");
         return RB200_ERR_UNSUPPORTED;
     }
-    if ((impl == RB200_IMPL_FUSED_MEGA || impl == RB200_IMPL_FUSED_BF16) && h->mega == nullptr) {
+    if ((impl == RB200_IMPL_FUSED_BF16 && h->mega == nullptr) ||
+        (impl == RB200_IMPL_FUSED_MEGA && h->mega == nullptr && h->conv_mega == nullptr)) {
         set_error("single-kernel path not available for this model");
         return RB200_ERR_UNSUPPORTED;
     }

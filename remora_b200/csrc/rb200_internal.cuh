@@ -65,6 +65,7 @@ struct DebugTensor {
 struct FusedWeights;  // rb200_fused.cu
 struct TiledWeights;  // rb200_tiled.cu
 struct MegaWeights;   // rb200_mega.cu
+struct ConvMegaWeights;  // rb200_mega.cu
 
 }  // namespace rb200
 
@@ -85,6 +86,7 @@ struct rb200_model {
     rb200::FusedWeights *fused = nullptr;           // non-null when the fused path applies
     rb200::TiledWeights *tiled = nullptr;           // weight layouts of the register-tiled layer kernels
     rb200::MegaWeights *mega = nullptr;             // single-kernel path (rb200_mega.cu)
+    rb200::ConvMegaWeights *conv_mega = nullptr;    // Conv_w_ref single-kernel path (rb200_mega.cu)
     // pinned + device staging for rb200_infer_host
     char *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -175,6 +177,13 @@ int mega_create(rb200_model *m, const float *blob_host);
 void mega_destroy(rb200_model *m);
 bool mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
 int mega_read_flags(rb200_model *m, int *out, bool clear);
+bool conv_mega_supported(const rb200_model_desc &d);
+int conv_mega_create(rb200_model *m, const float *blob_host);
+void conv_mega_destroy(rb200_model *m);
+bool conv_mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
+int conv_mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
+                              const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
+                              cudaStream_t stream);
 struct GatherTarget {            // rb200_forward_compact_gather: where the classifier epilogue stores
     float *const *peers_dev;     // device array of n_peers buffer base pointers (peer mapped)
     int n_peers;

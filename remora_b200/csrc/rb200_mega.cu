@@ -910,6 +910,635 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
 #undef MG_STAMP
 }
 
+
+// =========================================================================================================
+// Conv_w_ref (models/Conv_w_ref.py:44-62) in one kernel, same machinery: fp16 hi/lo split operands on
+// tcgen05, K-major unswizzled tiles, taps as descriptor shifts, residue tiles for the strided layers.
+// =========================================================================================================
+//   sig : conv(1->4,k11) conv(4->16,k11) [FFMA]        -> residue-3 tiles -> conv(16->64,k9,s3) [MMA]
+//   seq : conv(36->16,k11) on the one-hot = gather-add  -> q1 tile (row = chunk*96 + t)
+//         conv(16->32,k11) [MMA, 3 M tiles, tap = shift] -> residue-3 tiles -> conv(32->64,k9,s3) [MMA]
+//   merge: cat -> conv(128->64,k5) -> conv(64->64,k5) -> residue-2 tiles -> conv(64->64,k3,s2)
+//          -> residue-2 tiles -> conv(64->64,k3,s2) -> fc over the flattened [64][m4] block
+// Four chunks per CTA, two CTAs per SM.  Seven MMA layers, 288 MMAs and 59 weight stages (472 KB) per CTA.
+namespace cw {
+constexpr int KW1 = 11, KW3 = 9, KWM = 5, KW2 = 3;
+constexpr int U1 = 96;                       // row pitch per chunk of the q1 tile (stride-1 conv over 90 steps)
+constexpr int Q1_ROWS = G * U1;              // 384 = 3 M tiles
+constexpr int Q1_RP = Q1_ROWS + 16;          // rows stored per K chunk (tap shifts up to 10)
+constexpr int Q1_LBO = Q1_RP * 16;           // 6400
+constexpr int Q1_HALF = 2 * Q1_LBO;          // 12800: 16 channels, hi (or lo)
+constexpr int RP3 = MROWS + 4;               // residue-3 tiles: shifts up to 2
+constexpr int LBO3 = RP3 * 16;               // 2112
+constexpr int XS_T = 2 * LBO3;               // sig residue tile (16 ch): 4224
+constexpr int XQ_T = 4 * LBO3;               // seq residue tile (32 ch): 8448
+constexpr int T64 = 8 * LBO_A;               // a 64-channel tile, hi (or lo): 17408
+// constants blob (floats)
+constexpr int C_WS1 = 0;                     // [j][co]       44 (+4 pad)
+constexpr int C_BS1 = 48;                    //                4
+constexpr int C_WS2 = 52;                    // [j][ci][co]  704
+constexpr int C_BS2 = 756;                   //               16
+constexpr int C_BQ1 = 772;                   //               16
+constexpr int C_BQ2 = 788;                   //               32
+constexpr int C_BS3 = 820;                   //               64
+constexpr int C_BQ3 = 884;                   //               64
+constexpr int C_BM = 948;                    // m1..m4       256
+constexpr int C_SC = 1204;                   // inverse scales: q2, s3, q3, m1, m2, m3, m4 (+1 pad)
+constexpr int CONST_FLOATS = 1216;
+constexpr int CONST_BYTES = CONST_FLOATS * 4;  // 4864
+// weight stages
+constexpr int NS_Q2 = (KW1 + 3) / 4;         // 3: four taps ([64 n][16 k] = 2 KB each) per stage
+constexpr int NS_S3 = (KW3 + 1) / 2;         // 5: two taps ([128][16] = 4 KB) per stage
+constexpr int NS_Q3 = KW3;                   // 9: one tap ([128][32] = 8 KB) per stage
+constexpr int NS_M1 = KWM * 4;               // 20: (channel block of 32, tap)
+constexpr int NS_M2 = KWM * 2;               // 10: (tap, half of the 64 channels)
+constexpr int NS_M3 = KW2 * 2, NS_M4 = KW2 * 2;
+constexpr int NS_TOTAL = NS_Q2 + NS_S3 + NS_Q3 + NS_M1 + NS_M2 + NS_M3 + NS_M4;  // 59
+// shared memory
+constexpr int OFF_CONST = 256;
+constexpr int OFF_RING = 5120;
+constexpr int OFF_A = OFF_RING + RING * STAGE_BYTES;   // 37888
+constexpr int A_BYTES = 77824;
+constexpr int SMEM_BYTES = OFF_A + A_BYTES;            // 115712: exactly half an SM
+constexpr int A_STG = 0, STG_BYTES = 3072;             // sig 1600, sidx 800, seq <= 256, map <= 384, len 16
+constexpr int STG_SIDX = 1600, STG_SEQ = 2400, STG_MAP = 2656, STG_LEN = 3040;
+constexpr int A_GS = 3072, GS_CAP = 17664;             // >= 20 x 11 x 80 B             // per-base sums of ONE chunk: <= 20 bases x 11 taps x 80 B
+constexpr int A_S1 = 3072;                             // sig_conv1 output (over the dead sums): 4 x 90 x 16 B
+constexpr int A_Q1 = 20736;                            // q1 tile hi + lo: 25600
+constexpr int A_XS = A_BYTES - 6 * XS_T;               // 52480: signal residue tiles (3 x {hi, lo})
+constexpr int A_XQ = 0;                                // sequence residue tiles: 6 x 8448 = 50688
+constexpr int MAX_T = 100, MAX_SEQ_W = 64, MAX_MAP_W = 21;  // map_width - 1 <= 20 bases per chunk
+static_assert(STG_LEN + 16 <= STG_BYTES && A_STG + STG_BYTES <= A_GS, "staging does not fit");
+static_assert(A_GS + GS_CAP <= A_Q1 && A_Q1 + 2 * Q1_HALF <= A_XS, "front-phase tiles overlap");
+static_assert(A_XQ + 6 * XQ_T <= A_XS && 2 * CAT_HALF <= A_BYTES && 4 * T64 <= A_BYTES, "tiles do not fit");
+static_assert(SMEM_BYTES <= 115712, "two CTAs per SM need <= 113 KB each");
+
+struct Bars {
+    uint64_t w_full[RING], w_empty[RING], front, done[7];
+    uint32_t tmem_base;
+};
+
+struct Params {
+    const float *sigs;
+    const int8_t *seqs;
+    const int16_t *maps;
+    const int16_t *lens;
+    int seq_width, map_width, B, T, kmer_len, num_out, fc_in;
+    const float *consts, *gtab;
+    int gtab_bytes;
+    const uint8_t *wstream;
+    const float *fcw, *fcb;
+    float *logits;
+    float *dbg_cat, *dbg_m4;
+    int *flags;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void load_stage_c(int s, const uint8_t *wstream, uint8_t *ring, Bars *bars) {
+    if (s >= NS_TOTAL) return;
+    const int slot = s & (RING - 1);
+    if (s >= RING) mbar_wait(&bars->w_empty[slot], ((s >> 2) - 1) & 1);
+    mbar_expect_tx(&bars->w_full[slot], STAGE_BYTES);
+    bulk_g2s(ring + slot * STAGE_BYTES, wstream + (size_t)s * STAGE_BYTES, STAGE_BYTES, &bars->w_full[slot]);
+}
+__device__ __forceinline__ uint32_t wait_stage(int s, uint8_t *ring, Bars *bars) {
+    const int slot = s & (RING - 1);
+    mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
+    tc_fence_after();
+    return smem_addr(ring + slot * STAGE_BYTES);
+}
+
+// 64-channel merge-type layer: `taps` taps, tap j reads tile (tile_of[j]) shifted by shift_of[j] rows;
+// weights: two stages (K = 32 each) per tap.  A tiles are [8 K chunks][RP rows] hi at `a`, lo at a + T64.
+template <int TAPS>
+__device__ __forceinline__ void issue_merge64(const uint32_t (&a_tile)[TAPS], const int (&shift)[TAPS], uint32_t d,
+                                              int &s, uint8_t *ring, Bars *bars) {
+    constexpr uint32_t id_main = idesc_h(128, 128, 0), id_corr = idesc_h(128, 64, 0);
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h, ++s) {
+            const uint32_t b0 = wait_stage(s, ring, bars);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t a = a_tile[j] + (uint32_t)((4 * h + 2 * kk) * LBO_A + shift[j] * 16);
+                const uint32_t b = b0 + kk * 2 * 2048;
+                mma_h(d, desc_ns(a, LBO_A), desc_ns(b, 2048), id_main, (j | h | kk) ? 1u : 0u);
+                mma_h(d + 64, desc_ns(a + T64, LBO_A), desc_ns(b, 2048), id_corr, 1u);
+            }
+            umma_commit(&bars->w_empty[s & (RING - 1)]);
+        }
+    }
+}
+
+// accumulator (main + correction columns) -> bias + swish for the 32 channels [32 wh, 32 wh + 32) of row `lane`
+__device__ __forceinline__ void drain32(uint32_t tb, int wh, const float *bias, float inv, float (&o)[32]) {
+    float v2[32];
+    tmem_ld32(tb + 32 * wh, o);
+    tmem_ld32(tb + 64 + 32 * wh, v2);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = swishf_fast(fmaf(o[i] + v2[i], inv, bias[32 * wh + i]));
+}
+
+__global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    Bars *bars = reinterpret_cast<Bars *>(sm);
+    float *cst = reinterpret_cast<float *>(sm + OFF_CONST);
+    uint8_t *ring = sm + OFF_RING;
+    uint8_t *ra = sm + OFF_A;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk0 = blockIdx.x * G;
+    const int C = min(G, p.B - chunk0);
+    const int T = p.T, S1 = T - (KW1 - 1), S2 = S1 - (KW1 - 1), S3 = (S2 - KW3) / 3 + 1;
+    const int M1 = S3 - (KWM - 1), M2 = M1 - (KWM - 1), M3 = (M2 - KW2) / 2 + 1, M4 = (M3 - KW2) / 2 + 1;
+    const int seq_width = p.seq_width, map_width = p.map_width, K = p.kmer_len;
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(&bars->w_full[i], 1);
+            mbar_init(&bars->w_empty[i], 1);
+        }
+        mbar_init(&bars->front, 1);
+        for (int i = 0; i < 7; ++i) mbar_init(&bars->done[i], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_addr(&bars->tmem_base)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) {  // constants, and the gather table into the (still idle) weight ring
+        mbar_expect_tx(&bars->front, CONST_BYTES + p.gtab_bytes);
+        bulk_g2s(cst, p.consts, CONST_BYTES, &bars->front);
+        bulk_g2s(ring, p.gtab, p.gtab_bytes, &bars->front);
+    }
+    // ---- stage the compact inputs, move-table expansion ------------------------------------------------------
+    float *sig_s = reinterpret_cast<float *>(ra + A_STG);
+    int16_t *sidx_s = reinterpret_cast<int16_t *>(ra + A_STG + STG_SIDX);
+    int8_t *seq_s = reinterpret_cast<int8_t *>(ra + A_STG + STG_SEQ);
+    int16_t *map_s = reinterpret_cast<int16_t *>(ra + A_STG + STG_MAP);
+    int *len_s = reinterpret_cast<int *>(ra + A_STG + STG_LEN);
+    for (int i = tid; i < C * T; i += THREADS) {
+        sig_s[i] = p.sigs[(size_t)chunk0 * T + i];
+        sidx_s[i] = -1;
+    }
+    if (tid < C) {
+        int L = p.lens[chunk0 + tid];
+        L = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
+        len_s[tid] = L;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * seq_width; i += THREADS) {
+        const int c = i / seq_width, s = i - c * seq_width;
+        seq_s[i] = s < len_s[c] + K - 1 ? p.seqs[(size_t)(chunk0 + c) * seq_width + s] : (int8_t)-1;
+    }
+    for (int i = tid; i < C * map_width; i += THREADS) {
+        const int c = i / map_width, s = i - c * map_width;
+        map_s[i] = s <= len_s[c] ? p.maps[(size_t)(chunk0 + c) * map_width + s] : (int16_t)0;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * (map_width - 1); i += THREADS) {
+        const int c = i / (map_width - 1), s = i - c * (map_width - 1);
+        if (s < len_s[c]) {
+            const int st = max((int)map_s[c * map_width + s], 0);
+            const int en = min((int)map_s[c * map_width + s + 1], T);
+            for (int t = st; t < en; ++t) sidx_s[c * T + t] = (int16_t)s;
+        }
+    }
+    mbar_wait(&bars->front, 0);
+    __syncthreads();
+
+    // ---- seq_conv1 (36 -> 16, k11) on the virtual one-hot: two-stage gather-add, one chunk at a time ---------
+    {
+        const float *gt = reinterpret_cast<const float *>(ring);
+        const int zero_off = KW1 * K * 4 * GROW;
+        float *gs = reinterpret_cast<float *>(ra + A_GS);
+        uint8_t *q_hi = ra + A_Q1, *q_lo = q_hi + Q1_HALF;
+        const int LM = map_width - 1;
+        for (int c = 0; c < C; ++c) {
+            for (int i = tid; i < LM * KW1; i += THREADS) {
+                const int sb = i / KW1, j = i - sb * KW1;
+                if (sb >= len_s[c]) continue;
+                float2 a[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) a[o] = make_float2(0.f, 0.f);
+                const int8_t *sp = seq_s + c * seq_width + sb;
+                const int joff = j * K * 4 * GROW;
+                for (int pp = 0; pp < K; ++pp) {
+                    const int base = sp[pp];
+                    const int off = (base >= 0 && base <= 3) ? joff + (pp * 4 + base) * GROW : zero_off;
+                    const float4 *wv = reinterpret_cast<const float4 *>(gt + off);
+                    const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
+                    a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
+                    a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
+                    a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
+                    a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
+                    a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
+                    a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
+                    a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
+                    a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+                }
+                float4 *dst = reinterpret_cast<float4 *>(gs + (size_t)i * GROW);
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    dst[o] = make_float4(a[2 * o].x, a[2 * o].y, a[2 * o + 1].x, a[2 * o + 1].y);
+            }
+            __syncthreads();
+            // one thread per (output step, 8-channel half): 11 rows of 8 floats, swish, one 16-byte K chunk
+            for (int i = tid; i < S1 * 2; i += THREADS) {
+                const int t = i >> 1, half = i & 1;
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = cst[C_BQ1 + 8 * half + e];
+#pragma unroll
+                for (int j = 0; j < KW1; ++j) {
+                    const int sb = sidx_s[c * T + t + j];
+                    if (sb < 0) continue;
+                    const float4 *gv = reinterpret_cast<const float4 *>(gs + (size_t)(sb * KW1 + j) * GROW + 8 * half);
+                    const float4 v0 = gv[0], v1 = gv[1];
+                    acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+                    acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = swishf_fast(acc[e]);
+                store_chunk8<0>(q_hi, q_lo, half * Q1_LBO + (c * U1 + t) * 16, acc);
+            }
+            __syncthreads();
+        }
+    }
+    fence_async_smem();
+    __syncthreads();  // the gather table is dead: the ring starts streaming weights
+
+    int s_next = 0;  // stage counter of the issuing thread
+    int p_next = RING;  // producer (warp 1 lane 0) position
+    // ---- seq_conv2 (16 -> 32, k11, stride 1) on the tensor core, under sig_conv1 / sig_conv2 on warps 1..7 ----
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int s = 0; s < RING; ++s) load_stage_c(s, p.wstream, ring, bars);
+            constexpr uint32_t id_main = idesc_h(128, 64, 0), id_corr = idesc_h(128, 32, 0);
+            const uint32_t q_hi = smem_addr(ra + A_Q1), q_lo = q_hi + Q1_HALF;
+            for (int st = 0; st < NS_Q2; ++st, ++s_next) {
+                const uint32_t b0 = wait_stage(s_next, ring, bars);
+#pragma unroll
+                for (int tp = 0; tp < 4; ++tp) {
+                    const int j = st * 4 + tp;
+                    if (j < KW1) {
+#pragma unroll
+                        for (int mt = 0; mt < 3; ++mt) {
+                            const uint32_t aoff = (uint32_t)((mt * 128 + j) * 16);
+                            const uint32_t b = b0 + tp * 2048;
+                            mma_h(tmem + mt * 64, desc_ns(q_hi + aoff, Q1_LBO), desc_ns(b, 1024), id_main, j ? 1u : 0u);
+                            mma_h(tmem + mt * 64 + 32, desc_ns(q_lo + aoff, Q1_LBO), desc_ns(b, 1024), id_corr, 1u);
+                        }
+                    }
+                }
+                umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+                // self-loading while the other warps compute: RING stages ahead would block on this stage's own MMAs
+                if (s_next >= 1) load_stage_c(s_next + RING - 1, p.wstream, ring, bars);
+            }
+            umma_commit(&bars->done[0]);
+        }
+        __syncwarp();
+    } else {
+        const int wt = tid - 32, NW = THREADS - 32;
+        float *s1_s = reinterpret_cast<float *>(ra + A_S1);
+        for (int i = wt; i < C * S1; i += NW) {
+            const int c = i / S1, t = i - c * S1;
+            const float *x = sig_s + c * T + t;
+            float4 a = *reinterpret_cast<const float4 *>(cst + C_BS1);
+#pragma unroll
+            for (int j = 0; j < KW1; ++j) {
+                const float xv = x[j];
+                const float4 wv = *reinterpret_cast<const float4 *>(cst + C_WS1 + 4 * j);
+                a.x = fmaf(wv.x, xv, a.x);
+                a.y = fmaf(wv.y, xv, a.y);
+                a.z = fmaf(wv.z, xv, a.z);
+                a.w = fmaf(wv.w, xv, a.w);
+            }
+            *reinterpret_cast<float4 *>(s1_s + (size_t)i * 4) =
+                make_float4(swishf_fast(a.x), swishf_fast(a.y), swishf_fast(a.z), swishf_fast(a.w));
+        }
+        nbar_sync(1, NW);
+        uint8_t *xs = ra + A_XS;
+        for (int i = wt; i < C * S2 * 2; i += NW) {
+            const int half = i & 1, ct = i >> 1;
+            const int c = ct / S2, t = ct - c * S2;
+            float acc[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] = cst[C_BS2 + half * 8 + o];
+#pragma unroll
+            for (int j = 0; j < KW1; ++j) {
+                const float4 xv = *reinterpret_cast<const float4 *>(s1_s + (size_t)(c * S1 + t + j) * 4);
+                const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const float4 *wp = reinterpret_cast<const float4 *>(cst + C_WS2 + (j * 4 + ci) * 16 + half * 8);
+                    const float4 wa = wp[0], wb = wp[1];
+                    acc[0] = fmaf(wa.x, xs4[ci], acc[0]);
+                    acc[1] = fmaf(wa.y, xs4[ci], acc[1]);
+                    acc[2] = fmaf(wa.z, xs4[ci], acc[2]);
+                    acc[3] = fmaf(wa.w, xs4[ci], acc[3]);
+                    acc[4] = fmaf(wb.x, xs4[ci], acc[4]);
+                    acc[5] = fmaf(wb.y, xs4[ci], acc[5]);
+                    acc[6] = fmaf(wb.z, xs4[ci], acc[6]);
+                    acc[7] = fmaf(wb.w, xs4[ci], acc[7]);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] = swishf_fast(acc[o]);
+            const int r = t % 3, u = t / 3;
+            uint8_t *t_hi = xs + (2 * r) * XS_T;
+            store_chunk8<0>(t_hi, t_hi + XS_T, half * LBO3 + (c * U + u) * 16, acc);
+        }
+        fence_async_smem();
+    }
+    __syncthreads();
+    // M1 loaded stages up to NS_Q2 + RING - 2 (it skips the look-ahead of its first stage)
+    p_next = NS_Q2 + RING - 1;
+    const int q = warp & 3, wh = warp >> 2;
+    const int row = q * U + lane;
+    const bool chunk_ok = q < C;
+    bool overflow = false;
+
+    // ---- epilogue of seq_conv2: 3 M tiles (rows chunk * 96 + t) -> residue-3 tiles of 32 channels -------------
+    if (tid == 32) {  // keep the ring full while everybody drains
+        for (; p_next < NS_Q2 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
+    }
+    __syncwarp();
+    mbar_wait(&bars->done[0], 0);
+    tc_fence_after();
+    {
+        const float inv = cst[C_SC + 0];
+        uint8_t *xq = ra + A_XQ;
+#pragma unroll 1
+        for (int mt = 0; mt < 3; ++mt) {
+            const int r384 = mt * 128 + q * 32 + lane;
+            const int c = r384 / U1, t = r384 - c * U1;
+            float v[16], v2[16];
+            const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + mt * 64 + 16 * wh;
+            tmem_ld16(tb, v);
+            tmem_ld16(tb + 32, v2);
+            if (c < C && t < S2) {
+                const int r = t % 3, u = t / 3;
+                uint8_t *t_hi = xq + (2 * r) * XQ_T;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        o[e] = swishf_fast(fmaf(v[8 * j + e] + v2[8 * j + e], inv, cst[C_BQ2 + 16 * wh + 8 * j + e]));
+                        if (!(fabsf(o[e]) < 65504.f)) overflow = true;
+                    }
+                    store_chunk8<0>(t_hi, t_hi + XQ_T, (2 * wh + j) * LBO3 + (c * U + u) * 16, o);
+                }
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- sig_conv3 (16 -> 64) and seq_conv3 (32 -> 64), k9 stride 3, from the residue tiles --------------------
+    if (tid == 0) {
+        constexpr uint32_t id_main = idesc_h(128, 128, 0), id_corr = idesc_h(128, 64, 0);
+        const uint32_t xs = smem_addr(ra + A_XS), xq = smem_addr(ra + A_XQ);
+        for (int st = 0; st < NS_S3; ++st, ++s_next) {
+            const uint32_t b0 = wait_stage(s_next, ring, bars);
+#pragma unroll
+            for (int tp = 0; tp < 2; ++tp) {
+                const int j = st * 2 + tp;
+                if (j < KW3) {
+                    const uint32_t a = xs + (2 * (j % 3)) * XS_T + (j / 3) * 16;
+                    const uint32_t b = b0 + tp * 4096;
+                    mma_h(tmem, desc_ns(a, LBO3), desc_ns(b, 2048), id_main, j ? 1u : 0u);
+                    mma_h(tmem + 64, desc_ns(a + XS_T, LBO3), desc_ns(b, 2048), id_corr, 1u);
+                }
+            }
+            umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+        }
+        for (int j = 0; j < KW3; ++j, ++s_next) {
+            const uint32_t b0 = wait_stage(s_next, ring, bars);
+            const uint32_t a0 = xq + (2 * (j % 3)) * XQ_T + (j / 3) * 16;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t a = a0 + kk * 2 * LBO3, b = b0 + kk * 2 * 2048;
+                mma_h(tmem + 128, desc_ns(a, LBO3), desc_ns(b, 2048), id_main, (j | kk) ? 1u : 0u);
+                mma_h(tmem + 192, desc_ns(a + XQ_T, LBO3), desc_ns(b, 2048), id_corr, 1u);
+            }
+            umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+        }
+        umma_commit(&bars->done[1]);
+    } else if (tid == 32) {
+        for (; p_next < NS_Q2 + NS_S3 + NS_Q3 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
+    }
+    __syncwarp();
+    mbar_wait(&bars->done[1], 0);
+    tc_fence_after();
+    {   // cat tile: channels 0..63 = signal track, 64..127 = sequence track; this warp: track wh... two passes
+        uint8_t *cat_hi = ra, *cat_lo = ra + CAT_HALF;
+#pragma unroll 1
+        for (int trk = 0; trk < 2; ++trk) {
+            float o[32];
+            drain32(tmem + ((uint32_t)(q * 32) << 16) + trk * 128, wh, cst + (trk ? C_BQ3 : C_BS3),
+                    cst[C_SC + (trk ? 2 : 1)], o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o8[e] = o[8 * j + e];
+                    if (chunk_ok && lane < S3 && !(fabsf(o8[e]) < 65504.f)) overflow = true;
+                }
+                const int kc = trk * 8 + 4 * wh + j;
+                store_chunk8<0>(cat_hi, cat_lo, kc * LBO_A + row * 16, o8);
+                if (p.dbg_cat && chunk_ok && lane < S3) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) p.dbg_cat[((size_t)(chunk0 + q) * 128 + kc * 8 + e) * S3 + lane] = o8[e];
+                }
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- merge_conv1 (128 -> 64, k5): taps are shifts of the cat tile ----------------------------------------------
+    if (tid == 0) {
+        constexpr uint32_t id_main = idesc_h(128, 128, 0), id_corr = idesc_h(128, 64, 0);
+        const uint32_t cat_hi = smem_addr(ra), cat_lo = cat_hi + CAT_HALF;
+        for (int st = 0; st < NS_M1; ++st, ++s_next) {
+            const int kb = st / KWM, tap = st - kb * KWM;
+            const uint32_t b0 = wait_stage(s_next, ring, bars);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t aoff = (uint32_t)((kb * 4 + 2 * kk) * LBO_A + tap * 16);
+                const uint32_t b = b0 + kk * 2 * 2048;
+                mma_h(tmem, desc_ns(cat_hi + aoff, LBO_A), desc_ns(b, 2048), id_main, (st | kk) ? 1u : 0u);
+                mma_h(tmem + 64, desc_ns(cat_lo + aoff, LBO_A), desc_ns(b, 2048), id_corr, 1u);
+            }
+            umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+        }
+        umma_commit(&bars->done[2]);
+    } else if (tid == 32) {
+        for (; p_next < NS_Q2 + NS_S3 + NS_Q3 + NS_M1 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
+    }
+    __syncwarp();
+    mbar_wait(&bars->done[2], 0);
+    tc_fence_after();
+    {   // -> m1 tile (rows chunk * 32 + t), hi at 0, lo at T64
+        float o[32];
+        drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM, cst[C_SC + 3], o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                o8[e] = o[8 * j + e];
+                if (chunk_ok && lane < M1 && !(fabsf(o8[e]) < 65504.f)) overflow = true;
+            }
+            store_chunk8<0>(ra, ra + T64, (4 * wh + j) * LBO_A + row * 16, o8);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- merge_conv2 (64 -> 64, k5) ---------------------------------------------------------------------------------
+    if (tid == 0) {
+        const uint32_t a0 = smem_addr(ra);
+        const uint32_t a_tile[KWM] = {a0, a0, a0, a0, a0};
+        const int shift[KWM] = {0, 1, 2, 3, 4};
+        issue_merge64<KWM>(a_tile, shift, tmem, s_next, ring, bars);
+        umma_commit(&bars->done[3]);
+    } else if (tid == 32) {
+        for (; p_next < NS_TOTAL - NS_M3 - NS_M4 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
+    }
+    __syncwarp();
+    mbar_wait(&bars->done[3], 0);
+    tc_fence_after();
+    {   // -> residue-2 tiles Y_r (row = chunk * 32 + t / 2): tile r at r * 2 * T64 (hi), + T64 (lo)
+        float o[32];
+        drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM + 64, cst[C_SC + 4], o);
+        if (lane < M2) {
+            uint8_t *t_hi = ra + (lane & 1) * 2 * T64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o8[e] = o[8 * j + e];
+                    if (chunk_ok && !(fabsf(o8[e]) < 65504.f)) overflow = true;
+                }
+                store_chunk8<0>(t_hi, t_hi + T64, (4 * wh + j) * LBO_A + (q * U + (lane >> 1)) * 16, o8);
+            }
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- merge_conv3 (64 -> 64, k3, stride 2): tap j = residue j & 1 shifted by j >> 1 -------------------------------
+    if (tid == 0) {
+        const uint32_t y0 = smem_addr(ra), y1 = y0 + 2 * T64;
+        const uint32_t a_tile[KW2] = {y0, y1, y0};
+        const int shift[KW2] = {0, 0, 1};
+        issue_merge64<KW2>(a_tile, shift, tmem, s_next, ring, bars);
+        umma_commit(&bars->done[4]);
+    } else if (tid == 32) {
+        for (; p_next < NS_TOTAL - NS_M4 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
+    }
+    __syncwarp();
+    mbar_wait(&bars->done[4], 0);
+    tc_fence_after();
+    {
+        float o[32];
+        drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM + 128, cst[C_SC + 5], o);
+        if (lane < M3) {
+            uint8_t *t_hi = ra + (lane & 1) * 2 * T64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o8[e] = o[8 * j + e];
+                    if (chunk_ok && !(fabsf(o8[e]) < 65504.f)) overflow = true;
+                }
+                store_chunk8<0>(t_hi, t_hi + T64, (4 * wh + j) * LBO_A + (q * U + (lane >> 1)) * 16, o8);
+            }
+        }
+    }
+    if (overflow && p.flags) atomicOr(p.flags, 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- merge_conv4 (64 -> 64, k3, stride 2) + fc over the flattened [64][M4] block ---------------------------------
+    if (tid == 0) {
+        const uint32_t y0 = smem_addr(ra), y1 = y0 + 2 * T64;
+        const uint32_t a_tile[KW2] = {y0, y1, y0};
+        const int shift[KW2] = {0, 0, 1};
+        issue_merge64<KW2>(a_tile, shift, tmem, s_next, ring, bars);
+        umma_commit(&bars->done[5]);
+    } else if (tid == 32) {
+        for (; p_next < NS_TOTAL; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
+    }
+    __syncwarp();
+    mbar_wait(&bars->done[5], 0);
+    tc_fence_after();
+    float *part = reinterpret_cast<float *>(sm + OFF_RING);  // [2 halves][4 chunks][num_out <= 8]: the ring is idle
+    {
+        float o[32];
+        drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM + 192, cst[C_SC + 6], o);
+        if (p.dbg_m4 && chunk_ok && lane < M4) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) p.dbg_m4[((size_t)(chunk0 + q) * SIZE + 32 * wh + e) * M4 + lane] = o[e];
+        }
+        for (int oc = 0; oc < p.num_out; ++oc) {
+            float acc = 0.f;
+            if (lane < M4) {
+                const float *w = p.fcw + (size_t)oc * p.fc_in + (32 * wh) * M4 + lane;  // flatten index = channel * M4 + t
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(w + e * M4), o[e], acc);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) part[(wh * G + q) * 8 + oc] = acc;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+    pdl_wait();
+    if (tid < C * p.num_out) {
+        const int c = tid / p.num_out, oc = tid - c * p.num_out;
+        p.logits[(size_t)(chunk0 + c) * p.num_out + oc] = part[c * 8 + oc] + part[(G + c) * 8 + oc] + p.fcb[oc];
+    }
+}
+}  // namespace cw
+
 }  // namespace mega
 
 // =========================================================================================================
@@ -1132,12 +1761,16 @@ void mega_destroy(rb200_model *m) {
     m->mega = nullptr;
 }
 
+struct ConvMegaWeights;
+int *conv_mega_flags(rb200_model *m);
+
 int mega_read_flags(rb200_model *m, int *out, bool clear) {
     *out = 0;
-    if (!m->mega) return RB200_OK;
+    int *flags = m->mega ? m->mega->flags : conv_mega_flags(m);
+    if (!flags) return RB200_OK;
     RB200_CUDA_TRY(cudaDeviceSynchronize());
-    RB200_CUDA_TRY(cudaMemcpy(out, m->mega->flags, sizeof(int), cudaMemcpyDeviceToHost));
-    if (clear) RB200_CUDA_TRY(cudaMemset(m->mega->flags, 0, sizeof(int)));
+    RB200_CUDA_TRY(cudaMemcpy(out, flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (clear) RB200_CUDA_TRY(cudaMemset(flags, 0, sizeof(int)));
     return RB200_OK;
 }
 
@@ -1244,6 +1877,234 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     }
     m->launches += 1;
     m->last_impl = mode == 0 ? RB200_IMPL_FUSED_MEGA : RB200_IMPL_FUSED_BF16;
+    return RB200_OK;
+}
+
+// ---- Conv_w_ref single kernel: host side ------------------------------------------------------------------
+struct ConvMegaWeights {
+    float *dev = nullptr;
+    size_t off_consts = 0, off_gtab = 0, off_stream = 0, off_fcw = 0, off_fcb = 0;
+    int gtab_bytes = 0, kmer_len = 0, num_out = 0, fc_in = 0;
+    int *flags = nullptr;
+};
+
+int *conv_mega_flags(rb200_model *m) { return m->conv_mega ? m->conv_mega->flags : nullptr; }
+
+bool conv_mega_supported(const rb200_model_desc &d) {
+    using namespace mega;
+    if (d.arch != RB200_ARCH_CONV_W_REF || d.size != SIZE || d.num_out > 8) return false;
+    if (d.n_sig_conv != 3 || d.n_seq_conv != 3 || d.n_merge_conv != 4 || d.n_lstm != 0) return false;
+    auto is = [](const rb200_conv_desc &c, int ci, int co, int kw, int st) {
+        return c.c_in == ci && c.c_out == co && c.kw == kw && c.stride == st;
+    };
+    if ((cw::KW1 * d.kmer_len * 4 + 1) * GROW * 4 > RING * STAGE_BYTES) return false;  // the table borrows the ring
+    return is(d.sig_conv[0], 1, 4, cw::KW1, 1) && is(d.sig_conv[1], 4, 16, cw::KW1, 1) &&
+           is(d.sig_conv[2], 16, SIZE, cw::KW3, 3) && is(d.seq_conv[0], 4 * d.kmer_len, 16, cw::KW1, 1) &&
+           is(d.seq_conv[1], 16, 32, cw::KW1, 1) && is(d.seq_conv[2], 32, SIZE, cw::KW3, 3) &&
+           is(d.merge_conv[0], 2 * SIZE, SIZE, cw::KWM, 1) && is(d.merge_conv[1], SIZE, SIZE, cw::KWM, 1) &&
+           is(d.merge_conv[2], SIZE, SIZE, cw::KW2, 2) && is(d.merge_conv[3], SIZE, SIZE, cw::KW2, 2);
+}
+
+bool conv_mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width) {
+    using namespace mega;
+    if (m->conv_mega == nullptr) return false;
+    if (T > cw::MAX_T || seq_width > cw::MAX_SEQ_W || map_width > cw::MAX_MAP_W || map_width < 2) return false;
+    const int S2 = T - 2 * (cw::KW1 - 1);
+    if (S2 < cw::KW3) return false;
+    const int S3 = (S2 - cw::KW3) / 3 + 1, M2 = S3 - 2 * (cw::KWM - 1);
+    if (S3 > MAX_T3 || M2 < cw::KW2) return false;
+    const int M3 = (M2 - cw::KW2) / 2 + 1;
+    if (M3 < cw::KW2) return false;
+    const int M4 = (M3 - cw::KW2) / 2 + 1;
+    return m->conv_mega->fc_in == SIZE * M4;  // stock model: chunk_len 100 -> 3 steps -> 192 inputs
+}
+
+int conv_mega_create(rb200_model *m, const float *blob) {
+    using namespace mega;
+    const rb200_model_desc &d = m->desc;
+    const int K = d.kmer_len;
+    ConvMegaWeights *mw = new ConvMegaWeights();
+    mw->kmer_len = K;
+    mw->num_out = d.num_out;
+    mw->fc_in = d.fc_in;
+    std::vector<float> host;
+    auto reserve = [&](size_t n_floats) {
+        size_t at = host.size();
+        host.resize(at + ((n_floats + 31) & ~(size_t)31), 0.f);
+        return at;
+    };
+    const float *w_q2 = blob + d.seq_conv[1].w_off, *w_s3 = blob + d.sig_conv[2].w_off, *w_q3 = blob + d.seq_conv[2].w_off;
+    const float *w_m[4] = {blob + d.merge_conv[0].w_off, blob + d.merge_conv[1].w_off, blob + d.merge_conv[2].w_off,
+                           blob + d.merge_conv[3].w_off};
+    const float sc[7] = {pow2_scale(w_q2, (size_t)32 * 16 * cw::KW1), pow2_scale(w_s3, (size_t)SIZE * 16 * cw::KW3),
+                         pow2_scale(w_q3, (size_t)SIZE * 32 * cw::KW3), pow2_scale(w_m[0], (size_t)SIZE * 128 * cw::KWM),
+                         pow2_scale(w_m[1], (size_t)SIZE * SIZE * cw::KWM), pow2_scale(w_m[2], (size_t)SIZE * SIZE * cw::KW2),
+                         pow2_scale(w_m[3], (size_t)SIZE * SIZE * cw::KW2)};
+    mw->off_consts = reserve(cw::CONST_FLOATS);
+    {
+        float *f = host.data() + mw->off_consts;
+        const float *w = blob + d.sig_conv[0].w_off;  // [4][1][11]
+        for (int j = 0; j < cw::KW1; ++j)
+            for (int co = 0; co < 4; ++co) f[cw::C_WS1 + j * 4 + co] = w[co * cw::KW1 + j];
+        memcpy(f + cw::C_BS1, blob + d.sig_conv[0].b_off, 4 * sizeof(float));
+        w = blob + d.sig_conv[1].w_off;  // [16][4][11]
+        for (int j = 0; j < cw::KW1; ++j)
+            for (int ci = 0; ci < 4; ++ci)
+                for (int co = 0; co < 16; ++co) f[cw::C_WS2 + (j * 4 + ci) * 16 + co] = w[(co * 4 + ci) * cw::KW1 + j];
+        memcpy(f + cw::C_BS2, blob + d.sig_conv[1].b_off, 16 * sizeof(float));
+        memcpy(f + cw::C_BQ1, blob + d.seq_conv[0].b_off, 16 * sizeof(float));
+        memcpy(f + cw::C_BQ2, blob + d.seq_conv[1].b_off, 32 * sizeof(float));
+        memcpy(f + cw::C_BS3, blob + d.sig_conv[2].b_off, SIZE * sizeof(float));
+        memcpy(f + cw::C_BQ3, blob + d.seq_conv[2].b_off, SIZE * sizeof(float));
+        for (int l = 0; l < 4; ++l) memcpy(f + cw::C_BM + 64 * l, blob + d.merge_conv[l].b_off, SIZE * sizeof(float));
+        for (int i = 0; i < 7; ++i) f[cw::C_SC + i] = 1.f / sc[i];
+    }
+    {
+        const int rows = cw::KW1 * K * 4 + 1;
+        mw->gtab_bytes = ((rows * GROW * 4) + 15) & ~15;
+        mw->off_gtab = reserve((size_t)rows * GROW);
+        const float *w = blob + d.seq_conv[0].w_off;  // [16][4K][11]
+        for (int j = 0; j < cw::KW1; ++j)
+            for (int rw = 0; rw < 4 * K; ++rw)
+                for (int co = 0; co < 16; ++co)
+                    host[mw->off_gtab + (size_t)(j * 4 * K + rw) * GROW + co] = w[(co * 4 * K + rw) * cw::KW1 + j];
+    }
+    mw->off_stream = reserve((size_t)cw::NS_TOTAL * STAGE_BYTES / 4);
+    {
+        uint8_t *st0 = reinterpret_cast<uint8_t *>(host.data() + mw->off_stream);
+        // tile [K chunk][n_rows hi + n_rows lo][8 halves]: element (n, k), hi in rows [0, n_out), lo in [n_out, 2 n_out)
+        auto put_w = [&](uint8_t *base, int lbo, int n_out, int n, int k, float wv, float scale) {
+            const uint16_t hi = f2h(wv * scale);
+            const uint16_t lo = f2h(wv * scale - h2f(hi));
+            memcpy(base + (size_t)(k >> 3) * lbo + (size_t)n * 16 + (k & 7) * 2, &hi, 2);
+            memcpy(base + (size_t)(k >> 3) * lbo + (size_t)(n + n_out) * 16 + (k & 7) * 2, &lo, 2);
+        };
+        int s = 0;
+        for (int st = 0; st < cw::NS_Q2; ++st, ++s)  // seq_conv2 [32][16][11]: four taps per stage
+            for (int tp = 0; tp < 4; ++tp) {
+                const int j = st * 4 + tp;
+                if (j >= cw::KW1) continue;
+                uint8_t *base = st0 + (size_t)s * STAGE_BYTES + (size_t)tp * 2048;
+                for (int n = 0; n < 32; ++n)
+                    for (int k = 0; k < 16; ++k) put_w(base, 1024, 32, n, k, w_q2[(n * 16 + k) * cw::KW1 + j], sc[0]);
+            }
+        for (int st = 0; st < cw::NS_S3; ++st, ++s)  // sig_conv3 [64][16][9]: two taps per stage
+            for (int tp = 0; tp < 2; ++tp) {
+                const int j = st * 2 + tp;
+                if (j >= cw::KW3) continue;
+                uint8_t *base = st0 + (size_t)s * STAGE_BYTES + (size_t)tp * 4096;
+                for (int n = 0; n < SIZE; ++n)
+                    for (int k = 0; k < 16; ++k) put_w(base, 2048, SIZE, n, k, w_s3[(n * 16 + k) * cw::KW3 + j], sc[1]);
+            }
+        for (int j = 0; j < cw::KW3; ++j, ++s) {  // seq_conv3 [64][32][9]: one tap per stage
+            uint8_t *base = st0 + (size_t)s * STAGE_BYTES;
+            for (int n = 0; n < SIZE; ++n)
+                for (int k = 0; k < 32; ++k) put_w(base, 2048, SIZE, n, k, w_q3[(n * 32 + k) * cw::KW3 + j], sc[2]);
+        }
+        for (int st = 0; st < cw::NS_M1; ++st, ++s) {  // merge_conv1 [64][128][5]: (channel block, tap)
+            const int kb = st / cw::KWM, tap = st - kb * cw::KWM;
+            uint8_t *base = st0 + (size_t)s * STAGE_BYTES;
+            for (int n = 0; n < SIZE; ++n)
+                for (int k = 0; k < 32; ++k)
+                    put_w(base, 2048, SIZE, n, k, w_m[0][(n * 128 + kb * 32 + k) * cw::KWM + tap], sc[3]);
+        }
+        for (int l = 1; l < 4; ++l) {  // merge_conv2..4 [64][64][kw]: (tap, channel half)
+            const int kw = l == 1 ? cw::KWM : cw::KW2;
+            for (int j = 0; j < kw; ++j)
+                for (int h = 0; h < 2; ++h, ++s) {
+                    uint8_t *base = st0 + (size_t)s * STAGE_BYTES;
+                    for (int n = 0; n < SIZE; ++n)
+                        for (int k = 0; k < 32; ++k)
+                            put_w(base, 2048, SIZE, n, k, w_m[l][(n * SIZE + 32 * h + k) * kw + j], sc[3 + l]);
+                }
+        }
+        if (s != cw::NS_TOTAL) {
+            set_error("internal: Conv_w_ref weight stream has %d stages, expected %d", s, cw::NS_TOTAL);
+            delete mw;
+            return RB200_ERR_INVALID;
+        }
+    }
+    mw->off_fcw = reserve((size_t)d.num_out * d.fc_in);
+    memcpy(host.data() + mw->off_fcw, blob + d.fc_w_off, (size_t)d.num_out * d.fc_in * sizeof(float));
+    mw->off_fcb = reserve(d.num_out);
+    memcpy(host.data() + mw->off_fcb, blob + d.fc_b_off, d.num_out * sizeof(float));
+    cudaError_t e = cudaMalloc(&mw->dev, host.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(mw->dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&mw->flags, 16);
+    if (e == cudaSuccess) e = cudaMemset(mw->flags, 0, 16);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(cw::conv_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cw::SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("Conv_w_ref single-kernel path set-up failed: %s", cudaGetErrorString(e));
+        if (mw->dev) cudaFree(mw->dev);
+        if (mw->flags) cudaFree(mw->flags);
+        delete mw;
+        return RB200_ERR_CUDA;
+    }
+    m->conv_mega = mw;
+    return RB200_OK;
+}
+
+void conv_mega_destroy(rb200_model *m) {
+    if (!m->conv_mega) return;
+    if (m->conv_mega->dev) cudaFree(m->conv_mega->dev);
+    if (m->conv_mega->flags) cudaFree(m->conv_mega->flags);
+    delete m->conv_mega;
+    m->conv_mega = nullptr;
+}
+
+int conv_mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
+                              const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
+                              cudaStream_t stream) {
+    using namespace mega;
+    const ConvMegaWeights *mw = m->conv_mega;
+    RB200_REQUIRE(conv_mega_shape_ok(m, T, seq_width, map_width), "chunk shape not supported by the single-kernel path");
+    const int S3 = (T - 2 * (cw::KW1 - 1) - cw::KW3) / 3 + 1;
+    const int M3 = (S3 - 2 * (cw::KWM - 1) - cw::KW2) / 2 + 1, M4 = (M3 - cw::KW2) / 2 + 1;
+    cw::Params p;
+    p.sigs = sigs;
+    p.seqs = seqs;
+    p.maps = maps;
+    p.lens = lens;
+    p.seq_width = seq_width;
+    p.map_width = map_width;
+    p.B = B;
+    p.T = T;
+    p.kmer_len = mw->kmer_len;
+    p.num_out = mw->num_out;
+    p.fc_in = mw->fc_in;
+    p.consts = mw->dev + mw->off_consts;
+    p.gtab = mw->dev + mw->off_gtab;
+    p.gtab_bytes = mw->gtab_bytes;
+    p.wstream = reinterpret_cast<const uint8_t *>(mw->dev + mw->off_stream);
+    p.fcw = mw->dev + mw->off_fcw;
+    p.fcb = mw->dev + mw->off_fcb;
+    p.logits = logits;
+    p.dbg_cat = p.dbg_m4 = nullptr;
+    p.flags = mw->flags;
+    if (m->keep_debug) {
+        const size_t n_cat = (size_t)B * 128 * S3, n_m4 = (size_t)B * SIZE * M4;
+        int rc = ws.ensure(align256(n_cat * 4) + align256(n_m4 * 4));
+        if (rc) return rc;
+        p.dbg_cat = reinterpret_cast<float *>(ws.base);
+        p.dbg_m4 = reinterpret_cast<float *>(ws.base + align256(n_cat * 4));
+        m->debug.clear();
+        m->debug.push_back({"cat", p.dbg_cat, B, 128, S3});
+        m->debug.push_back({"merge4", p.dbg_m4, B, SIZE, M4});
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((B + G - 1) / G);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = cw::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = m->keep_debug ? 0 : 1;
+    RB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, cw::conv_mega_kernel, p));
+    m->launches += 1;
+    m->last_impl = RB200_IMPL_FUSED_MEGA;
     return RB200_OK;
 }
 

@@ -81,7 +81,7 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
     __shared__ uint32_t s_key[kThreads];
     __shared__ int s_pref[kThreads];
     __shared__ int s_warp[kThreads / 32];
-    __shared__ __align__(16) uint32_t s_data[(2 * kTile + 16) / 4];
+    __shared__ __align__(16) uint32_t s_data[(2 * kTile + 32) / 4];
     __shared__ int16_t s_delta[kThreads * 34];
 
     const int row = blockIdx.y, tile = blockIdx.x;
@@ -108,17 +108,34 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
     const uint8_t *data = base + nk;
     int16_t *dst = out + out_off[row];
 
-    // ---- 0: data bytes consumed by the row's earlier tiles
-    int prior = 0;
-    for (int k = j; k < tile * (kTile / 8); k += kThreads) prior += __popc((uint32_t)base[k]);
-    const int64_t data_pos = (int64_t)t0 + cta_sum(prior, s_warp);
-
-    // ---- 1: key word of 32 samples per thread, bits past the row end cleared
+    // ---- 0 + 1: this thread's key word (32 samples) and its share of the row's EARLIER key bytes, all
+    // loads issued before the first use (one memory round trip, not two); the earlier keys are read as
+    // aligned 16-byte words with the bytes outside [0, tile * 1024) masked off
     const int64_t kb = (t0 >> 3) + 4 * j;  // first key byte of this thread's word
     uint32_t key = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b)
         if (kb + b < nk) key |= (uint32_t)base[kb + b] << (8 * b);
+    int prior = 0;
+    {
+        const int n_prior = tile * (kTile / 8);                          // bytes [0, n_prior) of the row
+        const int lead = (int)(reinterpret_cast<uintptr_t>(base) & 15);  // bytes before `base` in its 16-byte word
+        const uint4 *w16 = reinterpret_cast<const uint4 *>(base - lead);
+        const int n16 = (lead + n_prior + 15) >> 4;
+        for (int k = j; k < n16; k += kThreads) {
+            const uint4 v = __ldg(w16 + k);
+            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b0 = 16 * k + 4 * e - lead;  // row byte index of this word's first byte
+                uint32_t m = 0xFFFFFFFFu;
+                if (b0 < 0) m = b0 <= -4 ? 0u : (m << (8 * -b0));
+                if (b0 + 4 > n_prior) m = b0 >= n_prior ? 0u : (m & (0xFFFFFFFFu >> (8 * (b0 + 4 - n_prior))));
+                prior += __popc(wds[e] & m);
+            }
+        }
+    }
+    const int64_t data_pos = (int64_t)t0 + cta_sum(prior, s_warp);
     const int first = t0 + 32 * j;  // first sample of this thread's word
     const int valid = n - first;    // samples of the word inside the row
     if (valid < 32) key = valid > 0 ? (key & ((1u << valid) - 1u)) : 0u;
@@ -136,10 +153,12 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
     s_pref[j] = pref - 32 * j;  // popcount of the key bits before this word (+0 for full words)
     // ---- 2: stage the tile's data bytes (aligned words; the buffer is padded by the caller)
     const uint8_t *src = data + data_pos;
-    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
-    const uint32_t *src_w = reinterpret_cast<const uint32_t *>(src - mis);
-    const int words = (mis + tile_bytes + 3) >> 2;
-    for (int k = j; k < words; k += kThreads) s_data[k] = src_w[k];
+    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    const uint4 *src_w = reinterpret_cast<const uint4 *>(src - mis);
+    const int words = (mis + tile_bytes + 15) >> 4;  // 16-byte words: <= 1025 (the caller pads the buffer)
+    uint4 *s_data4 = reinterpret_cast<uint4 *>(s_data);
+#pragma unroll 4
+    for (int k = j; k < words; k += kThreads) s_data4[k] = __ldg(src_w + k);
     __syncthreads();
     // ---- 3: interleaved decode into the padded delta array
     const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data) + mis;

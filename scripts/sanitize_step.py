@@ -27,7 +27,9 @@ if want("forward"):
     for name, T in (("convlstm_s64_k9_hot", 100), ("convlstm_s64_k9_hot", 64), ("convlstm_s16_k6_o3", 55),
                     ("conv_s64_k9", 100)):
         model, md = model_util.load_model(os.path.join(G, name + ".pt"), device=dev, eval_only=True)
-        impls = ["layers", "tiled"] + (["fused", "fused_tc"] if name.startswith("convlstm_s64") else [])
+        impls = ["layers", "tiled"] + (["fused", "fused_tc", "fused_mega", "fused_bf16"]
+                                       if name.startswith("convlstm_s64") else []) + \
+            (["fused_mega"] if name == "conv_s64_k9" else [])
         for B in (1, 7, 13):
             d = synth_chunks(B, T, tuple(md["kmer_context_bases"]), seed=B)
             args = [torch.from_numpy(d[k]).to(dev) for k in ("signal", "sequence", "sequence_to_signal_mapping",

@@ -31,6 +31,8 @@ def impls_for(model, T=100):
     """CUDA paths to check for this model: the plain and the register-tiled layer kernels always; for
     ConvLSTM_w_ref/64 also the fused fp32 FFMA2 kernels, the tcgen05 (3xTF32) variant and - for
     chunk_len <= 100 - the single-kernel path (fp16 hi/lo split operands on tcgen05, fp32 parity)."""
+    if model.info["arch"] == "Conv_w_ref" and model.info["size"] == 64 and T == 100:
+        return ["layers", "tiled", "fused_mega"]  # Conv_w_ref has its own single kernel (stock chunk_len)
     if not (model.info["arch"] == "ConvLSTM_w_ref" and model.info["size"] == 64 and fused_available(model)):
         return ["layers", "tiled"]
     return ["layers", "tiled", "fused", "fused_tc"] + (["fused_mega"] if T <= 100 else [])
@@ -339,17 +341,36 @@ def test_tiled_layer_kernels_match_plain_layer_kernels(name, T, B):
     assert float((dense - logits["layers"]).abs().max()) < 5e-5
 
 
-def test_conv_w_ref_auto_is_tiled_and_matches_oracle():
+@pytest.mark.parametrize("B", [1, 3, 300, 4099])
+def test_conv_w_ref_single_kernel_matches_oracle(B):
+    """Conv_w_ref (stock chunk_len 100): AUTO = the single kernel (seven GEMM-shaped layers on tcgen05 with
+    fp16 hi/lo split operands); every CUDA path against the oracle on every chunk, intermediates of the
+    single kernel (cat, last merge conv) against the plain layer kernels."""
     model, md = gpu_model("conv_s64_k9")
     sd, _ = load_golden_model("conv_s64_k9")
-    d = synth_chunks(300, 100, (4, 4), seed=5)
+    d = synth_chunks(B, 100, (4, 4), seed=5 + B)
     args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
                                              "sequence_lengths")]
-    got = model.forward_compact(*args).cpu().numpy()
-    assert model.last_impl == "tiled"
     want = ro.oracle_infer_compact(sd, (4, 4), d["signal"], d["sequence"],
                                    d["sequence_to_signal_mapping"], d["sequence_lengths"])
+    model.set_impl("auto")
+    got = model.forward_compact(*args).cpu().numpy()
+    assert model.last_impl == "fused_mega"
     assert np.abs(got - want).max() < LOGIT_TOL
+    kept = {}
+    for impl in ("layers", "fused_mega", "tiled"):
+        model.set_impl(impl)
+        model.set_debug(True)
+        out = model.forward_compact(*args).cpu().numpy()
+        assert model.last_impl == impl and np.abs(out - want).max() < LOGIT_TOL, impl
+        if impl != "tiled":
+            kept[impl] = {n: model.debug_tensor(n).cpu() for n in ("cat", "merge4")}
+    model.set_debug(False)
+    model.set_impl("auto")
+    for n in ("cat", "merge4"):
+        a, b = kept["fused_mega"][n], kept["layers"][n]
+        assert a.shape == b.shape and float((a - b).abs().max()) < 2e-5 * max(1.0, float(b.abs().max())), n
+    assert model.get_flags(clear=True) == 0
 
 
 def test_conv_w_ref_chunk_len_200_matches_reference():
