@@ -923,8 +923,10 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
 // Four chunks per CTA, two CTAs per SM.  Seven MMA layers, 288 MMAs and 59 weight stages (472 KB) per CTA.
 namespace cw {
 constexpr int KW1 = 11, KW3 = 9, KWM = 5, KW2 = 3;
-constexpr int U1 = 96;                       // row pitch per chunk of the q1 tile (stride-1 conv over 90 steps)
-constexpr int Q1_ROWS = G * U1;              // 384 = 3 M tiles
+// Geometry: G chunks per CTA with U tile rows per chunk (G * U = 128 = one M tile) and U1 = 3 U rows per
+// chunk in the q1 tile (G * U1 = 384 = three M tiles): chunk_len <= 100 -> G = 4, U = 32; chunk_len <= 200
+// (BASELINE config 3) -> G = 2, U = 64.  Every tile has the same size in both cases.
+constexpr int Q1_ROWS = 384;                 // 3 M tiles
 constexpr int Q1_RP = Q1_ROWS + 16;          // rows stored per K chunk (tap shifts up to 10)
 constexpr int Q1_LBO = Q1_RP * 16;           // 6400
 constexpr int Q1_HALF = 2 * Q1_LBO;          // 12800: 16 channels, hi (or lo)
@@ -962,15 +964,17 @@ constexpr int A_BYTES = 77824;
 constexpr int SMEM_BYTES = OFF_A + A_BYTES;            // 115712: exactly half an SM
 constexpr int A_STG = 0, STG_BYTES = 3072;             // sig 1600, sidx 800, seq <= 256, map <= 384, len 16
 constexpr int STG_SIDX = 1600, STG_SEQ = 2400, STG_MAP = 2656, STG_LEN = 3040;
-constexpr int A_GS = 3072, GS_CAP = 17664;             // >= 20 x 11 x 80 B             // per-base sums of ONE chunk: <= 20 bases x 11 taps x 80 B
-constexpr int A_S1 = 3072;                             // sig_conv1 output (over the dead sums): 4 x 90 x 16 B
-constexpr int A_Q1 = 20736;                            // q1 tile hi + lo: 25600
-constexpr int A_XS = A_BYTES - 6 * XS_T;               // 52480: signal residue tiles (3 x {hi, lo})
-constexpr int A_XQ = 0;                                // sequence residue tiles: 6 x 8448 = 50688
-constexpr int MAX_T = 100, MAX_SEQ_W = 64, MAX_MAP_W = 21;  // map_width - 1 <= 20 bases per chunk
+constexpr int A_GS = 3072, GS_CAP = 35200;             // per-base sums of ONE chunk: <= 40 bases x 11 taps x 80 B
+constexpr int A_Q1 = 38400;                            // q1 tile hi + lo: 25600
+constexpr int A_XS = 0;                                // signal residue tiles (3 x {hi, lo}): 25344, written
+                                                       // by sig_conv2 over the dead staging / sums
+constexpr int A_S1 = 25600, S1_CAP = 6144;             // sig_conv1 output, inside the dead sums, clear of A_XS
+constexpr int A_XQ = A_BYTES - 6 * XQ_T;               // 27136: sequence residue tiles, over the dead s1 / q1
+constexpr int MAX_T = 200;
 static_assert(STG_LEN + 16 <= STG_BYTES && A_STG + STG_BYTES <= A_GS, "staging does not fit");
-static_assert(A_GS + GS_CAP <= A_Q1 && A_Q1 + 2 * Q1_HALF <= A_XS, "front-phase tiles overlap");
-static_assert(A_XQ + 6 * XQ_T <= A_XS && 2 * CAT_HALF <= A_BYTES && 4 * T64 <= A_BYTES, "tiles do not fit");
+static_assert(A_GS + GS_CAP <= A_Q1 && A_Q1 + 2 * Q1_HALF <= A_BYTES, "front-phase tiles overlap");
+static_assert(A_XS + 6 * XS_T <= A_S1 && A_S1 + S1_CAP <= A_Q1 && A_XS + 6 * XS_T <= A_XQ, "signal tiles overlap");
+static_assert(2 * CAT_HALF <= A_BYTES && 4 * T64 <= A_BYTES, "tiles do not fit");
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM need <= 113 KB each");
 
 struct Bars {
@@ -1058,9 +1062,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     uint8_t *ring = sm + OFF_RING;
     uint8_t *ra = sm + OFF_A;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk0 = blockIdx.x * G;
-    const int C = min(G, p.B - chunk0);
-    const int T = p.T, S1 = T - (KW1 - 1), S2 = S1 - (KW1 - 1), S3 = (S2 - KW3) / 3 + 1;
+    const int T = p.T;
+    const int GC = T <= 100 ? 4 : 2;          // chunks per CTA
+    const int UR = MROWS / GC;                // tile rows per chunk (32 | 64)
+    const int U1 = 3 * UR;                    // q1 tile rows per chunk (96 | 192)
+    const int chunk0 = blockIdx.x * GC;
+    const int C = min(GC, p.B - chunk0);
+    const int S1 = T - (KW1 - 1), S2 = S1 - (KW1 - 1), S3 = (S2 - KW3) / 3 + 1;
     const int M1 = S3 - (KWM - 1), M2 = M1 - (KWM - 1), M3 = (M2 - KW2) / 2 + 1, M4 = (M3 - KW2) / 2 + 1;
     const int seq_width = p.seq_width, map_width = p.map_width, K = p.kmer_len;
 
@@ -1265,7 +1273,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
             for (int o = 0; o < 8; ++o) acc[o] = swishf_fast(acc[o]);
             const int r = t % 3, u = t / 3;
             uint8_t *t_hi = xs + (2 * r) * XS_T;
-            store_chunk8<0>(t_hi, t_hi + XS_T, half * LBO3 + (c * U + u) * 16, acc);
+            store_chunk8<0>(t_hi, t_hi + XS_T, half * LBO3 + (c * UR + u) * 16, acc);
         }
         fence_async_smem();
     }
@@ -1273,8 +1281,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     // M1 loaded stages up to NS_Q2 + RING - 2 (it skips the look-ahead of its first stage)
     p_next = NS_Q2 + RING - 1;
     const int q = warp & 3, wh = warp >> 2;
-    const int row = q * U + lane;
-    const bool chunk_ok = q < C;
+    const int row = q * 32 + lane;            // this thread's row of every M = 128 tile (TMEM lane)
+    const int rc = row / UR, rt = row - rc * UR;  // = (chunk, step) of that row
+    const bool chunk_ok = rc < C;
     bool overflow = false;
 
     // ---- epilogue of seq_conv2: 3 M tiles (rows chunk * 96 + t) -> residue-3 tiles of 32 channels -------------
@@ -1306,7 +1315,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
                         o[e] = swishf_fast(fmaf(v[8 * j + e] + v2[8 * j + e], inv, cst[C_BQ2 + 16 * wh + 8 * j + e]));
                         if (!(fabsf(o[e]) < 65504.f)) overflow = true;
                     }
-                    store_chunk8<0>(t_hi, t_hi + XQ_T, (2 * wh + j) * LBO3 + (c * U + u) * 16, o);
+                    store_chunk8<0>(t_hi, t_hi + XQ_T, (2 * wh + j) * LBO3 + (c * UR + u) * 16, o);
                 }
             }
         }
@@ -1365,13 +1374,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     o8[e] = o[8 * j + e];
-                    if (chunk_ok && lane < S3 && !(fabsf(o8[e]) < 65504.f)) overflow = true;
+                    if (chunk_ok && rt < S3 && !(fabsf(o8[e]) < 65504.f)) overflow = true;
                 }
                 const int kc = trk * 8 + 4 * wh + j;
                 store_chunk8<0>(cat_hi, cat_lo, kc * LBO_A + row * 16, o8);
-                if (p.dbg_cat && chunk_ok && lane < S3) {
+                if (p.dbg_cat && chunk_ok && rt < S3) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) p.dbg_cat[((size_t)(chunk0 + q) * 128 + kc * 8 + e) * S3 + lane] = o8[e];
+                    for (int e = 0; e < 8; ++e) p.dbg_cat[((size_t)(chunk0 + rc) * 128 + kc * 8 + e) * S3 + rt] = o8[e];
                 }
             }
         }
@@ -1413,7 +1422,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 o8[e] = o[8 * j + e];
-                if (chunk_ok && lane < M1 && !(fabsf(o8[e]) < 65504.f)) overflow = true;
+                if (chunk_ok && rt < M1 && !(fabsf(o8[e]) < 65504.f)) overflow = true;
             }
             store_chunk8<0>(ra, ra + T64, (4 * wh + j) * LBO_A + row * 16, o8);
         }
@@ -1439,8 +1448,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     {   // -> residue-2 tiles Y_r (row = chunk * 32 + t / 2): tile r at r * 2 * T64 (hi), + T64 (lo)
         float o[32];
         drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM + 64, cst[C_SC + 4], o);
-        if (lane < M2) {
-            uint8_t *t_hi = ra + (lane & 1) * 2 * T64;
+        if (rt < M2) {
+            uint8_t *t_hi = ra + (rt & 1) * 2 * T64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float o8[8];
@@ -1449,7 +1458,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
                     o8[e] = o[8 * j + e];
                     if (chunk_ok && !(fabsf(o8[e]) < 65504.f)) overflow = true;
                 }
-                store_chunk8<0>(t_hi, t_hi + T64, (4 * wh + j) * LBO_A + (q * U + (lane >> 1)) * 16, o8);
+                store_chunk8<0>(t_hi, t_hi + T64, (4 * wh + j) * LBO_A + (rc * UR + (rt >> 1)) * 16, o8);
             }
         }
     }
@@ -1474,8 +1483,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     {
         float o[32];
         drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM + 128, cst[C_SC + 5], o);
-        if (lane < M3) {
-            uint8_t *t_hi = ra + (lane & 1) * 2 * T64;
+        if (rt < M3) {
+            uint8_t *t_hi = ra + (rt & 1) * 2 * T64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float o8[8];
@@ -1484,7 +1493,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
                     o8[e] = o[8 * j + e];
                     if (chunk_ok && !(fabsf(o8[e]) < 65504.f)) overflow = true;
                 }
-                store_chunk8<0>(t_hi, t_hi + T64, (4 * wh + j) * LBO_A + (q * U + (lane >> 1)) * 16, o8);
+                store_chunk8<0>(t_hi, t_hi + T64, (4 * wh + j) * LBO_A + (rc * UR + (rt >> 1)) * 16, o8);
             }
         }
     }
@@ -1507,24 +1516,29 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     __syncwarp();
     mbar_wait(&bars->done[5], 0);
     tc_fence_after();
-    float *part = reinterpret_cast<float *>(sm + OFF_RING);  // [2 halves][4 chunks][num_out <= 8]: the ring is idle
+    float *part = reinterpret_cast<float *>(sm + OFF_RING);  // [chunk][num_out <= 8]: the ring is idle now
+    if (tid < 4 * 8) part[tid] = 0.f;
+    __syncthreads();
     {
         float o[32];
         drain32(tmem + ((uint32_t)(q * 32) << 16), wh, cst + C_BM + 192, cst[C_SC + 6], o);
-        if (p.dbg_m4 && chunk_ok && lane < M4) {
+        if (p.dbg_m4 && chunk_ok && rt < M4) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) p.dbg_m4[((size_t)(chunk0 + q) * SIZE + 32 * wh + e) * M4 + lane] = o[e];
+            for (int e = 0; e < 32; ++e) p.dbg_m4[((size_t)(chunk0 + rc) * SIZE + 32 * wh + e) * M4 + rt] = o[e];
         }
-        for (int oc = 0; oc < p.num_out; ++oc) {
-            float acc = 0.f;
-            if (lane < M4) {
-                const float *w = p.fcw + (size_t)oc * p.fc_in + (32 * wh) * M4 + lane;  // flatten index = channel * M4 + t
+        // warps whose 32 rows hold no valid step of any chunk have nothing to add (uniform per warp)
+        if (((q * 32) % UR) < M4) {
+            for (int oc = 0; oc < p.num_out; ++oc) {
+                float acc = 0.f;
+                if (rt < M4) {
+                    const float *w = p.fcw + (size_t)oc * p.fc_in + (32 * wh) * M4 + rt;  // flatten index = channel * M4 + t
 #pragma unroll
-                for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(w + e * M4), o[e], acc);
+                    for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(w + e * M4), o[e], acc);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) atomicAdd(&part[((q * 32) / UR) * 8 + oc], acc);
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (lane == 0) part[(wh * G + q) * 8 + oc] = acc;
         }
     }
     tc_fence_before();
@@ -1534,7 +1548,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     pdl_wait();
     if (tid < C * p.num_out) {
         const int c = tid / p.num_out, oc = tid - c * p.num_out;
-        p.logits[(size_t)(chunk0 + c) * p.num_out + oc] = part[c * 8 + oc] + part[(G + c) * 8 + oc] + p.fcb[oc];
+        p.logits[(size_t)(chunk0 + c) * p.num_out + oc] = part[c * 8 + oc] + p.fcb[oc];
     }
 }
 }  // namespace cw
@@ -1908,11 +1922,16 @@ bool conv_mega_supported(const rb200_model_desc &d) {
 bool conv_mega_shape_ok(const rb200_model *m, int T, int seq_width, int map_width) {
     using namespace mega;
     if (m->conv_mega == nullptr) return false;
-    if (T > cw::MAX_T || seq_width > cw::MAX_SEQ_W || map_width > cw::MAX_MAP_W || map_width < 2) return false;
-    const int S2 = T - 2 * (cw::KW1 - 1);
-    if (S2 < cw::KW3) return false;
+    if (T > cw::MAX_T || map_width < 2) return false;
+    const int gc = T <= 100 ? 4 : 2, ur = MROWS / gc;
+    // staging areas and the per-chunk gather sums
+    if (gc * seq_width > 256 || gc * map_width * 2 > 384 || (map_width - 1) * cw::KW1 * GROW * 4 > cw::GS_CAP)
+        return false;
+    const int S1 = T - (cw::KW1 - 1), S2 = S1 - (cw::KW1 - 1);
+    if (S2 < cw::KW3 || gc * S1 * 16 > cw::S1_CAP) return false;
     const int S3 = (S2 - cw::KW3) / 3 + 1, M2 = S3 - 2 * (cw::KWM - 1);
-    if (S3 > MAX_T3 || M2 < cw::KW2) return false;
+    // tile rows per chunk: the stride-3 residue tiles hold ceil(S2 / 3) rows, the merge taps shift by <= 4
+    if ((S2 + 2) / 3 > ur || S3 + (cw::KWM - 1) > ur || S1 > 3 * ur || M2 < cw::KW2) return false;
     const int M3 = (M2 - cw::KW2) / 2 + 1;
     if (M3 < cw::KW2) return false;
     const int M4 = (M3 - cw::KW2) / 2 + 1;
@@ -2093,7 +2112,8 @@ int conv_mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, 
         m->debug.push_back({"merge4", p.dbg_m4, B, SIZE, M4});
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((B + G - 1) / G);
+    const int gc = T <= 100 ? 4 : 2;
+    cfg.gridDim = dim3((B + gc - 1) / gc);
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = cw::SMEM_BYTES;
     cfg.stream = stream;

@@ -13,9 +13,11 @@ import remora_oracle as ro  # noqa: E402
 from remora_b200 import model_util  # noqa: E402
 from remora_b200.synth import synth_chunks  # noqa: E402
 
-pt = os.path.join(ROOT, "tests", "golden", "conv_s64_k9.pt")
+name = sys.argv[1] if len(sys.argv) > 1 else "conv_s64_k9"
+pt = os.path.join(ROOT, "tests", "golden", name + ".pt")
 model, md = model_util.load_model(pt, device=torch.device("cuda:0"), eval_only=True)
 sd, _ = model_util._raw_load_torchscript(pt)
+TT = md["chunk_len"]
 
 
 def args_of(d):
@@ -24,7 +26,7 @@ def args_of(d):
 
 
 for B in (3, 64, 1024):
-    d = synth_chunks(B, 100, (4, 4), seed=200 + B)
+    d = synth_chunks(B, TT, (4, 4), seed=200 + B)
     a = args_of(d)
     want = ro.oracle_infer_compact(sd, (4, 4), d["signal"], d["sequence"], d["sequence_to_signal_mapping"],
                                    d["sequence_lengths"])
@@ -46,7 +48,7 @@ for B in (3, 64, 1024):
     print(f"     no-debug launch equals debug launch: {np.array_equal(got, got2)}", flush=True)
 
 for B in (1024, 4096):
-    pool = [args_of(synth_chunks(B, 100, (4, 4), seed=s)) for s in range(4)]
+    pool = [args_of(synth_chunks(B, TT, (4, 4), seed=s)) for s in range(4)]
     for impl in ("tiled", "fused_mega"):
         model.set_impl(impl)
         for i in range(10):

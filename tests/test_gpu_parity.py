@@ -31,8 +31,8 @@ def impls_for(model, T=100):
     """CUDA paths to check for this model: the plain and the register-tiled layer kernels always; for
     ConvLSTM_w_ref/64 also the fused fp32 FFMA2 kernels, the tcgen05 (3xTF32) variant and - for
     chunk_len <= 100 - the single-kernel path (fp16 hi/lo split operands on tcgen05, fp32 parity)."""
-    if model.info["arch"] == "Conv_w_ref" and model.info["size"] == 64 and T == 100:
-        return ["layers", "tiled", "fused_mega"]  # Conv_w_ref has its own single kernel (stock chunk_len)
+    if model.info["arch"] == "Conv_w_ref" and model.info["size"] == 64 and T in (100, 200):
+        return ["layers", "tiled", "fused_mega"]  # Conv_w_ref has its own single kernel
     if not (model.info["arch"] == "ConvLSTM_w_ref" and model.info["size"] == 64 and fused_available(model)):
         return ["layers", "tiled"]
     return ["layers", "tiled", "fused", "fused_tc"] + (["fused_mega"] if T <= 100 else [])
@@ -382,9 +382,10 @@ def test_conv_w_ref_chunk_len_200_matches_reference():
     g = np.load(os.path.join(GOLDEN, "conv_T200_cases.npz"))
     for key in ("n33", "n1"):
         args = [torch.from_numpy(g[key + k]) for k in ("_signal", "_seqs", "_maps", "_lens")]
-        for impl in ("layers", "tiled", "auto"):
+        for impl in ("layers", "tiled", "fused_mega", "auto"):
             model.set_impl(impl)
             got = model.forward_compact(*args).cpu().numpy()
+            assert model.last_impl == ("fused_mega" if impl == "auto" else impl)
             assert np.abs(got - g[key + "_logits"]).max() < LOGIT_TOL, (key, impl)
         enc = encoded_kmers.compute_encoded_kmer_batch(4, 4, g[key + "_seqs"], g[key + "_maps"], g[key + "_lens"])
         dense = model(torch.from_numpy(g[key + "_signal"]).cuda(), torch.from_numpy(enc).cuda()).cpu().numpy()
