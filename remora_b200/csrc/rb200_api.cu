@@ -136,7 +136,9 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
     // three-kernel tensor-core path (falls back to FFMA2 inside when the CTA's rows do not fit two M
     // tiles), else the tiled layer kernels
     const bool conv_mega_ok = compact && conv_mega_shape_ok(m, T, seq_width, map_width);
-    const bool mega_ok = compact && mega_shape_ok(m, T, seq_width, map_width);
+    // the dense interface reaches the single kernel through the dense seq_conv1 kernel (K0)
+    const bool mega_ok = compact ? mega_shape_ok(m, T, seq_width, map_width)
+                                 : (m->fused != nullptr && mega_shape_ok(m, T, m->desc.kmer_len, 2));
     if (impl == RB200_IMPL_AUTO)
         impl = (mega_ok || conv_mega_ok) ? RB200_IMPL_FUSED_MEGA : fused_ok ? RB200_IMPL_FUSED_TC : RB200_IMPL_TILED;
     if (impl == RB200_IMPL_FUSED_MEGA && conv_mega_ok)  // Conv_w_ref: its own single kernel
@@ -147,7 +149,7 @@ static int forward_common(rb200_model *m, const float *sigs, const float *enc, c
             return RB200_ERR_UNSUPPORTED;
         }
         return mega_forward_compact(m, ws, sigs, seqs, seq_width, maps, map_width, lens, B, T, logits, stream,
-                                    impl == RB200_IMPL_FUSED_BF16 ? 1 : 0);
+                                    impl == RB200_IMPL_FUSED_BF16 ? 1 : 0, nullptr, compact ? nullptr : enc);
     }
     if (impl == RB200_IMPL_FUSED || impl == RB200_IMPL_FUSED_TC) {
         if (!fused_ok) {

@@ -2074,6 +2074,20 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+int fused_dense_seq1(rb200_model *m, const float *enc_dense, float *q1_out, int B, int T, cudaStream_t stream) {
+    const FusedWeights *fw = m->fused;
+    RB200_REQUIRE(fw != nullptr, "dense seq_conv1 kernel not available for this model");
+    const int rows = 4 * fw->kmer_len;
+    const size_t smem0 = (4 + ((rows * T + 3) & ~3) + rows * KW_SEQ1 * 16) * sizeof(float);
+    RB200_REQUIRE(smem0 <= 227 * 1024, "chunk_len %d too long for the dense fused path", T);
+    k0_dense_seq1_kernel<<<B, 128, smem0, stream>>>(enc_dense, fw->dev + fw->off_wseq1_dense,
+                                                   fw->dev + fw->off_front_tc + front_offsets(fw->kmer_len, true).b_seq1,
+                                                   q1_out, B, T, rows);
+    RB200_CUDA_TRY(cudaGetLastError());
+    m->launches += 1;
+    return RB200_OK;
+}
+
 // chunks per CTA: minimise (waves * chunks-per-CTA), prefer the larger CTA on ties
 static int pick_cpb(int B, int cmax, int sm_count) {
     int best = 1;

@@ -166,6 +166,8 @@ int fused_create(rb200_model *m, const float *blob_host);
 void fused_destroy(rb200_model *m);
 bool fused_shape_ok(const rb200_model *m, int T, int seq_width, int map_width);
 size_t fused_workspace_bytes(const rb200_model *m, int B, int T);
+// K0 alone: q1 [B][T-4][16] = swish(seq_conv1(enc)) for the dense interface of the single-kernel path
+int fused_dense_seq1(rb200_model *m, const float *enc_dense, float *q1_out, int B, int T, cudaStream_t stream);
 int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs,
                           int seq_width, const int16_t *maps, int map_width, const int16_t *lens,
                           int B, int T, float *logits, cudaStream_t stream, bool want_tc,
@@ -193,6 +195,7 @@ struct GatherTarget {            // rb200_forward_compact_gather: where the clas
 };
 int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
                          const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
-                         cudaStream_t stream, int mode, const GatherTarget *gather = nullptr);
+                         cudaStream_t stream, int mode, const GatherTarget *gather = nullptr,
+                         const float *enc_dense = nullptr);
 
 }  // namespace rb200

@@ -115,6 +115,7 @@ struct Params {
     const float *gtab;       // seq_conv1 gather table [tap][kmer pos][base][GROW] + one zero row
     int gtab_bytes;
     const uint8_t *wstream;  // weight stages in execution order
+    const float *q1_in;      // dense interface: seq_conv1 output [B][T-4][16] (K0 kernel), else null
     const float4 *whh4;      // W_hh1 in the register layout of the recurrence
     const float *wih2T, *b2, *fcw, *fcb;
     float *logits;
@@ -395,9 +396,10 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     if (tid == 0) {
-        mbar_expect_tx(&bars->front, CONST_BYTES + p.gtab_bytes);
+        const bool dense = p.q1_in != nullptr;  // the materialised one-hot went through K0: no gather here
+        mbar_expect_tx(&bars->front, CONST_BYTES + (dense ? 0 : p.gtab_bytes));
         bulk_g2s(cst, p.consts, CONST_BYTES, &bars->front);
-        bulk_g2s(ra + A_TAB, p.gtab, p.gtab_bytes, &bars->front);
+        if (!dense) bulk_g2s(ra + A_TAB, p.gtab, p.gtab_bytes, &bars->front);
         for (int s = 0; s < RING - 1; ++s) load_stage(s, CF::NS_TOTAL, p.wstream, ring, bars);
     }
 
@@ -412,28 +414,31 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         sig_s[i] = p.sigs[(size_t)chunk0 * T + i];
         sidx_s[i] = -1;
     }
-    if (tid < C) {
-        int L = p.lens[chunk0 + tid];
-        L = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
-        len_s[tid] = L;
-    }
-    __syncthreads();
-    for (int i = tid; i < C * seq_width; i += THREADS) {
-        const int c = i / seq_width, s = i - c * seq_width;
-        // padding past seq_len + kmer_len - 1 is uninitialised in the reference's arrays: never read
-        seq_s[i] = s < len_s[c] + K - 1 ? p.seqs[(size_t)(chunk0 + c) * seq_width + s] : (int8_t)-1;
-    }
-    for (int i = tid; i < C * map_width; i += THREADS) {
-        const int c = i / map_width, s = i - c * map_width;
-        map_s[i] = s <= len_s[c] ? p.maps[(size_t)(chunk0 + c) * map_width + s] : (int16_t)0;
-    }
-    __syncthreads();
-    for (int i = tid; i < C * (map_width - 1); i += THREADS) {
-        const int c = i / (map_width - 1), s = i - c * (map_width - 1);
-        if (s < len_s[c]) {
-            const int st = max((int)map_s[c * map_width + s], 0);
-            const int en = min((int)map_s[c * map_width + s + 1], T);
-            for (int t = st; t < en; ++t) sidx_s[c * T + t] = (int16_t)s;
+    const bool dense = p.q1_in != nullptr;
+    if (!dense) {
+        if (tid < C) {
+            int L = p.lens[chunk0 + tid];
+            L = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
+            len_s[tid] = L;
+        }
+        __syncthreads();
+        for (int i = tid; i < C * seq_width; i += THREADS) {
+            const int c = i / seq_width, s = i - c * seq_width;
+            // padding past seq_len + kmer_len - 1 is uninitialised in the reference's arrays: never read
+            seq_s[i] = s < len_s[c] + K - 1 ? p.seqs[(size_t)(chunk0 + c) * seq_width + s] : (int8_t)-1;
+        }
+        for (int i = tid; i < C * map_width; i += THREADS) {
+            const int c = i / map_width, s = i - c * map_width;
+            map_s[i] = s <= len_s[c] ? p.maps[(size_t)(chunk0 + c) * map_width + s] : (int16_t)0;
+        }
+        __syncthreads();
+        for (int i = tid; i < C * (map_width - 1); i += THREADS) {
+            const int c = i / (map_width - 1), s = i - c * (map_width - 1);
+            if (s < len_s[c]) {
+                const int st = max((int)map_s[c * map_width + s], 0);
+                const int en = min((int)map_s[c * map_width + s + 1], T);
+                for (int t = st; t < en; ++t) sidx_s[c * T + t] = (int16_t)s;
+            }
         }
     }
     mbar_wait(&bars->front, 0);  // constants and the gather table have landed
@@ -442,9 +447,25 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
 
     // ---- P1: seq_conv1 on the (virtual) one-hot = gather-add of weight columns -> residue tiles ------------
     const int LM = map_width - 1;
-    const bool two_stage = C * LM * KW_SEQ1 * GROW * 4 <= GS_CAP;
+    const bool two_stage = dense || C * LM * KW_SEQ1 * GROW * 4 <= GS_CAP;
     uint8_t *xq = ra + (two_stage ? A_XQ : A_XS);
-    {
+    if (dense) {
+        // dense interface: q1 = swish(seq_conv1(enc_kmers)) was computed by K0 from the materialised one-hot;
+        // split it into the residue tiles exactly as the gather would have
+        for (int i = tid; i < C * Q1; i += THREADS) {
+            const int c = i / Q1, t = i - c * Q1;
+            const float4 *src = reinterpret_cast<const float4 *>(p.q1_in + ((size_t)(chunk0 + c) * Q1 + t) * 16);
+            const int r = t % 3, u = t / 3;
+            uint8_t *t_hi = xq + (2 * r) * XT_BYTES;
+            const int off = (c * U + u) * 16;
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                const float4 v0 = __ldg(src + 2 * kc), v1 = __ldg(src + 2 * kc + 1);
+                const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, kc * LBO_A + off, v);
+            }
+        }
+    } else {
         const float *gt = reinterpret_cast<const float *>(ra + A_TAB);
         const int zero_off = KW_SEQ1 * K * 4 * GROW;  // all-zero row: N bases contribute nothing
         float *gs = reinterpret_cast<float *>(ra + A_GS);
@@ -1792,9 +1813,13 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
                          const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,
-                         cudaStream_t stream, int mode, const GatherTarget *gather) {
+                         cudaStream_t stream, int mode, const GatherTarget *gather, const float *enc_dense) {
     using namespace mega;
     const MegaWeights *mw = m->mega;
+    if (enc_dense) {  // dense interface: the sizes of the (absent) compact arrays only pass the shape check
+        seq_width = mw->kmer_len;
+        map_width = 2;
+    }
     RB200_REQUIRE(mega_shape_ok(m, T, seq_width, map_width), "chunk shape not supported by the single-kernel path");
     const int T3 = (T - 8 - KW_SIG3) / 3 + 1, TM = T3 - (KW_MRG - 1);
     Params p;
@@ -1820,6 +1845,19 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     p.logits = logits;
     p.dbg_cat = p.dbg_m = p.dbg_xp = nullptr;
     p.flags = mw->flags;
+    p.q1_in = nullptr;
+    size_t q1_bytes = 0;
+    if (enc_dense) {
+        // K0 (rb200_fused.cu): the honest dense seq_conv1 + BN + swish over the materialised one-hot
+        q1_bytes = align256((size_t)B * (T - (KW_SEQ1 - 1)) * 16 * sizeof(float));
+        RB200_REQUIRE(!m->keep_debug, "debug tensors are not kept on the dense single-kernel path");
+        int rc = ws.ensure(q1_bytes);
+        if (rc) return rc;
+        float *q1 = reinterpret_cast<float *>(ws.base);
+        rc = fused_dense_seq1(m, enc_dense, q1, B, T, stream);
+        if (rc) return rc;
+        p.q1_in = q1;
+    }
     p.stamps = nullptr;
     p.peers = nullptr;
     p.n_peers = 0;
