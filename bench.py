@@ -433,7 +433,8 @@ def ours(args):
             # NVLink (symmetric memory), no collective launch at all; NCCL stays as the fallback
             try:
                 from remora_b200.parallel import PeerLogitRing
-                peer_ring = PeerLogitRing(model, slots=2, steps=G, batch=BATCH, multicast=args.multicast)
+                peer_ring = PeerLogitRing(model, slots=2, steps=G, batch=BATCH, multicast=args.multicast,
+                                          deferred=not args.immediate)
                 model.forward_compact(*dev_batch(0))
                 if model.last_impl not in ("fused_mega", "fused_bf16"):
                     raise RuntimeError("single-kernel path not selected")
@@ -467,6 +468,8 @@ def ours(args):
                                                         async_op=True)
 
     def drain():
+        if peer_ring is not None:
+            peer_ring.flush()  # deferred exchange: the last step's block leaves with a one-block launch
         for slot in range(2):
             if pending[slot] is not None:
                 pending[slot].wait()
@@ -497,6 +500,21 @@ def ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = model.launch_count - launches0
+    if args.diag:  # diagnostic only (stderr): the same window a few more times, per rank, with host enqueue time
+        for rep in range(args.diag):
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            h0 = time.perf_counter()
+            d0.record()
+            for i in range(args.steps):
+                step(i, last=i == args.steps - 1)
+            drain()
+            d1.record()
+            h1 = time.perf_counter()
+            barrier()
+            print(f"[diag] rank {rank} window {rep}: device {d0.elapsed_time(d1) / args.steps * 1e3:.2f} us/step, "
+                  f"host enqueue {(h1 - h0) / args.steps * 1e6:.2f} us/step (first window: "
+                  f"{ms / args.steps * 1e3:.2f})", file=sys.stderr, flush=True)
 
     # ---- untimed check of the exchange step (N > 1): the gathered ring slot holds, for every rank in
     # rank order and every step of the group in step order, exactly the logits a single GPU computes for
@@ -674,13 +692,16 @@ def ours(args):
                        "batch_per_gpu": BATCH, "global_batch": world * BATCH,
                        "chunk_len": CHUNK_LEN, "kmer_context": list(KMER_CONTEXT),
                        "parallelism": ("single GPU" if world == 1 else
-                                       f"batch-shard x{world}; exchange fused into the kernel: the classifier "
-                                       f"epilogue stores every step's logits into every rank's ring over NVLink "
+                                       f"batch-shard x{world}; exchange fused into the kernel: "
+                                       + ("one extra thread block of every launch ships the previous step's logits "
+                                          if peer_ring.deferred else "the classifier epilogue stores every step's logits ")
+                                       + f"into every rank's ring over NVLink "
                                        f"(symmetric memory{', NVLS multicast' if peer_ring.multicast_ptr else ''}), "
                                        f"no collective launch" if peer_ring is not None else
                                        f"batch-shard x{world}, logits all-gathered (NCCL) in groups of "
                                        f"{G} steps, asynchronously"),
                        "gather": gather_mode,
+                       "gather_deferred": bool(peer_ring.deferred) if peer_ring is not None else None,
                        "impl": impl_used,
                        "l2_policy": f"inputs larger than L2: each step reads a different batch of a "
                                     f"{pool_bytes / 1e6:.0f} MB resident pool ({n_pool} batches)"},
@@ -869,9 +890,13 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange of the logits: fused peer stores from the kernel (default) or NCCL")
     ap.add_argument("--multicast", action="store_true", help="p2p gather through the NVLS multicast address")
+    ap.add_argument("--immediate", action="store_true",
+                    help="p2p gather: every thread block stores to every rank itself (rb200_forward_compact_gather) "
+                         "instead of the one-step-behind shipping block (rb200_forward_compact_ship)")
     ap.add_argument("--signal", action="store_true",
                     help="p2p gather: also bump the per-step arrival counters on every rank (system-scope fence "
                          "per thread block); the bench reads the ring only after a barrier and leaves it off")
+    ap.add_argument("--diag", type=int, default=0, help="repeat the timed window this many times, report to stderr")
     ap.add_argument("--pool-batches", type=int, default=400,
                     help="resident batches of compact inputs (400 x 1024 x 480 B = 197 MB > L2)")
     args = ap.parse_args()

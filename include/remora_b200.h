@@ -172,6 +172,21 @@ int rb200_forward_compact_gather(rb200_handle h, const float *sigs_dev, const in
                                  void *const *peer_bases_dev, int32_t n_peers, int64_t dst_offset,
                                  void *multicast_base, int64_t flag_word, void *stream);
 
+/* The same exchange one step behind the compute, so that no compute thread block ever waits on a remote
+ * store: the kernel's blocks write this call's logits to logits_dev only (this rank's own block of its ring),
+ * and ONE extra thread block of the same launch waits for the previous launch on the stream
+ * (griddepcontrol.wait) and ships the block an EARLIER call produced - ship_src_dev[0 .. ship_count) - to float
+ * offset ship_dst_offset of every other rank's buffer (peer stores, or multimem.st through multicast_base).
+ * flag_word >= 0: a uint32 arrival counter bumped by ONE on every rank after the shipped block is visible.
+ * B == 0 ships only (the flush after the last step).  The caller keeps track of what is pending
+ * (remora_b200.parallel.PeerLogitRing).  ship_src_dev, ship_dst_offset must be 16-byte aligned. */
+int rb200_forward_compact_ship(rb200_handle h, const float *sigs_dev, const int8_t *seqs_dev,
+                               int32_t seq_width, const int16_t *maps_dev, int32_t map_width,
+                               const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
+                               void *const *peer_bases_dev, int32_t n_peers, int32_t self_rank,
+                               const float *ship_src_dev, int64_t ship_dst_offset, int64_t ship_count,
+                               void *multicast_base, int64_t flag_word, void *stream);
+
 /* End-to-end convenience for host callers (the bench's e2e leg and non-torch hosts): copies the
  * compact arrays host->device through pinned staging, runs rb200_forward_compact, copies the
  * logits back and synchronises.  Host buffers may be pageable. */

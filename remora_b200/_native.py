@@ -23,6 +23,7 @@ EXPORTS = (
     "rb200_softmax_ml", "rb200_set_profile", "rb200_get_profile", "rb200_infer_host_async", "rb200_chunk_plan", "rb200_chunk_fill",
     "rb200_refine_normalize", "rb200_refine_scratch_bytes", "rb200_refine_dp", "rb200_svb16_decode",
     "rb200_get_flags", "rb200_forward_compact_gather", "rb200_svb16_scratch_bytes",
+    "rb200_forward_compact_ship",
 )
 
 
@@ -80,6 +81,8 @@ def load_library():
     lib.rb200_forward_dense.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.rb200_forward_compact.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp]
     lib.rb200_forward_compact_gather.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i64, vp, i64, vp]
+    lib.rb200_forward_compact_ship.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp, i64,
+                                               i64, vp, i64, vp]
     lib.rb200_infer_host.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, i32, vp]
     lib.rb200_infer_host_async.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp]
     lib.rb200_softmax_ml.argtypes = [vp, i32, i32, vp, vp, vp]

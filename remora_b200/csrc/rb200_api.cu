@@ -423,6 +423,45 @@ int rb200_forward_compact_gather(rb200_handle h, const float *sigs_dev, const in
                                 impl == RB200_IMPL_FUSED_BF16 ? 1 : 0, &g);
 }
 
+int rb200_forward_compact_ship(rb200_handle h, const float *sigs_dev, const int8_t *seqs_dev,
+                               int32_t seq_width, const int16_t *maps_dev, int32_t map_width,
+                               const int16_t *lens_dev, int32_t B, int32_t T, float *logits_dev,
+                               void *const *peer_bases_dev, int32_t n_peers, int32_t self_rank,
+                               const float *ship_src_dev, int64_t ship_dst_offset, int64_t ship_count,
+                               void *multicast_base, int64_t flag_word, void *stream_v) {
+    RB200_REQUIRE(h != nullptr, "null handle");
+    RB200_REQUIRE(B >= 0 && T > 0, "bad batch (%d) / chunk_len (%d)", B, T);
+    RB200_REQUIRE(B == 0 || (sigs_dev && seqs_dev && maps_dev && lens_dev && logits_dev), "null buffer");
+    RB200_REQUIRE(peer_bases_dev != nullptr && n_peers >= 1 && n_peers <= 32 && self_rank >= 0 &&
+                      self_rank < n_peers && ship_dst_offset >= 0 && ship_count >= 0 &&
+                      ship_count <= (int64_t)1 << 30,
+                  "bad gather target");
+    if (B == 0 && (ship_src_dev == nullptr || ship_count == 0)) return RB200_OK;
+    RB200_REQUIRE(map_width >= 2 && seq_width >= h->desc.kmer_len, "compact arrays too narrow");
+    DeviceGuard guard(h->device);
+    RB200_REQUIRE(guard.ok, "cannot select device %d", h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
+    const int impl = h->impl;
+    if (!(impl == RB200_IMPL_AUTO || impl == RB200_IMPL_FUSED_MEGA || impl == RB200_IMPL_FUSED_BF16) ||
+        !mega_shape_ok(h, T, seq_width, map_width)) {
+        set_error("the fused exchange needs the single-kernel path (model / shape / selected implementation)");
+        return RB200_ERR_UNSUPPORTED;
+    }
+    GatherTarget g;
+    g.peers_dev = reinterpret_cast<float *const *>(peer_bases_dev);
+    g.n_peers = n_peers;
+    g.dst_offset = ship_dst_offset;
+    g.multicast_base = static_cast<float *>(multicast_base);
+    g.flag_offset = flag_word;
+    g.deferred = true;
+    g.self_rank = self_rank;
+    g.ship_src = ship_count > 0 ? ship_src_dev : nullptr;
+    g.ship_count = ship_count;
+    return mega_forward_compact(h, h->workspaces[stream_v], sigs_dev, seqs_dev, seq_width, maps_dev, map_width,
+                                lens_dev, B, T, logits_dev, static_cast<cudaStream_t>(stream_v),
+                                impl == RB200_IMPL_FUSED_BF16 ? 1 : 0, &g);
+}
+
 int rb200_infer_host(rb200_handle h, const float *sigs_host, const int8_t *seqs_host,
                      int32_t seq_width, const int16_t *maps_host, int32_t map_width,
                      const int16_t *lens_host, int32_t B, int32_t T, float *logits_host) {

@@ -192,6 +192,12 @@ struct GatherTarget {            // rb200_forward_compact_gather: where the clas
     long long dst_offset;        // float offset of the [B][num_out] block inside every buffer
     float *multicast_base;       // NVLS multicast alias of the buffers, or null
     long long flag_offset;       // uint32 word index of the arrival counter inside every buffer, or -1
+    // deferred form (rb200_forward_compact_ship): compute CTAs store locally, one extra CTA ships an EARLIER
+    // launch's block [ship_src, ship_src + ship_count) to float offset dst_offset of every other rank's buffer
+    bool deferred = false;
+    int self_rank = -1;
+    const float *ship_src = nullptr;
+    long long ship_count = 0;
 };
 int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const int8_t *seqs, int seq_width,
                          const int16_t *maps, int map_width, const int16_t *lens, int B, int T, float *logits,

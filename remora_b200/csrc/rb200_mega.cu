@@ -37,6 +37,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "rb200_internal.cuh"
 
@@ -122,12 +123,21 @@ struct Params {
     float *dbg_cat, *dbg_m, *dbg_xp;  // optional canonical [B][C][T] copies of the intermediates
     int *flags;                       // [0] != 0: an activation left the fp16 range (MODE 0)
     long long *stamps;                // optional phase timestamps of CTA 0 (profiling aid)
+    long long *trace;                 // optional per-CTA record {smid, start ns, end ns, cycles} (profiling aid)
     // fused exchange step (multi-GPU): the classifier epilogue stores the logits into every rank's buffer
     float *const *peers;              // n_peers base pointers (peer-mapped over NVLink), or null
     int n_peers;
     long long peer_off;               // float offset of this call's [B][num_out] block in every buffer
     float *mc_base;                   // NVLS multicast alias of the same buffers (one store reaches all), or null
     long long flag_off;               // >= 0: uint32 slot (counted in 4-byte words) incremented once per CTA
+    // deferred form of the exchange: one extra CTA (the last of the grid) waits for the PREVIOUS grid and ships
+    // that grid's finished block to every peer, so no compute CTA ever waits on a remote store
+    int ship_cta;                     // 1: gridDim.x - 1 is the shipping CTA
+    int self_rank;
+    const float *ship_src;            // local block of an earlier launch on this stream (may be null: nothing yet)
+    long long ship_off;               // its float offset inside every buffer
+    int ship_n;                       // floats
+    long long ship_flag;              // >= 0: uint32 word bumped by one on every rank after the block is out
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------
@@ -372,7 +382,52 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
 
 #define MG_STAMP(i) do { if (p.stamps && blockIdx.x == 0 && tid == 0) p.stamps[i] = clock64(); } while (0)
     MG_STAMP(0);
+    long long trace_t0 = 0, trace_c0 = 0;
+    if (p.trace && tid == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+        trace_c0 = clock64();
+    }
     pdl_launch_dependents();  // the next batch may start as soon as SM resources free up
+    if (p.ship_cta && blockIdx.x == gridDim.x - 1) {
+        // the exchange step, one step behind the compute: the previous grid's block is complete and visible
+        // after griddepcontrol.wait; peer stores leave from this CTA only (NVLink / NVSwitch)
+        pdl_wait();
+        if (p.ship_src != nullptr) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.ship_src);
+            const int n4 = p.ship_n >> 2;
+            if (p.mc_base != nullptr) {
+                for (int i = tid; i < n4; i += THREADS) {
+                    const float4 v = __ldcg(src + i);
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                     p.mc_base + p.ship_off + 4 * (size_t)i),
+                                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                 : "memory");
+                }
+                for (int i = 4 * n4 + tid; i < p.ship_n; i += THREADS)
+                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.mc_base + p.ship_off + i),
+                                 "f"(__ldcg(p.ship_src + i))
+                                 : "memory");
+            } else {
+                for (int i = tid; i < n4; i += THREADS) {
+                    const float4 v = __ldcg(src + i);
+                    for (int r = 0; r < p.n_peers; ++r)
+                        if (r != p.self_rank) reinterpret_cast<float4 *>(p.peers[r] + p.ship_off)[i] = v;
+                }
+                for (int i = 4 * n4 + tid; i < p.ship_n; i += THREADS) {
+                    const float v = __ldcg(p.ship_src + i);
+                    for (int r = 0; r < p.n_peers; ++r)
+                        if (r != p.self_rank) p.peers[r][p.ship_off + i] = v;
+                }
+            }
+            if (p.ship_flag >= 0) {
+                __threadfence_system();
+                __syncthreads();
+                if (tid < p.n_peers)
+                    atomicAdd_system(reinterpret_cast<unsigned int *>(p.peers[tid]) + p.ship_flag, 1u);
+            }
+        }
+        return;
+    }
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) {
             mbar_init(&bars->w_full[i], 1);
@@ -907,7 +962,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             const float val = part + p.fcb[o];  // every lane holds the sum
             const size_t idx = (size_t)(chunk0 + warp) * p.num_out + o;
             if (p.logits != nullptr && lane == 0) p.logits[idx] = val;
-            if (p.n_peers > 0) {
+            if (p.n_peers > 0 && !p.ship_cta) {
                 // the exchange step of the path, fused into the producing kernel: lane r stores into rank
                 // r's buffer through its peer mapping (NVLink / NVSwitch), or one multimem store reaches
                 // every rank through the switch
@@ -922,11 +977,22 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             }
         }
     }
-    if (p.n_peers > 0 && p.flag_off >= 0) {  // arrival counter per destination: complete when it reaches gridDim.x
+    if (p.n_peers > 0 && !p.ship_cta && p.flag_off >= 0) {  // arrival counter per destination: complete when it reaches gridDim.x
         __threadfence_system();
         __syncthreads();
         if (tid < p.n_peers)
             atomicAdd_system(reinterpret_cast<unsigned int *>(p.peers[tid]) + p.flag_off, 1u);
+    }
+    if (p.trace && tid == 0) {
+        long long t1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *rec = p.trace + (size_t)blockIdx.x * 4;
+        rec[0] = smid;
+        rec[1] = trace_t0;
+        rec[2] = t1;
+        rec[3] = clock64() - trace_c0;
     }
 #undef MG_STAMP
 }
@@ -1822,7 +1888,7 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     }
     RB200_REQUIRE(mega_shape_ok(m, T, seq_width, map_width), "chunk shape not supported by the single-kernel path");
     const int T3 = (T - 8 - KW_SIG3) / 3 + 1, TM = T3 - (KW_MRG - 1);
-    Params p;
+    Params p = {};
     p.sigs = sigs;
     p.seqs = seqs;
     p.maps = maps;
@@ -1864,7 +1930,30 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     p.peer_off = 0;
     p.mc_base = nullptr;
     p.flag_off = -1;
-    if (gather != nullptr) {
+    p.ship_cta = 0;
+    p.self_rank = -1;
+    p.ship_src = nullptr;
+    p.ship_off = 0;
+    p.ship_n = 0;
+    p.ship_flag = -1;
+    if (gather != nullptr && gather->deferred) {
+        RB200_REQUIRE(gather->n_peers >= 1 && gather->n_peers <= 32 && gather->peers_dev != nullptr &&
+                          gather->self_rank >= 0 && gather->self_rank < gather->n_peers,
+                      "deferred gather target needs 1..32 peer buffers and this rank's index");
+        RB200_REQUIRE(gather->ship_src == nullptr ||
+                          (gather->ship_count > 0 && (gather->dst_offset & 3) == 0 &&
+                           (reinterpret_cast<uintptr_t>(gather->ship_src) & 15) == 0),
+                      "shipped block must be 16-byte aligned in the source and in every buffer");
+        p.peers = gather->peers_dev;
+        p.n_peers = gather->n_peers;
+        p.ship_cta = 1;  // compute CTAs store locally only
+        p.self_rank = gather->self_rank;
+        p.ship_src = gather->ship_src;
+        p.ship_off = gather->dst_offset;
+        p.ship_n = (int)gather->ship_count;
+        p.ship_flag = gather->flag_offset;
+        p.mc_base = gather->multicast_base;
+    } else if (gather != nullptr) {
         RB200_REQUIRE(gather->n_peers >= 1 && gather->n_peers <= 32 && gather->peers_dev != nullptr,
                       "gather target needs 1..32 peer buffers");
         p.peers = gather->peers_dev;
@@ -1872,6 +1961,36 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
         p.peer_off = gather->dst_offset;
         p.mc_base = gather->multicast_base;
         p.flag_off = gather->flag_offset;
+    }
+    // profiling aid: RB200_MEGA_TRACE=<file> records {smid, start, end, cycles} of every CTA of 64 consecutive
+    // launches (after 300 earlier ones: steady state) and writes them to <file> as text
+    static const char *trace_path = getenv("RB200_MEGA_TRACE");
+    static long long *trace_dev = nullptr;
+    static int trace_launch = 0;
+    constexpr int TRACE_SKIP = 300, TRACE_N = 64, TRACE_GRID = 1024;
+    p.trace = nullptr;
+    const int grid_ctas = (B + G - 1) / G;
+    if (trace_path && grid_ctas <= TRACE_GRID) {
+        if (!trace_dev) {
+            cudaMalloc(&trace_dev, (size_t)TRACE_N * TRACE_GRID * 4 * sizeof(long long));
+            cudaMemset(trace_dev, 0, (size_t)TRACE_N * TRACE_GRID * 4 * sizeof(long long));
+        }
+        const int k = trace_launch - TRACE_SKIP;
+        if (k >= 0 && k < TRACE_N) p.trace = trace_dev + (size_t)k * TRACE_GRID * 4;
+        if (k == TRACE_N + 8) {
+            cudaStreamSynchronize(stream);
+            std::vector<long long> h((size_t)TRACE_N * TRACE_GRID * 4);
+            cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(trace_path, "w")) {
+                for (int l = 0; l < TRACE_N; ++l)
+                    for (int c = 0; c < grid_ctas; ++c) {
+                        const long long *r = &h[((size_t)l * TRACE_GRID + c) * 4];
+                        fprintf(f, "%d %d %lld %lld %lld %lld\n", l, c, r[0], r[1], r[2], r[3]);
+                    }
+                fclose(f);
+            }
+        }
+        ++trace_launch;
     }
     static const bool want_stamps = getenv("RB200_MEGA_STAMPS") != nullptr;  // profiling aid
     static long long *stamps_dev = nullptr;
@@ -1892,7 +2011,7 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
         m->debug.push_back({"xproj", p.dbg_xp, B, 256, TM});
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((B + G - 1) / G);
+    cfg.gridDim = dim3((B + G - 1) / G + p.ship_cta);
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;

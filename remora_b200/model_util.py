@@ -297,6 +297,35 @@ class B200Model(nn.Module):
             stream)
         _native.check(rc, "rb200_forward_compact_gather")
 
+    def forward_compact_ship(self, arrays, out, peer_bases_dev, n_peers, self_rank, ship_src=None,
+                             ship_dst_offset=0, multicast_ptr=0, flag_word=-1, shape_hint=None):
+        """``forward_compact`` into ``out`` (this rank's own block) while ONE extra thread block of the same
+        launch ships an earlier call's finished block ``ship_src`` (a contiguous float32 device tensor) to
+        float offset ``ship_dst_offset`` of every other rank's buffer (``rb200_forward_compact_ship``).
+        ``arrays=None`` ships only (the flush after the last step); ``shape_hint`` = (chunk_len, seq_width,
+        map_width) of the batches, needed then."""
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+        n_ship = int(ship_src.numel()) if ship_src is not None else 0
+        if arrays is None:
+            T, seq_w, map_w = shape_hint
+            sigs = seqs = maps = lens = None
+            B = 0
+        else:
+            sigs = self._prep(arrays[0], torch.float32, "sigs")
+            seqs = self._prep(arrays[1], torch.int8, "sequence")
+            maps = self._prep(arrays[2], torch.int16, "seq_to_sig_map")
+            lens = self._prep(arrays[3], torch.int16, "seq_lens")
+            B, T, seq_w, map_w = sigs.shape[0], sigs.shape[-1], seqs.shape[1], maps.shape[1]
+            if (out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * self.num_out):
+                raise RemoraError("out must be a contiguous float32 [B, num_out] tensor")
+        rc = self._lib.rb200_forward_compact_ship(
+            self._handle, _ptr(sigs) if B else None, _ptr(seqs) if B else None, seq_w,
+            _ptr(maps) if B else None, map_w, _ptr(lens) if B else None, B, T, _ptr(out) if B else None,
+            ctypes.c_void_p(int(peer_bases_dev)), int(n_peers), int(self_rank),
+            _ptr(ship_src) if n_ship else None, int(ship_dst_offset), n_ship,
+            ctypes.c_void_p(int(multicast_ptr)) if multicast_ptr else None, int(flag_word), stream)
+        _native.check(rc, "rb200_forward_compact_ship")
+
     def softmax_ml(self, logits, want_probs=True):
         """Post-processing on the device (``rb200_softmax_ml``): row softmax of float32 logits
         [N, num_out], class 0 dropped -> (probs float32 [N, num_out-1] or None, ML bytes uint8

@@ -95,15 +95,21 @@ class PeerLogitRing:
     counter per (slot, step, source rank).  ``forward(model, arrays, slot, step)`` runs this rank's
     batch and lands its logits in block [slot][rank][step] everywhere; ``block(slot)`` is the local view
     [world, steps, batch, num_out] in rank order - the same tensor an all-gather would have produced.
-    The NCCL path (``ShardedCaller.gather``) stays as the checked fallback."""
+    The NCCL path (``ShardedCaller.gather``) stays as the checked fallback.
 
-    def __init__(self, model, slots, steps, batch, group=None, multicast=False):
+    ``deferred=True`` (default): the kernel's compute blocks store into this rank's own block only and one
+    extra thread block of the NEXT launch ships the finished block to the peers
+    (``rb200_forward_compact_ship``), so a remote store never sits between a compute block and the SM slot
+    it frees; ``flush()`` ships the last block.  ``deferred=False``: every compute block stores to every rank
+    itself (``rb200_forward_compact_gather``)."""
+
+    def __init__(self, model, slots, steps, batch, group=None, multicast=False, deferred=True):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.slots, self.steps, self.batch, self.num_out = slots, steps, batch, model.num_out
-        self.block_floats = batch * model.num_out
+        self.block_floats = (batch * model.num_out + 3) // 4 * 4   # blocks stay 16-byte aligned
         self.n_data = slots * self.world * steps * self.block_floats
         self.n_flags = slots * steps * self.world
         self.buf = symm_mem.empty(self.n_data + self.n_flags, dtype=torch.float32, device=model.device)
@@ -113,6 +119,10 @@ class PeerLogitRing:
         self.multicast_ptr = 0
         if multicast and getattr(self.handle, "has_multicast_support", False):
             self.multicast_ptr = int(self.handle.multicast_ptr or 0)
+        self.deferred = deferred
+        self._pending = None     # (local block tensor, float offset, flag word) still to be shipped
+        self._shape_hint = None
+        self._model = model
         self.handle.barrier()
 
     def offset(self, slot, step, rank=None):
@@ -127,13 +137,32 @@ class PeerLogitRing:
         """``signal``: also bump the per-(slot, step, source) arrival counters on every rank (one
         system-scope fence + atomic per thread block); consumers that only read after a stream / group
         synchronisation can switch it off."""
-        model.forward_compact_gather(*arrays, self.peers_dev, self.world, self.offset(slot, step),
-                                     multicast_ptr=self.multicast_ptr,
-                                     flag_word=self.flag_word(slot, step) if signal else -1)
+        if not self.deferred:
+            model.forward_compact_gather(*arrays, self.peers_dev, self.world, self.offset(slot, step),
+                                         multicast_ptr=self.multicast_ptr,
+                                         flag_word=self.flag_word(slot, step) if signal else -1)
+            return
+        off = self.offset(slot, step)
+        mine = self.buf[off:off + arrays[0].shape[0] * self.num_out]
+        pend = self._pending or (None, 0, -1)
+        model.forward_compact_ship(arrays, mine, self.peers_dev, self.world, self.rank, ship_src=pend[0],
+                                   ship_dst_offset=pend[1], multicast_ptr=self.multicast_ptr, flag_word=pend[2])
+        self._pending = (mine, off, self.flag_word(slot, step) if signal else -1)
+        self._shape_hint = (arrays[0].shape[-1], arrays[1].shape[1], arrays[2].shape[1])
+
+    def flush(self):
+        """Ship the block of the last ``forward`` (deferred mode; a one-block launch on the current stream)."""
+        if self._pending is None:
+            return
+        pend, self._pending = self._pending, None
+        self._model.forward_compact_ship(None, None, self.peers_dev, self.world, self.rank, ship_src=pend[0],
+                                         ship_dst_offset=pend[1], multicast_ptr=self.multicast_ptr,
+                                         flag_word=pend[2], shape_hint=self._shape_hint)
 
     def block(self, slot):
         n = self.world * self.steps * self.block_floats
-        return self.buf[slot * n:(slot + 1) * n].view(self.world, self.steps, self.batch, self.num_out)
+        return self.buf[slot * n:(slot + 1) * n].view(self.world, self.steps, self.block_floats)[
+            :, :, :self.batch * self.num_out].view(self.world, self.steps, self.batch, self.num_out)
 
     def arrivals(self, slot):
         """uint32 arrival counters [steps, world] of a slot (CTAs that have delivered, cumulative)."""

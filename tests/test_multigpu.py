@@ -66,7 +66,7 @@ def test_nccl_shard_gather_is_bitwise_single_gpu(tmp_path, n_chunks):
     assert np.array_equal(g[0], s[0])      # shard + gather == one GPU, bit for bit, in chunk order
 
 
-def _p2p_worker(rank, world, port, out_dir):
+def _p2p_worker(rank, world, port, out_dir, deferred):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -77,8 +77,8 @@ def _p2p_worker(rank, world, port, out_dir):
     from remora_b200 import model_util, parallel
     from remora_b200.synth import synth_chunks
     model, md = model_util.load_model(os.path.join(GOLDEN, "convlstm_s64_k9_hot.pt"), device=dev, eval_only=True)
-    B, steps = 1000, 3
-    ring = parallel.PeerLogitRing(model, slots=2, steps=steps, batch=B)
+    B, steps = 1000 if not deferred else 1001, 3
+    ring = parallel.PeerLogitRing(model, slots=2, steps=steps, batch=B, deferred=deferred)
     mine, wants = [], []
     for k in range(steps):
         d = synth_chunks(B, 100, (4, 4), seed=100 * rank + k)
@@ -86,6 +86,7 @@ def _p2p_worker(rank, world, port, out_dir):
                                                            "sequence_lengths")]
         ring.forward(model, arrays, slot=1, step=k)
         mine.append(arrays)
+    ring.flush()
     torch.cuda.synchronize(dev)
     ring.barrier()
     # what a single GPU computes for EVERY rank's batches (inputs regenerated from the seeds)
@@ -98,19 +99,22 @@ def _p2p_worker(rank, world, port, out_dir):
             want = model.forward_compact(*arrays)
             ok = ok and bool(torch.equal(ring.block(1)[r, k], want))
     arrivals = ring.arrivals(1).cpu().numpy()
-    np.save(os.path.join(out_dir, f"p2p{rank}.npy"), np.array([int(ok), int((arrivals == (B + 3) // 4).all()),
+    per_step = 1 if deferred else (B + 3) // 4   # one increment per shipped block | per thread block
+    np.save(os.path.join(out_dir, f"p2p{rank}.npy"), np.array([int(ok), int((arrivals == per_step).all()),
                                                               int(ring.block(0).abs().sum().item() == 0)]))
     dist.barrier(device_ids=[rank])
     dist.destroy_process_group()
 
 
-def test_kernel_fused_peer_gather_is_bitwise_single_gpu(tmp_path):
-    """rb200_forward_compact_gather: the kernel's classifier epilogue stores its logits into every
-    rank's symmetric-memory ring over NVLink.  Every rank must hold, in rank and step order, exactly the
-    bits a single GPU computes; the arrival counters must read one increment per CTA; the untouched slot
-    stays zero."""
+@pytest.mark.parametrize("deferred", [False, True])
+def test_kernel_fused_peer_gather_is_bitwise_single_gpu(tmp_path, deferred):
+    """rb200_forward_compact_gather / rb200_forward_compact_ship: the kernel stores its logits into every
+    rank's symmetric-memory ring over NVLink - every thread block itself, or (deferred) one extra thread
+    block of the next launch.  Every rank must hold, in rank and step order, exactly the bits a single GPU
+    computes; the arrival counters must read one increment per CTA (per shipped block when deferred); the
+    untouched slot stays zero."""
     import torch.multiprocessing as mp
-    mp.spawn(_p2p_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_p2p_worker, args=(2, _free_port(), str(tmp_path), deferred), nprocs=2, join=True)
     for r in range(2):
         ok, counted, clean = np.load(tmp_path / f"p2p{r}.npy")
         assert ok == 1 and counted == 1 and clean == 1, (r, ok, counted, clean)
