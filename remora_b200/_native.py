@@ -13,7 +13,9 @@ ARCH_CONVLSTM_W_REF = 1
 ARCH_CONV_W_REF = 2
 IMPL_AUTO, IMPL_LAYERS, IMPL_FUSED, IMPL_FUSED_TC, IMPL_TILED, IMPL_FUSED_MEGA, IMPL_FUSED_BF16 = 0, 1, 2, 3, 4, 5, 6
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "librb200.so")
+# RB200_LIB: load another build of the same library (kernel experiments, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("RB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                        "librb200.so")
 
 # every symbol include/remora_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (

@@ -25,9 +25,11 @@
 //     (BASELINE.json configs[1]): one pass, bf16 operands, fp32 accumulate, fp32 gates.
 //   * weights stream from L2 through a 4-stage ring of 8 KB TMA bulk copies (mbarrier full/empty,
 //     tcgen05.commit frees a stage); one elected thread issues TMA and MMA.
-//   * the recurrence keeps W_hh in registers (thread = 4 gate rows x 16 k, transposing shuffle butterfly),
-//     reads the input projection from shared memory ([t][chunk][256], drained from TMEM once), then does
-//     the single needed step of the reversed LSTM2 and the classifier.
+//   * the recurrence keeps W_hh in registers (thread = the four gates of one hidden unit x 16 k; a transposing
+//     shuffle butterfly leaves the four gate pre-activations of one (unit, chunk) cell in one lane, so the
+//     cell update never leaves the registers: one barrier per step), reads the input projection from shared
+//     memory ([t][chunk][256], drained from TMEM once), then does the single needed step of the reversed
+//     LSTM2 and the classifier.
 //   * consecutive batches overlap: the kernel triggers its dependents at once (PDL) and only orders its
 //     final 8 B/chunk store after the previous grid (griddepcontrol.wait), it has no global scratch.
 #include <cuda_bf16.h>
@@ -57,7 +59,9 @@ constexpr int STAGE_BYTES = 8192;    // one weight stage
 constexpr int RING = 4;
 constexpr int TMEM_COLS = 256;
 constexpr int HG = 16 * G + 4;       // floats per k-group of h
-constexpr int XPS = G * 256 + 4;     // floats per time step of the staged input projection
+constexpr int XCS = 256 + 8;         // floats per (time step, chunk) of the staged input projection: +8 keeps the
+                                     // recurrence's (unit, chunk) reads on distinct banks
+constexpr int XPS = G * XCS + 4;     // floats per time step (= 4 mod 32: E3's float4 rows hit distinct banks)
 constexpr int MAX_T3 = U - (KW_MRG - 1);  // 28
 constexpr int MAX_TM = MAX_T3 - (KW_MRG - 1);  // 24
 
@@ -315,50 +319,13 @@ __device__ __forceinline__ void issue_conv3(uint32_t xset, uint32_t d_tmem, int 
     }
 }
 
-// ---- recurrence helpers (same scheme as rb200_fused.cu K3, one half-batch of 4 chunks) ------------------
+// ---- recurrence helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int mask) {
     return make_float2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
 }
 __device__ __forceinline__ float2 sel2(bool take_a, float2 a, float2 b) {
     return make_float2(take_a ? a.x : b.x, take_a ? a.y : b.y);
 }
-// gate pre-activations: g[c][r] = xin[c] + sum_k W_hh[r][k] h[k][c]; thread (rb = tid >> 2, kg = tid & 3) holds
-// W_hh[4 rb .. 4 rb + 3][16 kg .. 16 kg + 15]; two-round transposing butterfly leaves row tid in this thread
-__device__ __forceinline__ void lstm_matvec(const float (&w)[4][16], const float *__restrict__ hk,
-                                            const float (&xin)[G], float *__restrict__ g_s, int r, bool hi2,
-                                            bool hi1) {
-    float2 a[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i][0] = a[i][1] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int kl = 0; kl < 16; ++kl) {
-        const float4 hv = *reinterpret_cast<const float4 *>(hk + kl * G);
-        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            a[i][0] = ffma2(h01, w[i][kl], a[i][0]);
-            a[i][1] = ffma2(h23, w[i][kl], a[i][1]);
-        }
-    }
-    float2 rA[2][2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const float2 send = sel2(hi2, a[j][p], a[2 + j][p]);
-            const float2 keep = sel2(hi2, a[2 + j][p], a[j][p]);
-            rA[j][p] = __fadd2_rn(keep, shfl_xor2(send, 2));
-        }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const float2 send = sel2(hi1, rA[0][p], rA[1][p]);
-        const float2 keep = sel2(hi1, rA[1][p], rA[0][p]);
-        const float2 g2 = __fadd2_rn(keep, shfl_xor2(send, 1));
-        g_s[(2 * p) * 256 + r] = g2.x + xin[2 * p];
-        g_s[(2 * p + 1) * 256 + r] = g2.y + xin[2 * p + 1];
-    }
-}
-
 // =========================================================================================================
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant__ Params p) {
@@ -850,7 +817,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     {
         const float inv = cst[C_SCALE + 3];
         const float *b1 = cst + C_B1 + 128 * wh;
-        float *dst = xp_s + lane * XPS + q * 256 + 128 * wh;
+        float *dst = xp_s + lane * XPS + q * XCS + 128 * wh;
 #pragma unroll 1
         for (int cq = 0; cq < 4; ++cq) {
             float v[32];
@@ -880,7 +847,11 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
 
     MG_STAMP(10);
     // ---- R: LSTM1 recurrence, W_hh in registers ---------------------------------------------------------------
-    const int kg = lane & 3;
+    // thread (u = tid >> 2, kg = tid & 3) holds W_hh[gate * 64 + u][16 kg .. 16 kg + 15] for the four gates of
+    // hidden unit u.  The two-round transposing butterfly over the four k-slices leaves the four gate
+    // pre-activations of cell (u, chunk kg) in lane kg, so the cell update stays in registers: no gate
+    // exchange through shared memory, ONE barrier per step (h is double buffered).
+    const int kg = lane & 3, u = tid >> 2;
     float w[4][16];
 #pragma unroll
     for (int q4 = 0; q4 < 16; ++q4) {
@@ -890,32 +861,49 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         w[q4 >> 2][(q4 & 3) * 4 + 2] = v.z;
         w[q4 >> 2][(q4 & 3) * 4 + 3] = v.w;
     }
-    const float *hk = h_s + kg * HG;
     const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
     MG_STAMP(11);
-    const int u0 = tid & 63, cq = tid >> 6;             // cell (unit u0, chunk cq) owned in the update phase
-    const int hu = (u0 >> 4) * HG + (u0 & 15) * G;
+    const int hslot = (u >> 4) * HG + (u & 15) * G + kg;       // h of cell (u, chunk kg)
+    const float *xcell = xp_s + kg * XCS + u;                  // + t * XPS + 64 * gate
     float cstate = 0.f, hval = 0.f;
 #pragma unroll 1
     for (int t = 0; t < TM; ++t) {
-        float xin[G];
+        const float *hk = ((t & 1) ? g_s : h_s) + kg * HG;     // h(t - 1); g_s is free during the recurrence
+        float *hn = (t & 1) ? h_s : g_s;
+        const float *xt = xcell + t * XPS;
+        const float x0 = xt[0], x1 = xt[64], x2 = xt[128], x3 = xt[192];
+        float2 a[4][2];
 #pragma unroll
-        for (int c = 0; c < G; ++c) xin[c] = xp_s[t * XPS + c * 256 + tid];
-        lstm_matvec(w, hk, xin, g_s, tid, hi2, hi1);
-        __syncthreads();
-        {
-            const float *g = g_s + cq * 256;
-            const float ig = sigmoidf_fast(g[u0]), fg = sigmoidf_fast(g[64 + u0]);
-            const float gg = tanhf_fast(g[128 + u0]), og = sigmoidf_fast(g[192 + u0]);
-            cstate = fg * cstate + ig * gg;
-            hval = og * tanhf_fast(cstate);
-            h_s[hu + cq] = hval;
+        for (int g = 0; g < 4; ++g) a[g][0] = a[g][1] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int kl = 0; kl < 16; ++kl) {
+            const float4 hv = *reinterpret_cast<const float4 *>(hk + kl * G);
+            const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                a[g][0] = ffma2(h01, w[g][kl], a[g][0]);
+                a[g][1] = ffma2(h23, w[g][kl], a[g][1]);
+            }
         }
+        float pre[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float2 keep = sel2(hi2, a[g][1], a[g][0]), send = sel2(hi2, a[g][0], a[g][1]);
+            const float2 r = __fadd2_rn(keep, shfl_xor2(send, 2));
+            const float keepf = hi1 ? r.y : r.x, sendf = hi1 ? r.x : r.y;
+            pre[g] = keepf + __shfl_xor_sync(0xffffffffu, sendf, 1);
+        }
+        const float ig = sigmoidf_fast(pre[0] + x0), fg = sigmoidf_fast(pre[1] + x1);
+        const float gg = tanhf_fast(pre[2] + x2), og = sigmoidf_fast(pre[3] + x3);
+        cstate = fg * cstate + ig * gg;
+        hval = og * tanhf_fast(cstate);
+        hn[hslot] = hval;
         __syncthreads();
     }
     MG_STAMP(12);
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54) ----------------
-    h_s[hu + cq] = swishf(hval);
+    h_s[hslot] = swishf(hval);
+    const int u0 = tid & 63, cq = tid >> 6;             // cell (unit u0, chunk cq) owned in the tail
     __syncthreads();
     {
         float a2[G];
@@ -1822,7 +1810,7 @@ int mega_create(rb200_model *m, const float *blob) {
         for (int tid = 0; tid < 256; ++tid)
             for (int e = 0; e < 4; ++e) {
                 const int i = q >> 2, kl = (q & 3) * 4 + e;
-                const int row = 4 * (tid >> 2) + i, k = 16 * (tid & 3) + kl;
+                const int row = 64 * i + (tid >> 2), k = 16 * (tid & 3) + kl;  // gate i of hidden unit tid >> 2
                 host[mw->off_whh4 + (q * 256 + tid) * 4 + e] = blob[d.lstm_w_hh_off[0] + row * SIZE + k];
             }
     mw->off_wih2T = reserve(SIZE * 256);
