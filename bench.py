@@ -856,7 +856,7 @@ def ours(args):
                 line["next_rows"] = {"signal_mapping_refinement": {"error": str(e)[:200]}}
             try:
                 import vbz_times
-                v = vbz_times.vbz_bench(n_reads=256, cpu_seconds=1.5, verbose=False)
+                v = vbz_times.vbz_bench(n_reads=1024, cpu_seconds=1.5, verbose=False)
                 line["next_rows"]["pod5_signal_decode"] = {
                     "kernel": "svb16_decode_kernel", "unit": "samples/s", "value": v["samples_per_s"],
                     "ms": v["kernel_ms"], "samples": v["samples"], "packed_bytes_per_sample": v["bytes_per_sample"],

@@ -17,10 +17,10 @@
 //      tile, L2 hits), CTA reduction - no dependence on other CTAs
 //   1  256 key words (32 samples each) -> popcounts -> CTA exclusive scan = data offset of every word
 //   2  the tile's data bytes staged into shared memory with aligned 32-bit loads (coalesced)
-//   3  interleaved decode: thread j takes samples j, j+256, ... so neighbouring threads read neighbouring
-//      bytes; a sample's byte offset = index + popcount of the key bits before it; deltas go to an
-//      int16 [256][34] array (row pitch 17 words: conflict-free for the row-wise reads of step 4)
-//   4  blocked running sums: thread t sums row t (32 consecutive samples), CTA scan of the row totals
+//   3  thread j decodes the 32 samples of key word j sequentially, two per step: funnel shift to the byte
+//      position, one byte permute chosen by the two key bits, zig-zag and running sum on two 16-bit lanes
+//      at once (about 10 instructions per sample; the sample's byte position is a running counter)
+//   4  CTA scan of the per-thread totals
 //   5  the running sum carried in from the row's earlier tiles: every tile publishes the sum of ITS deltas
 //      (flag + 16-bit sum in one word) as soon as step 4 is done, and reads its predecessors' words -
 //      aggregates, not prefixes, so no tile waits on a chain; predecessors have lower block indices and
@@ -78,11 +78,8 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
                     const int32_t *__restrict__ row_samples, const int64_t *__restrict__ out_off,
                     int16_t *__restrict__ out, int32_t *__restrict__ status, uint32_t *__restrict__ agg,
                     int tiles_per_row) {
-    __shared__ uint32_t s_key[kThreads];
-    __shared__ int s_pref[kThreads];
     __shared__ int s_warp[kThreads / 32];
-    __shared__ __align__(16) uint32_t s_data[(2 * kTile + 32) / 4];
-    __shared__ int16_t s_delta[kThreads * 34];
+    __shared__ __align__(16) uint32_t s_data[(2 * kTile + 64) / 4];
 
     const int row = blockIdx.y, tile = blockIdx.x;
     const int n = row_samples[row];
@@ -149,8 +146,6 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
         }
         return;
     }
-    s_key[j] = key;
-    s_pref[j] = pref - 32 * j;  // popcount of the key bits before this word (+0 for full words)
     // ---- 2: stage the tile's data bytes (aligned words; the buffer is padded by the caller)
     const uint8_t *src = data + data_pos;
     const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15);
@@ -160,35 +155,41 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
 #pragma unroll 4
     for (int k = j; k < words; k += kThreads) s_data4[k] = __ldg(src_w + k);
     __syncthreads();
-    // ---- 3: interleaved decode into the padded delta array
-    const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data) + mis;
-    const int tile_n = min(kTile, n - t0);
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-        const int i = r * kThreads + j;  // sample within the tile
-        const int w = i >> 5, bit = i & 31;
-        int delta = 0;
-        if (i < tile_n) {
-            const uint32_t kw = s_key[w];
-            // bytes before sample i: one per earlier sample of the tile + one per earlier 2-byte value
-            const int off = i + s_pref[w] + __popc(kw & ((1u << bit) - 1u));
-            uint32_t u = sb[off];
-            if ((kw >> bit) & 1u) u |= (uint32_t)sb[off + 1] << 8;
-            delta = (int)(int16_t)((u >> 1) ^ (0u - (u & 1u)));
-        }
-        s_delta[w * 34 + bit] = (int16_t)delta;
-    }
-    __syncthreads();
-    // ---- 4: blocked running sums, 32 consecutive samples per thread
-    int vals[32];
-    int sum = 0;
+    // ---- 3: every thread decodes the 32 samples of its own key word, two at a time: the four bytes at the
+    // running byte position are aligned with one funnel shift, ONE byte permute (selector picked by the two
+    // key bits, a zero register supplying the absent high bytes) spreads them into two 16-bit lanes, zig-zag
+    // and the running sum are done on both lanes at once (d * 0x10001 = {d0, d0 + d1}; VIADD.16x2)
+    uint32_t outp[16];
+    int total = 0;
+    if (in_word > 0) {
+        uint32_t pos = (uint32_t)(mis + pref);  // byte offset of this word's first data byte in s_data
+        uint32_t kk = key, runb = 0;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        sum += s_delta[j * 34 + c];
-        vals[c] = sum;
+        for (int p = 0; p < 16; ++p) {
+            const uint32_t *wp = s_data + (pos >> 2);
+            const uint32_t a = __funnelshift_r(wp[0], wp[1], pos << 3);
+            const uint32_t k2 = kk & 3u;
+            kk >>= 2;
+            // key bits (sample 2p, sample 2p+1) -> output bytes {lo0, hi0, lo1, hi1}; source byte 4 is zero
+            // (a two-byte pick from the four 16-bit selectors held in two registers)
+            const uint32_t sel = __byte_perm(0x42104140u, 0x32102140u, k2 * 0x22u + 0x10u);
+            const uint32_t v = __byte_perm(a, 0u, sel);
+            const uint32_t neg = (v & 0x00010001u) * 0xFFFFu;       // 0xFFFF in the lanes whose low bit is set
+            const uint32_t d = ((v >> 1) & 0x7FFF7FFFu) ^ neg;      // zig-zag, both lanes
+            uint32_t o;
+            asm("add.u16x2 %0, %1, %2;" : "=r"(o) : "r"(d * 0x10001u), "r"(runb));
+            outp[p] = o;
+            runb = __byte_perm(o, 0u, 0x3232);                      // running sum = the high lane, in both lanes
+            pos += 2u + __popc(k2);
+        }
+        total = (int)(runb & 0xFFFFu);  // meaningful for full words (a partial word ends its row)
+    } else {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) outp[p] = 0u;
     }
+    // ---- 4: running sum across the threads of the tile
     int tile_sum;
-    int before = cta_exclusive_scan(sum, s_warp, &tile_sum);
+    int before = cta_exclusive_scan(total, s_warp, &tile_sum);
     // ---- 5: publish this tile's aggregate, collect the predecessors' (sums are taken modulo 2^16)
     if (j == 0) {
         __threadfence();
@@ -204,25 +205,19 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
         carry += (int)(v & 0xFFFFu);
     }
     if (tile > 0) before += cta_sum(carry, s_warp);
-    // ---- 6: store
+    const uint32_t bb = ((uint32_t)before & 0xFFFFu) * 0x10001u;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) asm("add.u16x2 %0, %1, %2;" : "=r"(outp[p]) : "r"(outp[p]), "r"(bb));
+    // ---- 6: store (64 contiguous bytes per thread)
     const int o0 = t0 + 32 * j;
     if (o0 + 32 <= n && ((reinterpret_cast<uintptr_t>(dst + o0) & 15) == 0)) {
         uint4 *d4 = reinterpret_cast<uint4 *>(dst + o0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t lo = (uint32_t)(vals[q * 8 + 2 * e] + before) & 0xFFFFu;
-                const uint32_t hi = (uint32_t)(vals[q * 8 + 2 * e + 1] + before) & 0xFFFFu;
-                w[e] = lo | (hi << 16);
-            }
-            d4[q] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        for (int q = 0; q < 4; ++q) d4[q] = make_uint4(outp[4 * q], outp[4 * q + 1], outp[4 * q + 2], outp[4 * q + 3]);
     } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-            if (o0 + c < n) dst[o0 + c] = (int16_t)(uint16_t)((uint32_t)(vals[c] + before) & 0xFFFFu);
+            if (o0 + c < n) dst[o0 + c] = (int16_t)(uint16_t)((outp[c >> 1] >> (16 * (c & 1))) & 0xFFFFu);
     }
     // the row's last tile knows where the stream ends: 1 = its length disagrees with the keys
     if (j == 0 && t0 + kTile >= n && data_pos + tile_bytes + nk != row_bytes) status[row] = 1;
