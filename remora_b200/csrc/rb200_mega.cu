@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             }
         }
     }
-    for (int i = tid; i < 4 * HG; i += THREADS) h_s[i] = 0.f;
+    for (int i = tid; i < 2 * 8 * 36; i += THREADS) reinterpret_cast<uint32_t *>(g_s)[i] = 0u;  // h(-1) = 0
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
@@ -847,62 +847,72 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
 
     MG_STAMP(10);
     // ---- R: LSTM1 recurrence, W_hh in registers ---------------------------------------------------------------
-    // thread (u = tid >> 2, kg = tid & 3) holds W_hh[gate * 64 + u][16 kg .. 16 kg + 15] for the four gates of
-    // hidden unit u.  The two-round transposing butterfly over the four k-slices leaves the four gate
-    // pre-activations of cell (u, chunk kg) in lane kg, so the cell update stays in registers: no gate
-    // exchange through shared memory, ONE barrier per step (h is double buffered).
-    const int kg = lane & 3, u = tid >> 2;
-    float w[4][16];
+    // The 256 x 64 mat-vec of every step runs on the tensor cores through the warp-level mma.sync path
+    // (HMMA.16816, operands in registers): measured 8.6 cycles per instruction and SM sub-partition, i.e. 7.7x
+    // the MAC rate of FFMA2, and the FMA pipe stays free for the co-resident CTA.
+    //   M = gate rows: warp w owns hidden units 8w .. 8w+7; its first 16-row tile holds their input and forget
+    //       gate rows, the second one their cell and output gate rows
+    //   N = 8 columns = 4 chunks x {h_hi, h_lo}: column 2c is the fp16 rounding of chunk c's h, column 2c+1 the
+    //       fp16 rounding of the remainder, so that c0 + c1 of an accumulator fragment is W . (h_hi + h_lo)
+    //   K = 64 hidden units = 4 k-tiles; W_hh is held as fp16 hi + lo A fragments (64 registers, pre-scaled by a
+    //       power of two), both accumulate into fp32: (W_hi + W_lo) . (h_hi + h_lo), all four products
+    // Thread (g = lane >> 2, t = lane & 3) ends up with the four gate pre-activations of cell (unit 8w+g,
+    // chunk t): the cell update stays in registers, one barrier per step (h operand tile double buffered).
+    const int g8 = lane >> 2, t4 = lane & 3, u = 8 * warp + g8;
+    uint32_t wa[16][4];  // [(m-tile * 4 + k-tile) * 2 + part][a0..a3]
 #pragma unroll
     for (int q4 = 0; q4 < 16; ++q4) {
-        const float4 v = p.whh4[q4 * 256 + tid];
-        w[q4 >> 2][(q4 & 3) * 4 + 0] = v.x;
-        w[q4 >> 2][(q4 & 3) * 4 + 1] = v.y;
-        w[q4 >> 2][(q4 & 3) * 4 + 2] = v.z;
-        w[q4 >> 2][(q4 & 3) * 4 + 3] = v.w;
+        const uint4 v = reinterpret_cast<const uint4 *>(p.whh4)[q4 * 256 + tid];
+        wa[q4][0] = v.x;
+        wa[q4][1] = v.y;
+        wa[q4][2] = v.z;
+        wa[q4][3] = v.w;
     }
-    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
     MG_STAMP(11);
-    const int hslot = (u >> 4) * HG + (u & 15) * G + kg;       // h of cell (u, chunk kg)
-    const float *xcell = xp_s + kg * XCS + u;                  // + t * XPS + 64 * gate
+    constexpr int HBP = 36;                                    // words per column of the h operand tile (+4: banks)
+    uint32_t *hb_s = reinterpret_cast<uint32_t *>(g_s);        // [2 buffers][8 columns][HBP] fp16 pairs along k
+    const float inv_hh = cst[C_SCALE + 4];
+    const float *xcell = xp_s + t4 * XCS + u;                  // + step * XPS + 64 * gate
     float cstate = 0.f, hval = 0.f;
 #pragma unroll 1
     for (int t = 0; t < TM; ++t) {
-        const float *hk = ((t & 1) ? g_s : h_s) + kg * HG;     // h(t - 1); g_s is free during the recurrence
-        float *hn = (t & 1) ? h_s : g_s;
+        const uint32_t *hb = hb_s + (t & 1) * 8 * HBP + g8 * HBP + t4;   // column g8 of h(t - 1)
+        __half *hn = reinterpret_cast<__half *>(hb_s + ((t + 1) & 1) * 8 * HBP);
         const float *xt = xcell + t * XPS;
         const float x0 = xt[0], x1 = xt[64], x2 = xt[128], x3 = xt[192];
-        float2 a[4][2];
+        float acc[4][4];  // [m-tile * 2 + part of W][c0..c3]: four independent accumulation chains
 #pragma unroll
-        for (int g = 0; g < 4; ++g) a[g][0] = a[g][1] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll
-        for (int kl = 0; kl < 16; ++kl) {
-            const float4 hv = *reinterpret_cast<const float4 *>(hk + kl * G);
-            const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+        for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t b0 = hb[8 * kt], b1 = hb[8 * kt + 4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                a[g][0] = ffma2(h01, w[g][kl], a[g][0]);
-                a[g][1] = ffma2(h23, w[g][kl], a[g][1]);
+            for (int mp = 0; mp < 4; ++mp) {
+                const uint32_t(&a)[4] = wa[((mp >> 1) * 4 + kt) * 2 + (mp & 1)];
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                    "{%0,%1,%2,%3};"
+                    : "+f"(acc[mp][0]), "+f"(acc[mp][1]), "+f"(acc[mp][2]), "+f"(acc[mp][3])
+                    : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
             }
         }
-        float pre[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const float2 keep = sel2(hi2, a[g][1], a[g][0]), send = sel2(hi2, a[g][0], a[g][1]);
-            const float2 r = __fadd2_rn(keep, shfl_xor2(send, 2));
-            const float keepf = hi1 ? r.y : r.x, sendf = hi1 ? r.x : r.y;
-            pre[g] = keepf + __shfl_xor_sync(0xffffffffu, sendf, 1);
-        }
-        const float ig = sigmoidf_fast(pre[0] + x0), fg = sigmoidf_fast(pre[1] + x1);
-        const float gg = tanhf_fast(pre[2] + x2), og = sigmoidf_fast(pre[3] + x3);
+        // rows g8 (c0, c1) / g8 + 8 (c2, c3); columns 2 t4 (h_hi) and 2 t4 + 1 (h_lo); W_hi and W_lo parts
+        const float pi = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
+        const float pf = (acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3]);
+        const float pg = (acc[2][0] + acc[2][1]) + (acc[3][0] + acc[3][1]);
+        const float po = (acc[2][2] + acc[2][3]) + (acc[3][2] + acc[3][3]);
+        const float ig = sigmoidf_fast(fmaf(pi, inv_hh, x0)), fg = sigmoidf_fast(fmaf(pf, inv_hh, x1));
+        const float gg = tanhf_fast(fmaf(pg, inv_hh, x2)), og = sigmoidf_fast(fmaf(po, inv_hh, x3));
         cstate = fg * cstate + ig * gg;
         hval = og * tanhf_fast(cstate);
-        hn[hslot] = hval;
+        const __half hh = __float2half_rn(hval);
+        hn[(2 * t4) * (2 * HBP) + u] = hh;
+        hn[(2 * t4 + 1) * (2 * HBP) + u] = __float2half_rn(hval - __half2float(hh));
         __syncthreads();
     }
     MG_STAMP(12);
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54) ----------------
-    h_s[hslot] = swishf(hval);
+    h_s[(u >> 4) * HG + (u & 15) * G + t4] = swishf(hval);
     const int u0 = tid & 63, cq = tid >> 6;             // cell (unit u0, chunk cq) owned in the tail
     __syncthreads();
     {
@@ -1806,13 +1816,34 @@ int mega_create(rb200_model *m, const float *blob) {
     }
     // ---- recurrence / tail weights (same layouts as rb200_fused.cu K3) ----
     mw->off_whh4 = reserve(SIZE * 256);
-    for (int q = 0; q < 16; ++q)
-        for (int tid = 0; tid < 256; ++tid)
-            for (int e = 0; e < 4; ++e) {
-                const int i = q >> 2, kl = (q & 3) * 4 + e;
-                const int row = 64 * i + (tid >> 2), k = 16 * (tid & 3) + kl;  // gate i of hidden unit tid >> 2
-                host[mw->off_whh4 + (q * 256 + tid) * 4 + e] = blob[d.lstm_w_hh_off[0] + row * SIZE + k];
-            }
+    {
+        // W_hh as the A fragments of mma.sync.m16n8k16 (row-major 16 x 16, fp16): register a of fragment
+        // ((m-tile * 4 + k-tile) * 2 + part) of thread (warp w, g = lane >> 2, t = lane & 3) holds
+        // W[row][k], W[row][k + 1] with row = gate * 64 + 8 w + g, gate = 2 * m-tile + (a & 1),
+        // k = 16 * k-tile + 2 t + 8 * (a >> 1); part 0 = fp16(S w), part 1 = fp16(S w - part 0)
+        const float *whh = blob + d.lstm_w_hh_off[0];
+        const float s_hh = pow2_scale(whh, (size_t)256 * SIZE);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(host.data() + mw->off_whh4);
+        for (int tid = 0; tid < 256; ++tid) {
+            const int w = tid >> 5, g = (tid & 31) >> 2, t = tid & 3;
+            for (int mt = 0; mt < 2; ++mt)
+                for (int kt = 0; kt < 4; ++kt)
+                    for (int part = 0; part < 2; ++part)
+                        for (int a = 0; a < 4; ++a) {
+                            const int row = (2 * mt + (a & 1)) * 64 + 8 * w + g;
+                            const int k = 16 * kt + 2 * t + 8 * (a >> 1);
+                            uint16_t h2[2];
+                            for (int e = 0; e < 2; ++e) {
+                                const float v = whh[row * SIZE + k + e] * s_hh;
+                                const uint16_t hi = f2h(v);
+                                h2[e] = part == 0 ? hi : f2h(v - h2f(hi));
+                            }
+                            const int q = (mt * 4 + kt) * 2 + part;
+                            dst[((size_t)q * 256 + tid) * 4 + a] = (uint32_t)h2[0] | ((uint32_t)h2[1] << 16);
+                        }
+        }
+        for (int mode = 0; mode < 2; ++mode) host[mw->off_consts[mode] + C_SCALE + 4] = 1.f / s_hh;
+    }
     mw->off_wih2T = reserve(SIZE * 256);
     for (int k = 0; k < SIZE; ++k)
         for (int r = 0; r < 256; ++r) host[mw->off_wih2T + k * 256 + r] = blob[d.lstm_w_ih_off[1] + r * SIZE + k];

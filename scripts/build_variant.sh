@@ -8,7 +8,7 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p remora_b200/lib/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 \
-  -Wno-deprecated-gpu-targets -I include -I remora_b200/csrc "$@" -c remora_b200/csrc/rb200_mega.cu \
+  -Wno-deprecated-gpu-targets -I include -I remora_b200/csrc "$@" -c ${MEGA_SRC:-remora_b200/csrc/rb200_mega.cu} \
   -o remora_b200/lib/variants/mega_$name.o
 objs=$(ls remora_b200/lib/*.o | grep -v rb200_mega.o)
 nvcc -shared -o remora_b200/lib/variants/librb200_$name.so $objs remora_b200/lib/variants/mega_$name.o -lcudart
