@@ -74,7 +74,7 @@ constexpr int C_BSEQ1 = 360;    //                    16
 constexpr int C_BSIG3 = 376;    //                    64
 constexpr int C_BSEQ2 = 440;    //                    64
 constexpr int C_BMRG = 504;     //                    64
-constexpr int C_SCALE = 568;    // inverse weight scales: seq2, sig3, merge, xproj (+4 pad)
+constexpr int C_SCALE = 568;    // inverse weight scales: seq2, sig3, merge, xproj, W_hh1, -, W_ih2 (+1 pad)
 constexpr int C_B1 = 576;       // LSTM1 bias        256
 constexpr int CONST_FLOATS = 832;
 constexpr int CONST_BYTES = CONST_FLOATS * 4;  // 3328
@@ -422,7 +422,14 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         mbar_expect_tx(&bars->front, CONST_BYTES + (dense ? 0 : p.gtab_bytes));
         bulk_g2s(cst, p.consts, CONST_BYTES, &bars->front);
         if (!dense) bulk_g2s(ra + A_TAB, p.gtab, p.gtab_bytes, &bars->front);
+        const long long tl0 = p.stamps && blockIdx.x == 0 ? clock64() : 0;
         for (int s = 0; s < RING - 1; ++s) load_stage(s, CF::NS_TOTAL, p.wstream, ring, bars);
+        if (p.stamps && blockIdx.x == 0) {  // profiling aid: how long the first TMA loads take to land
+            mbar_wait(&bars->w_full[0], 0);
+            const long long tl1 = clock64();
+            mbar_wait(&bars->w_full[RING - 2], 0);
+            p.stamps[15] = (tl1 - tl0) | ((clock64() - tl0) << 32);
+        }
     }
 
     MG_STAMP(1);
@@ -438,20 +445,24 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     }
     const bool dense = p.q1_in != nullptr;
     if (!dense) {
+        // every load of the compact arrays is issued at once (one memory round trip): each element reads its
+        // chunk's length itself and masks what lies past it (that padding is uninitialised in the reference's
+        // arrays and never used)
         if (tid < C) {
             int L = p.lens[chunk0 + tid];
-            L = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
-            len_s[tid] = L;
+            len_s[tid] = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
         }
-        __syncthreads();
         for (int i = tid; i < C * seq_width; i += THREADS) {
             const int c = i / seq_width, s = i - c * seq_width;
-            // padding past seq_len + kmer_len - 1 is uninitialised in the reference's arrays: never read
-            seq_s[i] = s < len_s[c] + K - 1 ? p.seqs[(size_t)(chunk0 + c) * seq_width + s] : (int8_t)-1;
+            const int L = max(0, min((int)p.lens[chunk0 + c], min(map_width - 1, seq_width - K + 1)));
+            const int8_t v = p.seqs[(size_t)(chunk0 + c) * seq_width + s];
+            seq_s[i] = s < L + K - 1 ? v : (int8_t)-1;
         }
         for (int i = tid; i < C * map_width; i += THREADS) {
             const int c = i / map_width, s = i - c * map_width;
-            map_s[i] = s <= len_s[c] ? p.maps[(size_t)(chunk0 + c) * map_width + s] : (int16_t)0;
+            const int L = max(0, min((int)p.lens[chunk0 + c], min(map_width - 1, seq_width - K + 1)));
+            const int16_t v = p.maps[(size_t)(chunk0 + c) * map_width + s];
+            map_s[i] = s <= L ? v : (int16_t)0;
         }
         __syncthreads();
         for (int i = tid; i < C * (map_width - 1); i += THREADS) {
@@ -912,40 +923,51 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     }
     MG_STAMP(12);
     // ---- LSTM2: only the first step of the reversed pass is consumed (ConvLSTM_w_ref.py:53-54) ----------------
-    h_s[(u >> 4) * HG + (u & 15) * G + t4] = swishf(hval);
-    const int u0 = tid & 63, cq = tid >> 6;             // cell (unit u0, chunk cq) owned in the tail
+    // same shape as a recurrence step (zero initial state: gates = W_ih2 x + b2, the forget gate is unused):
+    // W_ih2 arrives as the same A fragments, straight from L2 into the registers W_hh just left (all 16 loads in
+    // flight at once), x = swish(h1) goes through the operand tile, the cell stays in registers
+#pragma unroll
+    for (int q4 = 0; q4 < 16; ++q4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.wih2T) + q4 * 256 + tid);
+        wa[q4][0] = v.x;
+        wa[q4][1] = v.y;
+        wa[q4][2] = v.z;
+        wa[q4][3] = v.w;
+    }
+    {
+        const float x = swishf(hval);
+        const __half xh = __float2half_rn(x);
+        __half *hn = reinterpret_cast<__half *>(hb_s);
+        hn[(2 * t4) * (2 * HBP) + u] = xh;
+        hn[(2 * t4 + 1) * (2 * HBP) + u] = __float2half_rn(x - __half2float(xh));
+    }
+    const float bi = p.b2[u], bg = p.b2[128 + u], bo = p.b2[192 + u];
     __syncthreads();
     {
-        float a2[G];
-        const float bias = p.b2[tid];
+        const uint32_t *hb = hb_s + g8 * HBP + t4;
+        float acc[4][4];
 #pragma unroll
-        for (int c = 0; c < G; ++c) a2[c] = bias;
-        // W_ih2^T comes straight from L2 (coalesced, read once): all loads of a half are issued before the
-        // first use so that the kernel pays two L2 round trips here, not one per unrolled group
-#pragma unroll 1
-        for (int k0 = 0; k0 < SIZE; k0 += 32) {
-            float wv[32];
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) wv[k] = __ldg(p.wih2T + (k0 + k) * 256 + tid);
+        for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t b0 = hb[8 * kt], b1 = hb[8 * kt + 4];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const float4 hv =
-                    *reinterpret_cast<const float4 *>(h_s + ((k0 + k) >> 4) * HG + ((k0 + k) & 15) * G);
-                a2[0] = fmaf(wv[k], hv.x, a2[0]);
-                a2[1] = fmaf(wv[k], hv.y, a2[1]);
-                a2[2] = fmaf(wv[k], hv.z, a2[2]);
-                a2[3] = fmaf(wv[k], hv.w, a2[3]);
+            for (int mp = 0; mp < 4; ++mp) {
+                const uint32_t(&a)[4] = wa[((mp >> 1) * 4 + kt) * 2 + (mp & 1)];
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                    "{%0,%1,%2,%3};"
+                    : "+f"(acc[mp][0]), "+f"(acc[mp][1]), "+f"(acc[mp][2]), "+f"(acc[mp][3])
+                    : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
             }
         }
-#pragma unroll
-        for (int c = 0; c < G; ++c) g_s[c * 256 + tid] = a2[c];
-    }
-    __syncthreads();
-    {
-        const float *g = g_s + cq * 256;
-        const float c2 = sigmoidf_acc(g[u0]) * tanhf(g[128 + u0]);
-        const float h2 = sigmoidf_acc(g[192 + u0]) * tanhf(c2);
-        y_s[cq * SIZE + u0] = swishf(h2);
+        const float inv2 = cst[C_SCALE + 6];
+        const float pi = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
+        const float pg = (acc[2][0] + acc[2][1]) + (acc[3][0] + acc[3][1]);
+        const float po = (acc[2][2] + acc[2][3]) + (acc[3][2] + acc[3][3]);
+        const float c2 = sigmoidf_acc(fmaf(pi, inv2, bi)) * tanhf(fmaf(pg, inv2, bg));
+        const float h2 = sigmoidf_acc(fmaf(po, inv2, bo)) * tanhf(c2);
+        y_s[t4 * SIZE + u] = swishf(h2);
     }
     __syncthreads();
     MG_STAMP(13);
@@ -1815,15 +1837,13 @@ int mega_create(rb200_model *m, const float *blob) {
         }
     }
     // ---- recurrence / tail weights (same layouts as rb200_fused.cu K3) ----
-    mw->off_whh4 = reserve(SIZE * 256);
-    {
-        // W_hh as the A fragments of mma.sync.m16n8k16 (row-major 16 x 16, fp16): register a of fragment
-        // ((m-tile * 4 + k-tile) * 2 + part) of thread (warp w, g = lane >> 2, t = lane & 3) holds
-        // W[row][k], W[row][k + 1] with row = gate * 64 + 8 w + g, gate = 2 * m-tile + (a & 1),
-        // k = 16 * k-tile + 2 t + 8 * (a >> 1); part 0 = fp16(S w), part 1 = fp16(S w - part 0)
-        const float *whh = blob + d.lstm_w_hh_off[0];
-        const float s_hh = pow2_scale(whh, (size_t)256 * SIZE);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(host.data() + mw->off_whh4);
+    // W_hh1 and W_ih2 as the A fragments of mma.sync.m16n8k16 (row-major 16 x 16, fp16): register a of fragment
+    // ((m-tile * 4 + k-tile) * 2 + part) of thread (warp w, g = lane >> 2, t = lane & 3) holds
+    // W[row][k], W[row][k + 1] with row = gate * 64 + 8 w + g, gate = 2 * m-tile + (a & 1),
+    // k = 16 * k-tile + 2 t + 8 * (a >> 1); part 0 = fp16(S w), part 1 = fp16(S w - part 0)
+    auto put_gate_frags = [&](size_t off, const float *wsrc, int scale_slot) {
+        const float sc = pow2_scale(wsrc, (size_t)256 * SIZE);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(host.data() + off);
         for (int tid = 0; tid < 256; ++tid) {
             const int w = tid >> 5, g = (tid & 31) >> 2, t = tid & 3;
             for (int mt = 0; mt < 2; ++mt)
@@ -1834,7 +1854,7 @@ int mega_create(rb200_model *m, const float *blob) {
                             const int k = 16 * kt + 2 * t + 8 * (a >> 1);
                             uint16_t h2[2];
                             for (int e = 0; e < 2; ++e) {
-                                const float v = whh[row * SIZE + k + e] * s_hh;
+                                const float v = wsrc[row * SIZE + k + e] * sc;
                                 const uint16_t hi = f2h(v);
                                 h2[e] = part == 0 ? hi : f2h(v - h2f(hi));
                             }
@@ -1842,11 +1862,12 @@ int mega_create(rb200_model *m, const float *blob) {
                             dst[((size_t)q * 256 + tid) * 4 + a] = (uint32_t)h2[0] | ((uint32_t)h2[1] << 16);
                         }
         }
-        for (int mode = 0; mode < 2; ++mode) host[mw->off_consts[mode] + C_SCALE + 4] = 1.f / s_hh;
-    }
+        for (int mode = 0; mode < 2; ++mode) host[mw->off_consts[mode] + C_SCALE + scale_slot] = 1.f / sc;
+    };
+    mw->off_whh4 = reserve(SIZE * 256);
+    put_gate_frags(mw->off_whh4, blob + d.lstm_w_hh_off[0], 4);
     mw->off_wih2T = reserve(SIZE * 256);
-    for (int k = 0; k < SIZE; ++k)
-        for (int r = 0; r < 256; ++r) host[mw->off_wih2T + k * 256 + r] = blob[d.lstm_w_ih_off[1] + r * SIZE + k];
+    put_gate_frags(mw->off_wih2T, blob + d.lstm_w_ih_off[1], 6);
     mw->off_b2 = reserve(256);
     memcpy(host.data() + mw->off_b2, blob + d.lstm_b_off[1], 256 * sizeof(float));
     mw->off_fcw = reserve((size_t)d.num_out * SIZE);
@@ -2063,7 +2084,8 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
                                         "lstm2", "pdl_wait"};
         fprintf(stderr, "[mega stamps, cycles]");
         for (int i = 0; i < 14; ++i) fprintf(stderr, " %s %lld |", names[i], h[i + 1] - h[i]);
-        fprintf(stderr, " total %lld\n", h[14] - h[0]);
+        fprintf(stderr, " total %lld | first weight stage landed after %lld, first three after %lld\n", h[14] - h[0],
+                h[15] & 0xFFFFFFFFll, h[15] >> 32);
     }
     m->launches += 1;
     m->last_impl = mode == 0 ? RB200_IMPL_FUSED_MEGA : RB200_IMPL_FUSED_BF16;
