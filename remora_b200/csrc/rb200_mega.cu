@@ -201,6 +201,18 @@ __device__ __forceinline__ void mma_h(uint32_t d_tmem, uint64_t a, uint64_t b, u
         "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// accumulate flag known at compile time: no predicate set-up in the issuing thread's instruction stream
+template <bool ACC>
+__device__ __forceinline__ void mma_hc(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+// descriptor of the same tile `byte_off` further on (the start-address field counts 16-byte units and never
+// carries out of its 14 bits for shared-memory addresses)
+__device__ __forceinline__ uint64_t desc_at(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
                  : "memory");
@@ -291,27 +303,36 @@ __device__ __forceinline__ void produce_until(int &next, int upto, int total, co
     for (; next < end; ++next) load_stage(next, total, wstream, ring, bars);
 }
 
-template <int MODE, int KW, bool SELF_LOAD>
-__device__ __forceinline__ void issue_conv3(uint32_t xset, uint32_t d_tmem, int &s, const uint8_t *wstream,
-                                            uint8_t *ring, Bars *bars) {
+// The issuing thread's loop is fully unrolled with compile-time stage numbers: ring slot, barrier parity and
+// every descriptor offset are immediates, so one MMA costs a couple of integer adds to issue.  (With run-time
+// stage counters the descriptor arithmetic of the single issuing thread, ~125 cycles per MMA, was what bounded
+// the tensor-core phases - the MMAs themselves run at 64 (N = 128) / 50 (N = 64) cycles,
+// scripts/microbench/umma_rate.cu.)
+template <int MODE, int KW, int S0, bool SELF_LOAD>
+__device__ __forceinline__ void issue_conv3(uint32_t xset, uint32_t d_tmem, const uint8_t *wstream, uint8_t *ring,
+                                            Bars *bars, long long *dbg = nullptr) {
     using C = Cfg<MODE>;
     constexpr int NS = (KW + C::TAPS - 1) / C::TAPS;
     constexpr uint32_t id_main = idesc_h(128, C::NB, MODE), id_corr = idesc_h(128, 64, MODE);
-    for (int st = 0; st < NS; ++st, ++s) {
-        const int slot = s & (RING - 1);
+    const uint64_t da = desc_ns(xset, LBO_A), db = desc_ns(smem_addr(ring), C::B_LBO);
+#pragma unroll
+    for (int st = 0; st < NS; ++st) {
+        const int s = S0 + st, slot = s & (RING - 1);
         mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
+        if (dbg) dbg[st] = clock64();
         tc_fence_after();
-        const uint32_t b0 = smem_addr(ring + slot * STAGE_BYTES);
 #pragma unroll
         for (int tp = 0; tp < C::TAPS; ++tp) {
             const int j = st * C::TAPS + tp;
             if (j < KW) {
                 const int r = j % 3, i = j / 3;
-                const uint32_t a_hi = xset + (2 * r) * XT_BYTES + i * 16;
-                const uint32_t b = b0 + tp * 2 * C::B_LBO;
-                mma_h(d_tmem, desc_ns(a_hi, LBO_A), desc_ns(b, C::B_LBO), id_main, j ? 1u : 0u);
-                if (MODE == 0)
-                    mma_h(d_tmem + 64, desc_ns(a_hi + XT_BYTES, LBO_A), desc_ns(b, C::B_LBO), id_corr, 1u);
+                const uint64_t a_hi = desc_at(da, (2 * r) * XT_BYTES + i * 16);
+                const uint64_t b = desc_at(db, slot * STAGE_BYTES + tp * 2 * C::B_LBO);
+                if (j == 0)
+                    mma_hc<false>(d_tmem, a_hi, b, id_main);
+                else
+                    mma_hc<true>(d_tmem, a_hi, b, id_main);
+                if (MODE == 0) mma_hc<true>(d_tmem + 64, desc_at(a_hi, XT_BYTES), b, id_corr);
             }
         }
         umma_commit(&bars->w_empty[slot]);
@@ -594,16 +615,23 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     __syncthreads();
     MG_STAMP(3);
 
-    // ---- M1 (warp 0) || P2 (warps 1..7): seq_conv2 on the tensor core under sig_conv1 / sig_conv2 ----------
-    int s_next = 0;  // weight stage counter of the issuing thread
+    // ---- M1 (warp 0) || P2 (warps 2..7): seq_conv2 on the tensor core under sig_conv1 / sig_conv2 ----------
+    // warp 1's lane 0 is the TMA producer of the weight ring for the rest of the kernel: it keeps RING stages in
+    // flight and re-fills a slot as soon as the MMAs that read it have completed, so the issuing thread only
+    // ever waits for data (when it also produced, every stage cost it a completion round trip)
+    int p_next = RING - 1;
     if (warp == 0) {
         if (lane == 0) {
-            issue_conv3<MODE, KW_SEQ2, true>(smem_addr(xq), tmem, s_next, p.wstream, ring, bars);
+            issue_conv3<MODE, KW_SEQ2, 0, false>(smem_addr(xq), tmem, p.wstream, ring, bars,
+                                                 p.stamps && blockIdx.x == 0 ? p.stamps + 25 : nullptr);
             umma_commit(&bars->seq_done);
         }
         __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) produce_until(p_next, CF::NS_SEQ + RING, CF::NS_TOTAL, p.wstream, ring, bars);
+        __syncwarp();
     } else {
-        const int wt = tid - 32, NW = THREADS - 32;
+        const int wt = tid - 64, NW = THREADS - 64;
         float *s1_s = reinterpret_cast<float *>(ra + A_S1);
         {
             const float *w = cst + C_WSIG1, *bb = cst + C_BSIG1;
@@ -635,9 +663,9 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
                 const int half = i & 1;
                 const int ct = i >> 1;
                 const int c = ct / T2, t = ct - c * T2;
-                float acc[8];
+                float2 a2[4];
 #pragma unroll
-                for (int o = 0; o < 8; ++o) acc[o] = bb[half * 8 + o];
+                for (int o = 0; o < 4; ++o) a2[o] = make_float2(bb[half * 8 + 2 * o], bb[half * 8 + 2 * o + 1]);
 #pragma unroll
                 for (int j = 0; j < KW_SIG2; ++j) {
                     const float4 xv = *reinterpret_cast<const float4 *>(s1_s + (size_t)(c * T1 + t + j) * 4);
@@ -646,18 +674,18 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
                     for (int ci = 0; ci < 4; ++ci) {
                         const float4 *wp = reinterpret_cast<const float4 *>(w + (j * 4 + ci) * 16 + half * 8);
                         const float4 wa = wp[0], wb = wp[1];
-                        acc[0] = fmaf(wa.x, xs4[ci], acc[0]);
-                        acc[1] = fmaf(wa.y, xs4[ci], acc[1]);
-                        acc[2] = fmaf(wa.z, xs4[ci], acc[2]);
-                        acc[3] = fmaf(wa.w, xs4[ci], acc[3]);
-                        acc[4] = fmaf(wb.x, xs4[ci], acc[4]);
-                        acc[5] = fmaf(wb.y, xs4[ci], acc[5]);
-                        acc[6] = fmaf(wb.z, xs4[ci], acc[6]);
-                        acc[7] = fmaf(wb.w, xs4[ci], acc[7]);
+                        a2[0] = ffma2(make_float2(wa.x, wa.y), xs4[ci], a2[0]);
+                        a2[1] = ffma2(make_float2(wa.z, wa.w), xs4[ci], a2[1]);
+                        a2[2] = ffma2(make_float2(wb.x, wb.y), xs4[ci], a2[2]);
+                        a2[3] = ffma2(make_float2(wb.z, wb.w), xs4[ci], a2[3]);
                     }
                 }
+                float acc[8];
 #pragma unroll
-                for (int o = 0; o < 8; ++o) acc[o] = swishf_fast(acc[o]);
+                for (int o = 0; o < 4; ++o) {
+                    acc[2 * o] = swishf_fast(a2[o].x);
+                    acc[2 * o + 1] = swishf_fast(a2[o].y);
+                }
                 const int r = t % 3, u = t / 3;
                 uint8_t *t_hi = xs + (2 * r) * XT_BYTES;
                 store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, half * LBO_A + (c * U + u) * 16, acc);
@@ -669,11 +697,10 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     MG_STAMP(4);
 
     // ---- M2: sig_conv3; E1: both accumulators -> bias + swish -> cat tile (hi / lo) -------------------------
-    // from here on warp 1's lane 0 is the TMA producer of the weight ring (M1 left it RING - 1 stages ahead)
-    int p_next = CF::NS_SEQ + RING - 1;
     if (tid == 0) {
-        s_next = CF::NS_SEQ;
-        issue_conv3<MODE, KW_SIG3, false>(smem_addr(ra + A_XS), tmem + 128, s_next, p.wstream, ring, bars);
+        issue_conv3<MODE, KW_SIG3, CF::NS_SEQ, false>(smem_addr(ra + A_XS), tmem + 128, p.wstream, ring, bars,
+                                                      p.stamps && blockIdx.x == 0 ? p.stamps + 16 : nullptr);
+        if (p.stamps && blockIdx.x == 0) p.stamps[16 + 8] = clock64();
         umma_commit(&bars->conv_done);
     } else if (tid == 32) {
         produce_until(p_next, CF::NS_SEQ + CF::NS_SIG + RING, CF::NS_TOTAL, p.wstream, ring, bars);
@@ -729,26 +756,27 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     MG_STAMP(6);
     // ---- M3: merge_conv1 (K = 5 taps x 128 channels), tap = descriptor shift; E2 -> m tiles -----------------
     if (tid == 0) {
-        int s = CF::NS_SEQ + CF::NS_SIG;
+        constexpr int S0 = CF::NS_SEQ + CF::NS_SIG;
         constexpr uint32_t id_main = idesc_h(128, CF::NB, MODE), id_corr = idesc_h(128, 64, MODE);
-        const uint32_t cat_hi = smem_addr(ra), cat_lo = cat_hi + CAT_HALF;
-        constexpr int KBLKS = 16 / CF::MRG_KC;  // channel blocks per tap
-        for (int st = 0; st < CF::NS_MRG; ++st, ++s) {
+        const uint64_t da = desc_ns(smem_addr(ra), LBO_A), db = desc_ns(smem_addr(ring), CF::B_LBO);
+#pragma unroll
+        for (int st = 0; st < CF::NS_MRG; ++st) {  // unrolled: slots, parities and descriptor offsets are immediates
+            const int s = S0 + st, slot = s & (RING - 1);
             const int kb = st / KW_MRG, tap = st - kb * KW_MRG;
-            const int slot = s & (RING - 1);
             mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
             tc_fence_after();
-            const uint32_t b0 = smem_addr(ring + slot * STAGE_BYTES);
 #pragma unroll
             for (int k16 = 0; k16 < CF::MRG_KC / 2; ++k16) {
-                const uint32_t aoff = (kb * CF::MRG_KC + 2 * k16) * LBO_A + tap * 16;
-                const uint32_t b = b0 + k16 * 2 * CF::B_LBO;
-                mma_h(tmem, desc_ns(cat_hi + aoff, LBO_A), desc_ns(b, CF::B_LBO), id_main, (st | k16) ? 1u : 0u);
-                if (MODE == 0) mma_h(tmem + 64, desc_ns(cat_lo + aoff, LBO_A), desc_ns(b, CF::B_LBO), id_corr, 1u);
+                const uint64_t a = desc_at(da, (kb * CF::MRG_KC + 2 * k16) * LBO_A + tap * 16);
+                const uint64_t b = desc_at(db, slot * STAGE_BYTES + k16 * 2 * CF::B_LBO);
+                if (st == 0 && k16 == 0)
+                    mma_hc<false>(tmem, a, b, id_main);
+                else
+                    mma_hc<true>(tmem, a, b, id_main);
+                if (MODE == 0) mma_hc<true>(tmem + 64, desc_at(a, CAT_HALF), b, id_corr);
             }
             umma_commit(&bars->w_empty[slot]);
         }
-        (void)KBLKS;
         umma_commit(&bars->mrg_done);
     } else if (tid == 32) {
         produce_until(p_next, CF::NS_SEQ + CF::NS_SIG + CF::NS_MRG + RING, CF::NS_TOTAL, p.wstream, ring, bars);
@@ -795,25 +823,32 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     MG_STAMP(8);
     // ---- M4: LSTM1 input projection (N = 256 gate rows, K = 64); E3 -> xp_s[t][chunk][256] ------------------
     if (tid == 0) {
-        int s = CF::NS_SEQ + CF::NS_SIG + CF::NS_MRG;
+        constexpr int S0 = CF::NS_SEQ + CF::NS_SIG + CF::NS_MRG;
         constexpr uint32_t id_x = idesc_h(128, 256, MODE);
-        const uint32_t m_hi = smem_addr(ra), m_lo = m_hi + M_HALF;
-        for (int st = 0; st < CF::NS_XP; ++st, ++s) {
-            const int slot = s & (RING - 1);
+        const uint64_t da = desc_ns(smem_addr(ra), LBO_A), db = desc_ns(smem_addr(ring), 4096);
+#pragma unroll
+        for (int st = 0; st < CF::NS_XP; ++st) {
+            const int s = S0 + st, slot = s & (RING - 1);
             mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
             tc_fence_after();
-            const uint32_t b = smem_addr(ring + slot * STAGE_BYTES);
+            const uint64_t b = desc_at(db, slot * STAGE_BYTES);
             if (MODE == 0) {
                 const int k16 = st >> 1, lo_stage = st & 1;
-                const uint32_t aoff = 2 * k16 * LBO_A;
+                const uint64_t m_hi = desc_at(da, 2 * k16 * LBO_A), m_lo = desc_at(m_hi, M_HALF);
                 if (!lo_stage) {  // W_hi: m_hi * W_hi, m_lo * W_hi
-                    mma_h(tmem, desc_ns(m_hi + aoff, LBO_A), desc_ns(b, 4096), id_x, st ? 1u : 0u);
-                    mma_h(tmem, desc_ns(m_lo + aoff, LBO_A), desc_ns(b, 4096), id_x, 1u);
+                    if (st == 0)
+                        mma_hc<false>(tmem, m_hi, b, id_x);
+                    else
+                        mma_hc<true>(tmem, m_hi, b, id_x);
+                    mma_hc<true>(tmem, m_lo, b, id_x);
                 } else {  // W_lo: m_hi * W_lo
-                    mma_h(tmem, desc_ns(m_hi + aoff, LBO_A), desc_ns(b, 4096), id_x, 1u);
+                    mma_hc<true>(tmem, m_hi, b, id_x);
                 }
             } else {
-                mma_h(tmem, desc_ns(m_hi + 2 * st * LBO_A, LBO_A), desc_ns(b, 4096), id_x, st ? 1u : 0u);
+                if (st == 0)
+                    mma_hc<false>(tmem, desc_at(da, 2 * st * LBO_A), b, id_x);
+                else
+                    mma_hc<true>(tmem, desc_at(da, 2 * st * LBO_A), b, id_x);
             }
             umma_commit(&bars->w_empty[slot]);
         }
@@ -2035,7 +2070,7 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     static const bool want_stamps = getenv("RB200_MEGA_STAMPS") != nullptr;  // profiling aid
     static long long *stamps_dev = nullptr;
     if (want_stamps) {
-        if (!stamps_dev) cudaMalloc(&stamps_dev, 16 * sizeof(long long));
+        if (!stamps_dev) cudaMalloc(&stamps_dev, 32 * sizeof(long long));
         p.stamps = stamps_dev;
     }
     if (m->keep_debug) {
@@ -2076,7 +2111,7 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
         for (int i = 0; i < 4; ++i) m->prof_events.push_back(ev[i]);
     }
     if (want_stamps) {
-        long long h[16];
+        long long h[32];
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, stamps_dev, sizeof(h), cudaMemcpyDeviceToHost);
         static const char *names[14] = {"prologue", "stage+sidx", "gather", "seq2||sig12", "sig3 mma", "E1 cat",
@@ -2086,6 +2121,11 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
         for (int i = 0; i < 14; ++i) fprintf(stderr, " %s %lld |", names[i], h[i + 1] - h[i]);
         fprintf(stderr, " total %lld | first weight stage landed after %lld, first three after %lld\n", h[14] - h[0],
                 h[15] & 0xFFFFFFFFll, h[15] >> 32);
+        fprintf(stderr, "   sig3 stages ready at (cycles after the phase start):");
+        for (int i = 0; i < 5; ++i) fprintf(stderr, " %lld", h[16 + i] - h[4]);
+        fprintf(stderr, " | all issued %lld | done %lld\n   seq2 stages ready at:", h[24] - h[4], h[5] - h[4]);
+        for (int i = 0; i < 7; ++i) fprintf(stderr, " %lld", h[25 + i] - h[3]);
+        fprintf(stderr, "\n");
     }
     m->launches += 1;
     m->last_impl = mode == 0 ? RB200_IMPL_FUSED_MEGA : RB200_IMPL_FUSED_BF16;
