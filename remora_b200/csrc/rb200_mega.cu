@@ -1158,30 +1158,37 @@ __device__ __forceinline__ void load_stage_c(int s, const uint8_t *wstream, uint
     mbar_expect_tx(&bars->w_full[slot], STAGE_BYTES);
     bulk_g2s(ring + slot * STAGE_BYTES, wstream + (size_t)s * STAGE_BYTES, STAGE_BYTES, &bars->w_full[slot]);
 }
-__device__ __forceinline__ uint32_t wait_stage(int s, uint8_t *ring, Bars *bars) {
+// stage `s` (a compile-time number in the unrolled issue loops) has landed; returns its byte offset in the ring
+__device__ __forceinline__ uint32_t wait_stage(int s, Bars *bars) {
     const int slot = s & (RING - 1);
     mbar_wait(&bars->w_full[slot], (s >> 2) & 1);
     tc_fence_after();
-    return smem_addr(ring + slot * STAGE_BYTES);
+    return (uint32_t)(slot * STAGE_BYTES);
 }
 
 // 64-channel merge-type layer: `taps` taps, tap j reads tile (tile_of[j]) shifted by shift_of[j] rows;
 // weights: two stages (K = 32 each) per tap.  A tiles are [8 K chunks][RP rows] hi at `a`, lo at a + T64.
-template <int TAPS>
+template <int TAPS, int S0>
 __device__ __forceinline__ void issue_merge64(const uint32_t (&a_tile)[TAPS], const int (&shift)[TAPS], uint32_t d,
-                                              int &s, uint8_t *ring, Bars *bars) {
+                                              uint8_t *ring, Bars *bars) {
     constexpr uint32_t id_main = idesc_h(128, 128, 0), id_corr = idesc_h(128, 64, 0);
+    const uint64_t db = desc_ns(smem_addr(ring), 2048);
 #pragma unroll
     for (int j = 0; j < TAPS; ++j) {
+        const uint64_t da = desc_ns(a_tile[j] + shift[j] * 16, LBO_A);
 #pragma unroll
-        for (int h = 0; h < 2; ++h, ++s) {
-            const uint32_t b0 = wait_stage(s, ring, bars);
+        for (int h = 0; h < 2; ++h) {
+            const int s = S0 + 2 * j + h;
+            const uint32_t b0 = wait_stage(s, bars);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-                const uint32_t a = a_tile[j] + (uint32_t)((4 * h + 2 * kk) * LBO_A + shift[j] * 16);
-                const uint32_t b = b0 + kk * 2 * 2048;
-                mma_h(d, desc_ns(a, LBO_A), desc_ns(b, 2048), id_main, (j | h | kk) ? 1u : 0u);
-                mma_h(d + 64, desc_ns(a + T64, LBO_A), desc_ns(b, 2048), id_corr, 1u);
+                const uint64_t a = desc_at(da, (4 * h + 2 * kk) * LBO_A);
+                const uint64_t b = desc_at(db, b0 + kk * 2 * 2048);
+                if (j == 0 && h == 0 && kk == 0)
+                    mma_hc<false>(d, a, b, id_main);
+                else
+                    mma_hc<true>(d, a, b, id_main);
+                mma_hc<true>(d + 64, desc_at(a, T64), b, id_corr);
             }
             umma_commit(&bars->w_empty[s & (RING - 1)]);
         }
@@ -1336,32 +1343,39 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     fence_async_smem();
     __syncthreads();  // the gather table is dead: the ring starts streaming weights
 
-    int s_next = 0;  // stage counter of the issuing thread
+    // stage numbers of the unrolled issue loops (compile time: slots, parities, descriptor offsets are immediates)
+    constexpr int S_Q2 = 0, S_S3 = NS_Q2, S_Q3 = S_S3 + NS_S3, S_M1 = S_Q3 + NS_Q3, S_M2 = S_M1 + NS_M1,
+                  S_M3 = S_M2 + NS_M2, S_M4 = S_M3 + NS_M3;
     int p_next = RING;  // producer (warp 1 lane 0) position
     // ---- seq_conv2 (16 -> 32, k11, stride 1) on the tensor core, under sig_conv1 / sig_conv2 on warps 1..7 ----
     if (warp == 0) {
         if (lane == 0) {
             for (int s = 0; s < RING; ++s) load_stage_c(s, p.wstream, ring, bars);
             constexpr uint32_t id_main = idesc_h(128, 64, 0), id_corr = idesc_h(128, 32, 0);
-            const uint32_t q_hi = smem_addr(ra + A_Q1), q_lo = q_hi + Q1_HALF;
-            for (int st = 0; st < NS_Q2; ++st, ++s_next) {
-                const uint32_t b0 = wait_stage(s_next, ring, bars);
+            const uint64_t dq = desc_ns(smem_addr(ra + A_Q1), Q1_LBO), db = desc_ns(smem_addr(ring), 1024);
+#pragma unroll
+            for (int st = 0; st < NS_Q2; ++st) {
+                const int s = S_Q2 + st;
+                const uint32_t b0 = wait_stage(s, bars);
 #pragma unroll
                 for (int tp = 0; tp < 4; ++tp) {
                     const int j = st * 4 + tp;
                     if (j < KW1) {
 #pragma unroll
                         for (int mt = 0; mt < 3; ++mt) {
-                            const uint32_t aoff = (uint32_t)((mt * 128 + j) * 16);
-                            const uint32_t b = b0 + tp * 2048;
-                            mma_h(tmem + mt * 64, desc_ns(q_hi + aoff, Q1_LBO), desc_ns(b, 1024), id_main, j ? 1u : 0u);
-                            mma_h(tmem + mt * 64 + 32, desc_ns(q_lo + aoff, Q1_LBO), desc_ns(b, 1024), id_corr, 1u);
+                            const uint64_t a = desc_at(dq, (mt * 128 + j) * 16);
+                            const uint64_t b = desc_at(db, b0 + tp * 2048);
+                            if (j == 0)
+                                mma_hc<false>(tmem + mt * 64, a, b, id_main);
+                            else
+                                mma_hc<true>(tmem + mt * 64, a, b, id_main);
+                            mma_hc<true>(tmem + mt * 64 + 32, desc_at(a, Q1_HALF), b, id_corr);
                         }
                     }
                 }
-                umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+                umma_commit(&bars->w_empty[s & (RING - 1)]);
                 // self-loading while the other warps compute: RING stages ahead would block on this stage's own MMAs
-                if (s_next >= 1) load_stage_c(s_next + RING - 1, p.wstream, ring, bars);
+                if (s >= 1) load_stage_c(s + RING - 1, p.wstream, ring, bars);
             }
             umma_commit(&bars->done[0]);
         }
@@ -1470,31 +1484,42 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     // ---- sig_conv3 (16 -> 64) and seq_conv3 (32 -> 64), k9 stride 3, from the residue tiles --------------------
     if (tid == 0) {
         constexpr uint32_t id_main = idesc_h(128, 128, 0), id_corr = idesc_h(128, 64, 0);
-        const uint32_t xs = smem_addr(ra + A_XS), xq = smem_addr(ra + A_XQ);
-        for (int st = 0; st < NS_S3; ++st, ++s_next) {
-            const uint32_t b0 = wait_stage(s_next, ring, bars);
+        const uint64_t dxs = desc_ns(smem_addr(ra + A_XS), LBO3), dxq = desc_ns(smem_addr(ra + A_XQ), LBO3),
+                       db = desc_ns(smem_addr(ring), 2048);
+#pragma unroll
+        for (int st = 0; st < NS_S3; ++st) {
+            const int s = S_S3 + st;
+            const uint32_t b0 = wait_stage(s, bars);
 #pragma unroll
             for (int tp = 0; tp < 2; ++tp) {
                 const int j = st * 2 + tp;
                 if (j < KW3) {
-                    const uint32_t a = xs + (2 * (j % 3)) * XS_T + (j / 3) * 16;
-                    const uint32_t b = b0 + tp * 4096;
-                    mma_h(tmem, desc_ns(a, LBO3), desc_ns(b, 2048), id_main, j ? 1u : 0u);
-                    mma_h(tmem + 64, desc_ns(a + XS_T, LBO3), desc_ns(b, 2048), id_corr, 1u);
+                    const uint64_t a = desc_at(dxs, (2 * (j % 3)) * XS_T + (j / 3) * 16);
+                    const uint64_t b = desc_at(db, b0 + tp * 4096);
+                    if (j == 0)
+                        mma_hc<false>(tmem, a, b, id_main);
+                    else
+                        mma_hc<true>(tmem, a, b, id_main);
+                    mma_hc<true>(tmem + 64, desc_at(a, XS_T), b, id_corr);
                 }
             }
-            umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+            umma_commit(&bars->w_empty[s & (RING - 1)]);
         }
-        for (int j = 0; j < KW3; ++j, ++s_next) {
-            const uint32_t b0 = wait_stage(s_next, ring, bars);
-            const uint32_t a0 = xq + (2 * (j % 3)) * XQ_T + (j / 3) * 16;
+#pragma unroll
+        for (int j = 0; j < KW3; ++j) {
+            const int s = S_Q3 + j;
+            const uint32_t b0 = wait_stage(s, bars);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-                const uint32_t a = a0 + kk * 2 * LBO3, b = b0 + kk * 2 * 2048;
-                mma_h(tmem + 128, desc_ns(a, LBO3), desc_ns(b, 2048), id_main, (j | kk) ? 1u : 0u);
-                mma_h(tmem + 192, desc_ns(a + XQ_T, LBO3), desc_ns(b, 2048), id_corr, 1u);
+                const uint64_t a = desc_at(dxq, (2 * (j % 3)) * XQ_T + (j / 3) * 16 + kk * 2 * LBO3);
+                const uint64_t b = desc_at(db, b0 + kk * 2 * 2048);
+                if (j == 0 && kk == 0)
+                    mma_hc<false>(tmem + 128, a, b, id_main);
+                else
+                    mma_hc<true>(tmem + 128, a, b, id_main);
+                mma_hc<true>(tmem + 192, desc_at(a, XQ_T), b, id_corr);
             }
-            umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+            umma_commit(&bars->w_empty[s & (RING - 1)]);
         }
         umma_commit(&bars->done[1]);
     } else if (tid == 32) {
@@ -1535,18 +1560,23 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
     // ---- merge_conv1 (128 -> 64, k5): taps are shifts of the cat tile ----------------------------------------------
     if (tid == 0) {
         constexpr uint32_t id_main = idesc_h(128, 128, 0), id_corr = idesc_h(128, 64, 0);
-        const uint32_t cat_hi = smem_addr(ra), cat_lo = cat_hi + CAT_HALF;
-        for (int st = 0; st < NS_M1; ++st, ++s_next) {
+        const uint64_t dc = desc_ns(smem_addr(ra), LBO_A), db = desc_ns(smem_addr(ring), 2048);
+#pragma unroll
+        for (int st = 0; st < NS_M1; ++st) {
+            const int s = S_M1 + st;
             const int kb = st / KWM, tap = st - kb * KWM;
-            const uint32_t b0 = wait_stage(s_next, ring, bars);
+            const uint32_t b0 = wait_stage(s, bars);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-                const uint32_t aoff = (uint32_t)((kb * 4 + 2 * kk) * LBO_A + tap * 16);
-                const uint32_t b = b0 + kk * 2 * 2048;
-                mma_h(tmem, desc_ns(cat_hi + aoff, LBO_A), desc_ns(b, 2048), id_main, (st | kk) ? 1u : 0u);
-                mma_h(tmem + 64, desc_ns(cat_lo + aoff, LBO_A), desc_ns(b, 2048), id_corr, 1u);
+                const uint64_t a = desc_at(dc, (kb * 4 + 2 * kk) * LBO_A + tap * 16);
+                const uint64_t b = desc_at(db, b0 + kk * 2 * 2048);
+                if (st == 0 && kk == 0)
+                    mma_hc<false>(tmem, a, b, id_main);
+                else
+                    mma_hc<true>(tmem, a, b, id_main);
+                mma_hc<true>(tmem + 64, desc_at(a, CAT_HALF), b, id_corr);
             }
-            umma_commit(&bars->w_empty[s_next & (RING - 1)]);
+            umma_commit(&bars->w_empty[s & (RING - 1)]);
         }
         umma_commit(&bars->done[2]);
     } else if (tid == 32) {
@@ -1579,7 +1609,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
         const uint32_t a0 = smem_addr(ra);
         const uint32_t a_tile[KWM] = {a0, a0, a0, a0, a0};
         const int shift[KWM] = {0, 1, 2, 3, 4};
-        issue_merge64<KWM>(a_tile, shift, tmem, s_next, ring, bars);
+        issue_merge64<KWM, S_M2>(a_tile, shift, tmem, ring, bars);
         umma_commit(&bars->done[3]);
     } else if (tid == 32) {
         for (; p_next < NS_TOTAL - NS_M3 - NS_M4 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
@@ -1614,7 +1644,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
         const uint32_t y0 = smem_addr(ra), y1 = y0 + 2 * T64;
         const uint32_t a_tile[KW2] = {y0, y1, y0};
         const int shift[KW2] = {0, 0, 1};
-        issue_merge64<KW2>(a_tile, shift, tmem, s_next, ring, bars);
+        issue_merge64<KW2, S_M3>(a_tile, shift, tmem, ring, bars);
         umma_commit(&bars->done[4]);
     } else if (tid == 32) {
         for (; p_next < NS_TOTAL - NS_M4 + RING; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
@@ -1650,7 +1680,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_mega_kernel(const __grid_cons
         const uint32_t y0 = smem_addr(ra), y1 = y0 + 2 * T64;
         const uint32_t a_tile[KW2] = {y0, y1, y0};
         const int shift[KW2] = {0, 0, 1};
-        issue_merge64<KW2>(a_tile, shift, tmem, s_next, ring, bars);
+        issue_merge64<KW2, S_M4>(a_tile, shift, tmem, ring, bars);
         umma_commit(&bars->done[5]);
     } else if (tid == 32) {
         for (; p_next < NS_TOTAL; ++p_next) load_stage_c(p_next, p.wstream, ring, bars);
