@@ -729,33 +729,45 @@ def ours(args):
             h_peak = float(peaks.get("bf16_tflops", 1590.0))  # measured dense bf16 GEMM; fp16 runs at the same rate
             n_prod = 3 if impl_used == "fused_mega" else 1
             kname = "mega_kernel<0>" if impl_used == "fused_mega" else "mega_kernel<1>"
-            # per chunk, T = 100: MACs of the layers that run on tcgen05 ...
+            # per chunk, T = 100: dense MACs of the layers on tcgen05 (seq_conv2, sig_conv3,
+            # merge_conv1, LSTM1 input projection) ...
             mac_tensor = 258048 + 372736 + 983040 + 393216
-            # ... and of the FFMA2 / FADD2 work: LSTM1 recurrence, sig_conv1/2, the single LSTM2 step + fc,
-            # gather-add of seq_conv1 (adds counted as MACs)
-            mac_fma = 393216 + 1920 + 29440 + 16384 + 128 + 69120
+            # ... of the layers on the warp-level tensor-core path (mma.sync): LSTM1 recurrence (24 steps x 256 x
+            # 64) and the single LSTM2 step ...
+            mac_hmma = 393216 + 16384
+            # ... and of the FFMA2 / FADD2 work: sig_conv1/2, classifier, gather-add of seq_conv1 (adds as MACs)
+            mac_fma = 1920 + 29440 + 128 + 69120
             mac_dense = int(DENSE_MFLOP * 1e6 / 2)
+            n_prod_hmma = 4  # (W_hi + W_lo) . (h_hi + h_lo): all four products, fp16 operands, fp32 accumulate
+            hmma_peak = 148 * 955.0 * 2 * sm_mhz * 1e6 / 1e12  # measured: 8.6 cycles per HMMA.16816 and SM sub-partition
             traffic = ncu_traffic_bytes("mega_kernel")
             ncu_pipes = ncu_pipe_counters("mega_kernel")
-            ach = BATCH * 2.0 * mac_tensor / step_s / 1e12
+            ach = BATCH * 2.0 * (mac_tensor + mac_hmma) / step_s / 1e12
+            ach_t = BATCH * 2.0 * mac_tensor / step_s / 1e12
+            ach_h = BATCH * 2.0 * mac_hmma / step_s / 1e12
             line["roofline"] = {
                 "kernel": kname, "bound": "tensor", "achieved": ach, "peak": h_peak, "unit": "TFLOP/s",
-                "frac": ach / h_peak, "executed_frac": n_prod * ach / h_peak,
+                "frac": ach / h_peak, "executed_frac": (n_prod * ach_t + n_prod_hmma * ach_h) / h_peak,
                 "traffic": (traffic or (None, None))[0], "traffic_source": (traffic or (None, None))[1],
                 "peak_source": peak_src,
                 "duration_ms": step_s * 1e3, "isolated_launch_ms": prof["mega_kernel_isolated_ms"],
-                "note": f"one kernel per step; achieved = the tensor-core layers' dense MACs (2 007 040 per chunk, "
-                        f"counted ONCE) x 2 x {BATCH} / the average launch duration in the timed region (= "
-                        f"ms_per_step: consecutive launches overlap, two CTAs per SM); the kernel executes "
-                        f"{n_prod} product(s) per MAC (fp16 hi/lo split: ah*bh + ah*bl + al*bh), executed_frac "
-                        f"counts them.  Neither the tensor pipe nor HBM is the binding resource: the step is "
-                        f"bound by the 24-step LSTM dependency chain and the CUDA-core phases between the MMAs "
+                "note": f"one kernel per step; achieved = the dense MACs of the layers that run on the tensor cores "
+                        f"(tcgen05: 2 007 040 per chunk, mma.sync: 409 600 per chunk, each counted ONCE) x 2 x {BATCH} / "
+                        f"the average launch duration in the timed region (= ms_per_step: consecutive launches "
+                        f"overlap, two CTAs per SM); the kernel executes {n_prod} (tcgen05) / {n_prod_hmma} (mma.sync) "
+                        f"fp16 products per MAC for fp32 parity, executed_frac counts them.  Neither the tensor "
+                        f"pipe nor HBM is the binding resource: the step is bound by each CTA's dependency chain "
+                        f"(24-step LSTM, CUDA-core phases between the MMA phases) times the two chains an SM holds "
                         f"(roofline_compute, phase stamps in profiles/)"}
             line["roofline_compute"] = {
                 "tensor": {"executed_mac_per_chunk": n_prod * mac_tensor, "dense_mac_per_chunk": mac_tensor,
-                           "executed_tflops": n_prod * ach, "peak_tflops": h_peak,
-                           "frac_executed": n_prod * ach / h_peak, "frac_dense": ach / h_peak,
+                           "executed_tflops": n_prod * ach_t, "peak_tflops": h_peak,
+                           "frac_executed": n_prod * ach_t / h_peak, "frac_dense": ach_t / h_peak,
                            "ncu_pipe_tensor_pct": (ncu_pipes or {}).get("tensor")},
+                "mma_sync": {"executed_mac_per_chunk": n_prod_hmma * mac_hmma, "dense_mac_per_chunk": mac_hmma,
+                             "executed_tflops": n_prod_hmma * ach_h, "peak_tflops": hmma_peak,
+                             "frac_executed": n_prod_hmma * ach_h / hmma_peak,
+                             "note": "LSTM recurrence + LSTM2 step on HMMA.16816 from registers"},
                 "ffma2": {"executed_mac_per_chunk": mac_fma,
                           "executed_tflops": BATCH * 2.0 * mac_fma / step_s / 1e12, "peak_tflops": fp32_peak,
                           "frac_executed": BATCH * 2.0 * mac_fma / step_s / 1e12 / fp32_peak,
@@ -764,7 +776,8 @@ def ours(args):
                                     "tflops": BATCH * DENSE_MFLOP * 1e6 / step_s / 1e12,
                                     "note": "what the reference executes (full LSTM2, dense one-hot conv); "
                                             "the kernel skips 23/24 of LSTM2 and gathers seq_conv1 (SURVEY a3.4, a3.9)"},
-                "peak_source": f"tensor: MEASURED_PEAKS bf16_tflops (burst); ffma2: 148 SM x 128 lanes x 2 flop x "
+                "peak_source": f"tensor: MEASURED_PEAKS bf16_tflops (burst); mma_sync: 148 SM x 955 MAC/clk (measured, "
+                               f"scripts/microbench/hmma_rate.cu) x {sm_mhz:.0f} MHz; ffma2: 148 SM x 128 lanes x 2 flop x "
                                f"{sm_mhz:.0f} MHz (sampled clock)",
                 "ncu_source": (ncu_pipes or {}).get("source")}
             line["roofline_step"] = {

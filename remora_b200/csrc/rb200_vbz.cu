@@ -199,9 +199,7 @@ svb16_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restric
     for (int k = j; k < tile; k += kThreads) {
         const volatile uint32_t *pa = agg + (size_t)row * tiles_per_row + k;
         uint32_t v;
-        do {
-            v = *pa;
-        } while (!(v & kAggFlag));
+        while (!((v = *pa) & kAggFlag)) __nanosleep(40);  // the spinning warp leaves the issue slots to the others
         carry += (int)(v & 0xFFFFu);
     }
     if (tile > 0) before += cta_sum(carry, s_warp);
