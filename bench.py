@@ -479,6 +479,10 @@ def ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.6)  # nvidia-smi needs a few hundred ms before its first sample (GPU idle: before warm-up)
+    # every rank starts the settle phase together: a rank that got here early would otherwise settle, then sit
+    # idle (clocks and power state dropping) at the barrier before the timed region until the slowest rank
+    # arrives - measured at 2 GPUs: that rank's first 20-step window ran 11 % slower than its later ones
+    barrier()
     # untimed settle phase: touch the whole resident pool once (first-touch page faults, TLB fill, L2
     # state, clocks back up after the idle wait above), i.e. >= 200 forwards, so that a short --steps
     # window reads the steady state; the --warmup steps follow and lead straight into the timed region
