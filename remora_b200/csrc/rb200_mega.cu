@@ -74,7 +74,7 @@ constexpr int C_BSEQ1 = 360;    //                    16
 constexpr int C_BSIG3 = 376;    //                    64
 constexpr int C_BSEQ2 = 440;    //                    64
 constexpr int C_BMRG = 504;     //                    64
-constexpr int C_SCALE = 568;    // inverse weight scales: seq2, sig3, merge, xproj, W_hh1, -, W_ih2 (+1 pad)
+constexpr int C_SCALE = 568;    // inverse weight scales: seq2, sig3, merge, xproj, W_hh1, seq1, W_ih2 (+1 pad)
 constexpr int C_B1 = 576;       // LSTM1 bias        256
 constexpr int CONST_FLOATS = 832;
 constexpr int CONST_BYTES = CONST_FLOATS * 4;  // 3328
@@ -98,10 +98,11 @@ constexpr int A_XQ = 32768;
 constexpr int A_S1 = A_TAB + TAB_CAP;                    // 58880: sig_conv1 output [G][T1][4] fp32
 constexpr int A_STG = A_S1 + G * 96 * 16;                // 65024: staged compact inputs
 constexpr int STG_SIG = 0, STG_SIDX = 1600, STG_SEQ = 2400, STG_MAP = 3040, STG_LEN = 4080;
+constexpr int STG_NOBASE = 4096;                         // 16 bytes of -1: the k-mer of a sample no base covers
 constexpr int MAX_T = 100, MAX_SEQ_W = 160, MAX_MAP_W = 130;
 constexpr int SMEM_BYTES = OFF_A + A_BYTES;              // 112512  (two CTAs per SM: <= 115712)
 static_assert(OFF_TILES + TILES_BYTES <= OFF_RING, "tiles overlap the ring");
-static_assert(A_STG + STG_LEN + 16 <= A_BYTES, "staging does not fit region A");
+static_assert(A_STG + STG_NOBASE + 16 <= A_BYTES, "staging does not fit region A");
 static_assert(OFF_RING + MAX_TM * XPS * 4 <= SMEM_BYTES, "staged projection does not fit");
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM need <= 113 KB each");
 
@@ -117,7 +118,7 @@ struct Params {
     const int16_t *lens;
     int seq_width, map_width, B, T, kmer_len, num_out;
     const float *consts;     // CONST_FLOATS
-    const float *gtab;       // seq_conv1 gather table [tap][kmer pos][base][GROW] + one zero row
+    const float *gtab;       // seq_conv1 weights as mma.sync B fragments [tap][k-tile][n-tile][hi, lo][lane][2]
     int gtab_bytes;
     const uint8_t *wstream;  // weight stages in execution order
     const float *q1_in;      // dense interface: seq_conv1 output [B][T-4][16] (K0 kernel), else null
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             int L = p.lens[chunk0 + tid];
             len_s[tid] = max(0, min(L, min(map_width - 1, seq_width - K + 1)));
         }
+        if (tid >= 32 && tid < 36) reinterpret_cast<uint32_t *>(ra + A_STG + STG_NOBASE)[tid - 32] = 0xFFFFFFFFu;
         for (int i = tid; i < C * seq_width; i += THREADS) {
             const int c = i / seq_width, s = i - c * seq_width;
             const int L = max(0, min((int)p.lens[chunk0 + c], min(map_width - 1, seq_width - K + 1)));
@@ -520,52 +522,77 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             }
         }
     } else {
-        const float *gt = reinterpret_cast<const float *>(ra + A_TAB);
-        const int zero_off = KW_SEQ1 * K * 4 * GROW;  // all-zero row: N bases contribute nothing
+        // seq_conv1 weights as mma.sync B fragments (fp16 hi + lo, the products with a one-hot are exact); the A
+        // fragment of a row is built in registers from ONE sequence byte: lane (g, t4) owns k-mer position
+        // 4 kt + t4, its slots {2 t4, 2 t4 + 1} are bases 0/1 and {2 t4 + 8, 2 t4 + 9} bases 2/3, so the fragment is
+        // 1.0 at the base that is there and 0 elsewhere (N bases, no base, positions past the k-mer: all zero)
+        const uint2 *bt = reinterpret_cast<const uint2 *>(ra + A_TAB);
+        const int KT = (K + 3) >> 2;
+        const int8_t *stg8 = reinterpret_cast<const int8_t *>(ra + A_STG);
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const float inv1 = cst[C_SCALE + 5];
         float *gs = reinterpret_cast<float *>(ra + A_GS);
         if (two_stage) {
-            // every sample covered by the same base shares its k-mer: sum the k columns once per (base, tap)
-            for (int i = tid; i < C * LM * KW_SEQ1; i += THREADS) {
-                const int j = i % KW_SEQ1;
-                const int cs = i / KW_SEQ1;
-                const int c = cs / LM, sb = cs - c * LM;
-                if (sb >= len_s[c]) continue;
-                float2 a[8];
+            // every sample covered by the same base shares its k-mer: the k columns are summed once per (base,
+            // tap) - a [chunk x base] x [k-mer one-hot] x [tap x channel] GEMM, work unit = (16 bases, tap)
+            const int n_rows = C * LM, n_mt = (n_rows + 15) >> 4;
+            for (int unit = warp; unit < n_mt * KW_SEQ1; unit += THREADS / 32) {
+                const int mt = unit / KW_SEQ1, j = unit - mt * KW_SEQ1;
+                int rb[2], rr[2];
 #pragma unroll
-                for (int o = 0; o < 8; ++o) a[o] = make_float2(0.f, 0.f);
-                const int8_t *sp = seq_s + c * seq_width + sb;
-                const int joff = j * K * 4 * GROW;
-                for (int pp = 0; pp < K; ++pp) {
-                    const int base = sp[pp];
-                    const int off = (base >= 0 && base <= 3) ? joff + (pp * 4 + base) * GROW : zero_off;
-                    const float4 *wv = reinterpret_cast<const float4 *>(gt + off);
-                    const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
-                    a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
-                    a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
-                    a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
-                    a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
-                    a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
-                    a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
-                    a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
-                    a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+                for (int h = 0; h < 2; ++h) {
+                    const int R = 16 * mt + g8 + 8 * h, c = R / LM, sb = R - c * LM;
+                    rr[h] = R;
+                    rb[h] = (R < n_rows && sb < len_s[min(c, G - 1)] ? STG_SEQ + c * seq_width + sb : STG_NOBASE) + t4;
                 }
-                float4 *dst = reinterpret_cast<float4 *>(gs + (size_t)i * GROW);
+                float acc[2][4];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) dst[o] = make_float4(a[2 * o].x, a[2 * o].y, a[2 * o + 1].x, a[2 * o + 1].y);
+                for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt) {
+                    if (kt >= KT) break;
+                    uint32_t af[4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int base = stg8[rb[h] + 4 * kt];
+                        const uint32_t one = 0x3C00u << ((base & 1) << 4);  // fp16 1.0 in the low or the high half
+                        af[h] = (base >> 1) == 0 ? one : 0u;                // bases 0 / 1
+                        af[2 + h] = (base >> 1) == 1 ? one : 0u;            // bases 2 / 3
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            const uint2 bf = bt[((((j * KT + kt) * 2 + nt) * 2 + part) << 5) + lane];
+                            asm volatile(
+                                "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+                                "{%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                                : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(bf.x), "r"(bf.y));
+                        }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (rr[h] < n_rows) {
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+                            *reinterpret_cast<float2 *>(gs + ((size_t)rr[h] * KW_SEQ1 + j) * GROW + 8 * nt + 2 * t4) =
+                                make_float2(acc[nt][2 * h] * inv1, acc[nt][2 * h + 1] * inv1);
+                    }
             }
             __syncthreads();  // sums complete; the table is dead: the sequence tiles may overwrite it
         }
         const float *b = cst + C_BSEQ1;
-        for (int i = tid; i < C * Q1; i += THREADS) {
-            const int c = i / Q1, t = i - c * Q1;
-            float2 a[8];
+        if (two_stage) {
+            for (int i = tid; i < C * Q1; i += THREADS) {
+                const int c = i / Q1, t = i - c * Q1;
+                float2 a[8];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
+                for (int o = 0; o < 8; ++o) a[o] = make_float2(b[2 * o], b[2 * o + 1]);
 #pragma unroll
-            for (int j = 0; j < KW_SEQ1; ++j) {
-                const int sb = sidx_s[c * T + t + j];
-                if (sb < 0) continue;  // sample not covered by any base: no one-hot entries
-                if (two_stage) {
+                for (int j = 0; j < KW_SEQ1; ++j) {
+                    const int sb = sidx_s[c * T + t + j];
+                    if (sb < 0) continue;  // sample not covered by any base: no one-hot entries
                     const float4 *gv =
                         reinterpret_cast<const float4 *>(gs + ((size_t)(c * LM + sb) * KW_SEQ1 + j) * GROW);
                     const float4 v0 = gv[0], v1 = gv[1], v2 = gv[2], v3 = gv[3];
@@ -577,37 +604,100 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
                     a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
                     a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
                     a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
-                } else {
-                    const int8_t *sp = seq_s + c * seq_width + sb;
-                    const int joff = j * K * 4 * GROW;
-                    for (int pp = 0; pp < K; ++pp) {
-                        const int base = sp[pp];
-                        const int off = (base >= 0 && base <= 3) ? joff + (pp * 4 + base) * GROW : zero_off;
-                        const float4 *wv = reinterpret_cast<const float4 *>(gt + off);
-                        const float4 v0 = wv[0], v1 = wv[1], v2 = wv[2], v3 = wv[3];
-                        a[0] = __fadd2_rn(a[0], make_float2(v0.x, v0.y));
-                        a[1] = __fadd2_rn(a[1], make_float2(v0.z, v0.w));
-                        a[2] = __fadd2_rn(a[2], make_float2(v1.x, v1.y));
-                        a[3] = __fadd2_rn(a[3], make_float2(v1.z, v1.w));
-                        a[4] = __fadd2_rn(a[4], make_float2(v2.x, v2.y));
-                        a[5] = __fadd2_rn(a[5], make_float2(v2.z, v2.w));
-                        a[6] = __fadd2_rn(a[6], make_float2(v3.x, v3.y));
-                        a[7] = __fadd2_rn(a[7], make_float2(v3.z, v3.w));
+                }
+                const int r = t % 3, u = t / 3;
+                uint8_t *t_hi = xq + (2 * r) * XT_BYTES;
+                const int off = (c * U + u) * 16;
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[2 * e] = swishf_fast(a[4 * kc + e].x);
+                        v[2 * e + 1] = swishf_fast(a[4 * kc + e].y);
+                    }
+                    store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, kc * LBO_A + off, v);
+                }
+            }
+        } else {
+            // more bases per chunk than the per-base sums have room for: the whole layer as ONE implicit GEMM over
+            // rows = (chunk, output step): 4 x 96 = 24 tiles of 16, three per warp; K = (tap, k-mer position, base)
+            int rowbase[3][2][KW_SEQ1];  // byte offset (in the staging area) of the k-mer position t4 of (row, tap)
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                const int mtile = 3 * warp + mt, c = mtile / 6, tb = (mtile - 6 * c) * 16 + g8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = tb + 8 * h;
+                    const bool live = c < C && t < Q1;
+#pragma unroll
+                    for (int j = 0; j < KW_SEQ1; ++j) {
+                        const int sb = live ? (int)sidx_s[c * T + t + j] : -1;
+                        rowbase[mt][h][j] = (sb < 0 ? STG_NOBASE : STG_SEQ + c * seq_width + sb) + t4;
                     }
                 }
             }
-            const int r = t % 3, u = t / 3;
-            uint8_t *t_hi = xq + (2 * r) * XT_BYTES;
-            const int off = (c * U + u) * 16;
+            float acc[3][2][4];
 #pragma unroll
-            for (int kc = 0; kc < 2; ++kc) {
-                float v[8];
+            for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    v[2 * e] = swishf_fast(a[4 * kc + e].x);
-                    v[2 * e + 1] = swishf_fast(a[4 * kc + e].y);
+                for (int nt = 0; nt < 2; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+            for (int j = 0; j < KW_SEQ1; ++j) {
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt) {  // KT <= 4 (k-mers up to 16 bases): unrolled so that loads run ahead
+                    if (kt >= KT) break;
+                    uint2 bf[2][2];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int part = 0; part < 2; ++part)
+                            bf[nt][part] = bt[((((j * KT + kt) * 2 + nt) * 2 + part) << 5) + lane];
+#pragma unroll
+                    for (int mt = 0; mt < 3; ++mt) {
+                        uint32_t a[4];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int base = stg8[rowbase[mt][h][j] + 4 * kt];
+                            const uint32_t one = 0x3C00u << ((base & 1) << 4);  // fp16 1.0 in the low or the high half
+                            a[h] = (base >> 1) == 0 ? one : 0u;                 // bases 0 / 1
+                            a[2 + h] = (base >> 1) == 1 ? one : 0u;             // bases 2 / 3
+                        }
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int part = 0; part < 2; ++part)
+                                asm volatile(
+                                    "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+                                    "{%8,%9}, {%0,%1,%2,%3};"
+                                    : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                                    : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bf[nt][part].x), "r"(bf[nt][part].y));
+                    }
                 }
-                store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, kc * LBO_A + off, v);
+            }
+            // bias + swish -> residue tiles (row g8 of a fragment holds c0, c1, row g8 + 8 holds c2, c3; channels
+            // 8 nt + 2 t4, + 1)
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) {
+                const int mtile = 3 * warp + mt, c = mtile / 6, tb = (mtile - 6 * c) * 16 + g8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = tb + 8 * h;
+                    if (t >= Q1) continue;
+                    const int r = t % 3, uu = t / 3;
+                    uint8_t *t_hi = xq + (2 * r) * XT_BYTES + (c * U + uu) * 16 + 4 * t4;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const float o0 = swishf_fast(fmaf(acc[mt][nt][2 * h], inv1, b[8 * nt + 2 * t4]));
+                        const float o1 = swishf_fast(fmaf(acc[mt][nt][2 * h + 1], inv1, b[8 * nt + 2 * t4 + 1]));
+                        const uint32_t hi = pack2<MODE>(o0, o1);
+                        *reinterpret_cast<uint32_t *>(t_hi + nt * LBO_A) = hi;
+                        if (MODE == 0) {
+                            const float2 hf = unpack_h2(hi);
+                            *reinterpret_cast<uint32_t *>(t_hi + XT_BYTES + nt * LBO_A) = pack2<0>(o0 - hf.x, o1 - hf.y);
+                        }
+                    }
+                }
             }
         }
     }
@@ -1746,7 +1836,7 @@ bool mega_supported(const rb200_model_desc &d) {
         return c.c_in == ci && c.c_out == co && c.kw == kw && c.stride == st;
     };
     if (d.kmer_len > 16) return false;
-    if ((KW_SEQ1 * d.kmer_len * 4 + 1) * GROW * 4 > TAB_CAP) return false;
+    if (KW_SEQ1 * ((d.kmer_len + 3) / 4) * 1024 > TAB_CAP) return false;  // seq_conv1 weight fragments
     return is(d.sig_conv[0], 1, 4, KW_SIG1, 1) && is(d.sig_conv[1], 4, 16, KW_SIG2, 1) &&
            is(d.sig_conv[2], 16, SIZE, KW_SIG3, 3) && is(d.seq_conv[0], 4 * d.kmer_len, 16, KW_SEQ1, 1) &&
            is(d.seq_conv[1], 16, SIZE, KW_SEQ2, 3) && is(d.merge_conv[0], 2 * SIZE, SIZE, KW_MRG, 1);
@@ -1831,16 +1921,33 @@ int mega_create(rb200_model *m, const float *blob) {
         for (int i = 0; i < 4; ++i) f[C_SCALE + i] = mode == 0 ? 1.f / sc[i] : 1.f;
         memcpy(f + C_B1, blob + d.lstm_b_off[0], 256 * sizeof(float));
     }
-    // ---- gather table [tap][kmer pos][base][GROW] + zero row ----
+    // ---- seq_conv1 weights as mma.sync.m16n8k16 B fragments: [tap][k-tile][n-tile][hi, lo][lane][b0, b1] ----
+    // lane (g = lane >> 2, t = lane & 3): channel n = 8 * n-tile + g, k-mer position pp = 4 * k-tile + t;
+    // b0 = {w[base 0], w[base 1]}, b1 = {w[base 2], w[base 3]} (zero past the k-mer), fp16 of S w and of the rest
     {
-        const int rows = KW_SEQ1 * K * 4 + 1;
-        mw->gtab_bytes = ((rows * GROW * 4) + 15) & ~15;
-        mw->off_gtab = reserve((size_t)rows * GROW);
-        const float *w = blob + d.seq_conv[0].w_off;  // [16][4K][5], input row = 4 p + base
+        const int KT = (K + 3) / 4;
+        const float *w = blob + d.seq_conv[0].w_off;  // [16][4K][5], input row = 4 pp + base
+        const float s1 = pow2_scale(w, (size_t)16 * 4 * K * KW_SEQ1);
+        mw->gtab_bytes = KW_SEQ1 * KT * 2 * 2 * 32 * 8;
+        mw->off_gtab = reserve((size_t)mw->gtab_bytes / 4);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(host.data() + mw->off_gtab);
         for (int j = 0; j < KW_SEQ1; ++j)
-            for (int rw = 0; rw < 4 * K; ++rw)
-                for (int co = 0; co < 16; ++co)
-                    host[mw->off_gtab + (size_t)(j * 4 * K + rw) * GROW + co] = w[(co * 4 * K + rw) * KW_SEQ1 + j];
+            for (int kt = 0; kt < KT; ++kt)
+                for (int nt = 0; nt < 2; ++nt)
+                    for (int part = 0; part < 2; ++part)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int n = 8 * nt + (lane >> 2), pp = 4 * kt + (lane & 3);
+                            uint16_t h[4];
+                            for (int base = 0; base < 4; ++base) {
+                                const float v = pp < K ? w[(n * 4 * K + 4 * pp + base) * KW_SEQ1 + j] * s1 : 0.f;
+                                const uint16_t hi = f2h(v);
+                                h[base] = part == 0 ? hi : f2h(v - h2f(hi));
+                            }
+                            uint32_t *o = dst + (((((size_t)j * KT + kt) * 2 + nt) * 2 + part) * 32 + lane) * 2;
+                            o[0] = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+                            o[1] = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+                        }
+        for (int mode = 0; mode < 2; ++mode) host[mw->off_consts[mode] + C_SCALE + 5] = 1.f / s1;
     }
     // ---- weight streams ----
     for (int mode = 0; mode < 2; ++mode) {

@@ -16,7 +16,7 @@ import numpy as np
 
 
 def synth_chunks(n, chunk_len=100, kmer_context_bases=(4, 4), seed=0, stride=5,
-                 frac_n=0.01, frac_edge=0.05, max_seq_len=None, garbage_padding=True):
+                 frac_n=0.01, frac_edge=0.05, max_seq_len=None, garbage_padding=True, seq_len_range=None):
     rng = np.random.default_rng(seed)
     kmer_len = sum(kmer_context_bases) + 1
     T = int(chunk_len)
@@ -33,6 +33,8 @@ def synth_chunks(n, chunk_len=100, kmer_context_bases=(4, 4), seed=0, stride=5,
     # number of bases per chunk: mean dwell ~ 8-12 samples, at least 1, at most lmax
     lo = max(1, T // 12)
     hi = max(lo, min(lmax, T // 8))
+    if seq_len_range is not None:  # explicit range of bases per chunk (short dwells, zero-dwell bases)
+        lo, hi = max(1, int(seq_len_range[0])), min(lmax, int(seq_len_range[1]))
     seq_lens = rng.integers(lo, hi + 1, size=n).astype(np.int16)
     for i in range(n):
         L = int(seq_lens[i])

@@ -278,6 +278,29 @@ def test_batch_sizes_and_ragged_batches(B):
     model.set_impl("auto")
 
 
+@pytest.mark.parametrize("T,max_seq_len,lens,stride", [
+    (100, 20, None, 5), (100, 20, (15, 20), 3), (100, 21, None, 5), (100, 40, (25, 40), 2), (100, 100, (60, 100), 1),
+    (64, 30, (10, 30), 2), (37, 12, None, 5)])
+def test_single_kernel_mapping_widths(T, max_seq_len, lens, stride):
+    """The single kernel has two forms of seq_conv1: per-base sums (up to 20 bases per chunk fit their buffer)
+    and, for wider mapping arrays, the layer as one implicit GEMM; both, at several chunk lengths, against
+    the oracle, and the AUTO choice must stay on the single kernel."""
+    model, md = gpu_model("convlstm_s64_k9_hot")
+    sd, _ = load_golden_model("convlstm_s64_k9_hot")
+    B = 37
+    d = synth_chunks(B, T, (4, 4), seed=1000 * T + max_seq_len, max_seq_len=max_seq_len, seq_len_range=lens,
+                     stride=stride)
+    args = [torch.from_numpy(d[k]) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                             "sequence_lengths")]
+    want = ro.oracle_infer_compact(sd, (4, 4), d["signal"], d["sequence"],
+                                   d["sequence_to_signal_mapping"], d["sequence_lengths"])
+    model.set_impl("auto")
+    got = model.forward_compact(*args).cpu().numpy()
+    assert model.last_impl == "fused_mega"
+    err = float(np.abs(got - want).max())
+    assert err < LOGIT_TOL, f"T={T} max_seq_len={max_seq_len}: max-abs err {err:.3e}"
+
+
 def test_full_baseline_batch_against_oracle():
     """The whole BASELINE batch (1024 chunks, T=100) against the oracle (the reference's arithmetic on
     CPU), every chunk, for every CUDA implementation - not a prefix and not another CUDA path."""
