@@ -2121,8 +2121,9 @@ int fused_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, cons
     bool use_tc = want_tc && cpb * g.T3 <= 256 && tc::smem_layout(tc_rpad).total <= 227 * 1024;
     const int k1_nw =
         tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, 3).total <= 227 * 1024 ? 3 : 2;
+    static const bool no_k1tc = getenv("RB200_NO_K1TC") != nullptr;  // measurement aid, read once
     const bool use_tc_k1 =
-        use_tc && (enc_dense != nullptr || !getenv("RB200_NO_K1TC")) &&
+        use_tc && (enc_dense != nullptr || !no_k1tc) &&
         tc::k1tc_smem(g, cpb, fw->kmer_len, seq_width, map_width, tc_rpad, k1_nw).total <= 227 * 1024 &&
         // the per-base gather sums borrow the (not yet used) tile stages
         (size_t)cpb * (map_width - 1) * KW_SEQ1 * GROW * 4 <= (size_t)4 * tc_rpad * 128;

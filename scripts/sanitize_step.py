@@ -45,6 +45,16 @@ if want("forward"):
                     out2 = model(args[0], enc)
                     torch.cuda.synchronize()
                     assert torch.isfinite(out2).all()
+        if name == "convlstm_s64_k9_hot" and T == 100:
+            # mapping arrays wider than the per-base sums' buffer: seq_conv1 as one implicit GEMM
+            d = synth_chunks(9, T, tuple(md["kmer_context_bases"]), seed=77, max_seq_len=40, seq_len_range=(20, 40),
+                             stride=2)
+            args = [torch.from_numpy(d[k]).to(dev) for k in ("signal", "sequence", "sequence_to_signal_mapping",
+                                                             "sequence_lengths")]
+            model.set_impl("auto")
+            out = model.forward_compact(*args)
+            torch.cuda.synchronize()
+            assert torch.isfinite(out).all() and model.last_impl == "fused_mega"
         print("forward ok", name, T, flush=True)
 
 if want("read"):
