@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         }
         return;
     }
+    // Prologue without a block-wide barrier: thread 0 initialises the mbarriers and starts the TMA loads
+    // (constants, seq_conv1 weight fragments, first weight stages) at once; warp 2 allocates tensor memory
+    // meanwhile; everybody else goes straight to staging the inputs.  The barrier that closes the staging phase
+    // publishes the mbarriers and the TMEM base address.
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) {
             mbar_init(&bars->w_full[i], 1);
@@ -428,18 +432,6 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         mbar_init(&bars->mrg_done, 1);
         mbar_init(&bars->xp_done, 1);
         mbar_fence_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_addr(&bars->tmem_base)),
-                     "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    if (tid == 0) {
         const bool dense = p.q1_in != nullptr;  // the materialised one-hot went through K0: no gather here
         mbar_expect_tx(&bars->front, CONST_BYTES + (dense ? 0 : p.gtab_bytes));
         bulk_g2s(cst, p.consts, CONST_BYTES, &bars->front);
@@ -452,6 +444,13 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             mbar_wait(&bars->w_full[RING - 2], 0);
             p.stamps[15] = (tl1 - tl0) | ((clock64() - tl0) << 32);
         }
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_addr(&bars->tmem_base)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        tc_fence_before();
     }
 
     MG_STAMP(1);
@@ -497,8 +496,11 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
             }
         }
     }
-    mbar_wait(&bars->front, 0);  // constants and the gather table have landed
+    if (dense) __syncthreads();  // (the other form has passed a barrier above) the mbarriers are initialised
+    mbar_wait(&bars->front, 0);  // constants and the seq_conv1 weight fragments have landed
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
     MG_STAMP(2);
 
     // ---- P1: seq_conv1 on the (virtual) one-hot = gather-add of weight columns -> residue tiles ------------
@@ -978,7 +980,7 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     for (int i = tid; i < 2 * 8 * 36; i += THREADS) reinterpret_cast<uint32_t *>(g_s)[i] = 0u;  // h(-1) = 0
     tc_fence_before();
     __syncthreads();
-    if (warp == 0)
+    if (warp == 2)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 
     MG_STAMP(10);
