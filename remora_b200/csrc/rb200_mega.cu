@@ -720,69 +720,107 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) produce_until(p_next, CF::NS_SEQ + RING, CF::NS_TOTAL, p.wstream, ring, bars);
+        if (lane == 0) {
+            produce_until(p_next, CF::NS_SEQ + RING, CF::NS_TOTAL, p.wstream, ring, bars);
+            if (p.stamps && blockIdx.x == 0) p.stamps[22] = clock64();
+        }
         __syncwarp();
     } else {
         const int wt = tid - 64, NW = THREADS - 64;
         float *s1_s = reinterpret_cast<float *>(ra + A_S1);
         {
             const float *w = cst + C_WSIG1, *bb = cst + C_BSIG1;
-            for (int i = wt; i < C * T1; i += NW) {
-                const int c = i / T1, t = i - c * T1;
-                const float *x = sig_s + c * T + t;
-                float4 a = *reinterpret_cast<const float4 *>(bb);
+            const int npair = (T1 + 1) >> 1;  // two consecutive steps per thread: one round for chunk_len 100
+            for (int i = wt; i < C * npair; i += NW) {
+                const int c = i / npair, t = (i - c * npair) * 2;
+                const float *xp = sig_s + c * T + t;
+                float xv[KW_SIG1 + 1];
+#pragma unroll
+                for (int j = 0; j <= KW_SIG1; ++j) xv[j] = xp[min(j, T - 1 - t)];
+                float4 a = *reinterpret_cast<const float4 *>(bb), b2 = a;
 #pragma unroll
                 for (int j = 0; j < KW_SIG1; ++j) {
-                    const float xv = x[j];
                     const float4 wv = *reinterpret_cast<const float4 *>(w + 4 * j);
-                    a.x = fmaf(wv.x, xv, a.x);
-                    a.y = fmaf(wv.y, xv, a.y);
-                    a.z = fmaf(wv.z, xv, a.z);
-                    a.w = fmaf(wv.w, xv, a.w);
+                    a.x = fmaf(wv.x, xv[j], a.x);
+                    a.y = fmaf(wv.y, xv[j], a.y);
+                    a.z = fmaf(wv.z, xv[j], a.z);
+                    a.w = fmaf(wv.w, xv[j], a.w);
+                    b2.x = fmaf(wv.x, xv[j + 1], b2.x);
+                    b2.y = fmaf(wv.y, xv[j + 1], b2.y);
+                    b2.z = fmaf(wv.z, xv[j + 1], b2.z);
+                    b2.w = fmaf(wv.w, xv[j + 1], b2.w);
                 }
-                *reinterpret_cast<float4 *>(s1_s + (size_t)i * 4) =
+                float *dst = s1_s + (size_t)(c * T1 + t) * 4;
+                *reinterpret_cast<float4 *>(dst) =
                     make_float4(swishf_fast(a.x), swishf_fast(a.y), swishf_fast(a.z), swishf_fast(a.w));
+                if (t + 1 < T1)
+                    *reinterpret_cast<float4 *>(dst + 4) =
+                        make_float4(swishf_fast(b2.x), swishf_fast(b2.y), swishf_fast(b2.z), swishf_fast(b2.w));
             }
         }
+        if (p.stamps && blockIdx.x == 0 && tid == 64) p.stamps[21] = clock64();
         nbar_sync(1, NW);
         // the signal tiles reuse the gather sums' space; without gather sums (direct gather) that space holds
         // the sequence tiles, which the tensor core must have finished reading
         if (!two_stage) mbar_wait(&bars->seq_done, 0);
         {
+            // register tile: 4 consecutive output steps x 8 channels per thread - each weight pair is loaded once
+            // for four steps and the 16 accumulator chains are independent (only six warps, 1.5 per scheduler,
+            // run this phase: with one step per thread it was bound by the latency of its own chain).  For
+            // chunk_len 100 the 4 x 23 x 2 items fill the 192 threads once.
             const float *w = cst + C_WSIG2, *bb = cst + C_BSIG2;
             uint8_t *xs = ra + A_XS;
-            for (int i = wt; i < C * T2 * 2; i += NW) {
-                const int half = i & 1;
-                const int ct = i >> 1;
-                const int c = ct / T2, t = ct - c * T2;
-                float2 a2[4];
+            const int nblk = (T2 + 3) >> 2;
+            for (int i = wt; i < C * nblk * 2; i += NW) {
+                const int half = i & 1, cb = i >> 1;
+                const int c = cb / nblk, t0 = (cb - c * nblk) * 4;
+                float2 a2[4][4];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) a2[o] = make_float2(bb[half * 8 + 2 * o], bb[half * 8 + 2 * o + 1]);
+                for (int st = 0; st < 4; ++st)
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) a2[st][o] = make_float2(bb[half * 8 + 2 * o], bb[half * 8 + 2 * o + 1]);
+                float x[8][4];  // sig_conv1 rows t0 .. t0 + 7 (rows past the end only feed steps that are dropped)
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float4 xv =
+                        *reinterpret_cast<const float4 *>(s1_s + (size_t)(c * T1 + min(t0 + r, T1 - 1)) * 4);
+                    x[r][0] = xv.x;
+                    x[r][1] = xv.y;
+                    x[r][2] = xv.z;
+                    x[r][3] = xv.w;
+                }
 #pragma unroll
                 for (int j = 0; j < KW_SIG2; ++j) {
-                    const float4 xv = *reinterpret_cast<const float4 *>(s1_s + (size_t)(c * T1 + t + j) * 4);
-                    const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                     for (int ci = 0; ci < 4; ++ci) {
                         const float4 *wp = reinterpret_cast<const float4 *>(w + (j * 4 + ci) * 16 + half * 8);
                         const float4 wa = wp[0], wb = wp[1];
-                        a2[0] = ffma2(make_float2(wa.x, wa.y), xs4[ci], a2[0]);
-                        a2[1] = ffma2(make_float2(wa.z, wa.w), xs4[ci], a2[1]);
-                        a2[2] = ffma2(make_float2(wb.x, wb.y), xs4[ci], a2[2]);
-                        a2[3] = ffma2(make_float2(wb.z, wb.w), xs4[ci], a2[3]);
+#pragma unroll
+                        for (int st = 0; st < 4; ++st) {
+                            a2[st][0] = ffma2(make_float2(wa.x, wa.y), x[st + j][ci], a2[st][0]);
+                            a2[st][1] = ffma2(make_float2(wa.z, wa.w), x[st + j][ci], a2[st][1]);
+                            a2[st][2] = ffma2(make_float2(wb.x, wb.y), x[st + j][ci], a2[st][2]);
+                            a2[st][3] = ffma2(make_float2(wb.z, wb.w), x[st + j][ci], a2[st][3]);
+                        }
                     }
                 }
-                float acc[8];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    acc[2 * o] = swishf_fast(a2[o].x);
-                    acc[2 * o + 1] = swishf_fast(a2[o].y);
+                for (int st = 0; st < 4; ++st) {
+                    const int t = t0 + st;
+                    if (t >= T2) continue;
+                    float acc[8];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        acc[2 * o] = swishf_fast(a2[st][o].x);
+                        acc[2 * o + 1] = swishf_fast(a2[st][o].y);
+                    }
+                    const int r = t % 3, u = t / 3;
+                    uint8_t *t_hi = xs + (2 * r) * XT_BYTES;
+                    store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, half * LBO_A + (c * U + u) * 16, acc);
                 }
-                const int r = t % 3, u = t / 3;
-                uint8_t *t_hi = xs + (2 * r) * XT_BYTES;
-                store_chunk8<MODE>(t_hi, t_hi + XT_BYTES, half * LBO_A + (c * U + u) * 16, acc);
             }
         }
+        if (p.stamps && blockIdx.x == 0 && tid == 64) p.stamps[23] = clock64();
         fence_async_smem();
     }
     __syncthreads();
@@ -2264,7 +2302,8 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
         for (int i = 0; i < 5; ++i) fprintf(stderr, " %lld", h[16 + i] - h[4]);
         fprintf(stderr, " | all issued %lld | done %lld\n   seq2 stages ready at:", h[24] - h[4], h[5] - h[4]);
         for (int i = 0; i < 7; ++i) fprintf(stderr, " %lld", h[25 + i] - h[3]);
-        fprintf(stderr, "\n");
+        fprintf(stderr, " | sig_conv1 done %lld, producer done %lld, sig_conv2 done %lld\n", h[21] - h[3], h[22] - h[3],
+                h[23] - h[3]);
     }
     m->launches += 1;
     m->last_impl = mode == 0 ? RB200_IMPL_FUSED_MEGA : RB200_IMPL_FUSED_BF16;
