@@ -233,6 +233,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// eight consecutive columns of this thread's TMEM lane (issue only: pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void nbar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -369,7 +376,12 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
     const int T3 = (T2 - KW_SIG3) / 3 + 1, TM = T3 - (KW_MRG - 1);
     const int seq_width = p.seq_width, map_width = p.map_width, K = p.kmer_len;
 
-#define MG_STAMP(i) do { if (p.stamps && blockIdx.x == 0 && tid == 0) p.stamps[i] = clock64(); } while (0)
+    long long *trace_st = reinterpret_cast<long long *>(sm + OFF_BARS + 120);  // 16 phase stamps of this CTA
+#define MG_STAMP(i)                                                              \
+    do {                                                                         \
+        if (p.stamps && blockIdx.x == 0 && tid == 0) p.stamps[i] = clock64();    \
+        if (p.trace && tid == 0) trace_st[i] = clock64();                        \
+    } while (0)
     MG_STAMP(0);
     long long trace_t0 = 0, trace_c0 = 0;
     if (p.trace && tid == 0) {
@@ -850,31 +862,28 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         const float *bias = cst + (trk ? C_BSEQ2 : C_BSIG3);
         const float inv = cst[C_SCALE + (trk ? 0 : 1)];
         uint8_t *cat_hi = ra, *cat_lo = ra + CAT_HALF;
+        // a loop over the eight 8-channel groups of this warp's 64 channels: the body (two small TMEM loads,
+        // eight swish, one K chunk stored) is short enough to stay in the instruction cache after its first
+        // pass - unrolled, the epilogue's code was fetched cold once per CTA and that fetch was a third of it
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            float v[32];
-            tmem_ld32(tb + 32 * h, v);
-            if (MODE == 0) {
-                float v2[32];
-                tmem_ld32(tb + 64 + 32 * h, v2);
+        for (int g = 0; g < 8; ++g) {
+            uint32_t r0[8], r1[8];
+            tmem_ld8_issue(tb + 8 * g, r0);
+            if (MODE == 0) tmem_ld8_issue(tb + 64 + 8 * g, r1);
+            tmem_ld_wait();
+            float o[8];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += v2[i];
+            for (int e = 0; e < 8; ++e) {
+                float v = __uint_as_float(r0[e]);
+                if (MODE == 0) v += __uint_as_float(r1[e]);
+                o[e] = swishf_fast(fmaf(v, inv, bias[8 * g + e]));
+                if (MODE == 0 && row_ok && lane < T3 && !(fabsf(o[e]) < 65504.f)) overflow = true;
             }
+            const int kc = trk * 8 + g;
+            store_chunk8<MODE>(cat_hi, cat_lo, kc * LBO_A + row * 16, o);
+            if (p.dbg_cat && row_ok && lane < T3) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    o[e] = swishf_fast(fmaf(v[8 * j + e], inv, bias[32 * h + 8 * j + e]));
-                    if (MODE == 0 && row_ok && lane < T3 && !(fabsf(o[e]) < 65504.f)) overflow = true;
-                }
-                const int kc = trk * 8 + 4 * h + j;
-                store_chunk8<MODE>(cat_hi, cat_lo, kc * LBO_A + row * 16, o);
-                if (p.dbg_cat && row_ok && lane < T3) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        p.dbg_cat[((size_t)(chunk0 + q) * 128 + kc * 8 + e) * T3 + lane] = o[e];
-                }
+                for (int e = 0; e < 8; ++e) p.dbg_cat[((size_t)(chunk0 + q) * 128 + kc * 8 + e) * T3 + lane] = o[e];
             }
         }
     }
@@ -920,20 +929,18 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         const float *bias = cst + C_BMRG + 32 * wh;
         const float inv = cst[C_SCALE + 2];
         uint8_t *m_hi = ra, *m_lo = ra + M_HALF;
-        float v[32];
-        tmem_ld32(tb, v);
-        if (MODE == 0) {
-            float v2[32];
-            tmem_ld32(tb + 64, v2);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += v2[i];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {  // a short loop body, like epilogue 1
+            uint32_t r0[8], r1[8];
+            tmem_ld8_issue(tb + 8 * j, r0);
+            if (MODE == 0) tmem_ld8_issue(tb + 64 + 8 * j, r1);
+            tmem_ld_wait();
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                o[e] = swishf_fast(fmaf(v[8 * j + e], inv, bias[8 * j + e]));
+                float v = __uint_as_float(r0[e]);
+                if (MODE == 0) v += __uint_as_float(r1[e]);
+                o[e] = swishf_fast(fmaf(v, inv, bias[8 * j + e]));
                 if (MODE == 0 && row_ok && lane < TM && !(fabsf(o[e]) < 65504.f)) overflow = true;
             }
             const int kc = 4 * wh + j;
@@ -1173,7 +1180,8 @@ __global__ void __launch_bounds__(THREADS, 2) mega_kernel(const __grid_constant_
         unsigned smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        long long *rec = p.trace + (size_t)blockIdx.x * 4;
+        long long *rec = p.trace + (size_t)blockIdx.x * 20;
+        for (int i = 0; i < 15; ++i) rec[4 + i] = trace_st[i + 1] - trace_st[i];
         rec[0] = smid;
         rec[1] = trace_t0;
         rec[2] = t1;
@@ -2224,20 +2232,22 @@ int mega_forward_compact(rb200_model *m, Workspace &ws, const float *sigs, const
     const int grid_ctas = (B + G - 1) / G;
     if (trace_path && grid_ctas <= TRACE_GRID) {
         if (!trace_dev) {
-            cudaMalloc(&trace_dev, (size_t)TRACE_N * TRACE_GRID * 4 * sizeof(long long));
-            cudaMemset(trace_dev, 0, (size_t)TRACE_N * TRACE_GRID * 4 * sizeof(long long));
+            cudaMalloc(&trace_dev, (size_t)TRACE_N * TRACE_GRID * 20 * sizeof(long long));
+            cudaMemset(trace_dev, 0, (size_t)TRACE_N * TRACE_GRID * 20 * sizeof(long long));
         }
         const int k = trace_launch - TRACE_SKIP;
-        if (k >= 0 && k < TRACE_N) p.trace = trace_dev + (size_t)k * TRACE_GRID * 4;
+        if (k >= 0 && k < TRACE_N) p.trace = trace_dev + (size_t)k * TRACE_GRID * 20;
         if (k == TRACE_N + 8) {
             cudaStreamSynchronize(stream);
-            std::vector<long long> h((size_t)TRACE_N * TRACE_GRID * 4);
+            std::vector<long long> h((size_t)TRACE_N * TRACE_GRID * 20);
             cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
             if (FILE *f = fopen(trace_path, "w")) {
                 for (int l = 0; l < TRACE_N; ++l)
                     for (int c = 0; c < grid_ctas; ++c) {
-                        const long long *r = &h[((size_t)l * TRACE_GRID + c) * 4];
-                        fprintf(f, "%d %d %lld %lld %lld %lld\n", l, c, r[0], r[1], r[2], r[3]);
+                        const long long *r = &h[((size_t)l * TRACE_GRID + c) * 20];
+                        fprintf(f, "%d %d", l, c);  // then smid, start ns, end ns, cycles, 14 phase lengths (+1 spare)
+                        for (int i = 0; i < 19; ++i) fprintf(f, " %lld", r[i]);
+                        fprintf(f, "\n");
                     }
                 fclose(f);
             }

@@ -52,7 +52,13 @@ path = os.environ.get("RB200_MEGA_TRACE")
 if path and os.path.isfile(path):
     a = np.loadtxt(path, dtype=np.int64)
     a = a[a[:, 4] > 0]
-    launch, cta, smid, t_start, t_end, cyc = a.T
+    launch, cta, smid, t_start, t_end, cyc = a.T[:6]
+    if a.shape[1] >= 20:
+        names = ["prologue", "stage", "gather", "seq2||sig12", "sig3", "E1", "merge", "E2", "xproj", "E3", "whh",
+                 "recurrence", "lstm2", "pdl_wait"]
+        ph = a[:, 6:20]
+        print("steady-state phase lengths (cycles, mean over all CTAs): " +
+              ", ".join(f"{n} {ph[:, i].mean():.0f}" for i, n in enumerate(names)) + f"; sum {ph.sum(axis=1).mean():.0f}", flush=True)
     dur = (t_end - t_start) / 1e3
     print(f"trace: {len(a)} CTAs of {len(np.unique(launch))} launches; CTA life us: mean {dur.mean():.1f} "
           f"p10 {np.percentile(dur, 10):.1f} p50 {np.percentile(dur, 50):.1f} p90 {np.percentile(dur, 90):.1f} "
