@@ -85,6 +85,29 @@ def shard_by_work(work, world_size, rank):
     return sorted(mine)
 
 
+class LogitRingLayout:
+    """Where every block of the exchange ring lives (pure arithmetic, shared by ``PeerLogitRing`` and its CPU
+    tests): float32 ``[slots][world][steps][block_floats]`` then one uint32 arrival counter per
+    (slot, step, source rank).  ``block_floats`` = batch x num_out rounded up to a multiple of 4, so that every
+    block starts on a 16-byte boundary (the shipping thread block moves float4s)."""
+
+    def __init__(self, world, slots, steps, batch, num_out):
+        self.world, self.slots, self.steps, self.batch, self.num_out = world, slots, steps, batch, num_out
+        self.block_floats = (batch * num_out + 3) // 4 * 4
+        self.n_data = slots * world * steps * self.block_floats
+        self.n_flags = slots * steps * world
+
+    def offset(self, slot, step, rank):
+        if not (0 <= slot < self.slots and 0 <= step < self.steps and 0 <= rank < self.world):
+            raise IndexError(f"block (slot {slot}, step {step}, rank {rank}) outside the ring")
+        return ((slot * self.world + rank) * self.steps + step) * self.block_floats
+
+    def flag_word(self, slot, step, rank):
+        if not (0 <= slot < self.slots and 0 <= step < self.steps and 0 <= rank < self.world):
+            raise IndexError(f"counter (slot {slot}, step {step}, rank {rank}) outside the ring")
+        return self.n_data + (slot * self.steps + step) * self.world + rank
+
+
 class PeerLogitRing:
     """The exchange step without a collective call: a ring of logits blocks in symmetric memory
     (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into every process over
@@ -109,9 +132,9 @@ class PeerLogitRing:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.slots, self.steps, self.batch, self.num_out = slots, steps, batch, model.num_out
-        self.block_floats = (batch * model.num_out + 3) // 4 * 4   # blocks stay 16-byte aligned
-        self.n_data = slots * self.world * steps * self.block_floats
-        self.n_flags = slots * steps * self.world
+        self.layout = LogitRingLayout(self.world, slots, steps, batch, model.num_out)
+        self.block_floats, self.n_data, self.n_flags = (self.layout.block_floats, self.layout.n_data,
+                                                        self.layout.n_flags)
         self.buf = symm_mem.empty(self.n_data + self.n_flags, dtype=torch.float32, device=model.device)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, self.group)
@@ -126,12 +149,10 @@ class PeerLogitRing:
         self.handle.barrier()
 
     def offset(self, slot, step, rank=None):
-        rank = self.rank if rank is None else rank
-        return ((slot * self.world + rank) * self.steps + step) * self.block_floats
+        return self.layout.offset(slot, step, self.rank if rank is None else rank)
 
     def flag_word(self, slot, step, rank=None):
-        rank = self.rank if rank is None else rank
-        return self.n_data + (slot * self.steps + step) * self.world + rank
+        return self.layout.flag_word(slot, step, self.rank if rank is None else rank)
 
     def forward(self, model, arrays, slot, step, signal=True):
         """``signal``: also bump the per-(slot, step, source) arrival counters on every rank (one

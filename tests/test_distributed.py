@@ -114,3 +114,30 @@ def test_two_rank_read_sharding_of_a_bam(tmp_path):
     mp.spawn(_read_shard_worker, args=(2, _free_port(), bam, str(tmp_path)), nprocs=2, join=True)
     counts = np.load(tmp_path / "ids.npy")
     assert counts.sum() == 9 and counts.min() >= 3
+
+
+def test_logit_ring_layout_blocks_are_disjoint_and_aligned():
+    """Layout of the peer-store exchange ring (remora_b200.parallel.LogitRingLayout): every (slot, rank, step)
+    block is 16-byte aligned (the shipping thread block moves float4s), blocks and arrival counters never
+    overlap, and the rank-major order inside a slot is the order an all-gather would produce."""
+    from remora_b200.parallel import LogitRingLayout
+    for world, slots, steps, batch, num_out in ((2, 2, 8, 1024, 2), (8, 2, 3, 1001, 3), (3, 1, 1, 1, 2)):
+        lay = LogitRingLayout(world, slots, steps, batch, num_out)
+        assert lay.block_floats % 4 == 0 and lay.block_floats >= batch * num_out
+        seen = set()
+        last = -1
+        for slot in range(slots):
+            for rank in range(world):
+                for step in range(steps):
+                    off = lay.offset(slot, step, rank)
+                    assert off % 4 == 0 and off > last        # aligned, strictly increasing in (slot, rank, step)
+                    last = off
+                    span = range(off, off + batch * num_out)
+                    assert span[-1] < lay.n_data and not (seen & {span[0], span[-1]})
+                    seen.update((span[0], span[-1]))
+        words = {lay.flag_word(s_, k, r) for s_ in range(slots) for k in range(steps) for r in range(world)}
+        assert len(words) == lay.n_flags and min(words) == lay.n_data and max(words) == lay.n_data + lay.n_flags - 1
+        with pytest.raises(IndexError):
+            lay.offset(slots, 0, 0)
+        with pytest.raises(IndexError):
+            lay.flag_word(0, steps, 0)
