@@ -486,8 +486,11 @@ def ours(args):
     # untimed settle phase: touch the whole resident pool once (first-touch page faults, TLB fill, L2
     # state, clocks back up after the idle wait above), i.e. >= 200 forwards, so that a short --steps
     # window reads the steady state; the --warmup steps follow and lead straight into the timed region
-    for i in range(max(n_pool, 200)):
-        model.forward_compact(*dev_batch(i))
+    # (multi-GPU: through the exchange path, so that every ring slot and peer mapping has been written once)
+    n_settle = max(n_pool, 200)
+    for i in range(n_settle):
+        step(i, last=i == n_settle - 1)
+    drain()
     torch.cuda.synchronize(device)
     for i in range(args.warmup):
         step(i, last=i == args.warmup - 1)
