@@ -498,6 +498,9 @@ def ours(args):
     impl_used = model.last_impl
     launches0 = model.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()  # a collection inside a 20-step (0.8 ms) window stalls the enqueueing thread for longer than a step
     barrier()
     ev0.record()
     for i in range(args.steps):
@@ -505,6 +508,7 @@ def ours(args):
     drain()
     ev1.record()
     barrier()
+    gc.enable()
     ms = ev0.elapsed_time(ev1)
     launches = model.launch_count - launches0
     if args.diag:  # diagnostic only (stderr): the same window a few more times, per rank, with host enqueue time
@@ -589,12 +593,15 @@ def ours(args):
             checksum += float(e2e_out[slot][0, 0])
 
     e2e_run(args.warmup)
+    gc.collect()
+    gc.disable()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = args.steps
     e2e_run(e2e_steps)
     torch.cuda.synchronize(device)
     e2e_s = time.perf_counter() - t0
+    gc.enable()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
