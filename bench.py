@@ -482,6 +482,10 @@ def ours(args):
     # every rank starts the settle phase together: a rank that got here early would otherwise settle, then sit
     # idle (clocks and power state dropping) at the barrier before the timed region until the slowest rank
     # arrives - measured at 2 GPUs: that rank's first 20-step window ran 11 % slower than its later ones
+    import gc
+    gc.collect()
+    gc.disable()  # no collection inside the timed windows (a 20-step window is 0.8 ms); collected HERE, before the
+    #               settle phase, because a collection right before a window idles the GPU for tens of milliseconds
     barrier()
     # untimed settle phase: touch the whole resident pool once (first-touch page faults, TLB fill, L2
     # state, clocks back up after the idle wait above), i.e. >= 200 forwards, so that a short --steps
@@ -498,9 +502,6 @@ def ours(args):
     impl_used = model.last_impl
     launches0 = model.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    import gc
-    gc.collect()
-    gc.disable()  # a collection inside a 20-step (0.8 ms) window stalls the enqueueing thread for longer than a step
     barrier()
     ev0.record()
     for i in range(args.steps):
@@ -508,7 +509,6 @@ def ours(args):
     drain()
     ev1.record()
     barrier()
-    gc.enable()
     ms = ev0.elapsed_time(ev1)
     launches = model.launch_count - launches0
     if args.diag:  # diagnostic only (stderr): the same window a few more times, per rank, with host enqueue time
@@ -593,8 +593,6 @@ def ours(args):
             checksum += float(e2e_out[slot][0, 0])
 
     e2e_run(args.warmup)
-    gc.collect()
-    gc.disable()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = args.steps

@@ -108,6 +108,7 @@ class B200Model(nn.Module):
     def __init__(self, state_dict, device=None):
         super().__init__()
         self._lib = _native.load_library()
+        self._pinned_ok = set()   # (address, bytes) of host buffers already verified as pinned
         self._desc, self._blob, self.info = weights.pack_state_dict(state_dict)
         self._handle = ctypes.c_void_p()
         self._device = None
@@ -363,11 +364,20 @@ class B200Model(nn.Module):
         tensors (``torch.Tensor.pin_memory()``), ``out`` a pinned float32 [B, num_out] tensor.  Work is
         enqueued on ``stream`` (default: current stream) and the call returns immediately; synchronise
         the stream before reading ``out``."""
+        # is_pinned() is a driver query (~1.5 us each): a buffer that passed once is remembered by its storage
+        # address and size (pipelined callers reuse a handful of staging buffers)
+        seen = self._pinned_ok
         for t, name in ((sigs, "sigs"), (sequence, "sequence"), (seq_to_sig_map, "seq_to_sig_map"),
                         (seq_lens, "seq_lens"), (out, "out")):
-            if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.is_pinned()
-                    and t.is_contiguous()):
+            if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.is_contiguous()):
                 raise RemoraError(f"{name} must be a contiguous pinned CPU tensor")
+            key = (t.data_ptr(), t.numel() * t.element_size())
+            if key not in seen:
+                if not t.is_pinned():
+                    raise RemoraError(f"{name} must be a contiguous pinned CPU tensor")
+                if len(seen) > 4096:
+                    seen.clear()
+                seen.add(key)
         B, T = sigs.shape[0], sigs.shape[-1]
         if stream is None:
             stream = torch.cuda.current_stream(self._device)
