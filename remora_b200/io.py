@@ -1167,8 +1167,10 @@ def write_pod5(path, reads, chunk=102400, rows_per_batch=None):
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
-def _bgzf_block(data):
-    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+def _bgzf_block(data, level=1):
+    # deflate level 1: the compression level is not part of the format; at level 6 zlib was 40 % of the host
+    # time of the file pipeline's output stage (the move tables and ML arrays compress little anyway)
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15)
     cdata = comp.compress(data) + comp.flush()
     return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00"
             + struct.pack("<H", len(cdata) + 25) + cdata
@@ -1195,13 +1197,17 @@ def write_bam(path, header_text, references, records):
     body = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(references)))
     for name, length in references:
         body += struct.pack("<i", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<i", length)
-    code = {c: i for i, c in enumerate(_SEQ_CODES)}
+    lut = np.full(256, 15, dtype=np.uint8)  # 4-bit base codes by ASCII value ("=ACMGRSVTWYHKDBN"), N for the rest
+    for i, c in enumerate(_SEQ_CODES):
+        lut[ord(c)] = i
     for rec in records:
         seq = rec.get("query_sequence", "")
         name = rec["query_name"].encode() + b"\x00"
         cigar = rec.get("cigartuples", [])
-        nib = [code.get(c, 15) for c in seq] + ([0] if len(seq) % 2 else [])
-        packed = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+        nib = lut[np.frombuffer(seq.encode("latin-1", "replace"), dtype=np.uint8)]
+        if nib.size % 2:
+            nib = np.append(nib, np.uint8(0))
+        packed = ((nib[0::2] << 4) | nib[1::2]).tobytes()
         tags = b"".join(_encode_tag(t, ty, v) for t, ty, v in rec.get("tags", []))
         core = struct.pack("<iiBBHHHIiii", rec.get("reference_id", -1), rec.get("reference_start", -1),
                            len(name), rec.get("mapping_quality", 0), 4680, len(cigar), rec.get("flag", 4),
