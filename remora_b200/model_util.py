@@ -359,6 +359,27 @@ class B200Model(nn.Module):
         return out
 
 
+    @staticmethod
+    def pinned_batch(sigs, sequence, seq_to_sig_map, seq_lens):
+        """Copies the four compact arrays (numpy or CPU tensors) into ONE pinned block, each array starting on
+        the next 256-byte boundary - the layout ``rb200_infer_host_async`` recognises and moves with a single
+        host-to-device copy.  Returns the four pinned views (pass them to :meth:`infer_host_async`)."""
+        arrs = [torch.as_tensor(np.ascontiguousarray(a)) for a in (sigs, sequence, seq_to_sig_map, seq_lens)]
+        dts = (torch.float32, torch.int8, torch.int16, torch.int16)
+        arrs = [a.to(dt).contiguous() for a, dt in zip(arrs, dts)]
+        sizes = [a.numel() * a.element_size() for a in arrs]
+        offs, pos = [], 0
+        for n in sizes:
+            offs.append(pos)
+            pos += (n + 255) // 256 * 256
+        block = torch.empty(pos, dtype=torch.uint8).pin_memory()
+        views = []
+        for a, off, n in zip(arrs, offs, sizes):
+            v = block[off:off + n].view(a.dtype).view(a.shape)
+            v.copy_(a)
+            views.append(v)
+        return tuple(views)
+
     def infer_host_async(self, sigs, sequence, seq_to_sig_map, seq_lens, out, stream=None):
         """Pipelined host-buffer inference (rb200_infer_host_async): all arguments are PINNED CPU
         tensors (``torch.Tensor.pin_memory()``), ``out`` a pinned float32 [B, num_out] tensor.  Work is

@@ -584,6 +584,19 @@ def test_infer_host_async_pipelined(forward_cases):
         assert np.abs(outs[slot].numpy() - want).max() < LOGIT_TOL
     with pytest.raises(RemoraError):  # pageable buffers are refused
         model.infer_host_async(torch.from_numpy(sig), *pins[1:], outs[0])
+    # the four arrays in one pinned block (one host-to-device copy instead of four): same logits, and the views
+    # really are laid out the way rb200_infer_host_async recognises
+    packed = model.pinned_batch(sig, seqs, maps, lens)
+    up = lambda n: (n + 255) // 256 * 256  # noqa: E731
+    sizes = [t.numel() * t.element_size() for t in packed]
+    assert packed[1].data_ptr() == packed[0].data_ptr() + up(sizes[0])
+    assert packed[2].data_ptr() == packed[1].data_ptr() + up(sizes[1])
+    assert packed[3].data_ptr() == packed[2].data_ptr() + up(sizes[2])
+    assert all(t.is_pinned() for t in packed)
+    outs[0].zero_()
+    model.infer_host_async(*packed, outs[0], stream=streams[0])
+    streams[0].synchronize()
+    assert np.abs(outs[0].numpy() - want).max() < LOGIT_TOL
 
 
 def test_softmax_ml_kernel():
