@@ -724,7 +724,7 @@ def ours(args):
                     "d2h_bytes_per_step": d2h,
                     "path": "B200Model.infer_host_async -> rb200_infer_host_async, pinned host buffers (the four "
                             "arrays of a batch in one pinned block: one H2D copy per step), 4 "
-                            "streams in rotation (a slot's result is read on the host before the slot is "
+                            "streams in rotation, the kernel stores the logits straight into the pinned result buffer (a slot's result is read on the host before the slot is "
                             "reused); every step's H2D and D2H are in the timed region",
                     "blocking_single_call_value": e2e_sync_value,
                     "blocking_single_call_path": "B200Model.infer_host -> rb200_infer_host (pageable "

@@ -557,13 +557,34 @@ int rb200_infer_host_async(rb200_handle h, const float *sigs_pinned, const int8_
         RB200_CUDA_TRY(cudaMemcpyAsync(d + o_map, maps_pinned, n_map, cudaMemcpyHostToDevice, s));
         RB200_CUDA_TRY(cudaMemcpyAsync(d + o_len, lens_pinned, n_len, cudaMemcpyHostToDevice, s));
     }
+    // the 8 B/chunk of logits go straight into the caller's pinned buffer when the device can address it (pinned
+    // memory is mapped under unified addressing): the kernel's own stores are the device-to-host transfer, one
+    // runtime call less per step.  The mapping of a buffer is looked up once and remembered.
+    float *out_dev = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        auto it = h->mapped_out.find(logits_pinned);
+        if (it == h->mapped_out.end()) {
+            cudaPointerAttributes pa = {};
+            float *mapped = nullptr;
+            if (cudaPointerGetAttributes(&pa, logits_pinned) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                pa.devicePointer != nullptr)
+                mapped = static_cast<float *>(pa.devicePointer);
+            else
+                (void)cudaGetLastError();
+            if (h->mapped_out.size() > 1024) h->mapped_out.clear();
+            it = h->mapped_out.emplace(logits_pinned, mapped).first;
+        }
+        out_dev = it->second;
+    }
     int rc = rb200_forward_compact(h, reinterpret_cast<const float *>(d),
                                    reinterpret_cast<const int8_t *>(d + o_seq), seq_width,
                                    reinterpret_cast<const int16_t *>(d + o_map), map_width,
                                    reinterpret_cast<const int16_t *>(d + o_len), B, T,
-                                   reinterpret_cast<float *>(d + o_out), s);
+                                   out_dev != nullptr ? out_dev : reinterpret_cast<float *>(d + o_out), s);
     if (rc) return rc;
-    RB200_CUDA_TRY(cudaMemcpyAsync(logits_pinned, d + o_out, n_out, cudaMemcpyDeviceToHost, s));
+    if (out_dev == nullptr)
+        RB200_CUDA_TRY(cudaMemcpyAsync(logits_pinned, d + o_out, n_out, cudaMemcpyDeviceToHost, s));
     return RB200_OK;
 }
 

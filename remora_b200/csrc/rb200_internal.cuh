@@ -83,6 +83,7 @@ struct rb200_model {
     std::mutex mu;
     std::map<void *, rb200::Workspace> workspaces;  // keyed by stream
     std::map<void *, rb200::Workspace> host_staging;  // device-side input/output staging of rb200_infer_host_async
+    std::map<const void *, float *> mapped_out;       // pinned output buffers -> their device address (or null)
     rb200::FusedWeights *fused = nullptr;           // non-null when the fused path applies
     rb200::TiledWeights *tiled = nullptr;           // weight layouts of the register-tiled layer kernels
     rb200::MegaWeights *mega = nullptr;             // single-kernel path (rb200_mega.cu)
