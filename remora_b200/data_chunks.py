@@ -150,7 +150,7 @@ class RemoraRead:
                               f"({self.seq_to_sig_map.size}) sizes incompatible")
         if self.seq_to_sig_map[0] != 0:
             raise RemoraError("Invalid read: mapping start")
-        if self.seq_to_sig_map[-1] != self.sig.size:
+        if self.seq_to_sig_map[-1] != np.asarray(self.dacs).size:  # (not self.sig.size: that would normalise the signal)
             raise RemoraError("Invalid read: mapping end")
         if self.int_seq.max() > 3 or self.int_seq.min() < -1:
             raise RemoraError("Invalid read: Invalid base")
