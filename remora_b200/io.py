@@ -423,26 +423,31 @@ class ReadIndexedBam:
             self.references = bam.references
             self.ref_lengths = list(bam.lengths)  # binary reference dictionary (may exist without @SQ lines)
             for voff, read in bam.iter_with_offsets():
-                if self.child_read_id_subset is not None and read.query_name not in self.child_read_id_subset:
-                    self.skip_reasons["Child read ID filtered"] += 1
-                    continue
-                index_read_id = get_parent_id(read)
-                if self.parent_read_id_subset is not None and index_read_id not in self.parent_read_id_subset:
-                    self.skip_reasons["Parent read ID filtered"] += 1
-                    continue
-                if self.read_id_converter is not None:
-                    index_read_id = self.read_id_converter(index_read_id)
-                if self.req_tags is not None and self.req_tags.difference(t for t, _ in read.tags):
-                    self.skip_reasons["Missing BAM tags"] += 1
-                    continue
-                if self.skip_non_primary and not read_is_primary(read):
-                    self.skip_reasons["Non-primary alignment"] += 1
+                index_read_id, reason = self._index_key(read)
+                if reason is not None:  # same reasons, same order of the tests as the reference (io.py:255-307)
+                    self.skip_reasons[reason] += 1
                     continue
                 self.num_records += 1
                 idx[index_read_id].append(read if self.in_memory else voff)
                 self.seq_lens[index_read_id] = self.seq_lens.get(index_read_id, 0) + len(read.query_sequence)
         self._bam_idx = dict(idx)
         self.num_reads = len(self._bam_idx)
+
+    def _index_key(self, read):
+        """(id the record is filed under, None) or (None, why it is skipped)."""
+        keep_child, keep_parent = self.child_read_id_subset, self.parent_read_id_subset
+        if keep_child is not None and read.query_name not in keep_child:
+            return None, "Child read ID filtered"
+        key = get_parent_id(read)
+        if keep_parent is not None and key not in keep_parent:
+            return None, "Parent read ID filtered"
+        if self.read_id_converter is not None:
+            key = self.read_id_converter(key)
+        if self.req_tags is not None and not self.req_tags <= {t for t, _ in read.tags}:
+            return None, "Missing BAM tags"
+        if self.skip_non_primary and (read.is_supplementary or read.is_secondary):
+            return None, "Non-primary alignment"
+        return key, None
 
     def _materialise(self, entry):
         if self.in_memory:
@@ -484,18 +489,19 @@ class ReadIndexedBam:
 
 
 def parse_move_tag(mv_tag, sig_len, seq_len=None, check=True, reverse_signal=False):
-    """Move table -> first sample of every base (io.py:394-411)."""
-    stride = int(mv_tag[0])
-    mv_table = np.asarray(mv_tag[1:])
-    query_to_signal = np.nonzero(mv_table)[0] * stride
-    query_to_signal = np.concatenate([query_to_signal, [sig_len]])
-    if reverse_signal:
-        query_to_signal = sig_len - query_to_signal[::-1]
-    if check and seq_len is not None and query_to_signal.size - 1 != seq_len:
-        raise RemoraError("Move table discordant with basecalls")
-    if check and mv_table.size != sig_len // stride:
-        raise RemoraError("Move table discordant with signal")
-    return query_to_signal, mv_table, stride
+    """Move table (``mv`` tag: stride, then one flag per stride-sized signal block, 1 = a base starts here)
+    -> signal index at which every base starts, plus the end of the signal (io.py:394-411)."""
+    stride, moves = int(mv_tag[0]), np.asarray(mv_tag[1:])
+    starts = np.flatnonzero(moves) * stride
+    bounds = np.append(starts, sig_len)
+    if reverse_signal:  # the signal was flipped: measure from its other end
+        bounds = (sig_len - bounds)[::-1]
+    if check:
+        if seq_len is not None and bounds.size != seq_len + 1:
+            raise RemoraError("Move table discordant with basecalls")
+        if moves.size != sig_len // stride:
+            raise RemoraError("Move table discordant with signal")
+    return bounds, moves, stride
 
 
 def make_sequence_coordinate_mapping(cigar):
@@ -858,20 +864,24 @@ class Read:
 
     @property
     def pa_signal(self):
-        if self.scale_dacs_to_pa is None or self.shift_dacs_to_pa is None:
-            raise RemoraError("pA scaling factors not set")
-        return (self.dacs - self.shift_dacs_to_pa) / self.scale_dacs_to_pa
+        return self._rescaled(self.shift_dacs_to_pa, self.scale_dacs_to_pa, "pA scaling factors not set")
 
     @property
     def norm_signal(self):
-        if self.scale_dacs_to_norm is None or self.shift_dacs_to_norm is None:
-            raise RemoraError("Norm scaling factors not set")
-        return (self.dacs - self.shift_dacs_to_norm) / self.scale_dacs_to_norm
+        return self._rescaled(self.shift_dacs_to_norm, self.scale_dacs_to_norm, "Norm scaling factors not set")
+
+    def _rescaled(self, shift, scale, missing):
+        """(dacs - shift) / scale; ``missing`` is the reference's error text when a factor is unset."""
+        if shift is None or scale is None:
+            raise RemoraError(missing)
+        return (self.dacs - shift) / scale
 
     def compute_pa_to_norm_scaling(self, factor=PA_TO_NORM_SCALING_FACTOR):
         """median / MAD normalisation when the BAM carries no sm/sd tags (io.py:1851-1856)"""
-        self.shift_pa_to_norm = np.median(self.pa_signal)
-        self.scale_pa_to_norm = max(1.0, np.median(np.abs(self.pa_signal - self.shift_pa_to_norm)) * factor)
+        pa = self.pa_signal
+        centre = np.median(pa)
+        self.shift_pa_to_norm = centre
+        self.scale_pa_to_norm = max(1.0, factor * np.median(np.abs(pa - centre)))
 
     @property
     def sig_len(self):
@@ -881,25 +891,29 @@ class Read:
 
     @property
     def seq_len(self):
-        if self.query_to_signal is None:
-            return None if self.seq is None else len(self.seq)
-        return self.query_to_signal.size - 1
+        if self.query_to_signal is not None:
+            return self.query_to_signal.size - 1
+        return len(self.seq) if self.seq is not None else None
 
     @property
     def child_read_id(self):
         return self.read_id if self._child_read_id is None else self._child_read_id
 
+    # dacs -> zero-centred pA is the composition of dacs -> pA and pA -> zero-centred pA:
+    # ((d - s1) / c1 - s2) / c2 = (d - (s1 + c1 s2)) / (c1 c2)
     @property
     def shift_dacs_to_zc_pa(self):
-        if self.shift_dacs_to_pa is None or self.scale_dacs_to_pa is None or self.shift_pa_to_zc_pa is None:
+        parts = (self.shift_dacs_to_pa, self.scale_dacs_to_pa, self.shift_pa_to_zc_pa)
+        if any(v is None for v in parts):
             raise RemoraError("Zero-centered pA scaling factors not set")
-        return self.shift_dacs_to_pa + (self.scale_dacs_to_pa * self.shift_pa_to_zc_pa)
+        return parts[0] + parts[1] * parts[2]
 
     @property
     def scale_dacs_to_zc_pa(self):
-        if self.scale_dacs_to_pa is None or self.scale_pa_to_zc_pa is None:
+        parts = (self.scale_dacs_to_pa, self.scale_pa_to_zc_pa)
+        if any(v is None for v in parts):
             raise RemoraError("Zero-centered pA scaling factors not set")
-        return self.scale_dacs_to_pa * self.scale_pa_to_zc_pa
+        return parts[0] * parts[1]
 
     def copy(self):
         return dataclasses.replace(self)
@@ -1004,7 +1018,10 @@ class Read:
         return read
 
     def into_remora_read(self, use_reference_anchor):
-        """io.py:2123-2177"""
+        """The read as the chunking / inference layer wants it (io.py:2123-2177): the samples the sequence is
+        mapped to, a mapping that starts at 0, the sequence (basecalls, or the reference it aligns to), and
+        the scaling to the model's signal space (zero-centred pA when the model asks for it, else the
+        basecaller's normalisation)."""
         if use_reference_anchor:
             if self.ref_to_signal is None:
                 if self.cigar is None or self.ref_seq is None:
@@ -1012,23 +1029,18 @@ class Read:
                 self.ref_to_signal = compute_ref_to_signal(self.query_to_signal, self.cigar)
                 if self.ref_to_signal.size != len(self.ref_seq) + 1:
                     raise RemoraError("Discordant ref seq lengths")
-            trim_dacs = self.dacs[self.ref_to_signal[0]:self.ref_to_signal[-1]]
-            shift_seq_to_sig = self.ref_to_signal - self.ref_to_signal[0]
-            seq = self.ref_seq
+            bounds, seq = self.ref_to_signal, self.ref_seq
         else:
             if self.query_to_signal is None:
                 raise RemoraError("Missing query_to_signal (move table)")
-            trim_dacs = self.dacs[self.query_to_signal[0]:self.query_to_signal[-1]]
-            shift_seq_to_sig = self.query_to_signal - self.query_to_signal[0]
-            seq = self.seq
-        if self.shift_pa_to_zc_pa is None or self.scale_pa_to_zc_pa is None:
-            shift, scale = self.shift_dacs_to_norm, self.scale_dacs_to_norm
-        else:
-            shift, scale = self.shift_dacs_to_zc_pa, self.scale_dacs_to_zc_pa
-        remora_read = DC.RemoraRead(dacs=trim_dacs, shift=shift, scale=scale, seq_to_sig_map=shift_seq_to_sig,
-                                    str_seq=seq, read_id=self.read_id)
-        remora_read.check()
-        return remora_read
+            bounds, seq = self.query_to_signal, self.seq
+        zero_centred = self.shift_pa_to_zc_pa is not None and self.scale_pa_to_zc_pa is not None
+        shift = self.shift_dacs_to_zc_pa if zero_centred else self.shift_dacs_to_norm
+        scale = self.scale_dacs_to_zc_pa if zero_centred else self.scale_dacs_to_norm
+        out = DC.RemoraRead(dacs=self.dacs[bounds[0]:bounds[-1]], shift=shift, scale=scale,
+                            seq_to_sig_map=bounds - bounds[0], str_seq=seq, read_id=self.read_id)
+        out.check()
+        return out
 
 
 def iter_io_reads(pod5_path, bam_idx, num_reads=None, reverse_signal=False, pa_scaling=None, device=None,

@@ -485,32 +485,32 @@ class SigMapRefiner:
     device: object = None
 
     def __post_init__(self):
-        """refine_signal_map.py:276-322"""
-        if self._levels_array is not None and not np.array_equal(self._levels_array, np.array(None)):
-            self.is_loaded = True
-            self._levels_array = np.ascontiguousarray(self._levels_array, dtype=np.float32)
-            self.kmer_len = int(round(np.log(self._levels_array.size) / np.log(4)))
-            if 4 ** self.kmer_len != self._levels_array.size:
+        """Decide where the level table comes from - an array (model metadata), a k-mer level file, or a
+        {k-mer: level} dict - derive the k-mer length / dominant position from it, then validate the options
+        the way the reference does (refine_signal_map.py:276-322: same error messages)."""
+        have_array = self._levels_array is not None and np.ndim(self._levels_array) > 0
+        if have_array:
+            table = np.ascontiguousarray(self._levels_array, dtype=np.float32)
+            k = int(round(np.log2(table.size) / 2)) if table.size else 0
+            if table.size == 0 or 4 ** k != table.size:
                 raise RemoraError("levels array size is not a power of 4")
-        elif self.kmer_model_filename is not None:
-            self.load_kmer_table()
-            self.is_loaded = True
-            self.determine_dominant_pos()
-            if self.do_fix_guage:
-                self.fix_gauge()
-        elif self.str_kmer_levels is not None:
-            self.is_loaded = True
-            self.kmer_len = len(next(iter(self.str_kmer_levels)))
-            self.determine_dominant_pos()
-            if self.do_fix_guage:
-                self.fix_gauge()
+            self._levels_array, self.kmer_len, self.is_loaded = table, k, True
         else:
             self._levels_array = None
-        if not self.is_loaded and (self.do_rough_rescale or self.scale_iters >= 0):
-            raise RemoraError(
-                "Signal re-scaling is requested without levels table. "
-                f"is_loaded: {self.is_loaded} do_rough_rescale: {self.do_rough_rescale} "
-                f"scale_iters: {self.scale_iters}")
+            if self.kmer_model_filename is not None:
+                self.load_kmer_table()
+            elif self.str_kmer_levels is not None:
+                self.kmer_len = len(next(iter(self.str_kmer_levels)))
+            if self.str_kmer_levels is not None:
+                self.is_loaded = True
+                self.determine_dominant_pos()
+                if self.do_fix_guage:
+                    self.fix_gauge()
+        wants_refinement = self.do_rough_rescale or self.scale_iters >= 0
+        if wants_refinement and not self.is_loaded:
+            raise RemoraError("Signal re-scaling is requested without levels table. "
+                              f"is_loaded: {self.is_loaded} do_rough_rescale: {self.do_rough_rescale} "
+                              f"scale_iters: {self.scale_iters}")
         if self.sd_params is not None:
             self.sd_arr = compute_dwell_pen_array(*self.sd_params)
         if self.rough_rescale_method not in ROUGH_RESCALE_METHODS:
@@ -519,18 +519,18 @@ class SigMapRefiner:
     def __repr__(self):
         if not self.is_loaded:
             return "No Remora signal refine/map settings loaded"
-        r_str = f"Loaded {self.kmer_len}-mer table with {self.center_idx + 1} central position."
+        parts = [f"Loaded {self.kmer_len}-mer table with {self.center_idx + 1} central position."]
         if self.do_rough_rescale:
-            r_str += " Rough re-scaling will be executed."
+            parts.append("Rough re-scaling will be executed.")
         if self.scale_iters > 0:
-            r_str += (f" {self.scale_iters} rounds of signal mapping refinement followed by precise "
-                      "re-scaling will be executed.")
+            parts.append(f"{self.scale_iters} rounds of signal mapping refinement followed by precise "
+                         "re-scaling will be executed.")
         if self.scale_iters >= 0:
-            r_str += (" Signal mapping refinement will be executed using the "
-                      f"{self.algo} refinement method (band half width: {self.half_bandwidth}).")
+            parts.append("Signal mapping refinement will be executed using the "
+                         f"{self.algo} refinement method (band half width: {self.half_bandwidth}).")
             if self.algo == REFINE_ALGO_DWELL_PEN_NAME:
-                r_str += f" Short dwell penalty array set to {self.sd_arr}."
-        return r_str
+                parts.append(f"Short dwell penalty array set to {self.sd_arr}.")
+        return " ".join(parts)
 
     @property
     def bases_before(self):
@@ -538,77 +538,73 @@ class SigMapRefiner:
 
     @property
     def bases_after(self):
-        return self.kmer_len - self.center_idx - 1
+        return self.kmer_len - 1 - self.center_idx
 
     @property
     def is_valid(self):
-        if self.is_loaded:
-            return self.do_rough_rescale or self.scale_iters >= 0
-        return not self.do_rough_rescale and self.scale_iters < 0
+        """A loaded table must be used by at least one step; no table means no step may ask for one."""
+        return (self.do_rough_rescale or self.scale_iters >= 0) == bool(self.is_loaded)
 
     # -- level table ---------------------------------------------------------------------------
     def load_kmer_table(self):
-        """refine_signal_map.py:217-247"""
-        self.str_kmer_levels = {}
-        with open(self.kmer_model_filename) as kmer_fp:
-            for line in kmer_fp:
-                kmer, level = line.split()
-                kmer = kmer.upper()
-                if self.kmer_len is None:
-                    self.kmer_len = len(kmer)
-                if kmer in self.str_kmer_levels:
-                    raise RemoraError(f"K-mer found twice in levels file '{kmer}'.")
-                if self.kmer_len != len(kmer):
-                    raise RemoraError(
-                        f"K-mer lengths not all equal '{len(kmer)} != {self.kmer_len}' for {kmer}.")
-                try:
-                    value = float(level)
-                except ValueError:
-                    raise RemoraError(f"Could not convert level to float '{level}'")
-                self.str_kmer_levels[kmer] = 0 if np.isnan(value) else value
-        if len(self.str_kmer_levels) != 4 ** self.kmer_len:
-            raise RemoraError(
-                f"K-mer table contains fewer entries ({len(self.str_kmer_levels)}) than expected "
-                f"({4 ** self.kmer_len})")
+        """Whitespace-separated ``kmer level`` lines (reference format, refine_signal_map.py:217-247):
+        every k-mer of one length exactly once; NaN levels become 0."""
+        levels = {}
+        with open(self.kmer_model_filename) as fh:
+            rows = [ln.split() for ln in fh if ln.strip()]
+        k = len(rows[0][0]) if rows else 0
+        for kmer, text in rows:
+            kmer = kmer.upper()
+            if kmer in levels:
+                raise RemoraError(f"K-mer found twice in levels file '{kmer}'.")
+            if len(kmer) != k:
+                raise RemoraError(f"K-mer lengths not all equal '{len(kmer)} != {k}' for {kmer}.")
+            try:
+                value = float(text)
+            except ValueError:
+                raise RemoraError(f"Could not convert level to float '{text}'") from None
+            levels[kmer] = 0 if value != value else value
+        if len(levels) != 4 ** k:
+            raise RemoraError(f"K-mer table contains fewer entries ({len(levels)}) than expected ({4 ** k})")
+        self.kmer_len, self.str_kmer_levels = k, levels
 
     def determine_dominant_pos(self):
-        """Position in the k-mer whose base orders the levels most (Kruskal-Wallis H statistic per
-        position, refine_signal_map.py:249-274)."""
+        """The k-mer position whose base says most about the level: per position, the Kruskal-Wallis H
+        statistic of the four bases' rank groups in the level-sorted k-mer list (refine_signal_map.py:249-274);
+        the largest one becomes ``center_idx``."""
         if self.str_kmer_levels is None:
             return
         from scipy import stats
-        sorted_kmers = [kmer for _, kmer in sorted((lv, km) for km, lv in self.str_kmer_levels.items())]
-        self.kmer_idx_stats = []
-        for kmer_idx in range(self.kmer_len):
-            col = np.array([kmer[kmer_idx] for kmer in sorted_kmers])
-            groups = [np.nonzero(col == base)[0] for base in "ACGT"]
-            self.kmer_idx_stats.append(stats.kruskal(*groups)[0])
+        by_level = sorted(self.str_kmer_levels, key=lambda km: (self.str_kmer_levels[km], km))
+        letters = np.array([list(km) for km in by_level])          # [n_kmers, k], rows in rank order
+        ranks = np.arange(len(by_level))
+        self.kmer_idx_stats = [stats.kruskal(*(ranks[letters[:, pos] == base] for base in "ACGT"))[0]
+                               for pos in range(self.kmer_len)]
         self.center_idx = int(np.argmax(self.kmer_idx_stats))
 
     def fix_gauge(self):
-        """refine_signal_map.py:332-342"""
-        from itertools import product
-        med = np.median(self.levels_array)
-        mad = np.median(np.absolute(self.levels_array - med)) * 1.4826
-        self._levels_array = (self.levels_array - med) / mad
-        self.str_kmer_levels = {"".join(kmer): self._levels_array[index_from_kmer(kmer)]
-                                for kmer in product(*["ACGT"] * self.kmer_len)}
+        """Median / MAD standardisation of the table (MAD scaled to a standard deviation,
+        refine_signal_map.py:332-342); the dict view is rebuilt from the array."""
+        table = self.levels_array
+        centre = np.median(table)
+        spread = 1.4826 * np.median(np.abs(table - centre))
+        self._levels_array = (table - centre) / spread
+        self.str_kmer_levels = {km: self._levels_array[index_from_kmer(km)] for km in self.kmers}
 
     @property
     def levels_array(self):
-        if self._levels_array is None:
-            if self.str_kmer_levels is None:
-                return None
-            self._levels_array = np.empty(4 ** self.kmer_len, dtype=np.float32)
-            for kmer, level in self.str_kmer_levels.items():
-                self._levels_array[index_from_kmer(kmer)] = level
+        """float32 [4^k] in base-4 k-mer order, built from the dict on first use."""
+        if self._levels_array is None and self.str_kmer_levels is not None:
+            table = np.empty(4 ** self.kmer_len, dtype=np.float32)
+            for km, lv in self.str_kmer_levels.items():
+                table[index_from_kmer(km)] = lv
+            self._levels_array = table
         return self._levels_array
 
     @property
     def kmers(self):
-        from itertools import product
-        for kmer in product("ACGT", repeat=self.kmer_len):
-            yield "".join(kmer)
+        import itertools
+        return ("".join(t) for t in itertools.product("ACGT", repeat=self.kmer_len))
 
     def write_kmer_table(self, fh):
         for kmer in self.kmers:
