@@ -37,6 +37,9 @@ MODEL_PT = os.path.join(ROOT, "tests", "golden", "convlstm_s64_k9_hot.pt")
 BYTES_IFACE_A = 4 * CHUNK_LEN + 4 * 36 * CHUNK_LEN + 4 * 2   # 14 808 B: what the reference model call consumes
 DENSE_MFLOP = 6.989312                                       # 3 494 656 MAC, ConvLSTM_w_ref T=100
 METRIC = "chunks/sec (chunk_len=100, batch=1024)"
+# the workload both arms run (identical string in both lines)
+WORKLOAD = ("synthetic chunks, chunk_len=100, kmer_context=(4,4), ConvLSTM_w_ref size 64 (134082 params), "
+            "batch=1024 per device (BASELINE configs[1]), fp32")
 
 
 def measured_peaks():
@@ -257,9 +260,9 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic chunks, chunk_len=100, kmer_context=(4,4), "
-                               "ConvLSTM_w_ref size 64, batch=1024 (BASELINE configs[1])",
-                   "batch": BATCH, "chunk_len": CHUNK_LEN, "device": "host CPU"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH, "chunk_len": CHUNK_LEN,
+                   "kmer_context": list(KMER_CONTEXT),
+                   "arm": "the reference's own CPU implementation on this box's host cores (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind,
                          "sample": f"{args.steps} batches of {BATCH} chunks; {desc}"},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0,
@@ -697,15 +700,14 @@ def ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "synthetic chunks, chunk_len=100, kmer_context=(4,4), "
-                                   "ConvLSTM_w_ref size 64 (134082 params), batch=1024 per GPU "
-                                   "(BASELINE configs[1]); fp32-parity arithmetic: one sm_100a kernel per "
-                                   "batch, the four GEMM-shaped layers on tcgen05 with fp16 hi/lo split operands "
-                                   "(3 products, 22 significant bits) and fp32 TMEM accumulators, everything else "
-                                   "fp32 FFMA; logits within 1e-4 of the reference CPU forward (tests); the bf16 "
-                                   "variant the config names is timed in `variants`",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": BATCH, "global_batch": world * BATCH,
                        "chunk_len": CHUNK_LEN, "kmer_context": list(KMER_CONTEXT),
+                       "arm": "fp32-parity arithmetic: one sm_100a kernel per batch; the GEMM-shaped layers on tcgen05 "
+                              "with fp16 hi/lo split operands (3 products, 22 significant bits) and fp32 TMEM "
+                              "accumulators, the LSTM recurrence and the small GEMMs on mma.sync (4 products), the "
+                              "rest fp32 FFMA; logits within 1e-4 of the reference CPU forward (tests); the bf16 variant "
+                              "the config names is timed in `variants`",
                        "parallelism": ("single GPU" if world == 1 else
                                        f"batch-shard x{world}; exchange fused into the kernel: "
                                        + ("one extra thread block of every launch ships the previous step's logits "
