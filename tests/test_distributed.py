@@ -141,3 +141,60 @@ def test_logit_ring_layout_blocks_are_disjoint_and_aligned():
             lay.offset(slots, 0, 0)
         with pytest.raises(IndexError):
             lay.flag_word(0, steps, 0)
+
+
+def test_peer_ring_ships_one_step_behind_and_flushes():
+    """Bookkeeping of PeerLogitRing's deferred form without GPUs: every forward hands the kernel the block of the
+    PREVIOUS forward to ship (source view, destination offset, arrival counter), the first one ships nothing,
+    flush() ships the last one exactly once - emulated with a stand-in model that performs the 'peer stores'
+    into plain tensors."""
+    from remora_b200.parallel import LogitRingLayout, PeerLogitRing
+    world, rank, slots, steps, batch, num_out = 3, 1, 2, 2, 5, 2
+    lay = LogitRingLayout(world, slots, steps, batch, num_out)
+    peers = [torch.zeros(lay.n_data + lay.n_flags) for _ in range(world)]   # every rank's ring
+
+    class FakeModel:
+        num_out = 2
+        calls = []
+
+        def forward_compact_ship(self, arrays, out, peer_bases, n_peers, self_rank, ship_src=None, ship_dst_offset=0,
+                                 multicast_ptr=0, flag_word=-1, shape_hint=None):
+            self.calls.append((arrays is None, None if ship_src is None else int(ship_dst_offset), int(flag_word)))
+            if ship_src is not None:                     # the extra thread block: previous block -> every other rank
+                for r in range(n_peers):
+                    if r != self_rank:
+                        peers[r][ship_dst_offset:ship_dst_offset + ship_src.numel()] = ship_src
+                        if flag_word >= 0:
+                            peers[r][flag_word] += 1
+            if arrays is not None:                       # the compute blocks: this rank's own block only
+                out.copy_(arrays[0].reshape(-1)[:out.numel()])
+            else:
+                assert shape_hint == (7, 11, 4)
+
+    ring = object.__new__(PeerLogitRing)                 # the constructor needs symmetric memory: fill in by hand
+    model = FakeModel()
+    ring.world, ring.rank, ring.slots, ring.steps, ring.batch, ring.num_out = world, rank, slots, steps, batch, num_out
+    ring.layout, ring.block_floats, ring.n_data, ring.n_flags = lay, lay.block_floats, lay.n_data, lay.n_flags
+    ring.buf, ring.peers_dev, ring.multicast_ptr, ring.deferred = peers[rank], 0, 0, True
+    ring._pending, ring._shape_hint, ring._model = None, None, model
+    sent = []
+    for i in range(slots * steps):
+        slot, step = i // steps, i % steps
+        sig = torch.full((batch, 1, 7), float(i + 1))
+        arrays = (sig, torch.zeros((batch, 11), dtype=torch.int8), torch.zeros((batch, 4), dtype=torch.int16),
+                  torch.zeros(batch, dtype=torch.int16))
+        ring.forward(model, arrays, slot, step, signal=True)
+        sent.append((slot, step, float(i + 1)))
+    assert model.calls[0][1] is None                                    # nothing to ship with the first forward
+    assert [c[1] for c in model.calls[1:]] == [lay.offset(s_, k, rank) for s_, k, _ in sent[:-1]]   # one step behind
+    last = lay.offset(*sent[-1][:2], rank)
+    assert not torch.equal(peers[0][last:last + batch * num_out], peers[rank][last:last + batch * num_out])
+    ring.flush()
+    ring.flush()                                                        # idempotent: nothing pending any more
+    assert model.calls[-1][0] is True and sum(c[0] for c in model.calls) == 1
+    for r in range(world):                                              # every rank holds every block of this rank
+        for s_, k, val in sent:
+            off = lay.offset(s_, k, rank)
+            assert torch.all(peers[r][off:off + batch * num_out] == val)
+            if r != rank:
+                assert peers[r][lay.flag_word(s_, k, rank)] == 1       # one arrival per shipped block
