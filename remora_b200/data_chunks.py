@@ -337,9 +337,10 @@ class RemoraRead:
         dacs = np.ascontiguousarray(self.dacs)
         if dacs.dtype == np.int16:
             code = 0
-        elif dacs.dtype == np.float32:
-            code = 1
-        else:  # every other dtype is promoted to float64 by numpy in (dacs - shift) / scale
+        elif dacs.dtype == np.float32 and ((dacs[:1] - self.shift) / self.scale).dtype == np.float32:
+            code = 1  # python-float scalars: numpy stays in float32 (two float32 roundings)
+        else:  # everything else - incl. float32 samples with np.float64 shift / scale, as rough re-scaling leaves
+            # them - is computed in float64 by numpy in (dacs - shift) / scale; float32 -> float64 is exact
             dacs, code = dacs.astype(np.float64), 2
         ssm = np.ascontiguousarray(self.seq_to_sig_map, dtype=np.int32)
         focus = np.ascontiguousarray(self.focus_bases, dtype=np.int32)
